@@ -1,0 +1,245 @@
+/*
+ * tutu_b200.h — C ABI of libtutu_b200.so, the B200-native path-tracing core for TutuRenderer.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its two
+ * plugin interfaces are C++ virtuals that are `new`-ed by name in Renderer::Renderer
+ * (reference include/Renderer.hpp:35-54).  The entry points below are what C++ adapters deriving
+ * from those interfaces bind (see include/tutu_adapters.hpp and INTEGRATION.md):
+ *
+ *   IIntersectStrategy::UpdateInter      (reference include/IIntersectStrategy.h:10-11,
+ *                                         BVHStrategy.hpp:8-11 -> BVH.hpp:145 getIntersection)
+ *        -> tutu_trace_closest
+ *   isShadowRayBlocked / hasIntersection (reference include/IIntegrator.hpp:135-153, BVH.hpp:170-194)
+ *        -> tutu_trace_any
+ *   IIntegrator::integrate, PathTracing  (reference include/IIntegrator.hpp:17-24,
+ *                                         PathTracing.hpp:352-475,485-516,136-279)
+ *        -> tutu_render_path
+ *   Scene / BVHAccel / PPMGenerator state read by the integrator
+ *                                        (reference include/Scene.hpp:16-35, BVH.hpp:15-23,47-123,
+ *                                         PPMGenerator.hpp:36-53,317-324, Camera.hpp:81-97)
+ *        -> TutuSceneDesc + tutu_scene_upload (+ tutu_bvh_build for hosts without a reference tree)
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All functions return TUTU_OK (0) or a
+ * negative TUTU_E_* code; tutu_last_error() gives the message.  Nothing here ever falls back to
+ * a CPU implementation: a missing GPU/driver is an error (TUTU_E_CUDA).
+ */
+#ifndef TUTU_B200_H
+#define TUTU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TUTU_ABI_VERSION 1
+
+/* status codes */
+#define TUTU_OK 0
+#define TUTU_E_INVALID (-1) /* bad argument / malformed scene */
+#define TUTU_E_CUDA (-2)    /* CUDA runtime or driver error (includes "no device") */
+#define TUTU_E_STATE (-3)   /* call order (e.g. trace before scene upload) */
+#define TUTU_E_IO (-4)      /* scene file IO */
+#define TUTU_E_NOMEM (-5)
+
+/* primitive kinds — reference include/Object.hpp:9 (OBJTYPE {TRIANGLE, SPEHRE}) */
+#define TUTU_PRIM_TRIANGLE 0
+#define TUTU_PRIM_SPHERE 1
+
+/* material kinds, same order as reference include/Material.hpp:9-16 (MaterialType) */
+#define TUTU_MAT_LAMBERTIAN 0
+#define TUTU_MAT_PERFECT_REFLECTIVE 1
+#define TUTU_MAT_PERFECT_REFRACTIVE 2
+#define TUTU_MAT_MICROFACET_R 3
+#define TUTU_MAT_MICROFACET_T 4
+#define TUTU_MAT_UNLIT 5
+
+/* texture channels — reference include/PPMGenerator.hpp:36-39 */
+#define TUTU_TEX_DIFFUSE 0
+#define TUTU_TEX_NORMAL 1
+#define TUTU_TEX_ROUGHNESS 2
+#define TUTU_TEX_METALLIC 3
+
+/* reference include/Material.hpp:21-30 (same field order; 56 bytes) */
+typedef struct TutuMaterial {
+  float diffuse[3];
+  float specular[3];
+  float emission[3];
+  int32_t type;
+  float alpha;
+  float eta;
+  float roughness;
+  float metallic;
+} TutuMaterial;
+
+/* One reference Object (Triangle.hpp:11-18 / Sphere.hpp:8-9 + Object.hpp:26-35), 124 bytes.
+ * Triangle: v = v0,v1,v2; n = n0,n1,n2; uv = uv0,uv1,uv2.
+ * Sphere:   v[0..2] = centre, v[3] = radius; n, uv ignored. */
+typedef struct TutuPrim {
+  int32_t type;
+  float v[9];
+  float n[9];
+  float uv[6];
+  int32_t material;      /* index into TutuSceneDesc.materials */
+  int32_t tex_active;    /* Object::isTextureActivated */
+  int32_t tex_diffuse;   /* Object::textureIndex,      -1 = none */
+  int32_t tex_normal;    /* Object::normalMapIndex,    -1 = none */
+  int32_t tex_roughness; /* Object::roughnessMapIndex, -1 = none */
+  int32_t tex_metallic;  /* Object::metallicMapIndex,  -1 = none */
+} TutuPrim;
+
+/* Pre-order export of the reference's BVHNode tree (BVH.hpp:15-23): node 0 is the root, an
+ * internal node has left,right >= 0 and prim = -1; a leaf has left = right = -1 and
+ * prim = index into TutuSceneDesc.prims.  Bounds are recomputed by the library with the
+ * reference's own Union/fmin/fmax (BoundBox.hpp:97-124), which is exact. */
+typedef struct TutuBvhNode {
+  int32_t left;
+  int32_t right;
+  int32_t prim;
+} TutuBvhNode;
+
+/* reference include/Texture.hpp:9-14: row-major rgb floats, 3 per texel */
+typedef struct TutuTexture {
+  int32_t width;
+  int32_t height;
+  const float* rgb;
+} TutuTexture;
+
+/* Raw camera inputs as the config file gives them (PPMGenerator.hpp:41-47, Camera.hpp:81-91);
+ * the library derives the ray-generation constants exactly as PathTracing.hpp:357-391 does. */
+typedef struct TutuCamera {
+  float eye[3];
+  float viewdir[3];
+  float updir[3];
+  int32_t hfov_deg;
+  int32_t width;
+  int32_t height;
+  int32_t parallel_projection;
+} TutuCamera;
+
+typedef struct TutuSceneDesc {
+  uint32_t struct_size; /* = sizeof(TutuSceneDesc) */
+  uint32_t n_prims;
+  const TutuPrim* prims; /* Scene::objList order */
+  uint32_t n_materials;
+  uint32_t n_bvh_nodes; /* 0 => the library builds the midpoint BVH itself (tutu_bvh_build) */
+  const TutuMaterial* materials;
+  const TutuBvhNode* bvh_nodes;
+  const TutuTexture* tex[4]; /* indexed by TUTU_TEX_* */
+  uint32_t n_tex[4];
+  TutuCamera camera;
+  float bkgcolor[3];
+  float eta; /* scene index of refraction, PPMGenerator.hpp:48 */
+} TutuSceneDesc;
+
+/* Closest-hit record, 16 bytes.  prim = Scene::objList index, -1 on a miss (then t = FLT_MAX,
+ * u = v = 0).  u,v are the barycentric weights of v1 and v2 (Triangle.hpp:47-49); 0 for spheres. */
+typedef struct TutuHit {
+  int32_t prim;
+  float t;
+  float u;
+  float v;
+} TutuHit;
+
+/* Ray record, 32 bytes: {o.x,o.y,o.z,unused, d.x,d.y,d.z,tmax}.  tmax is only read by
+ * tutu_trace_any* (the `dis` argument of hasIntersection, BVH.hpp:170). */
+#define TUTU_RAY_FLOATS 8
+
+typedef struct TutuSceneInfo {
+  uint32_t n_prims;
+  uint32_t n_nodes;      /* reference-tree node count (2*n_prims-1) */
+  uint32_t n_inner;      /* device inner nodes (n_prims-1) */
+  uint32_t depth;        /* reference-tree depth, root = 0 */
+  uint32_t n_lights;     /* emissive prims, PPMGenerator.hpp:317-324 */
+  uint32_t n_materials;
+  uint32_t width, height;
+  uint64_t device_bytes; /* HBM held by the uploaded scene */
+} TutuSceneInfo;
+
+/* Counters of the last tutu_render_path* call (diagnostics and the roofline arithmetic). */
+typedef struct TutuRenderStats {
+  uint64_t paths;        /* camera samples started */
+  uint64_t extend_rays;  /* closest-hit rays traced */
+  uint64_t shadow_rays;  /* any-hit rays traced */
+  uint64_t shade_calls;  /* shading-vertex evaluations */
+  uint64_t nan_samples;  /* samples dropped by the NaN filter (PathTracing.hpp:510) */
+  uint64_t kernel_launches;
+  uint64_t iterations;   /* wavefront iterations */
+  float gpu_ms;          /* device time of the render, CUDA events on the render stream */
+  float extend_ms, shade_ms, shadow_ms, other_ms; /* only filled when profiling is enabled */
+} TutuRenderStats;
+
+typedef struct TutuCtx TutuCtx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int tutu_abi_version(void);
+/* device = CUDA ordinal.  Fails with TUTU_E_CUDA when no usable GPU exists (no CPU fallback). */
+int tutu_ctx_create(int device, TutuCtx** out);
+void tutu_ctx_destroy(TutuCtx* ctx);
+/* Message of the last failing call on this ctx (or, with ctx == NULL, on this thread). */
+const char* tutu_last_error(const TutuCtx* ctx);
+
+/* ---- scene ------------------------------------------------------------------------------ */
+/* Flatten + upload.  Host pointers are not retained past the call. */
+int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc);
+int tutu_scene_info(const TutuCtx* ctx, TutuSceneInfo* out);
+/* Change the frame size / camera without re-uploading geometry. */
+int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam);
+
+/* ---- ray batches: IIntersectStrategy::UpdateInter / hasIntersection --------------------- */
+/* Host buffers: H2D copy of rays, traversal, D2H copy of results, synchronous. */
+int tutu_trace_closest(TutuCtx* ctx, const float* rays, uint64_t n_rays, TutuHit* hits_out);
+int tutu_trace_any(TutuCtx* ctx, const float* rays, uint64_t n_rays, uint8_t* blocked_out);
+/* Device buffers (CUDA device pointers valid on the ctx's device), asynchronous on `stream`
+ * (a cudaStream_t / CUstream passed as void*, NULL = the ctx's own stream). */
+int tutu_trace_closest_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays,
+                              TutuHit* d_hits_out, void* stream);
+int tutu_trace_any_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays,
+                          uint8_t* d_blocked_out, void* stream);
+/* Traversal variant: 0 = ordered + t-pruned (default), 1 = unpruned both-children walk that
+ * mirrors the reference's recursion literally (used as a second opinion by the tests). */
+int tutu_set_traversal_mode(TutuCtx* ctx, int mode);
+/* Visit counters for the algorithmic-bytes figure: traces the batch with counting kernels and
+ * returns total inner-node fetches and primitive tests. */
+int tutu_trace_count_visits(TutuCtx* ctx, const float* d_rays, uint64_t n_rays, int any_hit,
+                            uint64_t* nodes_out, uint64_t* prims_out);
+
+/* ---- PathTracing::integrate ------------------------------------------------------------- */
+/* Whole render through host memory: spp samples per pixel, linear radiance written to
+ * rgb_out[(y*width+x)*3 + c] exactly where the reference writes cam.FrameBuffer.rgb
+ * (PathTracing.hpp:501,513).  Synchronous. */
+int tutu_render_path(TutuCtx* ctx, uint32_t spp, uint64_t seed, float* rgb_out);
+/* Multi-GPU building block: accumulate samples [sample_begin, sample_begin+sample_count) of
+ * every pixel as SUMS (NaN samples dropped) into d_accum (width*height*3 floats on the device,
+ * not cleared), asynchronous on `stream`.  The caller reduces d_accum across ranks and then calls
+ * tutu_finalize_device with inv_spp = 1/total_spp. */
+int tutu_render_path_accumulate_device(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count,
+                                       uint64_t seed, float* d_accum, void* stream);
+int tutu_finalize_device(TutuCtx* ctx, const float* d_accum, float inv_spp, float* d_rgb_out,
+                         void* stream);
+int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
+/* Knobs: paths in flight (0 = default), per-stage event timing on/off. */
+int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int profile_stages);
+
+/* ---- host-side helpers (no GPU needed) -------------------------------------------------- */
+/* Midpoint BVH with the reference's split rule (BVH.hpp:47-123).  nodes_out must hold
+ * 2*n_prims-1 entries (1 if n_prims <= 1). */
+int tutu_bvh_build(const TutuPrim* prims, uint32_t n_prims, TutuBvhNode* nodes_out,
+                   uint32_t* n_nodes_out);
+/* Scene files (tests, benches, the oracle harness): a flat little-endian dump of TutuSceneDesc. */
+typedef struct TutuSceneFile TutuSceneFile;
+int tutu_scene_file_load(const char* path, TutuSceneFile** out);
+const TutuSceneDesc* tutu_scene_file_desc(const TutuSceneFile* f);
+void tutu_scene_file_free(TutuSceneFile* f);
+int tutu_scene_file_save(const TutuSceneDesc* desc, const char* path);
+/* Synthetic workload of BASELINE.json configs[1]: a G x G height-field (2*G*G triangles) and
+ * ray batches against it.  prims_out must hold 2*G*G entries; rays_out n_rays*8 floats.
+ * kind: 0 = top-down rays (coherent, ~all hit), 1 = incoherent rays from inside the bounds. */
+int tutu_synth_heightfield(uint32_t G, uint64_t seed, TutuPrim* prims_out);
+int tutu_synth_rays(int kind, uint64_t seed, uint64_t first, uint64_t n_rays, float* rays_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TUTU_B200_H */

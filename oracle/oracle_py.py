@@ -1,0 +1,158 @@
+"""ctypes binding of the CPU oracle (oracle/libtutu_oracle.so) and of the compiled reference
+harness (oracle/_ref/ref_harness).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, tools/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under tuturenderer_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libtutu_oracle.so"
+REF_DIR = HERE / "_ref"
+REF_HARNESS = REF_DIR / "ref_harness"
+
+_lib = None
+
+
+def build(ref: bool = True) -> None:
+    """Compiles the oracle port and (when /root/reference is present) the reference harness."""
+    subprocess.run(["make", "-s", "-C", str(HERE), "port"], check=True)
+    if ref:
+        subprocess.run(["make", "-s", "-C", str(HERE), "ref"], check=True)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            build(ref=False)
+        l = C.CDLL(str(LIB_PATH))
+        P = C.c_void_p
+        l.oracle_scene_create.restype = P
+        l.oracle_scene_create.argtypes = [P]
+        l.oracle_scene_destroy.argtypes = [P]
+        l.oracle_bvh_node_count.restype = C.c_uint32
+        l.oracle_bvh_node_count.argtypes = [P]
+        l.oracle_bvh_export.restype = C.c_uint32
+        l.oracle_bvh_export.argtypes = [P, P]
+        l.oracle_trace_closest.argtypes = [P, P, C.c_uint64, P, C.c_int]
+        l.oracle_trace_any.argtypes = [P, P, C.c_uint64, P, C.c_int]
+        l.oracle_render_path.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, P, P, C.c_int]
+        l.oracle_primary_rays.argtypes = [P, P]
+        _lib = l
+    return _lib
+
+
+class OracleScene:
+    """The reference's algorithm restated on the CPU, over a tuturenderer_b200.api.Scene."""
+
+    def __init__(self, scene):
+        from tuturenderer_b200 import api  # PODs / dtypes only
+        self._api = api
+        self.scene = scene
+        d, keep = scene.to_c()
+        self._h = lib().oracle_scene_create(C.byref(d))
+        del keep
+        if not self._h:
+            raise RuntimeError("oracle_scene_create failed")
+
+    def close(self):
+        if self._h:
+            lib().oracle_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def bvh_export(self) -> np.ndarray:
+        n = lib().oracle_bvh_node_count(self._h)
+        out = np.zeros(max(n, 1), self._api.BVHNODE_DTYPE)
+        cnt = lib().oracle_bvh_export(self._h, out.ctypes.data)
+        return out[:cnt]
+
+    def trace_closest(self, rays: np.ndarray, threads: int = 0) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        out = np.empty(len(rays), self._api.HIT_DTYPE)
+        lib().oracle_trace_closest(self._h, rays.ctypes.data, len(rays), out.ctypes.data, threads)
+        return out
+
+    def trace_any(self, rays: np.ndarray, threads: int = 0) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        out = np.empty(len(rays), np.uint8)
+        lib().oracle_trace_any(self._h, rays.ctypes.data, len(rays), out.ctypes.data, threads)
+        return out
+
+    def render_path(self, spp: int, seed: int = 1, sample_begin: int = 0, total_spp: int | None = None,
+                    threads: int = 0, counters: bool = False):
+        out = np.empty((self.scene.height, self.scene.width, 3), np.float32)
+        cnt = np.zeros(3, np.uint64)
+        lib().oracle_render_path(self._h, sample_begin, spp, total_spp or spp, seed, out.ctypes.data,
+                                 cnt.ctypes.data, threads)
+        return (out, cnt) if counters else out
+
+    def primary_rays(self) -> np.ndarray:
+        out = np.empty((self.scene.height * self.scene.width, 8), np.float32)
+        lib().oracle_primary_rays(self._h, out.ctypes.data)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the compiled reference (oracle/_ref/ref_harness)
+# ------------------------------------------------------------------------------------------------
+def ref_available() -> bool:
+    return REF_HARNESS.exists() and os.access(REF_HARNESS, os.X_OK)
+
+
+def _run(args: list[str], timeout: float | None = None) -> dict:
+    res = subprocess.run([str(REF_HARNESS), *args], capture_output=True, text=True, timeout=timeout)
+    if res.returncode != 0:
+        raise RuntimeError(f"ref_harness {' '.join(args)} failed ({res.returncode}): {res.stderr[-2000:]}")
+    last = [l for l in res.stdout.strip().splitlines() if l.startswith("{")]
+    return json.loads(last[-1]) if last else {}
+
+
+def ref_dump_cornell(width: int, height: int, out_path) -> dict:
+    return _run(["dump-cornell", str(REF_DIR / "model"), str(width), str(height), str(out_path)])
+
+
+def ref_export_bvh(scene, out_path=None):
+    """Runs Scene::initializeBVH of the reference on `scene`; returns the scene with its tree."""
+    from tuturenderer_b200.api import Scene
+    with tempfile.TemporaryDirectory() as td:
+        src = Path(td) / "in.tscene"
+        dst = Path(out_path) if out_path else Path(td) / "out.tscene"
+        scene.save(src)
+        _run(["export-bvh", str(src), str(dst)])
+        return Scene.load(dst)
+
+
+def ref_trace(scene, rays: np.ndarray, kind: str = "closest", threads: int = 0):
+    """getIntersection / hasIntersection of the reference; returns (result, info)."""
+    from tuturenderer_b200.api import HIT_DTYPE
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    with tempfile.TemporaryDirectory() as td:
+        sp, rp, op = Path(td) / "s.tscene", Path(td) / "r.f32", Path(td) / "o.bin"
+        scene.save(sp)
+        rays.tofile(rp)
+        info = _run(["trace", str(sp), str(rp), kind, str(op), str(threads)])
+        out = np.fromfile(op, dtype=np.uint8 if kind == "any" else HIT_DTYPE)
+    return out, info
+
+
+def ref_render(scene, spp: int, mode: str = "rows", timeout: float | None = None):
+    """PathTracing::integrate of the reference; returns (linear float image, info)."""
+    with tempfile.TemporaryDirectory() as td:
+        sp, op = Path(td) / "s.tscene", Path(td) / "o.f32"
+        scene.save(sp)
+        info = _run(["render", str(sp), str(spp), str(op), mode], timeout=timeout)
+        img = np.fromfile(op, dtype=np.float32).reshape(scene.height, scene.width, 3)
+    return img, info

@@ -1,0 +1,111 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference (oracle/_ref/ref_harness, built by
+oracle/Makefile from /root/reference) in this container.  The fixtures travel to the GPU box,
+/root/reference does not.  Re-run:  python tools/make_golden.py [--renders]
+
+Fixtures:
+  cornell_256.tscene         scene of src/main_cornellBox.cpp via objl::Loader + loadObj, with the
+                             reference-built BVH topology (pre-order)
+  cornell_rays.f32           deterministic ray batch (64x64 primary rays + rays from inside the box)
+  cornell_closest.bin        getIntersection per ray {prim,t,u,v}
+  cornell_any.bin            hasIntersection per ray
+  hf24.tscene / hf24_*       24x24 height-field (1152 triangles) + both synthetic ray kinds
+  mixed.tscene / mixed_*     spheres + triangles, every material type, 4 texture channels
+  *_ref_mean_*.f32, stats.json   (with --renders) high-spp reference renders and noise statistics
+"""
+import json, sys
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from tuturenderer_b200 import api
+from oracle import oracle_py as O
+G = ROOT / "tests" / "golden"
+
+
+def cornell_rays(scene):
+    s64 = scene.with_size(64, 64)
+    prim = O.OracleScene(s64).primary_rays()
+    rng = np.random.default_rng(2024)
+    n = 12000
+    extra = np.zeros((n, 8), np.float32)
+    extra[:, 0:3] = rng.uniform([0, 0, 0], [556, 548, 559], (n, 3))
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    extra[:, 4:7] = d
+    extra[:, 7] = rng.uniform(5, 700, n)
+    # axis-parallel rays (zero direction components -> inf/NaN slabs) from points on box planes
+    ax = np.zeros((600, 8), np.float32)
+    ax[:, 0:3] = rng.choice([0.0, 130.0, 278.0, 548.8, 556.0, 559.2], (600, 3))
+    k = rng.integers(0, 3, 600)
+    ax[np.arange(600), 4 + k] = rng.choice([-1.0, 1.0], 600)
+    ax[:, 7] = 400.0
+    prim[:, 7] = 900.0
+    return np.concatenate([prim, extra, ax]).astype(np.float32)
+
+
+def main():
+    G.mkdir(parents=True, exist_ok=True)
+    O.build(ref=True)
+    assert O.ref_available(), "oracle/_ref/ref_harness missing (needs /root/reference)"
+    O.ref_dump_cornell(256, 256, G / "cornell_256.tscene")
+    sc = api.Scene.load(G / "cornell_256.tscene")
+    rays = cornell_rays(sc)
+    rays.tofile(G / "cornell_rays.f32")
+    O.ref_trace(sc, rays, "closest")[0].tofile(G / "cornell_closest.bin")
+    O.ref_trace(sc, rays, "any")[0].tofile(G / "cornell_any.bin")
+    print("cornell:", len(sc.prims), "prims", len(rays), "rays")
+
+    # height-field
+    prims = api.synth_heightfield(24, 12345)
+    hf = api.Scene(prims=prims, materials=api.default_material(), width=32, height=32,
+                   eye=(0.5, 1.5, 0.5), viewdir=(0, -1, 0), updir=(0, 0, 1))
+    hf = O.ref_export_bvh(hf, G / "hf24.tscene")
+    for kind in (0, 1):
+        r = api.synth_rays(kind, 6000, 12345)
+        r.tofile(G / f"hf24_rays{kind}.f32")
+        O.ref_trace(hf, r, "closest")[0].tofile(G / f"hf24_closest{kind}.bin")
+        O.ref_trace(hf, r, "any")[0].tofile(G / f"hf24_any{kind}.bin")
+    print("hf24:", len(hf.prims), "prims")
+
+    from tools.scenes import mixed_scene
+    mx = O.ref_export_bvh(mixed_scene(96, 96), G / "mixed.tscene")
+    rng = np.random.default_rng(7)
+    n = 8000
+    r = np.zeros((n, 8), np.float32)
+    r[:, 0:3] = rng.uniform([20, 20, 20], [530, 530, 530], (n, 3))
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r[:, 4:7] = d.astype(np.float32)
+    # Sphere::intersect assumes unit directions; renormalise in float like the reference would
+    r[:, 7] = rng.uniform(5, 700, n)
+    r = np.concatenate([O.OracleScene(mx).primary_rays(), r]).astype(np.float32)
+    r[:, 7] = np.where(r[:, 7] > 1e30, 900.0, r[:, 7])
+    r.tofile(G / "mixed_rays.f32")
+    O.ref_trace(mx, r, "closest")[0].tofile(G / "mixed_closest.bin")
+    O.ref_trace(mx, r, "any")[0].tofile(G / "mixed_any.bin")
+    print("mixed:", len(mx.prims), "prims")
+
+    if "--renders" in sys.argv:
+        stats = {}
+        c128 = sc.with_size(128, 128)
+        runs = [O.ref_render(c128, 2048)[0] for _ in range(2)]
+        mean = (runs[0] + runs[1]) * 0.5
+        mean.astype(np.float32).tofile(G / "cornell_128_ref_mean_4096.f32")
+        def rmse(a, b): return float(np.sqrt(((a - b) ** 2).mean()))
+        def relmse(a, b): return float((((a - b) ** 2) / (b ** 2 + 1e-2)).mean())
+        stats["cornell_128"] = {"ref_spp_total": 4096, "image_mean": float(mean.mean()),
+                                "channel_means": [float(x) for x in mean.mean((0, 1))],
+                                "run_to_run_rmse_2048": rmse(runs[0], runs[1])}
+        for spp in (16, 64):
+            imgs = [O.ref_render(c128, spp)[0] for _ in range(4)]
+            stats["cornell_128"][f"rmse_{spp}"] = float(np.mean([rmse(i, mean) for i in imgs]))
+            stats["cornell_128"][f"relmse_{spp}"] = float(np.mean([relmse(i, mean) for i in imgs]))
+        m96 = [O.ref_render(mx, 1024)[0] for _ in range(2)]
+        mm = (m96[0] + m96[1]) * 0.5
+        mm.astype(np.float32).tofile(G / "mixed_96_ref_mean_2048.f32")
+        stats["mixed_96"] = {"ref_spp_total": 2048, "image_mean": float(np.nanmean(mm)),
+                             "run_to_run_rmse_1024": rmse(m96[0], m96[1])}
+        (G / "stats.json").write_text(json.dumps(stats, indent=1))
+        print(json.dumps(stats, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,283 @@
+// trace.cuh — BVH closest-hit / any-hit traversal and primitive intersection for sm_100a.
+//
+// Arithmetic contract: everything that decides WHICH primitive is hit is written with explicit
+// round-to-nearest intrinsics (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn), which ptxas
+// never contracts into FMAs, in the operand order of the reference's scalar C++:
+//   BoundBox::IntersectRay  reference include/BoundBox.hpp:55-92
+//   Triangle::intersect     reference include/Triangle.hpp:23-74
+//   Sphere::intersect       reference include/Sphere.hpp:26-126 (+ solveQuadratic global.hpp:147-167)
+//   getIntersection         reference include/BVH.hpp:145-167   (tie: leftmost DFS leaf wins)
+//   hasIntersection         reference include/BVH.hpp:170-194
+// B200 has no RT cores: traversal is software, one ray per thread, a short per-thread stack,
+// one 64-byte inner node (both child boxes) fetched as 4 x LDG.128 through L1/L2.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tutu {
+
+constexpr int kStackSize = 32;          // >= tree depth; checked at upload
+constexpr uint32_t kSphereBit = 1u << 30;
+constexpr uint32_t kSlotMask = kSphereBit - 1u;
+
+struct DevScene {
+  const float4* __restrict__ inner;     // 4 x float4 per inner node
+  const float4* __restrict__ geom;      // 3 x float4 per leaf slot
+  const float4* __restrict__ shade;     // 4 x float4 per leaf slot
+  const int4* __restrict__ leaftex;     // per leaf slot, or nullptr when no prim is textured
+  const int* __restrict__ slot_to_prim;
+  const float4* __restrict__ materials; // 4 x float4 per material
+  const float4* __restrict__ lights;    // 8 x float4 per light
+  const int4* __restrict__ tex_headers[4];  // {width, height, offset, n_texels}
+  const float4* __restrict__ texels;
+  float root_lo[3];
+  float root_hi[3];
+  int root_ref;
+  int empty;
+  int n_lights;
+  float bkg[3];
+  float eta;
+};
+
+struct Ray {
+  float ox, oy, oz;
+  float dx, dy, dz;
+};
+
+struct Hit {
+  float t, u, v;
+  int slot;  // leaf slot (DFS order) | kSphereBit for spheres, -1 = miss
+};
+
+// ---- exact float helpers (Vector.hpp:186,213-225) ------------------------------------------
+__device__ __forceinline__ float dot_rn(float ax, float ay, float az, float bx, float by, float bz) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+__device__ __forceinline__ float cross_c(float a, float b, float c, float d) {  // a*b - c*d
+  return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+}
+// normalized(): mag = sqrtf(x*x+y*y+z*z); if (mag>0) v * (1/mag) else v
+__device__ __forceinline__ void normalize_rn(float& x, float& y, float& z) {
+  float mag = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+  if (mag > 0.f) {
+    float inv = __fdiv_rn(1.f, mag);
+    x = __fmul_rn(x, inv);
+    y = __fmul_rn(y, inv);
+    z = __fmul_rn(z, inv);
+  }
+}
+
+struct RayPre {  // per-ray constants of the slab test
+  float ox, oy, oz;
+  float ix, iy, iz;     // 1/d, IEEE (inf for 0)
+  bool nx, ny, nz;      // d < 0 (false for -0, like the reference's std::swap condition)
+};
+
+__device__ __forceinline__ RayPre make_pre(const Ray& r) {
+  RayPre p;
+  p.ox = r.ox, p.oy = r.oy, p.oz = r.oz;
+  p.ix = __fdiv_rn(1.f, r.dx);
+  p.iy = __fdiv_rn(1.f, r.dy);
+  p.iz = __fdiv_rn(1.f, r.dz);
+  p.nx = r.dx < 0.f;
+  p.ny = r.dy < 0.f;
+  p.nz = r.dz < 0.f;
+  return p;
+}
+
+// BoundBox::IntersectRay.  The reference computes tmin/tmax per axis and swaps them when d<0;
+// selecting the plane before the (identical) subtract-multiply gives the same two values.
+// The ternaries are kept literally: with NaN operands (0*inf) they are NOT fmaxf/fminf.
+__device__ __forceinline__ bool box_test(const RayPre& p, float lox, float loy, float loz, float hix,
+                                         float hiy, float hiz, float& t_enter) {
+  float tmin_x = __fmul_rn(__fsub_rn(p.nx ? hix : lox, p.ox), p.ix);
+  float tmax_x = __fmul_rn(__fsub_rn(p.nx ? lox : hix, p.ox), p.ix);
+  float tmin_y = __fmul_rn(__fsub_rn(p.ny ? hiy : loy, p.oy), p.iy);
+  float tmax_y = __fmul_rn(__fsub_rn(p.ny ? loy : hiy, p.oy), p.iy);
+  float tmin_z = __fmul_rn(__fsub_rn(p.nz ? hiz : loz, p.oz), p.iz);
+  float tmax_z = __fmul_rn(__fsub_rn(p.nz ? loz : hiz, p.oz), p.iz);
+  float buffer = tmin_y > tmin_z ? tmin_y : tmin_z;
+  t_enter = tmin_x > buffer ? tmin_x : buffer;
+  buffer = tmax_y < tmax_z ? tmax_y : tmax_z;
+  float t_exit = tmax_x < buffer ? tmax_x : buffer;
+  return t_enter <= t_exit && t_exit >= 0.f;
+}
+
+// Triangle::intersect with E1, E2 and the unit normal precomputed on the host (same float ops).
+__device__ __forceinline__ bool tri_test(const float4* __restrict__ g, const Ray& r, float& t, float& u,
+                                         float& v) {
+  const float4 a = __ldg(g + 0);  // v0.xyz, E1.x
+  const float4 b = __ldg(g + 1);  // E1.y, E1.z, E2.x, E2.y
+  const float4 c = __ldg(g + 2);  // E2.z, n.xyz
+  const float e1x = a.w, e1y = b.x, e1z = b.y;
+  const float e2x = b.z, e2y = b.w, e2z = c.x;
+  // FLOAT_EQUAL(dir.dot(normal), 0.f): fabs(x - 0) < 1e-4
+  const float dn = dot_rn(r.dx, r.dy, r.dz, c.y, c.z, c.w);
+  if (fabsf(dn) < 0.0001f) return false;
+  const float sx = __fsub_rn(r.ox, a.x), sy = __fsub_rn(r.oy, a.y), sz = __fsub_rn(r.oz, a.z);
+  // S1 = dir x E2, S2 = S x E1
+  const float s1x = cross_c(r.dy, e2z, r.dz, e2y);
+  const float s1y = cross_c(r.dz, e2x, r.dx, e2z);
+  const float s1z = cross_c(r.dx, e2y, r.dy, e2x);
+  const float det = dot_rn(s1x, s1y, s1z, e1x, e1y, e1z);
+  if (det == 0.f) return false;
+  const float s2x = cross_c(sy, e1z, sz, e1y);
+  const float s2y = cross_c(sz, e1x, sx, e1z);
+  const float s2z = cross_c(sx, e1y, sy, e1x);
+  const float left = __fdiv_rn(1.0f, det);
+  t = __fmul_rn(left, dot_rn(s2x, s2y, s2z, e2x, e2y, e2z));
+  u = __fmul_rn(left, dot_rn(s1x, s1y, s1z, sx, sy, sz));
+  v = __fmul_rn(left, dot_rn(s2x, s2y, s2z, r.dx, r.dy, r.dz));
+  return t > 0.f && __fsub_rn(__fsub_rn(1.f, u), v) > 0.f && u > 0.f && v > 0.f;
+}
+
+// Sphere::intersect.  C is summed in double (std::pow(float,int) promotes) and rounded once.
+__device__ __noinline__ bool sphere_test(const float4* __restrict__ g, const Ray& r, float& t) {
+  const float4 a = __ldg(g + 0);  // centre.xyz, radius
+  const float ocx = __fsub_rn(r.ox, a.x), ocy = __fsub_rn(r.oy, a.y), ocz = __fsub_rn(r.oz, a.z);
+  const float B = __fmul_rn(2.f, dot_rn(r.dx, r.dy, r.dz, ocx, ocy, ocz));
+  const double Cd = __dsub_rn(
+      __dadd_rn(__dadd_rn(__dmul_rn((double)ocx, (double)ocx), __dmul_rn((double)ocy, (double)ocy)),
+                __dmul_rn((double)ocz, (double)ocz)),
+      (double)__fmul_rn(a.w, a.w));
+  const float C = __double2float_rn(Cd);
+  // solveQuadratic with A = 1: B*B - 4*A*C
+  const float disc = __fsub_rn(__fmul_rn(B, B), __fmul_rn(4.f, C));
+  float t1, t2;
+  if (disc < 0.f) {
+    t1 = FLT_MAX;
+    t2 = FLT_MAX;
+  } else if (disc == 0.f) {
+    t1 = __fdiv_rn(__fadd_rn(-B, __fsqrt_rn(disc)), 2.f);
+    t2 = t1;
+  } else {
+    t1 = __fdiv_rn(__fadd_rn(-B, __fsqrt_rn(disc)), 2.f);
+    t2 = __fdiv_rn(__fsub_rn(-B, __fsqrt_rn(disc)), 2.f);
+  }
+  if (t1 > t2) {
+    float s = t1;
+    t1 = t2;
+    t2 = s;
+  }
+  const bool eq1 = fabsf(__fsub_rn(t1, FLT_MAX)) < 0.0001f;
+  const bool eq2 = fabsf(__fsub_rn(t2, FLT_MAX)) < 0.0001f;
+  if (eq1 && eq2) return false;
+  if (fabsf(__fsub_rn(t1, t2)) < 0.0001f) {  // "one solution"
+    if (t1 < 0.f) return false;
+    t = t1;
+    return true;
+  }
+  if (t1 > 0.f && t2 > 0.f) t = t1;
+  else if (t1 > 0.f && t2 < 0.f)
+    t = t1;
+  else if (t1 < 0.f && t2 > 0.f)
+    t = t2;
+  else
+    return false;
+  return true;
+}
+
+struct VisitCount {
+  unsigned nodes = 0, prims = 0;
+};
+
+// MODE 0: ordered (near child first) + pruned by the best t so far.  A subtree is skipped only
+//         when its box is entered strictly AFTER the best hit (t_enter > best_t); equal t is kept
+//         and resolved by the lower DFS leaf slot, which is the reference's tie rule.
+// MODE 1: literal mirror of the reference recursion: left then right, nothing pruned.
+// ANY:    hasIntersection — first accepted leaf ends the walk (the boolean is order independent).
+template <bool ANY, int MODE, bool COUNT>
+__device__ __forceinline__ bool traverse(const DevScene& sc, const Ray& r, float dis, Hit& best,
+                                         VisitCount* vc) {
+  best.t = FLT_MAX;
+  best.u = 0.f;
+  best.v = 0.f;
+  best.slot = -1;
+  if (sc.empty) return false;
+  const RayPre p = make_pre(r);
+  float te;
+  if (!box_test(p, sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1],
+                sc.root_hi[2], te))
+    return false;
+
+  int stack_ref[kStackSize];
+  float stack_t[kStackSize];
+  int sp = 0;
+  int cur = sc.root_ref;
+  const float limit_any = dis;
+
+  for (;;) {
+    if (cur >= 0) {
+      const float4* n = sc.inner + 4 * (size_t)cur;
+      const float4 a = __ldg(n + 0);
+      const float4 b = __ldg(n + 1);
+      const float4 c = __ldg(n + 2);
+      const int4 k = __ldg(reinterpret_cast<const int4*>(n + 3));
+      if (COUNT) vc->nodes++;
+      float tl, tr;
+      bool hl = box_test(p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
+      bool hr = box_test(p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+      if (MODE == 0) {
+        const float lim = ANY ? limit_any : best.t;
+        hl = hl && !(tl > lim);
+        hr = hr && !(tr > lim);
+      }
+      if (hl && hr) {
+        const bool left_first = (MODE == 1) || !(tr < tl);
+        const int near_ref = left_first ? k.x : k.y;
+        const int far_ref = left_first ? k.y : k.x;
+        stack_ref[sp] = far_ref;
+        stack_t[sp] = left_first ? tr : tl;
+        ++sp;
+        cur = near_ref;
+        continue;
+      }
+      if (hl) {
+        cur = k.x;
+        continue;
+      }
+      if (hr) {
+        cur = k.y;
+        continue;
+      }
+    } else {
+      const uint32_t code = ~(uint32_t)cur;
+      const uint32_t slot = code & kSlotMask;
+      const float4* g = sc.geom + 3 * (size_t)slot;
+      if (COUNT) vc->prims++;
+      float t, u = 0.f, v = 0.f;
+      bool hit;
+      if (code & kSphereBit)
+        hit = sphere_test(g, r, t);
+      else
+        hit = tri_test(g, r, t, u, v);
+      if (hit) {
+        if (ANY) {
+          // inter.t < dis && !FLOAT_EQUAL(inter.t, dis)
+          if (t < dis && !(fabsf(__fsub_rn(t, dis)) < 0.0001f)) {
+            best.t = t;
+            best.slot = (int)code;
+            return true;
+          }
+        } else if (t < best.t || (t == best.t && (int)slot < (best.slot & (int)kSlotMask))) {
+          // linter.t <= rinter.t ? linter : rinter  ==  lowest DFS leaf among equal t
+          best.t = t;
+          best.u = u;
+          best.v = v;
+          best.slot = (int)code;
+        }
+      }
+    }
+    // pop
+    for (;;) {
+      if (sp == 0) return best.slot >= 0;
+      --sp;
+      cur = stack_ref[sp];
+      if (MODE == 0 && !ANY && stack_t[sp] > best.t) continue;  // entered after the current best
+      break;
+    }
+  }
+}
+
+}  // namespace tutu

@@ -1,0 +1,675 @@
+// tutu_b200.cu — device side of libtutu_b200.so: context, scene upload, the ray-batch kernels
+// and the host loop of the wavefront path tracer, behind the C ABI of include/tutu_b200.h.
+// sm_100a only; there is no CPU fallback anywhere in this file.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "tutu_internal.hpp"
+#include "wavefront.cuh"
+
+using namespace tutu;
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct CudaError {
+  cudaError_t code;
+  const char* what;
+  const char* file;
+  int line;
+};
+
+#define CUDA_TRY(expr)                                                   \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) throw CudaError{_e, #expr, __FILE__, __LINE__}; \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    release();
+    CUDA_TRY(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+template <class T>
+void upload_vec(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
+  b.ensure(std::max<size_t>(v.size() * sizeof(T), 16));
+  if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+
+}  // namespace
+
+struct TutuCtx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  std::mutex mu;  // adapters may call UpdateInter from many host threads (PathTracing.hpp:394-429)
+
+  // scene
+  bool has_scene = false;
+  FlatScene flat;
+  DevScene dev{};
+  DevBuf d_inner, d_geom, d_shade, d_leaftex, d_slot_to_prim, d_materials, d_lights, d_texels;
+  DevBuf d_texh[4];
+  uint64_t scene_bytes = 0;
+  int traversal_mode = 0;
+
+  // ray batches
+  DevBuf d_rays, d_hits, d_blocked, d_counts;
+
+  // wavefront
+  DevBuf wf_pool, wf_ctl, d_accum, d_rgb;
+  WfBuffers wf{};
+  uint64_t wf_capacity = 0;
+  uint64_t paths_in_flight_cfg = 0;
+  int profile_stages = 0;
+  TutuRenderStats stats{};
+  int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_raygen = 0;
+};
+
+namespace {
+
+const char* ctx_error_hook(const TutuCtx* c) { return c->last_error.c_str(); }
+struct HookInstaller {
+  HookInstaller() { g_ctx_error_hook = &ctx_error_hook; }
+} g_hook_installer;
+
+int fail(TutuCtx* ctx, int code, const std::string& msg) {
+  set_error(msg);
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+int fail_cuda(TutuCtx* ctx, const CudaError& e) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e.code, cudaGetErrorString(e.code),
+           e.file, e.line, e.what);
+  cudaGetLastError();  // clear the sticky-less error state
+  return fail(ctx, TUTU_E_CUDA, buf);
+}
+
+#define API_BEGIN(ctx)                                                 \
+  if (!(ctx)) return fail(nullptr, TUTU_E_INVALID, "null context");    \
+  std::lock_guard<std::mutex> _lock((ctx)->mu);                        \
+  try {                                                                \
+    CUDA_TRY(cudaSetDevice((ctx)->device));
+#define API_END(ctx)                                                   \
+  }                                                                    \
+  catch (const CudaError& e) { return fail_cuda((ctx), e); }           \
+  catch (const std::bad_alloc&) { return fail((ctx), TUTU_E_NOMEM, "out of host memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// ray-batch kernels
+// ---------------------------------------------------------------------------------------------
+// One ray per thread; warps pull 32-ray packets from a global counter (persistent threads), so a
+// warp that drew short rays moves on instead of idling behind the block's slowest warp.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_trace_closest(const DevScene sc, const float4* __restrict__ rays, unsigned long long n,
+                TutuHit* __restrict__ out, unsigned long long* __restrict__ next) {
+  const unsigned lane = threadIdx.x & 31u;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(next, 32ull);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n) return;
+    const unsigned long long i = base + lane;
+    if (i < n) {
+      const float4 o = __ldg(rays + 2 * i);
+      const float4 d = __ldg(rays + 2 * i + 1);
+      Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
+      Hit h;
+      traverse<false, MODE, false>(sc, r, 0.f, h, nullptr);
+      TutuHit t;
+      t.prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
+      t.t = h.t;
+      t.u = h.u;
+      t.v = h.v;
+      reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(t.prim), t.t, t.u, t.v);
+    }
+    __syncwarp();
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_trace_any(const DevScene sc, const float4* __restrict__ rays, unsigned long long n,
+            uint8_t* __restrict__ out, unsigned long long* __restrict__ next) {
+  const unsigned lane = threadIdx.x & 31u;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(next, 32ull);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n) return;
+    const unsigned long long i = base + lane;
+    if (i < n) {
+      const float4 o = __ldg(rays + 2 * i);
+      const float4 d = __ldg(rays + 2 * i + 1);
+      Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
+      Hit h;
+      out[i] = traverse<true, MODE, false>(sc, r, d.w, h, nullptr) ? 1 : 0;
+    }
+    __syncwarp();
+  }
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(256)
+k_trace_count(const DevScene sc, const float4* __restrict__ rays, unsigned long long n,
+              unsigned long long* __restrict__ counts) {
+  unsigned long long nodes = 0, prims = 0;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float4 o = __ldg(rays + 2 * i);
+    const float4 d = __ldg(rays + 2 * i + 1);
+    Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
+    Hit h;
+    VisitCount vc;
+    traverse<ANY, 0, true>(sc, r, d.w, h, &vc);
+    nodes += vc.nodes;
+    prims += vc.prims;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nodes += __shfl_down_sync(0xFFFFFFFFu, nodes, o);
+    prims += __shfl_down_sync(0xFFFFFFFFu, prims, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(counts + 0, nodes);
+    atomicAdd(counts + 1, prims);
+  }
+}
+
+template <class K>
+int persistent_grid(TutuCtx* ctx, K kernel, int block) {
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
+  if (per_sm < 1) per_sm = 1;
+  return ctx->sm_count * per_sm;  // a multiple of the SM count: one resident wave
+}
+
+void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_out, cudaStream_t s) {
+  if (n == 0) return;
+  ctx->d_counts.ensure(64);
+  unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 4;
+  CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
+  const float4* rays = reinterpret_cast<const float4*>(d_rays);
+  if (ctx->traversal_mode == 1) {
+    int grid = persistent_grid(ctx, k_trace_closest<1>, 256);
+    k_trace_closest<1><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+  } else {
+    int grid = persistent_grid(ctx, k_trace_closest<0>, 256);
+    k_trace_closest<0><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t s) {
+  if (n == 0) return;
+  ctx->d_counts.ensure(64);
+  unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 5;
+  CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
+  const float4* rays = reinterpret_cast<const float4*>(d_rays);
+  if (ctx->traversal_mode == 1) {
+    int grid = persistent_grid(ctx, k_trace_any<1>, 256);
+    k_trace_any<1><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+  } else {
+    int grid = persistent_grid(ctx, k_trace_any<0>, 256);
+    k_trace_any<0><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
+int check_scene(TutuCtx* ctx) {
+  if (!ctx->has_scene) return fail(ctx, TUTU_E_STATE, "no scene uploaded (call tutu_scene_upload first)");
+  return TUTU_OK;
+}
+
+void fill_raygen(const FlatScene& f, RayGenK* k) {
+  memcpy(k->eye, f.raygen.eye, 12);
+  memcpy(k->ul, f.raygen.ul, 12);
+  memcpy(k->dh, f.raygen.delta_h, 12);
+  memcpy(k->dv, f.raygen.delta_v, 12);
+  memcpy(k->coh, f.raygen.c_off_h, 12);
+  memcpy(k->cov, f.raygen.c_off_v, 12);
+  k->width = f.raygen.width;
+  k->height = f.raygen.height;
+}
+
+// ---------------------------------------------------------------------------------------------
+// wavefront host loop
+// ---------------------------------------------------------------------------------------------
+void wf_prepare(TutuCtx* ctx, uint64_t total_paths) {
+  uint64_t cap = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)4 << 20;
+  cap = std::min<uint64_t>(cap, std::max<uint64_t>(total_paths, 1));
+  cap = (cap + 255) & ~(uint64_t)255;
+  if (cap > ctx->wf_capacity) {
+    // 2*(7 queues) + hit + 4 shadow arrays, float4 each
+    const size_t n_arrays = 2 * 7 + 1 + 4;
+    ctx->wf_pool.ensure(n_arrays * cap * sizeof(float4));
+    ctx->wf_capacity = cap;
+  }
+  cap = ctx->wf_capacity;
+  float4* p = ctx->wf_pool.as<float4>();
+  WfBuffers& b = ctx->wf;
+  for (int k = 0; k < 2; ++k) {
+    b.ray_o[k] = p, p += cap;
+    b.ray_d[k] = p, p += cap;
+    b.st0[k] = p, p += cap;
+    b.st1[k] = p, p += cap;
+    b.st2[k] = p, p += cap;
+    b.st3[k] = p, p += cap;
+    b.st4[k] = p, p += cap;
+  }
+  b.hit = p, p += cap;
+  b.sh_o = p, p += cap;
+  b.sh_d = p, p += cap;
+  b.sh_c = p, p += cap;
+  b.sh_L = p, p += cap;
+  ctx->wf_ctl.ensure(sizeof(WfCtl));
+  b.ctl = ctx->wf_ctl.as<WfCtl>();
+  b.capacity = (unsigned)cap;
+  if (!ctx->grid_extend) {
+    ctx->grid_extend = persistent_grid(ctx, wf_extend, 256);
+    ctx->grid_shade = persistent_grid(ctx, wf_shade, 256);
+    ctx->grid_shadow = persistent_grid(ctx, wf_shadow, 256);
+    ctx->grid_raygen = persistent_grid(ctx, wf_raygen, 256);
+  }
+}
+
+struct StageTimer {
+  bool on;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> tag;  // stage id of the interval that STARTS at event k
+  explicit StageTimer(bool enable) : on(enable) {}
+  ~StageTimer() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+  void mark(int stage, cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventRecord(e, s));
+    ev.push_back(e);
+    tag.push_back(stage);
+  }
+  void resolve(TutuRenderStats* st) {
+    if (!on) return;
+    for (size_t k = 0; k + 1 < ev.size(); ++k) {
+      float ms = 0;
+      CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      switch (tag[k]) {
+        case 1: st->extend_ms += ms; break;
+        case 2: st->shade_ms += ms; break;
+        case 3: st->shadow_ms += ms; break;
+        default: st->other_ms += ms; break;
+      }
+    }
+  }
+};
+
+// Accumulates samples [sample_begin, sample_begin+sample_count) of every pixel into d_accum.
+void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint64_t seed, float* d_accum,
+               cudaStream_t s) {
+  const FlatScene& f = ctx->flat;
+  const uint64_t npix = (uint64_t)f.raygen.width * f.raygen.height;
+  const uint64_t total = npix * sample_count;
+  ctx->stats = TutuRenderStats{};
+  if (total == 0) return;
+  wf_prepare(ctx, total);
+  WfBuffers b = ctx->wf;
+  b.accum = d_accum;
+  RayGenK rk;
+  fill_raygen(f, &rk);
+
+  WfCtl h{};
+  h.total_paths = total;
+  CUDA_TRY(cudaMemcpyAsync(b.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, s));
+  StageTimer timer(ctx->profile_stages != 0);
+
+  unsigned* done_host = nullptr;
+  CUDA_TRY(cudaMallocHost(&done_host, sizeof(WfCtl)));
+  WfCtl* ctl_host = reinterpret_cast<WfCtl*>(done_host);
+  memset(ctl_host, 0, sizeof(WfCtl));
+
+  int cur = 0;
+  uint64_t launches = 0;
+  const int poll_every = 8;
+  try {
+    for (uint64_t it = 0;; ++it) {
+      timer.mark(0, s);
+      wf_raygen<<<ctx->grid_raygen, 256, 0, s>>>(b, cur, rk, sample_begin);
+      wf_ctl_after_raygen<<<1, 1, 0, s>>>(b.ctl, b.capacity);
+      timer.mark(1, s);
+      wf_extend<<<ctx->grid_extend, 256, 0, s>>>(ctx->dev, b, cur);
+      timer.mark(2, s);
+      wf_shade<<<ctx->grid_shade, 256, 0, s>>>(ctx->dev, b, cur, seed);
+      timer.mark(3, s);
+      wf_shadow<<<ctx->grid_shadow, 256, 0, s>>>(ctx->dev, b, cur ^ 1);
+      timer.mark(0, s);
+      wf_ctl_after_iter<<<1, 1, 0, s>>>(b.ctl);
+      launches += 6;
+      cur ^= 1;
+      if ((it + 1) % poll_every == 0) {
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(ctl_host, b.ctl, sizeof(WfCtl), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (ctl_host->done) break;
+      }
+    }
+    timer.mark(0, s);
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    ctx->stats.gpu_ms = ms;
+    ctx->stats.paths = total;
+    ctx->stats.extend_rays = ctl_host->sum_extend;
+    ctx->stats.shadow_rays = ctl_host->sum_shadow;
+    ctx->stats.shade_calls = ctl_host->sum_extend;
+    ctx->stats.nan_samples = ctl_host->nan_samples;
+    ctx->stats.iterations = ctl_host->iterations;
+    ctx->stats.kernel_launches = launches;
+    timer.resolve(&ctx->stats);
+  } catch (...) {
+    cudaFreeHost(done_host);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    throw;
+  }
+  cudaFreeHost(done_host);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" int tutu_ctx_create(int device, TutuCtx** out) {
+  if (!out) return fail(nullptr, TUTU_E_INVALID, "tutu_ctx_create: null out pointer");
+  *out = nullptr;
+  try {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      cudaGetLastError();
+      return fail(nullptr, TUTU_E_CUDA,
+                  std::string("tutu_ctx_create: no usable CUDA device (") +
+                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                      "); libtutu_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, TUTU_E_INVALID, "tutu_ctx_create: bad device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+      return fail(nullptr, TUTU_E_CUDA,
+                  std::string("tutu_ctx_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                      std::to_string(prop.minor) + "; this library is built for sm_100a (B200) only");
+    std::unique_ptr<TutuCtx> ctx(new TutuCtx());
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    *out = ctx.release();
+    return TUTU_OK;
+  } catch (const CudaError& e) {
+    return fail_cuda(nullptr, e);
+  } catch (const std::bad_alloc&) {
+    return fail(nullptr, TUTU_E_NOMEM, "out of host memory");
+  }
+}
+
+extern "C" void tutu_ctx_destroy(TutuCtx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  delete ctx;
+}
+
+extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
+  API_BEGIN(ctx)
+  FlatScene fs;
+  int rc = flatten_scene(desc, &fs);
+  if (rc != TUTU_OK) return fail(ctx, rc, get_error());
+  if (fs.depth > (uint32_t)kStackSize)
+    return fail(ctx, TUTU_E_INVALID, "scene: BVH deeper than the traversal stack (" + std::to_string(fs.depth) + ")");
+  cudaStream_t s = ctx->stream;
+  upload_vec(ctx->d_inner, fs.inner, s);
+  upload_vec(ctx->d_geom, fs.geom, s);
+  upload_vec(ctx->d_shade, fs.shade, s);
+  upload_vec(ctx->d_leaftex, fs.leaftex, s);
+  upload_vec(ctx->d_slot_to_prim, fs.slot_to_prim, s);
+  upload_vec(ctx->d_materials, fs.materials, s);
+  upload_vec(ctx->d_lights, fs.lights, s);
+  upload_vec(ctx->d_texels, fs.texels, s);
+  for (int c = 0; c < 4; ++c) upload_vec(ctx->d_texh[c], fs.tex_headers[c], s);
+  CUDA_TRY(cudaStreamSynchronize(s));
+  DevScene& d = ctx->dev;
+  d.inner = ctx->d_inner.as<float4>();
+  d.geom = ctx->d_geom.as<float4>();
+  d.shade = ctx->d_shade.as<float4>();
+  d.leaftex = fs.leaftex.empty() ? nullptr : ctx->d_leaftex.as<int4>();
+  d.slot_to_prim = ctx->d_slot_to_prim.as<int>();
+  d.materials = ctx->d_materials.as<float4>();
+  d.lights = ctx->d_lights.as<float4>();
+  for (int c = 0; c < 4; ++c) d.tex_headers[c] = ctx->d_texh[c].as<int4>();
+  d.texels = ctx->d_texels.as<float4>();
+  memcpy(d.root_lo, fs.root_box.lo, 12);
+  memcpy(d.root_hi, fs.root_box.hi, 12);
+  d.root_ref = fs.root_ref;
+  d.empty = fs.empty ? 1 : 0;
+  d.n_lights = (int)fs.lights.size();
+  memcpy(d.bkg, fs.bkgcolor, 12);
+  d.eta = fs.eta;
+  ctx->scene_bytes = fs.inner.size() * sizeof(InnerNode) + fs.geom.size() * sizeof(LeafGeom) +
+                     fs.shade.size() * sizeof(LeafShade) + fs.leaftex.size() * sizeof(LeafTex) +
+                     fs.slot_to_prim.size() * 4 + fs.materials.size() * sizeof(DevMaterial) +
+                     fs.lights.size() * sizeof(DevLight) + fs.texels.size() * 4;
+  ctx->flat = std::move(fs);
+  ctx->has_scene = true;
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_scene_info(const TutuCtx* ctx, TutuSceneInfo* out) {
+  if (!ctx || !out) return fail(nullptr, TUTU_E_INVALID, "tutu_scene_info: null argument");
+  if (!ctx->has_scene) return fail(const_cast<TutuCtx*>(ctx), TUTU_E_STATE, "no scene uploaded");
+  const FlatScene& f = ctx->flat;
+  out->n_prims = f.n_prims;
+  out->n_nodes = f.n_ref_nodes;
+  out->n_inner = (uint32_t)f.inner.size();
+  out->depth = f.depth;
+  out->n_lights = (uint32_t)f.lights.size();
+  out->n_materials = (uint32_t)f.materials.size();
+  out->width = (uint32_t)f.raygen.width;
+  out->height = (uint32_t)f.raygen.height;
+  out->device_bytes = ctx->scene_bytes;
+  return TUTU_OK;
+}
+
+extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
+  if (!ctx || !cam) return fail(ctx, TUTU_E_INVALID, "tutu_scene_set_camera: null argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (!ctx->has_scene) return fail(ctx, TUTU_E_STATE, "no scene uploaded");
+  RayGen rg;
+  int rc = compute_raygen(cam, &rg);
+  if (rc != TUTU_OK) return fail(ctx, rc, get_error());
+  ctx->flat.raygen = rg;
+  ctx->flat.camera = *cam;
+  return TUTU_OK;
+}
+
+extern "C" int tutu_set_traversal_mode(TutuCtx* ctx, int mode) {
+  if (!ctx || (mode != 0 && mode != 1)) return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument");
+  ctx->traversal_mode = mode;
+  return TUTU_OK;
+}
+
+extern "C" int tutu_trace_closest_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays, TutuHit* d_hits_out,
+                                         void* stream) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (n_rays && (!d_rays || !d_hits_out)) return fail(ctx, TUTU_E_INVALID, "tutu_trace_closest_device: null buffer");
+  launch_closest(ctx, d_rays, n_rays, d_hits_out, stream ? (cudaStream_t)stream : ctx->stream);
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_trace_any_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays, uint8_t* d_blocked_out,
+                                     void* stream) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (n_rays && (!d_rays || !d_blocked_out)) return fail(ctx, TUTU_E_INVALID, "tutu_trace_any_device: null buffer");
+  launch_any(ctx, d_rays, n_rays, d_blocked_out, stream ? (cudaStream_t)stream : ctx->stream);
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_trace_closest(TutuCtx* ctx, const float* rays, uint64_t n_rays, TutuHit* hits_out) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (n_rays == 0) return TUTU_OK;
+  if (!rays || !hits_out) return fail(ctx, TUTU_E_INVALID, "tutu_trace_closest: null buffer");
+  cudaStream_t s = ctx->stream;
+  ctx->d_rays.ensure(n_rays * TUTU_RAY_FLOATS * sizeof(float));
+  ctx->d_hits.ensure(n_rays * sizeof(TutuHit));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_rays.p, rays, n_rays * TUTU_RAY_FLOATS * sizeof(float), cudaMemcpyHostToDevice, s));
+  launch_closest(ctx, ctx->d_rays.as<float>(), n_rays, ctx->d_hits.as<TutuHit>(), s);
+  CUDA_TRY(cudaMemcpyAsync(hits_out, ctx->d_hits.p, n_rays * sizeof(TutuHit), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_trace_any(TutuCtx* ctx, const float* rays, uint64_t n_rays, uint8_t* blocked_out) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (n_rays == 0) return TUTU_OK;
+  if (!rays || !blocked_out) return fail(ctx, TUTU_E_INVALID, "tutu_trace_any: null buffer");
+  cudaStream_t s = ctx->stream;
+  ctx->d_rays.ensure(n_rays * TUTU_RAY_FLOATS * sizeof(float));
+  ctx->d_blocked.ensure(n_rays);
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_rays.p, rays, n_rays * TUTU_RAY_FLOATS * sizeof(float), cudaMemcpyHostToDevice, s));
+  launch_any(ctx, ctx->d_rays.as<float>(), n_rays, ctx->d_blocked.as<uint8_t>(), s);
+  CUDA_TRY(cudaMemcpyAsync(blocked_out, ctx->d_blocked.p, n_rays, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_trace_count_visits(TutuCtx* ctx, const float* d_rays, uint64_t n_rays, int any_hit,
+                                       uint64_t* nodes_out, uint64_t* prims_out) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (!nodes_out || !prims_out || (n_rays && !d_rays)) return fail(ctx, TUTU_E_INVALID, "tutu_trace_count_visits: null argument");
+  cudaStream_t s = ctx->stream;
+  ctx->d_counts.ensure(64);
+  unsigned long long* c = ctx->d_counts.as<unsigned long long>();
+  CUDA_TRY(cudaMemsetAsync(c, 0, 16, s));
+  if (n_rays) {
+    const float4* rays = reinterpret_cast<const float4*>(d_rays);
+    const int grid = ctx->sm_count * 8;
+    if (any_hit)
+      k_trace_count<true><<<grid, 256, 0, s>>>(ctx->dev, rays, n_rays, c);
+    else
+      k_trace_count<false><<<grid, 256, 0, s>>>(ctx->dev, rays, n_rays, c);
+    CUDA_TRY(cudaGetLastError());
+  }
+  unsigned long long h[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(h, c, 16, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  *nodes_out = h[0];
+  *prims_out = h[1];
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int profile_stages) {
+  if (!ctx) return fail(nullptr, TUTU_E_INVALID, "null context");
+  if (paths_in_flight > ((uint64_t)1 << 31)) return fail(ctx, TUTU_E_INVALID, "paths_in_flight too large");
+  ctx->paths_in_flight_cfg = paths_in_flight;
+  ctx->profile_stages = profile_stages;
+  return TUTU_OK;
+}
+
+extern "C" int tutu_render_path_accumulate_device(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count,
+                                                  uint64_t seed, float* d_accum, void* stream) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (!d_accum) return fail(ctx, TUTU_E_INVALID, "tutu_render_path_accumulate_device: null accumulation buffer");
+  wf_render(ctx, sample_begin, sample_count, seed, d_accum, stream ? (cudaStream_t)stream : ctx->stream);
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_finalize_device(TutuCtx* ctx, const float* d_accum, float inv_spp, float* d_rgb_out,
+                                    void* stream) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (!d_accum || !d_rgb_out) return fail(ctx, TUTU_E_INVALID, "tutu_finalize_device: null buffer");
+  const size_t n = (size_t)ctx->flat.raygen.width * ctx->flat.raygen.height * 3;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  wf_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(d_accum, inv_spp, d_rgb_out, n);
+  CUDA_TRY(cudaGetLastError());
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_render_path(TutuCtx* ctx, uint32_t spp, uint64_t seed, float* rgb_out) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (!rgb_out || spp == 0) return fail(ctx, TUTU_E_INVALID, "tutu_render_path: null output or spp == 0");
+  const size_t n = (size_t)ctx->flat.raygen.width * ctx->flat.raygen.height * 3;
+  cudaStream_t s = ctx->stream;
+  ctx->d_accum.ensure(n * sizeof(float));
+  ctx->d_rgb.ensure(n * sizeof(float));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_accum.p, 0, n * sizeof(float), s));
+  wf_render(ctx, 0, spp, seed, ctx->d_accum.as<float>(), s);
+  wf_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctx->d_accum.as<float>(), 1.f / (float)spp, ctx->d_rgb.as<float>(), n);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(rgb_out, ctx->d_rgb.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out) {
+  if (!ctx || !out) return fail(nullptr, TUTU_E_INVALID, "tutu_render_stats: null argument");
+  *out = ctx->stats;
+  return TUTU_OK;
+}

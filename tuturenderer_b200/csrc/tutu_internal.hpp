@@ -1,0 +1,141 @@
+// Internal host-side declarations shared by host_scene.cpp (pure C++, no CUDA) and tutu_b200.cu.
+// Not part of the ABI.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/tutu_b200.h"
+
+namespace tutu {
+
+// Leaf reference encoding inside a device inner node: ref >= 0 -> inner node index;
+// ref < 0 -> ~ref = slot | (sphere ? SPHERE_BIT : 0), slot = leaf number in DFS (pre-order) order.
+constexpr uint32_t SPHERE_BIT = 1u << 30;
+constexpr uint32_t SLOT_MASK = SPHERE_BIT - 1u;
+
+struct Box {
+  float lo[3];
+  float hi[3];
+};
+
+// 64-byte inner node: both child boxes + child refs (one fetch decides both children).
+struct alignas(16) InnerNode {
+  float box[12];  // [0..2] left.lo, [3..5] left.hi, [6..8] right.lo, [9..11] right.hi
+  int32_t left;
+  int32_t right;
+  int32_t pad0;
+  int32_t pad1;
+};
+static_assert(sizeof(InnerNode) == 64, "InnerNode must be 64 bytes");
+
+// 48-byte intersection record per leaf slot.
+// triangle: {v0.xyz, E1.x} {E1.y, E1.z, E2.x, E2.y} {E2.z, n.xyz}; E1 = v1-v0, E2 = v2-v0,
+//           n = normalized(E1 x E2) evaluated with the reference's float expressions.
+// sphere:   {c.xyz, r} {0...}
+struct alignas(16) LeafGeom {
+  float f[12];
+};
+static_assert(sizeof(LeafGeom) == 48, "LeafGeom must be 48 bytes");
+
+// 64-byte shading record per leaf slot:
+// {n0.xyz, uv0.x} {n1.xyz, uv0.y} {n2.xyz, uv1.x} {uv1.y, uv2.x, uv2.y, bits(flags)}
+// flags: material index | TEX_ACTIVE_BIT | SPHERE flag bit 30
+struct alignas(16) LeafShade {
+  float f[15];
+  uint32_t flags;
+};
+static_assert(sizeof(LeafShade) == 64, "LeafShade must be 64 bytes");
+constexpr uint32_t TEX_ACTIVE_BIT = 1u << 31;
+constexpr uint32_t SHADE_SPHERE_BIT = 1u << 30;
+constexpr uint32_t MAT_MASK = (1u << 30) - 1u;
+
+struct alignas(16) LeafTex {
+  int32_t diffuse, normal, roughness, metallic;
+};
+
+// 64-byte material: {diffuse.xyz, type} {specular.xyz, alpha} {emission.xyz, eta}
+//                   {roughness, metallic, has_emission, 0}
+struct alignas(16) DevMaterial {
+  float diffuse[3];
+  int32_t type;
+  float specular[3];
+  float alpha;
+  float emission[3];
+  float eta;
+  float roughness;
+  float metallic;
+  int32_t has_emission;
+  int32_t pad;
+};
+static_assert(sizeof(DevMaterial) == 64, "DevMaterial must be 64 bytes");
+
+// Light table entry (PPMGenerator.hpp:317-324 order), 128 bytes.
+struct alignas(16) DevLight {
+  float v0[3];
+  float area;  // Object::getArea()
+  float v1[3];
+  int32_t type;  // TUTU_PRIM_*
+  float v2[3];
+  int32_t slot;
+  float n0[3];
+  float radius;
+  float n1[3];
+  int32_t material;
+  float n2[3];
+  int32_t pad0;
+  float emission[3];
+  int32_t pad1;
+  float pad2[4];
+};
+static_assert(sizeof(DevLight) == 128, "DevLight must be 128 bytes");
+
+struct TexHeader {
+  int32_t width, height;
+  uint32_t offset;  // in float4 texels into the texel pool
+  uint32_t n_texels;
+};
+
+// Ray-generation constants, PathTracing.hpp:357-391 + :503.
+struct RayGen {
+  float eye[3];
+  float ul[3];
+  float delta_h[3];
+  float delta_v[3];
+  float c_off_h[3];
+  float c_off_v[3];
+  int32_t width, height;
+};
+
+struct FlatScene {
+  uint32_t n_prims = 0;
+  uint32_t n_ref_nodes = 0;
+  uint32_t depth = 0;
+  int32_t root_ref = 0;  // inner index 0, or ~slot when the tree is a single leaf
+  bool empty = true;
+  Box root_box{};
+  std::vector<InnerNode> inner;
+  std::vector<LeafGeom> geom;
+  std::vector<LeafShade> shade;
+  std::vector<LeafTex> leaftex;
+  std::vector<int32_t> slot_to_prim;
+  std::vector<DevMaterial> materials;
+  std::vector<DevLight> lights;
+  std::vector<TexHeader> tex_headers[4];
+  std::vector<float> texels;  // float4 per texel (rgb + pad), all channels pooled
+  RayGen raygen{};
+  TutuCamera camera{};
+  float bkgcolor[3] = {0, 0, 0};
+  float eta = 1.f;
+};
+
+// Error plumbing (thread-local message, mirrored into the ctx by the callers in tutu_b200.cu).
+void set_error(const std::string& msg);
+const std::string& get_error();
+extern const char* (*g_ctx_error_hook)(const TutuCtx*);
+
+// Validates the desc, builds the BVH if none is given, flattens to device layout.
+int flatten_scene(const TutuSceneDesc* desc, FlatScene* out);
+int compute_raygen(const TutuCamera* cam, RayGen* out);
+
+}  // namespace tutu

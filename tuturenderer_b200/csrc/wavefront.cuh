@@ -1,0 +1,571 @@
+// wavefront.cuh — the PathTracing integrator (reference include/PathTracing.hpp:136-279 traceRay
+// MIS branch, :80-134 calcForRefractive, :352-475/:485-516 integrate + sub_render_pt) as a
+// wavefront pipeline:
+//
+//   raygen  -> extend (closest hit) -> shade (arrival MIS / roulette of the previous vertex,
+//              material, NEE sample, BSDF sample) -> shadow (any hit, adds the NEE term)
+//
+// The reference's recursion is tail-like (value = direct_k + coe_k * value_{k+1}); it becomes an
+// iteration carrying two throughputs: beta (product of every coe) and tp (the roulette tracker,
+// reset to 1 while depth <= MIN_DEPTH and after refractive vertices).  A path's radiance L is
+// kept per path and added to the frame buffer once, so the reference's per-sample NaN filter
+// (PathTracing.hpp:510) keeps its meaning.
+//
+// Queues live in HBM as float4 SoA, ping-pong per iteration; survivors and shadow rays are
+// appended through warp-aggregated atomics (one atomicAdd per warp).  Free slots are refilled by
+// raygen every iteration, so the wavefront stays full until the last samples.
+#pragma once
+#include "shade.cuh"
+
+namespace tutu {
+
+constexpr uint32_t kModeFresh = 0;   // ray traced by traceRay itself: miss -> bkgcolor
+constexpr uint32_t kModeXInter = 1;  // ray traced as x_inter of the previous vertex
+constexpr uint32_t kFlagMirror = 1u << 9;  // previous vertex PERFECT_REFLECTIVE (PathTracing.hpp:252)
+constexpr uint32_t kShadowFinal = 0xFFFFFFFFu;
+
+struct RayGenK {
+  float eye[3], ul[3], dh[3], dv[3], coh[3], cov[3];
+  int width, height;
+};
+
+struct WfCtl {
+  unsigned n_cur;
+  unsigned n_next;
+  unsigned n_shadow;
+  unsigned done;
+  unsigned long long next_path;
+  unsigned long long total_paths;
+  unsigned long long sum_extend;
+  unsigned long long sum_shadow;
+  unsigned long long nan_samples;
+  unsigned long long iterations;
+};
+
+struct WfBuffers {
+  // path queues, [2] = ping-pong
+  float4* ray_o[2];  // o.xyz, -
+  float4* ray_d[2];  // d.xyz, -
+  float4* st0[2];    // beta.xyz, bits(pixel)
+  float4* st1[2];    // tp.xyz, bits(sample)
+  float4* st2[2];    // L.xyz, bits(depth | mode<<8 | flags)
+  float4* st3[2];    // f_r*cos_theta of the previous vertex .xyz, mat_pdf
+  float4* st4[2];    // previous vertex position .xyz, -
+  float4* hit;       // t, u, v, bits(slot code)
+  // shadow queue
+  float4* sh_o;  // o.xyz, dist
+  float4* sh_d;  // d.xyz, bits(destination index in the next path queue | kShadowFinal)
+  float4* sh_c;  // beta * NEE term .xyz, bits(pixel)
+  float4* sh_L;  // L.xyz of a path that already ended (only for kShadowFinal)
+  WfCtl* ctl;
+  float* accum;  // width*height*3 sums
+  unsigned capacity;
+};
+
+__device__ __forceinline__ void accum_add(float* accum, WfCtl* ctl, uint32_t pixel, f3 L) {
+  // PathTracing.hpp:510-511: a sample with any NaN component is dropped (still divided by SPP)
+  if (any_nan(L)) {
+    atomicAdd(&ctl->nan_samples, 1ull);
+    return;
+  }
+  float* p = accum + (size_t)pixel * 3;
+  atomicAdd(p + 0, L.x);
+  atomicAdd(p + 1, L.y);
+  atomicAdd(p + 2, L.z);
+}
+
+// warp-aggregated append: one atomicAdd per warp, lanes take consecutive slots
+__device__ __forceinline__ unsigned warp_append(unsigned* counter, bool want) {
+  const unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
+  if (mask == 0u) return 0u;
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(mask) - 1;
+  unsigned base = 0u;
+  if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  return base + (unsigned)__popc(mask & ((1u << lane) - 1u));
+}
+
+// ---- control ---------------------------------------------------------------------------------
+__global__ void wf_ctl_after_raygen(WfCtl* ctl, unsigned capacity) {
+  const unsigned free_slots = capacity - ctl->n_cur;
+  const unsigned long long left = ctl->total_paths - ctl->next_path;
+  const unsigned add = (unsigned)(left < (unsigned long long)free_slots ? left : free_slots);
+  ctl->n_cur += add;
+  ctl->next_path += add;
+  ctl->n_next = 0;
+  ctl->n_shadow = 0;
+  ctl->sum_extend += ctl->n_cur;
+}
+__global__ void wf_ctl_after_iter(WfCtl* ctl) {
+  ctl->sum_shadow += ctl->n_shadow;
+  ctl->n_cur = ctl->n_next;
+  ctl->iterations += 1;
+  ctl->done = (ctl->n_cur == 0 && ctl->next_path >= ctl->total_paths) ? 1u : 0u;
+}
+
+// ---- raygen: PathTracing.hpp:499-509 ---------------------------------------------------------
+// path g -> pixel = g % npix, sample = sample_begin + g / npix; primary rays carry no jitter, the
+// pixel position is ul + x*delta_h + y*delta_v + c_off_v + c_off_v (sic), evaluated with the
+// reference's operation order in exact fp32.
+__global__ void __launch_bounds__(256)
+wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
+  const WfCtl c = *b.ctl;
+  const unsigned free_slots = b.capacity - c.n_cur;
+  const unsigned long long left = c.total_paths - c.next_path;
+  const unsigned add = (unsigned)(left < (unsigned long long)free_slots ? left : free_slots);
+  const unsigned npix = (unsigned)k.width * (unsigned)k.height;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < add; i += gridDim.x * blockDim.x) {
+    const unsigned long long g = c.next_path + i;
+    const unsigned pixel = (unsigned)(g % npix);
+    const unsigned sample = sample_begin + (unsigned)(g / npix);
+    const float x = (float)(pixel % (unsigned)k.width), y = (float)(pixel / (unsigned)k.width);
+    float px = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(k.ul[0], __fmul_rn(k.dh[0], x)), __fmul_rn(k.dv[0], y)), k.cov[0]), k.cov[0]);
+    float py = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(k.ul[1], __fmul_rn(k.dh[1], x)), __fmul_rn(k.dv[1], y)), k.cov[1]), k.cov[1]);
+    float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(k.ul[2], __fmul_rn(k.dh[2], x)), __fmul_rn(k.dv[2], y)), k.cov[2]), k.cov[2]);
+    float dx = __fsub_rn(px, k.eye[0]), dy = __fsub_rn(py, k.eye[1]), dz = __fsub_rn(pz, k.eye[2]);
+    normalize_rn(dx, dy, dz);
+    const unsigned s = c.n_cur + i;
+    b.ray_o[cur][s] = make_float4(k.eye[0], k.eye[1], k.eye[2], 0.f);
+    b.ray_d[cur][s] = make_float4(dx, dy, dz, 0.f);
+    b.st0[cur][s] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel));
+    b.st1[cur][s] = make_float4(1.f, 1.f, 1.f, __uint_as_float(sample));
+    b.st2[cur][s] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u | (kModeFresh << 8)));
+  }
+}
+
+// ---- extend: IIntersectStrategy::UpdateInter -> getIntersection -------------------------------
+__global__ void __launch_bounds__(256)
+wf_extend(const DevScene sc, WfBuffers b, int cur) {
+  const unsigned n = b.ctl->n_cur;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 o = b.ray_o[cur][i];
+    const float4 d = b.ray_d[cur][i];
+    Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
+    Hit h;
+    traverse<false, 0, false>(sc, r, 0.f, h, nullptr);
+    b.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.slot));
+  }
+}
+
+// ---- shadow: isShadowRayBlocked -> hasIntersection, then the deferred NEE add ------------------
+__global__ void __launch_bounds__(256)
+wf_shadow(const DevScene sc, WfBuffers b, int nxt) {
+  const unsigned n = b.ctl->n_shadow;
+  for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const float4 o = b.sh_o[j];
+    const float4 d = b.sh_d[j];
+    Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
+    Hit h;
+    const bool blocked = traverse<true, 0, false>(sc, r, o.w, h, nullptr);
+    const unsigned dst = __float_as_uint(d.w);
+    if (dst == kShadowFinal) {
+      const float4 c = b.sh_c[j];
+      const float4 L4 = b.sh_L[j];
+      f3 L = mk(L4.x, L4.y, L4.z);
+      if (!blocked) L = L + mk(c.x, c.y, c.z);
+      accum_add(b.accum, b.ctl, __float_as_uint(c.w), L);
+    } else if (!blocked) {
+      const float4 c = b.sh_c[j];
+      float4 s = b.st2[nxt][dst];
+      s.x += c.x, s.y += c.y, s.z += c.z;
+      b.st2[nxt][dst] = s;
+    }
+  }
+}
+
+// ---- shade -------------------------------------------------------------------------------------
+struct Surf {  // Intersection (Intersection.hpp:13-31) rebuilt from the 16-byte hit record
+  f3 pos, Ng, Ns;
+  float tu, tv;
+  Mat m;
+  bool textured;
+  bool sphere;
+  uint32_t slot;
+};
+
+__device__ __forceinline__ Surf load_surface(const DevScene& sc, const Ray& r, const float4 hit) {
+  Surf s;
+  const uint32_t code = __float_as_uint(hit.w);
+  s.slot = code & kSlotMask;
+  s.sphere = (code & kSphereBit) != 0u;
+  const float t = hit.x;
+  s.pos = mk(r.ox, r.oy, r.oz) + t * mk(r.dx, r.dy, r.dz);  // Triangle.hpp:54
+  const float4* sh = sc.shade + 4 * (size_t)s.slot;
+  const float4 s3 = __ldg(sh + 3);
+  const uint32_t flags = __float_as_uint(s3.w);
+  s.textured = (flags & 0x80000000u) != 0u;
+  s.m = load_material(sc, (int)(flags & 0x3FFFFFFFu));
+  s.tu = s.tv = 0.f;
+  if (s.sphere) {
+    const float4 g0 = __ldg(sc.geom + 3 * (size_t)s.slot);
+    s.Ng = normalized(s.pos - mk(g0.x, g0.y, g0.z));  // Sphere.hpp:54-55
+    s.Ns = s.Ng;
+    if (s.textured) {  // Sphere.hpp:58-72
+      float phi = acosf(s.Ng.z);
+      s.tv = phi / T_PI;
+      float theta = atan2f(s.Ng.y, s.Ng.x);
+      if (theta < 0) theta += 2 * T_PI;
+      s.tu = theta / (2.f * T_PI);
+    }
+  } else {
+    const float4 g2 = __ldg(sc.geom + 3 * (size_t)s.slot + 2);
+    s.Ng = mk(g2.y, g2.z, g2.w);
+    const float4 s0 = __ldg(sh + 0), s1 = __ldg(sh + 1), s2 = __ldg(sh + 2);
+    const float u = hit.y, v = hit.z, w = 1 - u - v;
+    // Triangle.hpp:56
+    s.Ns = normalized(mk(s0.x, s0.y, s0.z) * w + mk(s1.x, s1.y, s1.z) * u + mk(s2.x, s2.y, s2.z) * v);
+    if (s.textured) {  // Triangle.hpp:62-69
+      s.tu = s0.w * w + s2.w * u + s3.y * v;
+      s.tv = s1.w * w + s3.x * u + s3.z * v;
+    }
+  }
+  return s;
+}
+
+// textureModify + changeNormalDir, IIntegrator.hpp:27-127
+__device__ __noinline__ void texture_modify(const DevScene& sc, Surf& s) {
+  const int4 ti = __ldg(sc.leaftex + s.slot);
+  if (ti.x != -1) s.m.diffuse = tex_fetch(sc, 0, ti.x, s.tu, s.tv);
+  if (ti.y != -1) {
+    const f3 color = tex_fetch(sc, 1, ti.y, s.tu, s.tv);
+    f3 T, B, nDir;
+    if (!s.sphere) {
+      const float4* g = sc.geom + 3 * (size_t)s.slot;
+      const float4 a = __ldg(g + 0), b = __ldg(g + 1), c = __ldg(g + 2);
+      const f3 e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
+      const float4* sh = sc.shade + 4 * (size_t)s.slot;
+      const float4 s0 = __ldg(sh + 0), s1 = __ldg(sh + 1), s2 = __ldg(sh + 2), s3 = __ldg(sh + 3);
+      nDir = normalized(s.Ns);
+      const float deltaU1 = s2.w - s0.w, deltaV1 = s3.x - s1.w;
+      const float deltaU2 = s3.y - s0.w, deltaV2 = s3.z - s1.w;
+      const float coef = 1 / (-deltaU1 * deltaV2 + deltaV1 * deltaU2);
+      T = normalized(coef * (-deltaV2 * e1 + deltaV1 * e2));
+      B = normalized(coef * (-deltaU2 * e1 + deltaU1 * e2));
+    } else {
+      nDir = s.Ng;
+      const float q = sqrtf(nDir.x * nDir.x + nDir.y * nDir.y);
+      T = mk(-nDir.y / q, nDir.x / q, 0.f);
+      B = cross(nDir, T);
+    }
+    f3 res;
+    res.x = T.x * color.x + B.x * color.y + nDir.x * color.z;
+    res.y = T.y * color.x + B.y * color.y + nDir.y * color.z;
+    res.z = T.z * color.x + B.z * color.y + nDir.z * color.z;
+    s.Ns = normalized(res);
+  }
+  if (ti.z != -1) s.m.roughness = tex_fetch(sc, 2, ti.z, s.tu, s.tv).x;
+  if (ti.w != -1) s.m.metallic = tex_fetch(sc, 3, ti.w, s.tu, s.tv).x;
+}
+
+// Object::getArea of the primitive in a leaf slot (getLightPdf, IIntegrator.hpp:155-168)
+__device__ __forceinline__ float slot_area(const DevScene& sc, uint32_t slot, bool sphere) {
+  const float4* g = sc.geom + 3 * (size_t)slot;
+  const float4 a = __ldg(g + 0);
+  if (sphere) return a.w * a.w * T_PI;
+  const float4 b = __ldg(g + 1), c = __ldg(g + 2);
+  const f3 cr = cross(mk(a.w, b.x, b.y), mk(b.z, b.w, c.x));
+  return sqrtf(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z) * 0.5f;
+}
+
+struct LightSample {
+  f3 pos, Ns, emission;
+  float pdf;  // 1 / (size * area), IIntegrator.hpp:191
+};
+
+// sampleLight + Triangle/Sphere::samplePoint
+__device__ __forceinline__ LightSample sample_light(const DevScene& sc, float r_idx, float ra, float rb) {
+  const int size = sc.n_lights;
+  int index = (int)(r_idx * (size - 1) + 0.4999f);  // IIntegrator.hpp:184 (sic, non-uniform)
+  if (size == 1) index = 0;
+  const float4* L = sc.lights + 8 * (size_t)index;
+  const float4 l0 = __ldg(L + 0), l1 = __ldg(L + 1), l2 = __ldg(L + 2), l3 = __ldg(L + 3);
+  const float4 l4 = __ldg(L + 4), l5 = __ldg(L + 5), l6 = __ldg(L + 6);
+  LightSample s;
+  s.emission = mk(l6.x, l6.y, l6.z);
+  const float area = l0.w;
+  if (__float_as_int(l1.w) == TUTU_PRIM_SPHERE) {  // Sphere.hpp:139-164
+    const float radius = l3.w;
+    const float theta = ra * 2 * T_PI;
+    const float phi = rb * T_PI;
+    float st, ct, sp, cp;
+    sincosf(theta, &st, &ct);
+    sincosf(phi, &sp, &cp);
+    const f3 c = mk(l0.x, l0.y, l0.z);
+    s.pos = mk(c.x + radius * ct * sp, c.y + radius * st * sp, c.z + radius * cp);
+    s.Ns = normalized(s.pos - c);
+  } else {  // Triangle.hpp:119-142
+    const float u = ra;
+    const float v = rb * (1 - u);
+    const float w = 1 - u - v;
+    s.pos = w * mk(l0.x, l0.y, l0.z) + u * mk(l1.x, l1.y, l1.z) + v * mk(l2.x, l2.y, l2.z);
+    s.Ns = normalized(w * mk(l3.x, l3.y, l3.z) + u * mk(l4.x, l4.y, l4.z) + v * mk(l5.x, l5.y, l5.z));
+  }
+  s.pdf = 1.f / (size * area);
+  return s;
+}
+
+struct ShadeOut {
+  bool cont;      // a continuation ray goes to the next queue
+  bool shadow;    // an NEE shadow ray goes to the shadow queue
+  bool finished;  // the path ended at this vertex (L must reach the frame buffer)
+  // continuation
+  f3 o, d, beta, tp, fcos, prev_pos;
+  float mat_pdf;
+  uint32_t depth_mode;
+  // shadow
+  f3 so, sd, sc;
+  float sdist;
+};
+
+__device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, const Ray& ray,
+                                             const float4 hit, uint32_t pixel, uint32_t sample,
+                                             uint32_t depth, uint32_t mode, uint32_t flags, f3 beta,
+                                             f3 tp, f3& L, const float4 st3, const float4 st4,
+                                             ShadeOut& out) {
+  out.cont = out.shadow = false;
+  out.finished = true;
+  const int slotcode = __float_as_int(hit.w);
+  if (slotcode < 0) {
+    // PathTracing.hpp:150: only a ray traced by traceRay itself sees the background;
+    // a missed x_inter (:234) just ends the path.
+    if (mode == kModeFresh) L = L + beta * mk(sc.bkg[0], sc.bkg[1], sc.bkg[2]);
+    return;
+  }
+  Surf s = load_surface(sc, ray, hit);
+  const f3 dir = mk(ray.dx, ray.dy, ray.dz);
+
+  if (mode == kModeXInter) {
+    // ---- second half of the previous vertex, PathTracing.hpp:236-278 ----
+    const f3 fcos = mk(st3.x, st3.y, st3.z);  // f_r * cos_theta
+    const float mat_pdf = st3.w;
+    float light_pdf = 0.f;
+    if (s.m.has_emission && sc.n_lights > 0) light_pdf = 1 / (sc.n_lights * slot_area(sc, s.slot, s.sphere));
+    bool as_light = false;
+    if (light_pdf) {
+      const f3 light_N = normalized(s.Ns);
+      const float cos_theta_prime = dot(light_N, -dir);
+      if (cos_theta_prime > 0) {
+        as_light = true;
+        const float r2 = norm2(s.pos - mk(st4.x, st4.y, st4.z));
+        const float l_pdf_transformed = light_pdf * r2 / cos_theta_prime;
+        float mis_weight_m = getMisWeight(mat_pdf, l_pdf_transformed);
+        if ((flags & kFlagMirror) && mat_pdf == 1.f) mis_weight_m = 1.f;
+        if (mat_pdf < T_MIN_DIVISOR) return;
+        L = L + beta * (mis_weight_m * s.m.emission * fcos / mat_pdf);
+        return;
+      }
+    }
+    if (!as_light) {
+      // jmp2: Russian roulette on tp, reset while depth <= MIN_DEPTH (:265-273)
+      if (!(depth > T_MIN_DEPTH)) tp = mk(1.f);
+      const float rr_prob = max3(tp);
+      if (draw_slot5(seed, pixel, sample, depth) > rr_prob) return;
+      const f3 coe = fcos / (mat_pdf * rr_prob);
+      if (mat_pdf * rr_prob < T_MIN_DIVISOR) return;
+      tp = tp * coe;
+      beta = beta * coe;
+      depth += 1;
+      if (depth > T_MAX_DEPTH) {  // traceRay(depth+1) returns 0 (:140)
+        L = L + beta * 0.f;
+        return;
+      }
+    }
+  }
+
+  // ---- traceRay body at `depth` with inter = this hit (:152-232) ----
+  const f3 wo = -dir;
+  if (s.m.type == TUTU_MAT_PERFECT_REFRACTIVE || s.m.type == TUTU_MAT_MICROFACET_T) {
+    // calcForRefractive (:80-134): no textures, no NEE, no roulette
+    const Rand6 rn = draw6(seed, pixel, sample, depth);
+    float eta_i = sc.eta, eta_t = s.m.eta;
+    f3 wi = mk(0.f);
+    const int ok = sampleDirection(s.m, wo, s.Ns, wi, eta_i, rn.u[3], rn.u[4], rn.u[5]);
+    const bool TIR = (ok & 2) != 0;
+    wi = normalized(wi);
+    float pdf = mat_pdf_eval(s.m, wi, wo, s.Ns, eta_i, eta_t);
+    if (TIR) {
+      wi = normalized(getReflectionDir(wo, s.Ns));
+      pdf = 1;
+      if (s.m.type == TUTU_MAT_MICROFACET_T) {
+        f3 interNs = s.Ns;
+        if (dot(wo, s.Ng) < 0) {
+          const float sw = eta_i;
+          eta_i = eta_t;
+          eta_t = sw;
+          interNs = -interNs;
+        }
+        const f3 h = normalized(wo + wi);
+        const float cosTheta = fabsf(dot(interNs, h));
+        wi = normalized(getReflectionDir(wo, h));
+        pdf = 1 * D_ndf(h, interNs, s.m.roughness) * cosTheta / (4.f * dot(wo, h));
+      }
+    }
+    const f3 f_r = BxDF(s.m, wi, wo, s.Ng, s.Ns, eta_i, TIR);
+    f3 rayOrig = s.pos;
+    float cosv;
+    if (dot(wi, s.Ns) > 0) {
+      rayOrig = rayOrig + s.Ns * T_EPSILON;
+      cosv = fabsf(dot(s.Ng, wi));
+    } else {
+      rayOrig = rayOrig - s.Ns * T_EPSILON;
+      cosv = fabsf(dot(-s.Ng, wi));
+    }
+    // the reference recurses first and tests pdf afterwards (:128-133); testing first is equivalent
+    if (pdf < T_MIN_DIVISOR) return;
+    beta = beta * (cosv * f_r / pdf);
+    if (depth + 1 > T_MAX_DEPTH) {
+      L = L + beta * 0.f;
+      return;
+    }
+    out.cont = true;
+    out.finished = false;
+    out.o = rayOrig;
+    out.d = wi;
+    out.beta = beta;
+    out.tp = mk(1.f);
+    out.fcos = mk(0.f);
+    out.mat_pdf = 0.f;
+    out.prev_pos = s.pos;
+    out.depth_mode = (depth + 1) | (kModeFresh << 8);
+    return;
+  }
+
+  if (s.textured) texture_modify(sc, s);
+  if (s.m.type == TUTU_MAT_UNLIT) {  // :161
+    L = L + beta * s.m.diffuse;
+    return;
+  }
+  const bool emissive = s.m.emission.x || s.m.emission.y || s.m.emission.z;
+  if (emissive) {  // :164-170
+    L = L + beta * (depth > 0 ? mk(0.f) : s.m.emission);
+    return;
+  }
+
+  const Rand6 rn = draw6(seed, pixel, sample, depth);
+
+  // ---- NEE, :185-218 ----
+  if (sc.n_lights > 0) {
+    const LightSample ls = sample_light(sc, rn.u[0], rn.u[1], rn.u[2]);
+    const bool rayInside = dot(s.Ns, wo) < 0;
+    const f3 shadowRayOrig = rayInside ? s.pos - s.Ns * T_EPSILON : s.pos + s.Ns * T_EPSILON;
+    const f3 lightPos = ls.pos + ls.Ns * T_EPSILON;
+    f3 wi = ls.pos - s.pos;
+    const float r2 = norm2(wi);
+    wi = normalized(wi);
+    if (!(dot(wi, ls.Ns) > 0)) {
+      const float mat_pdf = mat_pdf_eval(s.m, wi, wo, s.Ns, sc.eta, s.m.eta);
+      const f3 light_N = normalized(ls.Ns);
+      const float cos_theta_prime = dot(light_N, -wi);
+      if (cos_theta_prime > 0) {
+        const float cos_theta = fabsf(dot(s.Ng, wi));
+        const float pdfl = ls.pdf;
+        const float light_pdf = pdfl * r2 / cos_theta_prime;
+        const float mis_weight_l = getMisWeight(light_pdf, mat_pdf);
+        const f3 f_r = BxDF(s.m, wi, wo, s.Ng, s.Ns, sc.eta);
+        // isShadowRayBlocked (IIntegrator.hpp:135-153)
+        const f3 sd = normalized(lightPos - shadowRayOrig);
+        const f3 dv = lightPos - shadowRayOrig;
+        const float dist = sqrtf(dv.x * dv.x + dv.y * dv.y + dv.z * dv.z);
+        if (r2 * pdfl < T_MIN_DIVISOR) {
+          // :215 — an unoccluded sample this close to the light ends the whole path; the
+          // decision needs the visibility now, so this rare case traces its shadow ray inline.
+          Ray sr{shadowRayOrig.x, shadowRayOrig.y, shadowRayOrig.z, sd.x, sd.y, sd.z};
+          Hit hh;
+          if (!traverse<true, 0, false>(sc, sr, dist, hh, nullptr)) return;
+        } else {
+          out.shadow = true;
+          out.so = shadowRayOrig;
+          out.sd = sd;
+          out.sdist = dist;
+          out.sc = beta * (mis_weight_l * ls.emission * f_r * cos_theta * cos_theta_prime / (r2 * pdfl));
+        }
+      }
+    }
+  }
+
+  // ---- BSDF sample, :221-232 ----
+  f3 wi = mk(0.f);
+  const int ok = sampleDirection(s.m, wo, s.Ns, wi, sc.eta, rn.u[3], rn.u[4], rn.u[5]);
+  if (!(ok & 1)) return;
+  const float mat_pdf = mat_pdf_eval(s.m, wi, wo, s.Ns, sc.eta, s.m.eta);
+  const bool inside = dot(wi, s.Ns) < 0;
+  const f3 rayOrig = inside ? s.pos - s.Ns * T_EPSILON : s.pos + s.Ns * T_EPSILON;
+  const float cos_theta = fabsf(dot(s.Ng, wi));
+  const f3 f_r = BxDF(s.m, wi, wo, s.Ng, s.Ns, sc.eta);
+  out.cont = true;
+  out.finished = false;
+  out.o = rayOrig;
+  out.d = wi;
+  out.beta = beta;
+  out.tp = tp;
+  out.fcos = f_r * cos_theta;
+  out.mat_pdf = mat_pdf;
+  out.prev_pos = s.pos;
+  out.depth_mode = depth | (kModeXInter << 8) | (s.m.type == TUTU_MAT_PERFECT_REFLECTIVE ? kFlagMirror : 0u);
+}
+
+__global__ void __launch_bounds__(256)
+wf_shade(const DevScene sc, WfBuffers b, int cur, uint64_t seed) {
+  const int nxt = cur ^ 1;
+  const unsigned n = b.ctl->n_cur;
+  const unsigned n_round = (n + 31u) & ~31u;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool valid = i < n;
+    ShadeOut out;
+    out.cont = out.shadow = out.finished = false;
+    f3 L = mk(0.f);
+    uint32_t pixel = 0;
+    float4 s1 = make_float4(0, 0, 0, 0);
+    if (valid) {
+      const float4 o = b.ray_o[cur][i];
+      const float4 d = b.ray_d[cur][i];
+      const float4 s0 = b.st0[cur][i];
+      s1 = b.st1[cur][i];
+      const float4 s2 = b.st2[cur][i];
+      const float4 hit = b.hit[i];
+      const uint32_t dm = __float_as_uint(s2.w);
+      const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
+      float4 s3 = make_float4(0, 0, 0, 0), s4 = make_float4(0, 0, 0, 0);
+      if (mode == kModeXInter) {
+        s3 = b.st3[cur][i];
+        s4 = b.st4[cur][i];
+      }
+      pixel = __float_as_uint(s0.w);
+      L = mk(s2.x, s2.y, s2.z);
+      Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
+      shade_vertex(sc, seed, r, hit, pixel, __float_as_uint(s1.w), depth, mode, dm, mk(s0.x, s0.y, s0.z),
+                   mk(s1.x, s1.y, s1.z), L, s3, s4, out);
+    }
+    // queue appends: all 32 lanes of the warp arrive here together
+    const unsigned ci = warp_append(&b.ctl->n_next, out.cont);
+    const unsigned si = warp_append(&b.ctl->n_shadow, out.shadow);
+    if (out.cont) {
+      b.ray_o[nxt][ci] = make_float4(out.o.x, out.o.y, out.o.z, 0.f);
+      b.ray_d[nxt][ci] = make_float4(out.d.x, out.d.y, out.d.z, 0.f);
+      b.st0[nxt][ci] = make_float4(out.beta.x, out.beta.y, out.beta.z, __uint_as_float(pixel));
+      b.st1[nxt][ci] = make_float4(out.tp.x, out.tp.y, out.tp.z, s1.w);
+      b.st2[nxt][ci] = make_float4(L.x, L.y, L.z, __uint_as_float(out.depth_mode));
+      if (((out.depth_mode >> 8) & 1u) == kModeXInter) {
+        b.st3[nxt][ci] = make_float4(out.fcos.x, out.fcos.y, out.fcos.z, out.mat_pdf);
+        b.st4[nxt][ci] = make_float4(out.prev_pos.x, out.prev_pos.y, out.prev_pos.z, 0.f);
+      }
+    }
+    if (out.shadow) {
+      b.sh_o[si] = make_float4(out.so.x, out.so.y, out.so.z, out.sdist);
+      b.sh_d[si] = make_float4(out.sd.x, out.sd.y, out.sd.z, __uint_as_float(out.cont ? ci : kShadowFinal));
+      b.sh_c[si] = make_float4(out.sc.x, out.sc.y, out.sc.z, __uint_as_float(pixel));
+      if (!out.cont) b.sh_L[si] = make_float4(L.x, L.y, L.z, 0.f);
+    } else if (valid && out.finished) {
+      accum_add(b.accum, b.ctl, pixel, L);
+    }
+  }
+}
+
+// ---- finalize: color = estimate * SPP_inv (PathTracing.hpp:513) -------------------------------
+__global__ void wf_finalize(const float* __restrict__ accum, float inv_spp, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = accum[i] * inv_spp;
+}
+
+}  // namespace tutu
