@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py — Cornell-box path tracing throughput (BASELINE.json configs[2]) + the ray-batch
+microbench (configs[1]) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one whole render: 1024x1024 pixels, 1024 samples per pixel, NEE+MIS path tracing of the
+reference's Cornell scene, the samples split across the N ranks (strong scaling) and the fp32
+accumulation buffers summed onto rank 0 with one NCCL reduce.  Rank 0 prints ONE JSON line.
+
+--impl reference times the UNMODIFIED reference (oracle/_ref/ref_harness, compiled from
+/root/reference by oracle/Makefile) on the host cores, same metric, a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WIDTH = HEIGHT = 1024
+SPP = 1024
+SEED = 20261018
+PUBLISHED_MPATHS = 0.283  # README's "spp512_1900sec" 1024x1024 Cornell render
+RAYS_G = 707               # 2*707^2 = 999 698 triangles
+RAYS_N = 1 << 24
+
+# queue record sizes of the wavefront (bytes), see DESIGN.md §4
+B_RAY, B_HIT, B_STATE, B_XSTATE, B_SHADOW = 32, 16, 48, 32, 48
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--spp", type=int, default=SPP)
+    p.add_argument("--no-rays", action="store_true", help="skip the ray-batch microbench")
+    p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    return p.parse_args()
+
+
+def cornell_scene(width=WIDTH, height=HEIGHT):
+    from tuturenderer_b200 import api
+    return api.Scene.load(ROOT / "tests" / "golden" / "cornell_256.tscene").with_size(width, height)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.file.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx, pw = float(f[1]), float(f[2]), float(f[3])
+            except ValueError:
+                continue
+            smax = max(smax, mx)
+            if pw > 250:  # under load
+                sm.append(clk)
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.file.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples_under_load": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (the reference compiled from its own sources; oracle port only if that is missing)
+# --------------------------------------------------------------------------------------------
+def cpu_paths_baseline(spp: int, modes=("rows", "stock")) -> dict:
+    from oracle import oracle_py as O
+    sc = cornell_scene()
+    cores = os.cpu_count() or 1
+    if O.ref_available():
+        best = None
+        for mode in modes:
+            _img, info = O.ref_render(sc, spp, mode=mode, timeout=600)
+            if best is None or info["mpaths_per_s"] > best["mpaths_per_s"]:
+                best = info
+        return {"value": best["mpaths_per_s"], "unit": "Mpaths/s", "cores": min(best["threads"], cores),
+                "threads": best["threads"], "kind": "reference",
+                "sample": f"Cornell {WIDTH}x{HEIGHT} @ {spp} spp ({WIDTH * HEIGHT * spp / 1e6:.1f} Mpaths), "
+                          f"reference PathTracing via oracle/_ref/ref_harness mode={best['mode']} "
+                          f"({best['seconds']:.1f} s); modes tried: {','.join(modes)}"}
+    t = time.perf_counter()
+    O.OracleScene(sc).render_path(spp, seed=1)
+    dt = time.perf_counter() - t
+    return {"value": WIDTH * HEIGHT * spp / dt * 1e-6, "unit": "Mpaths/s", "cores": cores, "kind": "port",
+            "sample": f"Cornell {WIDTH}x{HEIGHT} @ {spp} spp, oracle port ({dt:.1f} s); oracle/_ref not built"}
+
+
+def cpu_rays_baseline(scene, rays: np.ndarray) -> dict:
+    from oracle import oracle_py as O
+    cores = os.cpu_count() or 1
+    if O.ref_available():
+        _h, info = O.ref_trace(scene, rays, "closest", threads=cores)
+        _a, info_a = O.ref_trace(scene, rays, "any", threads=cores)
+        return {"value": info["rays"] / info["seconds"] * 1e-6, "any_value": info_a["rays"] / info_a["seconds"] * 1e-6,
+                "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                "sample": f"first {len(rays)} of the {RAYS_N} rays, reference getIntersection/hasIntersection "
+                          f"on {cores} std::threads ({info['seconds']:.1f} s + {info_a['seconds']:.1f} s)"}
+    osc = O.OracleScene(scene)
+    t = time.perf_counter()
+    osc.trace_closest(rays)
+    dt = time.perf_counter() - t
+    return {"value": len(rays) / dt * 1e-6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "sample": f"first {len(rays)} rays, oracle port"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_py as O
+    spp = 4  # bounded sample per step: 1024x1024 @ 4 spp = 4.2 Mpaths
+    sc = cornell_scene()
+    cores = os.cpu_count() or 1
+    times = []
+    mode = "rows"
+    for i in range(args.warmup + args.steps):
+        if O.ref_available():
+            _img, info = O.ref_render(sc, spp, mode=mode, timeout=900)
+            dt, kind, threads = info["seconds"], "reference", info["threads"]
+        else:
+            t = time.perf_counter()
+            O.OracleScene(sc).render_path(spp, seed=i)
+            dt, kind, threads = time.perf_counter() - t, "port", cores
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = WIDTH * HEIGHT * spp * len(times) / total * 1e-6
+    sample = (f"each step: Cornell {WIDTH}x{HEIGHT} @ {spp} spp ({WIDTH * HEIGHT * spp / 1e6:.1f} Mpaths) through "
+              f"the reference's PathTracing (sub_render_pt row worker on {threads} host threads)")
+    print(json.dumps({
+        "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": value / PUBLISHED_MPATHS, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": min(threads, cores), "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args) -> dict:
+    return {"workload": f"cornell_box_{WIDTH}x{HEIGHT}_path_tracing_nee_mis_{args.spp}spp (BASELINE.json configs[2]; "
+                        "scene = reference src/main_cornellBox.cpp via tests/golden/cornell_256.tscene)",
+            "width": WIDTH, "height": HEIGHT, "spp": args.spp, "max_depth": 6,
+            "parallelism": f"spp split over {args.gpus} GPU(s), one fp32 reduce of the {WIDTH * HEIGHT * 3 * 4 / 1e6:.1f} MB accumulation buffer",
+            "l2_policy": "wavefront queues (4 Mi paths x 304 B = 1.3 GB per iteration) exceed the 126 MB L2; no flush needed"}
+
+
+# --------------------------------------------------------------------------------------------
+# ray-batch microbench (configs[1])
+# --------------------------------------------------------------------------------------------
+def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict) -> dict:
+    from tuturenderer_b200 import api
+    prims = api.synth_heightfield(RAYS_G)
+    nodes = api.bvh_build(prims)
+    sc = api.Scene(prims=prims, materials=api.default_material(), bvh_nodes=nodes)
+    ctx = ctx_cls(torch.cuda.current_device())
+    ctx.upload(sc)
+    n_local = RAYS_N // world
+    first = rank * n_local
+    out = {}
+    stream = torch.cuda.current_stream().cuda_stream
+    for kind, label in ((0, "coherent_topdown"), (1, "incoherent_inside")):
+        h_rays = torch.empty((n_local, 8), dtype=torch.float32, pin_memory=True)
+        api.synth_rays(kind, n_local, first=first, out=h_rays.numpy())
+        d_rays = h_rays.cuda()
+        d_hits = torch.empty((n_local, 4), dtype=torch.float32, device="cuda")
+        d_any = torch.empty(n_local, dtype=torch.uint8, device="cuda")
+        h_hits = torch.empty((n_local, 4), dtype=torch.float32, pin_memory=True)
+        res = {}
+        for name, fn, dst in (("closest", ctx.trace_closest_device, d_hits), ("any", ctx.trace_any_device, d_any)):
+            for _ in range(3):
+                fn(d_rays.data_ptr(), n_local, dst.data_ptr(), stream)
+            torch.cuda.synchronize()
+            reps = 5
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn(d_rays.data_ptr(), n_local, dst.data_ptr(), stream)
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / reps
+        nodes_c, prims_c = ctx.count_visits(d_rays.data_ptr(), n_local, False)
+        nodes_a, prims_a = ctx.count_visits(d_rays.data_ptr(), n_local, True)
+        bytes_c = 32 + 16 + 64 * nodes_c / n_local + 48 * prims_c / n_local
+        bytes_a = 32 + 1 + 64 * nodes_a / n_local + 48 * prims_a / n_local
+        # end to end through the host-buffer entry point (pinned buffers): H2D + kernel + D2H
+        t0 = time.perf_counter()
+        ctx.trace_closest_ptr(h_rays.data_ptr(), n_local, h_hits.data_ptr())
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        out[label] = {
+            "closest_mrays_s": n_local * world / res["closest"] * 1e-3, "any_mrays_s": n_local * world / res["any"] * 1e-3,
+            "closest_ms": res["closest"], "any_ms": res["any"],
+            "nodes_per_ray": nodes_c / n_local, "prims_per_ray": prims_c / n_local,
+            "any_nodes_per_ray": nodes_a / n_local, "any_prims_per_ray": prims_a / n_local,
+            "bytes_per_ray": bytes_c, "any_bytes_per_ray": bytes_a,
+            "e2e_closest_mrays_s": n_local * world / e2e_ms * 1e-3,
+            "e2e_h2d_bytes": n_local * 32, "e2e_d2h_bytes": n_local * 16,
+            "roofline": {"bound": "hbm", "achieved": bytes_c * n_local / (res["closest"] * 1e-3) * 1e-9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": bytes_c * n_local / (res["closest"] * 1e-3) * 1e-9 / peaks["hbm_gbs"],
+                         "traffic": None, "kernel": "k_trace_closest<0>",
+                         "note": "algorithmic bytes = 48 + 64*nodes + 48*prims per ray; nodes are 64-byte "
+                                 "two-child records served mostly by L1/L2, so the fraction can exceed HBM traffic"},
+        }
+        if kind == 0 and do_cpu and rank == 0:
+            out["cpu_baseline"] = cpu_rays_baseline(sc, h_rays.numpy()[: 1 << 20])
+        del d_rays, d_hits, d_any, h_rays, h_hits
+    out["workload"] = (f"{len(prims)} triangle height-field ({RAYS_G}x{RAYS_G} quads), midpoint BVH {len(nodes)} nodes, "
+                       f"{RAYS_N} rays per batch (BASELINE.json configs[1])")
+    ctx.close()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# main arm
+# --------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tuturenderer_b200 import api
+    from tuturenderer_b200.multigpu import CudaRenderer, split_samples
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    peaks = json.loads(peaks_file.read_text()) if peaks_file.exists() else {"hbm_gbs": 6650.0, "fallback": True}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sc = cornell_scene()
+    r = CudaRenderer(sc, local_rank, paths_in_flight=0, profile_stages=True)
+    begin, count = split_samples(args.spp, world, rank)
+    npix = WIDTH * HEIGHT
+
+    def step(seed):
+        return r.render(args.spp, seed, rank, world)
+
+    for w in range(args.warmup):
+        step(SEED + w)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    agg = {k: 0.0 for k in ("extend_ms", "shade_ms", "shadow_ms", "other_ms", "gpu_ms")}
+    cnt = {k: 0 for k in ("extend_rays", "shadow_rays", "kernel_launches", "iterations", "nan_samples", "paths")}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        step(SEED + 100 + k)
+        st = r.ctx.stats()
+        for key in agg:
+            agg[key] += st[key]
+        for key in cnt:
+            cnt[key] += st[key]
+        cnt["kernel_launches"] += 2 if rank == 0 else 1  # accum.zero_ is torch's; finalize is ours
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    launches = torch.tensor([cnt["kernel_launches"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(ms.item())
+    paths_per_step = npix * args.spp
+    value = paths_per_step * args.steps / total_ms * 1e-3  # Mpaths/s, whole job
+
+    # ---- end to end through the host-buffer entry point: scene upload (H2D) + render + image D2H
+    host_img = torch.empty(npix * 3, dtype=torch.float32, pin_memory=True)
+    desc_bytes = int(sc.prims.nbytes + sc.materials.nbytes + (sc.bvh_nodes.nbytes if sc.bvh_nodes is not None else 0))
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step(seed):
+        r.ctx.upload(sc)  # host scene -> HBM, as IIntegrator::integrate(g) receives host objects
+        if world == 1:
+            r.ctx.render_path_ptr(args.spp, seed, host_img.data_ptr())  # tutu_render_path: render + D2H
+        else:
+            img = r.render(args.spp, seed, rank, world)
+            if rank == 0:
+                host_img.copy_(img.reshape(-1), non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_step(SEED + 7)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(SEED + 200 + k)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = paths_per_step * e2e_steps / float(e2e_s.item()) * 1e-6
+
+    # ---- roofline of the dominant wavefront kernel (this rank's share; per-launch = per iteration)
+    stage_ms = {"wf_extend": agg["extend_ms"], "wf_shade": agg["shade_ms"], "wf_shadow": agg["shadow_ms"]}
+    dominant = max(stage_ms, key=stage_ms.get)
+    ext, shd, pth = cnt["extend_rays"], cnt["shadow_rays"], cnt["paths"]
+    cont = max(ext - pth, 0)
+    alg = {
+        "wf_extend": ext * (B_RAY + B_HIT),
+        "wf_shade": ext * (B_RAY + B_STATE + B_HIT) + cont * B_XSTATE + cont * (B_RAY + B_STATE + B_XSTATE) + shd * B_SHADOW + pth * 12,
+        "wf_shadow": shd * (B_SHADOW + 32),
+    }
+    iters = max(cnt["iterations"], 1)
+    ach = alg[dominant] / (stage_ms[dominant] * 1e-3) * 1e-9 if stage_ms[dominant] > 0 else 0.0
+    prof = ROOT / "profiles" / "r01_traffic.json"
+    traffic = None
+    if prof.exists():
+        traffic = json.loads(prof.read_text()).get(dominant, {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+                "peak_source": "fallback 6650 GB/s" if peaks.get("fallback") else "MEASURED_PEAKS.json hbm_gbs (measured)",
+                "avg_launch_ms": stage_ms[dominant] / iters, "algorithmic_bytes_per_launch": alg[dominant] / iters,
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+                "stage_gbs": {k: (alg[k] / (v * 1e-3) * 1e-9 if v > 0 else 0.0) for k, v in stage_ms.items()},
+                "bytes_per_path": sum(alg.values()) / max(pth, 1),
+                "rays_per_path": {"extend": ext / max(pth, 1), "shadow": shd / max(pth, 1)},
+                "note": "Cornell's BVH is 6 KB and lives in L1: the wavefront kernels are issue/latency bound, "
+                        "the HBM fraction is reported because north_star asks for it"}
+
+    rays = None
+    if not args.no_rays:
+        rays = rays_bench(torch, api.Context, rank, world, do_cpu=(not args.no_cpu and world == 1), peaks=peaks)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_paths_baseline(16)
+
+    if rank == 0:
+        line = {
+            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": value / PUBLISHED_MPATHS, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": desc_bytes,
+                    "d2h_bytes_per_step": npix * 3 * 4, "steps": e2e_steps,
+                    "call": "tutu_scene_upload + tutu_render_path (host scene in, pinned host image out)"},
+            "gpu_launches": int(launches.item()),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "rays": rays,
+            "mrays_per_s_in_render": {"extend": ext * world / (agg["extend_ms"] * 1e-3) * 1e-6 if agg["extend_ms"] else None,
+                                      "shadow": shd * world / (agg["shadow_ms"] * 1e-3) * 1e-6 if agg["shadow_ms"] else None},
+            "nan_samples": cnt["nan_samples"],
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

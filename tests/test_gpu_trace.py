@@ -1,0 +1,186 @@
+"""Parity tests proper for the traversal kernels (through the C ABI, on a B200):
+bit-exact primitive ids / t / u / v against the reference's golden vectors and against the CPU
+oracle on seeded inputs; size-independent properties at BASELINE.json's full size."""
+import numpy as np
+import pytest
+
+from conftest import assert_hits_equal, load_rays, random_rays, random_soup
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("cornell_256", "cornell_rays.f32", "cornell_closest.bin", "cornell_any.bin"),
+         ("hf24", "hf24_rays0.f32", "hf24_closest0.bin", "hf24_any0.bin"),
+         ("hf24", "hf24_rays1.f32", "hf24_closest1.bin", "hf24_any1.bin"),
+         ("mixed", "mixed_rays.f32", "mixed_closest.bin", "mixed_any.bin")]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("scene,rays,closest,anyf", CASES)
+def test_golden_vectors_bit_exact(api, ctx, golden, scene, rays, closest, anyf, mode):
+    sc = api.Scene.load(golden / f"{scene}.tscene")
+    ctx.upload(sc)
+    ctx.set_traversal_mode(mode)
+    r = load_rays(golden / rays)
+    assert_hits_equal(ctx.trace_closest(r), np.fromfile(golden / closest, api.HIT_DTYPE))
+    assert np.array_equal(ctx.trace_any(r), np.fromfile(golden / anyf, np.uint8))
+
+
+def test_library_built_tree_equals_given_tree(api, ctx, golden):
+    sc = api.Scene.load(golden / "mixed.tscene")
+    r = load_rays(golden / "mixed_rays.f32")
+    ctx.upload(sc)
+    a = ctx.trace_closest(r)
+    sc.bvh_nodes = None  # library builds the midpoint BVH itself
+    ctx.upload(sc)
+    assert_hits_equal(ctx.trace_closest(r), a)
+
+
+@pytest.mark.parametrize("n_tris,n_spheres,dup,seed", [(1, 0, 0, 1), (2, 0, 0, 2), (3, 1, 0, 3), (50, 5, 10, 4),
+                                                        (2000, 40, 300, 5), (20000, 0, 2000, 6)])
+def test_random_soups_against_oracle(api, oracle, ctx, n_tris, n_spheres, dup, seed):
+    """Duplicated triangles give exact-t ties: the lowest DFS leaf must win (BVH.hpp:165)."""
+    prims = random_soup(api, n_tris, n_spheres, seed=seed, dup=dup)
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    osc = oracle.OracleScene(sc)
+    rays = random_rays(30000, seed=seed)
+    want_c, want_a = osc.trace_closest(rays), osc.trace_any(rays)
+    ctx.upload(sc)
+    for mode in (0, 1):
+        ctx.set_traversal_mode(mode)
+        assert_hits_equal(ctx.trace_closest(rays), want_c)
+        assert np.array_equal(ctx.trace_any(rays), want_a)
+    if dup:
+        assert (want_c["prim"] >= 0).any()
+
+
+def test_degenerate_rays(api, oracle, ctx, cornell):
+    """Zero direction components (inf / NaN slabs), rays in wall planes, zero-length directions."""
+    rng = np.random.default_rng(5)
+    n = 4000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.choice([0.0, 82.0, 130.0, 278.0, 330.0, 548.8, 556.0, 559.2], (n, 3))
+    k = rng.integers(0, 3, n)
+    rays[np.arange(n), 4 + k] = rng.choice([-1.0, 1.0], n)
+    two = rng.random(n) < 0.3
+    k2 = (k + 1) % 3
+    rays[two, 4 + k2[two]] = 0.70710678
+    rays[two, 4 + k[two]] *= 0.70710678
+    rays[:50, 4:7] = 0.0          # null direction
+    rays[50:80, 4] = -0.0          # negative zero is not "< 0" (BoundBox.hpp:70-72)
+    rays[:, 7] = 300.0
+    osc = oracle.OracleScene(cornell)
+    ctx.upload(cornell)
+    for mode in (0, 1):
+        ctx.set_traversal_mode(mode)
+        assert_hits_equal(ctx.trace_closest(rays), osc.trace_closest(rays))
+        assert np.array_equal(ctx.trace_any(rays), osc.trace_any(rays))
+
+
+def test_any_hit_distance_rule(api, oracle, ctx, cornell):
+    """hasIntersection accepts t < dis && !FLOAT_EQUAL(t, dis) (BVH.hpp:184)."""
+    osc = oracle.OracleScene(cornell)
+    rays = osc.primary_rays()[::7].copy()
+    hits = osc.trace_closest(rays)
+    ok = hits["prim"] >= 0
+    rays, t = rays[ok], hits["t"][ok]
+    ctx.upload(cornell)
+    for delta in (-1.0, -2e-4, -5e-5, 0.0, 5e-5, 2e-4, 1.0):
+        rays[:, 7] = t + np.float32(delta)
+        assert np.array_equal(ctx.trace_any(rays), osc.trace_any(rays)), delta
+
+
+def test_edge_batches_and_scenes(api, ctx, cornell):
+    ctx.upload(cornell)
+    assert len(ctx.trace_closest(np.zeros((0, 8), np.float32))) == 0
+    assert len(ctx.trace_any(np.zeros((0, 8), np.float32))) == 0
+    one = np.array([[278, 273, -800, 0, 0, 0, 1, 5000]], np.float32)
+    h = ctx.trace_closest(one)
+    assert h["prim"][0] >= 0 and h["t"][0] > 0
+    assert ctx.trace_any(one)[0] == 1
+    # odd batch sizes around the warp / packet size
+    for n in (31, 32, 33, 255, 257):
+        r = np.repeat(one, n, 0)
+        assert (ctx.trace_closest(r)["prim"] == h["prim"][0]).all()
+    # empty scene: every ray misses (prim -1, t FLT_MAX)
+    empty = api.Scene(prims=np.zeros(0, api.PRIM_DTYPE), materials=api.default_material())
+    ctx.upload(empty)
+    h = ctx.trace_closest(one)
+    assert h["prim"][0] == -1 and h["t"][0] == np.finfo(np.float32).max
+    assert ctx.trace_any(one)[0] == 0
+
+
+def test_errors(api, cornell):
+    c = api.Context(0)
+    with pytest.raises(api.TutuError) as e:
+        c.trace_closest(np.zeros((1, 8), np.float32))
+    assert e.value.code == -3  # TUTU_E_STATE
+    bad = api.Scene(prims=cornell.prims.copy(), materials=cornell.materials)
+    bad.prims["material"][3] = 99
+    with pytest.raises(api.TutuError) as e:
+        c.upload(bad)
+    assert e.value.code == -1 and "material" in str(e.value)
+    bad = api.Scene(prims=cornell.prims.copy(), materials=cornell.materials)
+    bad.prims["type"][0] = 7
+    with pytest.raises(api.TutuError):
+        c.upload(bad)
+    bad = api.Scene(prims=cornell.prims, materials=cornell.materials, bvh_nodes=cornell.bvh_nodes[:-2])
+    with pytest.raises(api.TutuError):
+        c.upload(bad)
+    bad = api.Scene(prims=cornell.prims.copy(), materials=cornell.materials)
+    bad.prims["tex_active"][0] = 1
+    bad.prims["tex_diffuse"][0] = 4  # IIntegrator.hpp:92-96: out-of-range map index
+    with pytest.raises(api.TutuError):
+        c.upload(bad)
+    with pytest.raises(api.TutuError):
+        api.Context(10 ** 6)
+    c.close()
+
+
+def test_full_size_properties(api, ctx):
+    """BASELINE.json configs[1] size: 999 698 triangles, 2^24 rays.  Too big for the CPU oracle, so
+    size-independent properties: the pruned traversal equals the literal both-children walk
+    bit for bit, any-hit agrees with closest-hit (blocked <=> t_closest < dis - 1e-4 for the hit
+    found), and every reported (t,u,v) reproduces a point inside its triangle."""
+    import torch
+    G, N = 707, 1 << 24
+    prims = api.synth_heightfield(G)
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    ctx.upload(sc)
+    info = ctx.info()
+    assert info.n_prims == 999698 and info.n_nodes == 2 * 999698 - 1
+    rays = torch.from_numpy(api.synth_rays(0, N)).cuda()
+    hits = torch.empty((N, 4), dtype=torch.float32, device="cuda")
+    blocked = torch.empty(N, dtype=torch.uint8, device="cuda")
+    ctx.trace_closest_device(rays.data_ptr(), N, hits.data_ptr())
+    ctx.trace_any_device(rays.data_ptr(), N, blocked.data_ptr())
+    torch.cuda.synchronize()
+    prim = hits.view(torch.int32)[:, 0]
+    t = hits[:, 1]
+    hit = prim >= 0
+    assert 0.9 < float(hit.float().mean()) <= 1.0
+    # closest vs any: the closest hit decides unless it sits in the FLOAT_EQUAL band around dis
+    dis = rays[:, 7]
+    decided = (t < dis - 2e-4) | ~hit | (t > dis + 2e-4)
+    want = hit & (t < dis)
+    assert bool((blocked.bool() == want)[decided].all())
+    # literal walk on a 2M-ray slice
+    M = 1 << 21
+    ctx.set_traversal_mode(1)
+    hits1 = torch.empty((M, 4), dtype=torch.float32, device="cuda")
+    blocked1 = torch.empty(M, dtype=torch.uint8, device="cuda")
+    ctx.trace_closest_device(rays.data_ptr(), M, hits1.data_ptr())
+    ctx.trace_any_device(rays.data_ptr(), M, blocked1.data_ptr())
+    torch.cuda.synchronize()
+    ctx.set_traversal_mode(0)
+    assert bool((hits1.view(torch.int32) == hits[:M].view(torch.int32)).all())
+    assert bool((blocked1 == blocked[:M]).all())
+    # geometric check of (t,u,v) on a sample
+    idx = torch.nonzero(hit)[:200000, 0].cpu().numpy()
+    h = hits[idx].cpu().numpy()
+    p = prims[prim[idx].cpu().numpy()]
+    v = p["v"].reshape(-1, 3, 3).astype(np.float64)
+    r = rays[idx].cpu().numpy().astype(np.float64)
+    pos = r[:, 0:3] + h[:, 1:2] * r[:, 4:7]
+    bary = v[:, 0] * (1 - h[:, 2:3] - h[:, 3:4]) + v[:, 1] * h[:, 2:3] + v[:, 2] * h[:, 3:4]
+    assert np.abs(pos - bary).max() < 1e-4
+    assert (h[:, 2] > 0).all() and (h[:, 3] > 0).all() and (1 - h[:, 2] - h[:, 3] > 0).all()

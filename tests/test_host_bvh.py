@@ -1,0 +1,79 @@
+"""Host logic: the product's midpoint BVH builder reproduces the reference-built topology, scene
+files round-trip, the synthetic generators are deterministic."""
+import numpy as np
+import pytest
+
+from conftest import random_soup
+
+
+@pytest.mark.parametrize("name", ["cornell_256", "hf24", "mixed"])
+def test_builder_matches_reference_tree(api, golden, name):
+    s = api.Scene.load(golden / f"{name}.tscene")
+    assert s.bvh_nodes is not None and len(s.bvh_nodes) == 2 * len(s.prims) - 1
+    assert np.array_equal(api.bvh_build(s.prims), s.bvh_nodes)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 64, 1000])
+def test_builder_matches_oracle_on_random_soups(api, oracle, n):
+    prims = random_soup(api, n, n_spheres=min(n // 4, 10), seed=n, dup=min(n // 3, 20))
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    mine = api.bvh_build(prims)
+    ref = oracle.OracleScene(sc).bvh_export()
+    assert np.array_equal(mine, ref)
+    leaves = mine[mine["left"] < 0]["prim"]
+    assert sorted(leaves.tolist()) == list(range(len(prims)))
+
+
+def test_builder_centroid_ties(api, oracle):
+    # many identical centroids: the split depends on std::sort's handling of equal keys
+    prims = random_soup(api, 40, seed=3)
+    prims["v"][:, :] = prims["v"][0]
+    prims["v"][20:, 0] += 1.0
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    assert np.array_equal(api.bvh_build(prims), oracle.OracleScene(sc).bvh_export())
+
+
+def test_builder_empty(api):
+    assert len(api.bvh_build(np.zeros(0, api.PRIM_DTYPE))) == 0
+
+
+def test_large_builder_is_threaded_and_consistent(api, oracle):
+    prims = api.synth_heightfield(160)  # 51200 triangles: crosses the parallel threshold
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    assert np.array_equal(api.bvh_build(prims), oracle.OracleScene(sc).bvh_export())
+
+
+def test_scene_file_roundtrip(api, mixed, tmp_path):
+    p = tmp_path / "m.tscene"
+    mixed.save(p)
+    back = api.Scene.load(p)
+    assert np.array_equal(back.prims, mixed.prims) and np.array_equal(back.materials, mixed.materials)
+    assert np.array_equal(back.bvh_nodes, mixed.bvh_nodes)
+    for c in range(4):
+        assert len(back.textures[c]) == len(mixed.textures[c])
+        for a, b in zip(back.textures[c], mixed.textures[c]):
+            assert np.array_equal(a, b)
+    assert back.eye == mixed.eye and back.hfov_deg == mixed.hfov_deg and back.bkgcolor == mixed.bkgcolor
+
+
+def test_scene_file_errors(api, tmp_path):
+    with pytest.raises(api.TutuError):
+        api.Scene.load(tmp_path / "missing.tscene")
+    bad = tmp_path / "bad.tscene"
+    bad.write_bytes(b"not a scene")
+    with pytest.raises(api.TutuError):
+        api.Scene.load(bad)
+
+
+def test_synth_is_deterministic(api, golden):
+    a, b = api.synth_heightfield(24, 12345), api.synth_heightfield(24, 12345)
+    assert np.array_equal(a, b)
+    hf = api.Scene.load(golden / "hf24.tscene")
+    assert np.array_equal(a, hf.prims)  # same generator as the committed fixture
+    for kind in (0, 1):
+        r = api.synth_rays(kind, 6000, 12345)
+        assert np.array_equal(r, np.fromfile(golden / f"hf24_rays{kind}.f32", np.float32).reshape(-1, 8))
+        # chunked generation is the same stream
+        assert np.array_equal(api.synth_rays(kind, 100, 12345, first=50), r[50:150])
+        n = np.linalg.norm(r[:, 4:7], axis=1)
+        assert np.allclose(n, 1, atol=1e-6)
