@@ -208,7 +208,7 @@ def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict)
     n_local = RAYS_N // world
     first = rank * n_local
     out = {}
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = api.stream_handle(torch.cuda.current_stream().cuda_stream)
     for kind, label in ((0, "coherent_topdown"), (1, "incoherent_inside")):
         h_rays = torch.empty((n_local, 8), dtype=torch.float32, pin_memory=True)
         api.synth_rays(kind, n_local, first=first, out=h_rays.numpy())

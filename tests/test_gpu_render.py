@@ -38,8 +38,11 @@ def test_same_stream_as_oracle(api, oracle, ctx, golden, name, size, spp):
     assert abs(g.mean() / o.mean() - 1) < 5e-3
     st = ctx.stats()
     assert st["paths"] == size * size * spp
-    # same number of rays as the reference algorithm traces (+-0.5 %)
-    assert abs(st["extend_rays"] / cnt[0] - 1) < 5e-3
+    # the reference recurses out of calcForRefractive BEFORE testing pdf < MIN_DIVISOR
+    # (PathTracing.hpp:128-133) and so traces sub-paths it then discards; the GPU tests first.
+    # Without refractive materials (Cornell) the ray counts agree to discrete flips.
+    assert st["extend_rays"] <= cnt[0] * 1.002
+    assert st["extend_rays"] >= cnt[0] * (0.998 if name.startswith("cornell") else 0.97)
     # the CPU traces every NEE shadow ray, the GPU only those whose contribution is not already
     # rejected by the facing tests (PathTracing.hpp:197,202), so it traces at most as many
     assert st["shadow_rays"] <= cnt[1]
@@ -94,6 +97,7 @@ def test_sample_ranges_compose(api, ctx, cornell):
     whole = ctx.render_path(8, seed=4)
     acc = torch.zeros(64 * 64 * 3, dtype=torch.float32, device="cuda")
     out = torch.empty_like(acc)
+    torch.cuda.synchronize()  # the library runs on its own stream here (stream = NULL)
     ctx.render_accumulate_device(0, 3, 4, acc.data_ptr())
     ctx.render_accumulate_device(3, 5, 4, acc.data_ptr())
     ctx.finalize_device(acc.data_ptr(), 1.0 / 8, out.data_ptr())

@@ -99,6 +99,15 @@ ABI = {
 
 _lib = None
 
+# torch's default stream has the handle 0, which the C ABI reads as "the ctx's own stream";
+# CUDA's explicit name for the legacy default stream is cudaStreamLegacy = 0x1.
+CUDA_STREAM_LEGACY = 1
+
+
+def stream_handle(stream: int) -> int:
+    """Maps a torch `cuda_stream` integer to the handle the C ABI expects."""
+    return stream if stream else CUDA_STREAM_LEGACY
+
 
 class TutuError(RuntimeError):
     def __init__(self, code: int, message: str):
@@ -351,7 +360,7 @@ class Context:
         self._ck(lib().tutu_trace_any(self._h, rays_ptr, n, out_ptr))
 
     def trace_closest_device(self, d_rays: int, n: int, d_hits: int, stream: int = 0) -> None:
-        self._ck(lib().tutu_trace_closest_device(self._h, d_rays, n, d_hits, stream or None))
+        self._ck(lib().tutu_trace_closest_device(self._h, d_rays, n, d_hits, stream or None))  # 0 = ctx stream
 
     def trace_any_device(self, d_rays: int, n: int, d_out: int, stream: int = 0) -> None:
         self._ck(lib().tutu_trace_any_device(self._h, d_rays, n, d_out, stream or None))

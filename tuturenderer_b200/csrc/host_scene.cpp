@@ -441,6 +441,7 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
       g.f[1] = p.v[1];
       g.f[2] = p.v[2];
       g.f[3] = p.v[3];
+      if (2.f * fabsf(p.v[3]) > fs->max_edge && fabsf(p.v[3]) < 1.0e38f) fs->max_edge = 2.f * fabsf(p.v[3]);
       sh.flags |= SHADE_SPHERE_BIT;
     } else {
       // Triangle.hpp:25-35: E1, E2 and the unit geometric normal are ray independent, so they
@@ -448,6 +449,14 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
       V3 v0 = ld3(p.v), v1 = ld3(p.v + 3), v2 = ld3(p.v + 6);
       V3 e1 = sub(v1, v0), e2 = sub(v2, v0);
       V3 nn = normalized(cross(e1, e2));
+      {
+        V3 e3 = sub(v2, v1);
+        float l1 = sqrtf(e1.x * e1.x + e1.y * e1.y + e1.z * e1.z);
+        float l2 = sqrtf(e2.x * e2.x + e2.y * e2.y + e2.z * e2.z);
+        float l3 = sqrtf(e3.x * e3.x + e3.y * e3.y + e3.z * e3.z);
+        float l = fmaxf(l1, fmaxf(l2, l3));
+        if (l > fs->max_edge && l < 3.0e38f) fs->max_edge = l;
+      }
       st3(g.f + 0, v0);
       st3(g.f + 3, e1);
       st3(g.f + 6, e2);

@@ -38,6 +38,10 @@ struct DevScene {
   int n_lights;
   float bkg[3];
   float eta;
+  // Pruning slack (see traverse()): a subtree is culled only when its box is entered later than
+  // best_t * (1 + prune_rel) + prune_abs.
+  float prune_rel;
+  float prune_abs;
 };
 
 struct Ray {
@@ -182,9 +186,16 @@ struct VisitCount {
   unsigned nodes = 0, prims = 0;
 };
 
-// MODE 0: ordered (near child first) + pruned by the best t so far.  A subtree is skipped only
-//         when its box is entered strictly AFTER the best hit (t_enter > best_t); equal t is kept
-//         and resolved by the lower DFS leaf slot, which is the reference's tie rule.
+// MODE 0: ordered (near child first) + pruned by the best t so far.  The reference never prunes, so
+//         culling must not remove a primitive it would have reported.  In exact arithmetic a
+//         triangle inside a box is hit no earlier than the box is entered; in fp32 the slab
+//         distances carry ~3 ulp of relative error, but a Cramer-rule t carries up to
+//         ~10 eps / (sin(E1,E2) * |d.n|) (|d.n| >= 1e-4 is enforced by the parallel test), i.e.
+//         up to a fraction of a percent for grazing rays.  A subtree is therefore skipped only
+//         when t_enter > best_t * (1 + prune_rel) + prune_abs (defaults 2^-7 and 2^-9 of the
+//         longest triangle edge); equal t is resolved by the lower DFS leaf slot, which is the
+//         reference's tie rule.  tests/ and bench.py compare MODE 0 with MODE 1 bit for bit on
+//         the full-size batches.
 // MODE 1: literal mirror of the reference recursion: left then right, nothing pruned.
 // ANY:    hasIntersection — first accepted leaf ends the walk (the boolean is order independent).
 template <bool ANY, int MODE, bool COUNT>
@@ -205,7 +216,7 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, const Ray& r, float
   float stack_t[kStackSize];
   int sp = 0;
   int cur = sc.root_ref;
-  const float limit_any = dis;
+  const float limit_any = fmaf(dis, sc.prune_rel, dis + sc.prune_abs);
 
   for (;;) {
     if (cur >= 0) {
@@ -219,7 +230,7 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, const Ray& r, float
       bool hl = box_test(p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
       bool hr = box_test(p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
       if (MODE == 0) {
-        const float lim = ANY ? limit_any : best.t;
+        const float lim = ANY ? limit_any : fmaf(best.t, sc.prune_rel, best.t + sc.prune_abs);
         hl = hl && !(tl > lim);
         hr = hr && !(tr > lim);
       }
@@ -274,7 +285,8 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, const Ray& r, float
       if (sp == 0) return best.slot >= 0;
       --sp;
       cur = stack_ref[sp];
-      if (MODE == 0 && !ANY && stack_t[sp] > best.t) continue;  // entered after the current best
+      if (MODE == 0 && !ANY && stack_t[sp] > fmaf(best.t, sc.prune_rel, best.t + sc.prune_abs))
+        continue;  // entered (well) after the current best
       break;
     }
   }

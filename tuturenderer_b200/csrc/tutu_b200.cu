@@ -3,6 +3,7 @@
 // sm_100a only; there is no CPU fallback anywhere in this file.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -496,6 +497,10 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   d.n_lights = (int)fs.lights.size();
   memcpy(d.bkg, fs.bkgcolor, 12);
   d.eta = fs.eta;
+  d.prune_rel = 1.0f / 128.0f;
+  d.prune_abs = fs.max_edge * (1.0f / 512.0f);
+  if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);  // experiments only
+  if (const char* e = getenv("TUTU_PRUNE_ABS")) d.prune_abs = (float)atof(e);
   ctx->scene_bytes = fs.inner.size() * sizeof(InnerNode) + fs.geom.size() * sizeof(LeafGeom) +
                      fs.shade.size() * sizeof(LeafShade) + fs.leaftex.size() * sizeof(LeafTex) +
                      fs.slot_to_prim.size() * 4 + fs.materials.size() * sizeof(DevMaterial) +

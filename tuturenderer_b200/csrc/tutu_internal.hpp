@@ -114,6 +114,7 @@ struct FlatScene {
   int32_t root_ref = 0;  // inner index 0, or ~slot when the tree is a single leaf
   bool empty = true;
   Box root_box{};
+  float max_edge = 0.f;  // longest triangle edge / sphere diameter (pruning slack)
   std::vector<InnerNode> inner;
   std::vector<LeafGeom> geom;
   std::vector<LeafShade> shade;

@@ -48,6 +48,7 @@ class CudaRenderer:
         import torch
         from . import api
         self.torch = torch
+        self.api = api
         self.device = device
         torch.cuda.set_device(device)
         self.ctx = api.Context(device)
@@ -60,12 +61,12 @@ class CudaRenderer:
 
     def accumulate(self, begin: int, count: int, accum=None, seed: int = 1) -> None:
         accum = self.accum if accum is None else accum
-        stream = self.torch.cuda.current_stream().cuda_stream
+        stream = self.api.stream_handle(self.torch.cuda.current_stream().cuda_stream)
         self.ctx.render_accumulate_device(begin, count, seed, accum.data_ptr(), stream)
 
     def finalize(self, spp: int, accum=None):
         accum = self.accum if accum is None else accum
-        stream = self.torch.cuda.current_stream().cuda_stream
+        stream = self.api.stream_handle(self.torch.cuda.current_stream().cuda_stream)
         self.ctx.finalize_device(accum.data_ptr(), 1.0 / spp, self.rgb.data_ptr(), stream)
         return self.rgb.view(self.scene.height, self.scene.width, 3)
 
