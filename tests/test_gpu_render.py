@@ -61,13 +61,15 @@ def test_cornell_statistics_against_reference(api, ctx, golden, cornell):
             vals_m.append(_relmse(img, ref))
         assert abs(np.mean(vals_r) / stats[f"rmse_{spp}"] - 1) < 0.10
         assert abs(np.mean(vals_m) / stats[f"relmse_{spp}"] - 1) < 0.10
-    # gate 3: deterministic pixel sets
+    # gate 3: deterministic pixel sets.  Where the reference's primary ray misses (exact bkgcolor)
+    # or hits the light (exact emission) the GPU pixel must be exactly that at any spp.
     img = ctx.render_path(16, seed=9)
-    assert np.array_equal((img == 0).all(-1), (ref == 0).all(-1))
+    assert ((img == 0).all(-1) >= (ref == 0).all(-1)).all()
     assert np.array_equal((img == LIGHT).all(-1), (ref == LIGHT).all(-1))
     # gate 2: bias.  16384 spp vs the 4096-spp reference mean: per-channel mean within 0.5 %,
     # per-pixel RMSE below 2x the reference's run-to-run RMSE at 2048 spp
     big = ctx.render_path(16384, seed=5)
+    assert np.array_equal((big == 0).all(-1), (ref == 0).all(-1))
     for c in range(3):
         assert abs(big[..., c].mean() / stats["channel_means"][c] - 1) < 0.005
     assert _rmse(big, ref) < 2 * stats["run_to_run_rmse_2048"]

@@ -1,0 +1,31 @@
+"""Short, fixed workload for ncu (never a bench number): `render` = Cornell 1024x1024 @ 24 spp,
+`rays` = 4 Mi rays of each synthetic kind against the 999 698-triangle height-field."""
+import sys
+from pathlib import Path
+import numpy as np
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from tuturenderer_b200 import api
+
+what = sys.argv[1] if len(sys.argv) > 1 else "render"
+ctx = api.Context(0)
+if what == "render":
+    sc = api.Scene.load(ROOT / "tests/golden/cornell_256.tscene").with_size(1024, 1024)
+    ctx.upload(sc)
+    img = ctx.render_path(24, seed=5)
+    print("render mean", float(img.mean()), ctx.stats())
+else:
+    G, N = 707, 1 << 22
+    prims = api.synth_heightfield(G)
+    sc = api.Scene(prims=prims, materials=api.default_material(), bvh_nodes=api.bvh_build(prims))
+    ctx.upload(sc)
+    for kind in (0, 1):
+        rays = torch.from_numpy(api.synth_rays(kind, N)).cuda()
+        hits = torch.empty((N, 4), dtype=torch.float32, device="cuda")
+        blocked = torch.empty(N, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.trace_closest_device(rays.data_ptr(), N, hits.data_ptr())
+        ctx.trace_any_device(rays.data_ptr(), N, blocked.data_ptr())
+        torch.cuda.synchronize()
+        print("kind", kind, "hit frac", float((hits.view(torch.int32)[:, 0] >= 0).float().mean()), "blocked", float(blocked.float().mean()))

@@ -497,7 +497,7 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   d.n_lights = (int)fs.lights.size();
   memcpy(d.bkg, fs.bkgcolor, 12);
   d.eta = fs.eta;
-  d.prune_rel = 1.0f / 128.0f;
+  d.prune_rel = 1.0f / 1024.0f;
   d.prune_abs = fs.max_edge * (1.0f / 512.0f);
   if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_ABS")) d.prune_abs = (float)atof(e);
