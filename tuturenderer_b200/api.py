@@ -119,10 +119,12 @@ def lib() -> C.CDLL:
     """Loads libtutu_b200.so; raises if it is not built (no fallback)."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
-            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m tuturenderer_b200.build` "
+        import os
+        path = Path(os.environ.get("TUTU_LIB", LIB_PATH))  # TUTU_LIB: experiment builds only
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing: build it with `python -m tuturenderer_b200.build` "
                                "(the CUDA library is the product; there is no CPU fallback)")
-        l = C.CDLL(str(LIB_PATH))
+        l = C.CDLL(str(path))
         for name, (res, args) in ABI.items():
             fn = getattr(l, name)  # AttributeError if the symbol is not exported
             fn.restype = res

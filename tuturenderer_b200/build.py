@@ -48,6 +48,15 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > t for p in SOURCES + HEADERS + [Path(__file__)])
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """Experiment builds (tools/): libtutu_b200_<name>.so with extra -D flags, picked up through TUTU_LIB."""
+    out = PKG / f"libtutu_b200_{name}.so"
+    res = subprocess.run(nvcc_command(out, [f"-D{d}" for d in defines]), capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(res.stdout + res.stderr)
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB

@@ -42,6 +42,7 @@ struct DevScene {
   // best_t * (1 + prune_rel) + prune_abs.
   float prune_rel;
   float prune_abs;
+  int refill_min;  // persistent tracer: refill once this many lanes of a warp are idle
 };
 
 struct Ray {
@@ -186,6 +187,45 @@ struct VisitCount {
   unsigned nodes = 0, prims = 0;
 };
 
+// Slab test for "regular" rays (every 1/d finite): then no NaN can appear, the reference's
+// swap-if-negative equals min/max of the two plane distances and its ternary max/min chains equal
+// fmaxf/fminf (up to the sign of a zero, which no comparison below distinguishes), so the same
+// decision is reached with FMNMX instead of FSETP+FSEL pairs.  Same subtract-multiply roundings.
+__device__ __forceinline__ bool box_test_regular(const RayPre& p, float lox, float loy, float loz,
+                                                 float hix, float hiy, float hiz, float& t_enter) {
+  const float ax = __fmul_rn(__fsub_rn(lox, p.ox), p.ix), bx = __fmul_rn(__fsub_rn(hix, p.ox), p.ix);
+  const float ay = __fmul_rn(__fsub_rn(loy, p.oy), p.iy), by = __fmul_rn(__fsub_rn(hiy, p.oy), p.iy);
+  const float az = __fmul_rn(__fsub_rn(loz, p.oz), p.iz), bz = __fmul_rn(__fsub_rn(hiz, p.oz), p.iz);
+  t_enter = fmaxf(fminf(ax, bx), fmaxf(fminf(ay, by), fminf(az, bz)));
+  const float t_exit = fminf(fmaxf(ax, bx), fminf(fmaxf(ay, by), fmaxf(az, bz)));
+  return t_enter <= t_exit && t_exit >= 0.f;
+}
+
+__device__ __forceinline__ bool ray_is_regular(const RayPre& p) {
+  return isfinite(p.ix) && isfinite(p.iy) && isfinite(p.iz);
+}
+
+template <bool REGULAR>
+__device__ __forceinline__ bool box_any(const RayPre& p, float lox, float loy, float loz, float hix,
+                                        float hiy, float hiz, float& t_enter) {
+  if (REGULAR) return box_test_regular(p, lox, loy, loz, hix, hiy, hiz, t_enter);
+  return box_test(p, lox, loy, loz, hix, hiy, hiz, t_enter);
+}
+
+// Per-ray traversal state.  The walk is cut into "rounds" (descend inner nodes until a leaf is
+// reached, test that one leaf, pop) so that a warp can (a) run the inner-node code and the
+// primitive code as two convergent phases instead of interleaving them lane by lane, and (b) hand
+// a finished lane a new ray between rounds (persistent threads, see trace_persistent()).
+struct Walk {
+  Ray r;
+  RayPre p;
+  Hit best;
+  float dis;      // any-hit distance limit
+  int cur;
+  int sp;
+  bool regular;
+};
+
 // MODE 0: ordered (near child first) + pruned by the best t so far.  The reference never prunes, so
 //         culling must not remove a primitive it would have reported.  In exact arithmetic a
 //         triangle inside a box is hit no earlier than the box is entered; in fp32 the slab
@@ -200,96 +240,195 @@ struct VisitCount {
 //         bench.py compare MODE 0 with MODE 1 bit for bit on the full-size batches.
 // MODE 1: literal mirror of the reference recursion: left then right, nothing pruned.
 // ANY:    hasIntersection — first accepted leaf ends the walk (the boolean is order independent).
+template <bool ANY>
+__device__ __forceinline__ float prune_limit(const DevScene& sc, const Walk& w) {
+  const float b = ANY ? w.dis : w.best.t;
+  return fmaf(b, sc.prune_rel, b + sc.prune_abs);
+}
+
+// Starts a walk: false when the ray cannot hit anything (empty scene / root box missed).
+__device__ __forceinline__ bool walk_begin(const DevScene& sc, Walk& w, const Ray& r, float dis) {
+  w.r = r;
+  w.dis = dis;
+  w.best.t = FLT_MAX;
+  w.best.u = 0.f;
+  w.best.v = 0.f;
+  w.best.slot = -1;
+  w.sp = 0;
+  w.cur = sc.root_ref;
+  if (sc.empty) return false;
+  w.p = make_pre(r);
+  w.regular = ray_is_regular(w.p);
+  float te;
+  return box_test(w.p, sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1],
+                  sc.root_hi[2], te);
+}
+
+template <bool ANY, int MODE>
+__device__ __forceinline__ bool walk_pop(const DevScene& sc, Walk& w, const int* stack_ref,
+                                         const float* stack_t) {
+  for (;;) {
+    if (w.sp == 0) return false;
+    --w.sp;
+    w.cur = stack_ref[w.sp];
+    if (MODE == 0 && !ANY && stack_t[w.sp] > prune_limit<ANY>(sc, w)) continue;  // entered after the best hit
+    return true;
+  }
+}
+
+// One round.  Returns false when the walk is over (result in w.best; for ANY best.slot >= 0 means
+// "blocked").  REGULAR selects the slab-test flavour for the whole warp-round.
+template <bool ANY, int MODE, bool COUNT, bool REGULAR>
+__device__ __forceinline__ bool walk_round(const DevScene& sc, Walk& w, int* stack_ref, float* stack_t,
+                                           VisitCount* vc) {
+  // phase 1: inner nodes until this lane holds a leaf
+  while (w.cur >= 0) {
+    const float4* n = sc.inner + 4 * (size_t)w.cur;
+    const float4 a = __ldg(n + 0);
+    const float4 b = __ldg(n + 1);
+    const float4 c = __ldg(n + 2);
+    const int4 k = __ldg(reinterpret_cast<const int4*>(n + 3));
+    if (COUNT) vc->nodes++;
+    float tl, tr;
+    bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
+    bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+    if (MODE == 0) {
+      const float lim = prune_limit<ANY>(sc, w);
+      hl = hl && !(tl > lim);
+      hr = hr && !(tr > lim);
+    }
+    if (hl && hr) {
+      const bool left_first = (MODE == 1) || !(tr < tl);
+      stack_ref[w.sp] = left_first ? k.y : k.x;
+      stack_t[w.sp] = left_first ? tr : tl;
+      ++w.sp;
+      w.cur = left_first ? k.x : k.y;
+    } else if (hl) {
+      w.cur = k.x;
+    } else if (hr) {
+      w.cur = k.y;
+    } else if (!walk_pop<ANY, MODE>(sc, w, stack_ref, stack_t)) {
+      return false;
+    }
+  }
+  // phase 2: one primitive
+  {
+    const uint32_t code = ~(uint32_t)w.cur;
+    const uint32_t slot = code & kSlotMask;
+    const float4* g = sc.geom + 3 * (size_t)slot;
+    if (COUNT) vc->prims++;
+    float t, u = 0.f, v = 0.f;
+    bool hit;
+    if (code & kSphereBit)
+      hit = sphere_test(g, w.r, t);
+    else
+      hit = tri_test(g, w.r, t, u, v);
+    if (hit) {
+      if (ANY) {
+        // inter.t < dis && !FLOAT_EQUAL(inter.t, dis)
+        if (t < w.dis && !(fabsf(__fsub_rn(t, w.dis)) < 0.0001f)) {
+          w.best.t = t;
+          w.best.slot = (int)code;
+          return false;
+        }
+      } else if (t < w.best.t || (t == w.best.t && (int)slot < (w.best.slot & (int)kSlotMask))) {
+        // linter.t <= rinter.t ? linter : rinter  ==  lowest DFS leaf among equal t
+        w.best.t = t;
+        w.best.u = u;
+        w.best.v = v;
+        w.best.slot = (int)code;
+      }
+    }
+  }
+  return walk_pop<ANY, MODE>(sc, w, stack_ref, stack_t);
+}
+
+// Whole walk of one ray on one thread (used for the rare inline shadow ray of the shade kernel,
+// the literal MODE 1 kernels and the visit counters).
 template <bool ANY, int MODE, bool COUNT>
 __device__ __forceinline__ bool traverse(const DevScene& sc, const Ray& r, float dis, Hit& best,
                                          VisitCount* vc) {
-  best.t = FLT_MAX;
-  best.u = 0.f;
-  best.v = 0.f;
-  best.slot = -1;
-  if (sc.empty) return false;
-  const RayPre p = make_pre(r);
-  float te;
-  if (!box_test(p, sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1],
-                sc.root_hi[2], te))
-    return false;
-
+  Walk w;
   int stack_ref[kStackSize];
   float stack_t[kStackSize];
-  int sp = 0;
-  int cur = sc.root_ref;
-  const float limit_any = fmaf(dis, sc.prune_rel, dis + sc.prune_abs);
-
-  for (;;) {
-    if (cur >= 0) {
-      const float4* n = sc.inner + 4 * (size_t)cur;
-      const float4 a = __ldg(n + 0);
-      const float4 b = __ldg(n + 1);
-      const float4 c = __ldg(n + 2);
-      const int4 k = __ldg(reinterpret_cast<const int4*>(n + 3));
-      if (COUNT) vc->nodes++;
-      float tl, tr;
-      bool hl = box_test(p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
-      bool hr = box_test(p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
-      if (MODE == 0) {
-        const float lim = ANY ? limit_any : fmaf(best.t, sc.prune_rel, best.t + sc.prune_abs);
-        hl = hl && !(tl > lim);
-        hr = hr && !(tr > lim);
-      }
-      if (hl && hr) {
-        const bool left_first = (MODE == 1) || !(tr < tl);
-        const int near_ref = left_first ? k.x : k.y;
-        const int far_ref = left_first ? k.y : k.x;
-        stack_ref[sp] = far_ref;
-        stack_t[sp] = left_first ? tr : tl;
-        ++sp;
-        cur = near_ref;
-        continue;
-      }
-      if (hl) {
-        cur = k.x;
-        continue;
-      }
-      if (hr) {
-        cur = k.y;
-        continue;
+  if (walk_begin(sc, w, r, dis)) {
+    if (w.regular) {
+      while (walk_round<ANY, MODE, COUNT, true>(sc, w, stack_ref, stack_t, vc)) {
       }
     } else {
-      const uint32_t code = ~(uint32_t)cur;
-      const uint32_t slot = code & kSlotMask;
-      const float4* g = sc.geom + 3 * (size_t)slot;
-      if (COUNT) vc->prims++;
-      float t, u = 0.f, v = 0.f;
-      bool hit;
-      if (code & kSphereBit)
-        hit = sphere_test(g, r, t);
-      else
-        hit = tri_test(g, r, t, u, v);
-      if (hit) {
-        if (ANY) {
-          // inter.t < dis && !FLOAT_EQUAL(inter.t, dis)
-          if (t < dis && !(fabsf(__fsub_rn(t, dis)) < 0.0001f)) {
-            best.t = t;
-            best.slot = (int)code;
-            return true;
-          }
-        } else if (t < best.t || (t == best.t && (int)slot < (best.slot & (int)kSlotMask))) {
-          // linter.t <= rinter.t ? linter : rinter  ==  lowest DFS leaf among equal t
-          best.t = t;
-          best.u = u;
-          best.v = v;
-          best.slot = (int)code;
-        }
+      while (walk_round<ANY, MODE, COUNT, false>(sc, w, stack_ref, stack_t, vc)) {
       }
     }
-    // pop
-    for (;;) {
-      if (sp == 0) return best.slot >= 0;
-      --sp;
-      cur = stack_ref[sp];
-      if (MODE == 0 && !ANY && stack_t[sp] > fmaf(best.t, sc.prune_rel, best.t + sc.prune_abs))
-        continue;  // entered (well) after the current best
-      break;
+  }
+  best = w.best;
+  return best.slot >= 0;
+}
+
+// Persistent-thread tracer: every warp owns a chunk of the ray queue (one global atomicAdd per
+// kChunk rays); between rounds the lanes whose ray is finished are handed the next rays of the
+// chunk (ballot + popc ranks, no further atomics), so a warp keeps its lanes busy instead of
+// idling behind its longest ray.
+//   src(i, ray, dis)  loads ray i;  sink(i, walk)  stores its result.
+constexpr unsigned kChunk = 256;
+
+template <bool ANY, class Src, class Sink>
+__device__ __forceinline__ void trace_persistent(const DevScene& sc, unsigned long long n,
+                                                 unsigned long long* cursor, Src src, Sink sink) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  Walk w;
+  int stack_ref[kStackSize];
+  float stack_t[kStackSize];
+  bool active = false;
+  unsigned long long my = 0;
+  unsigned long long chunk_next = 0, chunk_end = 0;  // warp-uniform
+  bool exhausted = false;                            // warp-uniform
+  for (;;) {
+    const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+    if (!exhausted && (need == 0xFFFFFFFFu || __popc(need) >= sc.refill_min)) {
+      if (chunk_next == chunk_end) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        chunk_next = base < n ? base : n;
+        chunk_end = base + kChunk < n ? base + kChunk : n;
+        if (chunk_next >= n) {
+          exhausted = true;
+          chunk_end = chunk_next;
+        }
+      }
+      const unsigned long long avail = chunk_end - chunk_next;
+      const unsigned rank = __popc(need & lt_mask);
+      if (!active && rank < avail) {
+        my = chunk_next + rank;
+        Ray r;
+        float dis;
+        src(my, r, dis);
+        if (walk_begin(sc, w, r, dis))
+          active = true;
+        else
+          sink(my, w);  // miss without entering the tree
+      }
+      const unsigned cnt = (unsigned)__popc(need);
+      chunk_next += cnt < avail ? cnt : avail;
+    }
+    const unsigned act = __ballot_sync(0xFFFFFFFFu, active);
+    if (act == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    // the exact (NaN-literal) slab test is valid for every ray; the FMNMX flavour only for regular ones
+    const bool all_regular = __all_sync(0xFFFFFFFFu, !active || w.regular);
+    if (active) {
+      bool more;
+      if (all_regular)
+        more = walk_round<ANY, 0, false, true>(sc, w, stack_ref, stack_t, nullptr);
+      else
+        more = walk_round<ANY, 0, false, false>(sc, w, stack_ref, stack_t, nullptr);
+      if (!more) {
+        sink(my, w);
+        active = false;
+      }
     }
   }
 }

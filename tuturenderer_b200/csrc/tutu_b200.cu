@@ -128,12 +128,28 @@ int fail_cuda(TutuCtx* ctx, const CudaError& e) {
 // ---------------------------------------------------------------------------------------------
 // ray-batch kernels
 // ---------------------------------------------------------------------------------------------
-// One ray per thread; warps pull 32-ray packets from a global counter (persistent threads), so a
-// warp that drew short rays moves on instead of idling behind the block's slowest warp.
+// MODE 0: persistent warps with per-lane ray refill (trace_persistent).  MODE 1: the literal
+// reference walk, one 32-ray packet per warp at a time (tests only).
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_trace_closest(const DevScene sc, const float4* __restrict__ rays, unsigned long long n,
                 TutuHit* __restrict__ out, unsigned long long* __restrict__ next) {
+  auto store = [&](unsigned long long i, const Hit& h) {
+    const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
+    reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), h.t, h.u, h.v);
+  };
+  if (MODE == 0) {
+    trace_persistent<false>(
+        sc, n, next,
+        [&](unsigned long long i, Ray& r, float& dis) {
+          const float4 o = __ldg(rays + 2 * i);
+          const float4 d = __ldg(rays + 2 * i + 1);
+          r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+          dis = 0.f;
+        },
+        [&](unsigned long long i, const Walk& w) { store(i, w.best); });
+    return;
+  }
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     unsigned long long base = 0;
@@ -146,13 +162,8 @@ k_trace_closest(const DevScene sc, const float4* __restrict__ rays, unsigned lon
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
       Hit h;
-      traverse<false, MODE, false>(sc, r, 0.f, h, nullptr);
-      TutuHit t;
-      t.prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
-      t.t = h.t;
-      t.u = h.u;
-      t.v = h.v;
-      reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(t.prim), t.t, t.u, t.v);
+      traverse<false, 1, false>(sc, r, 0.f, h, nullptr);
+      store(i, h);
     }
     __syncwarp();
   }
@@ -162,6 +173,18 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 k_trace_any(const DevScene sc, const float4* __restrict__ rays, unsigned long long n,
             uint8_t* __restrict__ out, unsigned long long* __restrict__ next) {
+  if (MODE == 0) {
+    trace_persistent<true>(
+        sc, n, next,
+        [&](unsigned long long i, Ray& r, float& dis) {
+          const float4 o = __ldg(rays + 2 * i);
+          const float4 d = __ldg(rays + 2 * i + 1);
+          r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+          dis = d.w;
+        },
+        [&](unsigned long long i, const Walk& w) { out[i] = w.best.slot >= 0 ? 1 : 0; });
+    return;
+  }
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     unsigned long long base = 0;
@@ -174,7 +197,7 @@ k_trace_any(const DevScene sc, const float4* __restrict__ rays, unsigned long lo
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
       Hit h;
-      out[i] = traverse<true, MODE, false>(sc, r, d.w, h, nullptr) ? 1 : 0;
+      out[i] = traverse<true, 1, false>(sc, r, d.w, h, nullptr) ? 1 : 0;
     }
     __syncwarp();
   }
@@ -499,6 +522,8 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   d.eta = fs.eta;
   d.prune_rel = 1.0f / 1024.0f;
   d.prune_abs = fs.max_edge * (1.0f / 512.0f);
+  d.refill_min = 4;
+  if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_ABS")) d.prune_abs = (float)atof(e);
   ctx->scene_bytes = fs.inner.size() * sizeof(InnerNode) + fs.geom.size() * sizeof(LeafGeom) +

@@ -40,6 +40,8 @@ struct WfCtl {
   unsigned long long sum_shadow;
   unsigned long long nan_samples;
   unsigned long long iterations;
+  unsigned long long cursor_extend;  // ray-queue cursors of the persistent tracers
+  unsigned long long cursor_shadow;
 };
 
 struct WfBuffers {
@@ -95,6 +97,8 @@ __global__ void wf_ctl_after_raygen(WfCtl* ctl, unsigned capacity) {
   ctl->next_path += add;
   ctl->n_next = 0;
   ctl->n_shadow = 0;
+  ctl->cursor_extend = 0;
+  ctl->cursor_shadow = 0;
   ctl->sum_extend += ctl->n_cur;
 }
 __global__ void wf_ctl_after_iter(WfCtl* ctl) {
@@ -138,40 +142,50 @@ wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
 __global__ void __launch_bounds__(256)
 wf_extend(const DevScene sc, WfBuffers b, int cur) {
   const unsigned n = b.ctl->n_cur;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 o = b.ray_o[cur][i];
-    const float4 d = b.ray_d[cur][i];
-    Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
-    Hit h;
-    traverse<false, 0, false>(sc, r, 0.f, h, nullptr);
-    b.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.slot));
-  }
+  const float4* __restrict__ ro = b.ray_o[cur];
+  const float4* __restrict__ rd = b.ray_d[cur];
+  float4* __restrict__ hit = b.hit;
+  trace_persistent<false>(
+      sc, n, &b.ctl->cursor_extend,
+      [&](unsigned long long i, Ray& r, float& dis) {
+        const float4 o = ro[i];
+        const float4 d = rd[i];
+        r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+        dis = 0.f;
+      },
+      [&](unsigned long long i, const Walk& w) {
+        hit[i] = make_float4(w.best.t, w.best.u, w.best.v, __int_as_float(w.best.slot));
+      });
 }
 
 // ---- shadow: isShadowRayBlocked -> hasIntersection, then the deferred NEE add ------------------
 __global__ void __launch_bounds__(256)
 wf_shadow(const DevScene sc, WfBuffers b, int nxt) {
   const unsigned n = b.ctl->n_shadow;
-  for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    const float4 o = b.sh_o[j];
-    const float4 d = b.sh_d[j];
-    Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
-    Hit h;
-    const bool blocked = traverse<true, 0, false>(sc, r, o.w, h, nullptr);
-    const unsigned dst = __float_as_uint(d.w);
-    if (dst == kShadowFinal) {
-      const float4 c = b.sh_c[j];
-      const float4 L4 = b.sh_L[j];
-      f3 L = mk(L4.x, L4.y, L4.z);
-      if (!blocked) L = L + mk(c.x, c.y, c.z);
-      accum_add(b.accum, b.ctl, __float_as_uint(c.w), L);
-    } else if (!blocked) {
-      const float4 c = b.sh_c[j];
-      float4 s = b.st2[nxt][dst];
-      s.x += c.x, s.y += c.y, s.z += c.z;
-      b.st2[nxt][dst] = s;
-    }
-  }
+  trace_persistent<true>(
+      sc, n, &b.ctl->cursor_shadow,
+      [&](unsigned long long j, Ray& r, float& dis) {
+        const float4 o = b.sh_o[j];
+        const float4 d = b.sh_d[j];
+        r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+        dis = o.w;
+      },
+      [&](unsigned long long j, const Walk& w) {
+        const bool blocked = w.best.slot >= 0;
+        const unsigned dst = __float_as_uint(b.sh_d[j].w);
+        if (dst == kShadowFinal) {
+          const float4 c = b.sh_c[j];
+          const float4 L4 = b.sh_L[j];
+          f3 L = mk(L4.x, L4.y, L4.z);
+          if (!blocked) L = L + mk(c.x, c.y, c.z);
+          accum_add(b.accum, b.ctl, __float_as_uint(c.w), L);
+        } else if (!blocked) {
+          const float4 c = b.sh_c[j];
+          float4 s = b.st2[nxt][dst];
+          s.x += c.x, s.y += c.y, s.z += c.z;
+          b.st2[nxt][dst] = s;
+        }
+      });
 }
 
 // ---- shade -------------------------------------------------------------------------------------
@@ -505,7 +519,10 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
   out.depth_mode = depth | (kModeXInter << 8) | (s.m.type == TUTU_MAT_PERFECT_REFLECTIVE ? kFlagMirror : 0u);
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef TUTU_SHADE_MIN_BLOCKS
+#define TUTU_SHADE_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, TUTU_SHADE_MIN_BLOCKS)
 wf_shade(const DevScene sc, WfBuffers b, int cur, uint64_t seed) {
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
