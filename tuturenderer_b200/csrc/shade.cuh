@@ -183,7 +183,9 @@ __device__ __forceinline__ f3 SphereLocal2world(f3 n, f3 dir) {  // :387-409
 }
 
 // ---- Material.hpp ----------------------------------------------------------------------------
-__device__ __noinline__ f3 BxDF_microfacet(const Mat& m, f3 wi, f3 wo, f3 Ns, float eta_scene,
+// (__noinline__ helpers take everything by value: a reference parameter would pin the caller's
+// material / direction registers to local memory on the common Lambertian path as well)
+__device__ __noinline__ f3 BxDF_microfacet(const Mat m, f3 wi, f3 wo, f3 Ns, float eta_scene,
                                            bool TIR, float correctNormal) {
   if (m.type == TUTU_MAT_MICROFACET_R) {  // Material.hpp:87-108
     f3 h = normalized(wi + wo);
@@ -232,7 +234,7 @@ __device__ __noinline__ f3 BxDF_microfacet(const Mat& m, f3 wi, f3 wo, f3 Ns, fl
   return mk(numerator / denominator * correctNormal);
 }
 
-__device__ __noinline__ f3 BxDF_glass(const Mat& m, f3 wi, f3 wo, f3 Ns, float eta_scene, bool TIR,
+__device__ __noinline__ f3 BxDF_glass(const Mat m, f3 wi, f3 wo, f3 Ns, float eta_scene, bool TIR,
                                       float correctNormal) {  // Material.hpp:159-186
   f3 refDir = normalized(getReflectionDir(wo, Ns));
   float eta_i = eta_scene, eta_t = m.eta;
@@ -288,9 +290,15 @@ __device__ __forceinline__ f3 ggx_local_h(float r0, float r1, float a2) {
   return normalized(mk(sintheta * cp, sintheta * sp, costheta));
 }
 
-// returns bit0 = success, bit1 = TIR ("special event").  ra, rb, rc = getRandomFloat() calls in order.
-__device__ __noinline__ int sampleDirection_special(const Mat& m, f3 wo, f3 N, f3& out, float eta_i,
-                                                    float ra, float rb, float rc) {
+struct DirSample {
+  f3 wi;
+  int flags;  // bit0 = success, bit1 = TIR ("special event")
+};
+// ra, rb, rc = getRandomFloat() calls in order.
+__device__ __noinline__ DirSample sampleDirection_special(const Mat m, f3 wo, f3 N, float eta_i,
+                                                          float ra, float rb, float rc) {
+  f3 out = mk(0.f);
+  const int flags = [&]() -> int {
   switch (m.type) {
     case TUTU_MAT_MICROFACET_R: {  // Material.hpp:203-229
       if (dot(wo, N) <= 0.0f) return 0;
@@ -341,6 +349,8 @@ __device__ __noinline__ int sampleDirection_special(const Mat& m, f3 wo, f3 N, f
     default:
       return 0;
   }
+  }();
+  return DirSample{out, flags};
 }
 
 __device__ __forceinline__ int sampleDirection(const Mat& m, f3 wo, f3 N, f3& out, float eta_i, float ra,
@@ -358,10 +368,12 @@ __device__ __forceinline__ int sampleDirection(const Mat& m, f3 wo, f3 N, f3& ou
     out = res;
     return 1;
   }
-  return sampleDirection_special(m, wo, N, out, eta_i, ra, rb, rc);
+  const DirSample ds = sampleDirection_special(m, wo, N, eta_i, ra, rb, rc);
+  if (ds.flags & 1) out = ds.wi;
+  return ds.flags;
 }
 
-__device__ __noinline__ float pdf_special(const Mat& m, f3 wi, f3 wo, f3 N, float eta_i, float eta_t) {
+__device__ __noinline__ float pdf_special(const Mat m, f3 wi, f3 wo, f3 N, float eta_i, float eta_t) {
   switch (m.type) {
     case TUTU_MAT_MICROFACET_R: {  // Material.hpp:362-373
       f3 h = normalized(wo + wi);

@@ -138,7 +138,14 @@ __device__ __forceinline__ bool tri_test(const float4* __restrict__ g, const Ray
 }
 
 // Sphere::intersect.  C is summed in double (std::pow(float,int) promotes) and rounded once.
-__device__ __noinline__ bool sphere_test(const float4* __restrict__ g, const Ray& r, float& t) {
+struct SphereHit {
+  bool hit;
+  float t;
+};
+// by-value arguments and result: a __noinline__ callee taking references would force the caller's
+// ray and walk state into local memory
+__device__ __noinline__ SphereHit sphere_test(const float4* __restrict__ g, const Ray r) {
+  float t = 0.f;
   const float4 a = __ldg(g + 0);  // centre.xyz, radius
   const float ocx = __fsub_rn(r.ox, a.x), ocy = __fsub_rn(r.oy, a.y), ocz = __fsub_rn(r.oz, a.z);
   const float B = __fmul_rn(2.f, dot_rn(r.dx, r.dy, r.dz, ocx, ocy, ocz));
@@ -167,11 +174,10 @@ __device__ __noinline__ bool sphere_test(const float4* __restrict__ g, const Ray
   }
   const bool eq1 = fabsf(__fsub_rn(t1, FLT_MAX)) < 0.0001f;
   const bool eq2 = fabsf(__fsub_rn(t2, FLT_MAX)) < 0.0001f;
-  if (eq1 && eq2) return false;
+  if (eq1 && eq2) return SphereHit{false, 0.f};
   if (fabsf(__fsub_rn(t1, t2)) < 0.0001f) {  // "one solution"
-    if (t1 < 0.f) return false;
-    t = t1;
-    return true;
+    if (t1 < 0.f) return SphereHit{false, 0.f};
+    return SphereHit{true, t1};
   }
   if (t1 > 0.f && t2 > 0.f) t = t1;
   else if (t1 > 0.f && t2 < 0.f)
@@ -179,8 +185,8 @@ __device__ __noinline__ bool sphere_test(const float4* __restrict__ g, const Ray
   else if (t1 < 0.f && t2 > 0.f)
     t = t2;
   else
-    return false;
-  return true;
+    return SphereHit{false, 0.f};
+  return SphereHit{true, t};
 }
 
 struct VisitCount {
@@ -319,10 +325,13 @@ __device__ __forceinline__ bool walk_round(const DevScene& sc, Walk& w, int* sta
     if (COUNT) vc->prims++;
     float t, u = 0.f, v = 0.f;
     bool hit;
-    if (code & kSphereBit)
-      hit = sphere_test(g, w.r, t);
-    else
+    if (code & kSphereBit) {
+      const SphereHit sh = sphere_test(g, w.r);
+      hit = sh.hit;
+      t = sh.t;
+    } else {
       hit = tri_test(g, w.r, t, u, v);
+    }
     if (hit) {
       if (ANY) {
         // inter.t < dis && !FLOAT_EQUAL(inter.t, dis)
@@ -357,6 +366,102 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, const Ray& r, float
       }
     } else {
       while (walk_round<ANY, MODE, COUNT, false>(sc, w, stack_ref, stack_t, vc)) {
+      }
+    }
+  }
+  best = w.best;
+  return best.slot >= 0;
+}
+
+// ---- single-thread walk flavours (compared in tools/gpu_variants.py) ---------------------------
+// LOOP: one loop whose body handles either an inner node or a leaf (per lane).
+template <bool ANY, int MODE, bool REGULAR>
+__device__ __forceinline__ void walk_loop(const DevScene& sc, Walk& w, int* stack_ref, float* stack_t) {
+  for (;;) {
+    if (w.cur >= 0) {
+      const float4* n = sc.inner + 4 * (size_t)w.cur;
+      const float4 a = __ldg(n + 0);
+      const float4 b = __ldg(n + 1);
+      const float4 c = __ldg(n + 2);
+      const int4 k = __ldg(reinterpret_cast<const int4*>(n + 3));
+      float tl, tr;
+      bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
+      bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+      if (MODE == 0) {
+        const float lim = prune_limit<ANY>(sc, w);
+        hl = hl && !(tl > lim);
+        hr = hr && !(tr > lim);
+      }
+      if (hl && hr) {
+        const bool left_first = (MODE == 1) || !(tr < tl);
+        stack_ref[w.sp] = left_first ? k.y : k.x;
+        stack_t[w.sp] = left_first ? tr : tl;
+        ++w.sp;
+        w.cur = left_first ? k.x : k.y;
+        continue;
+      }
+      if (hl) {
+        w.cur = k.x;
+        continue;
+      }
+      if (hr) {
+        w.cur = k.y;
+        continue;
+      }
+    } else {
+      const uint32_t code = ~(uint32_t)w.cur;
+      const uint32_t slot = code & kSlotMask;
+      const float4* g = sc.geom + 3 * (size_t)slot;
+      float t, u = 0.f, v = 0.f;
+      bool hit;
+      if (code & kSphereBit) {
+        const SphereHit sh = sphere_test(g, w.r);
+        hit = sh.hit;
+        t = sh.t;
+      } else {
+        hit = tri_test(g, w.r, t, u, v);
+      }
+      if (hit) {
+        if (ANY) {
+          if (t < w.dis && !(fabsf(__fsub_rn(t, w.dis)) < 0.0001f)) {
+            w.best.t = t;
+            w.best.slot = (int)code;
+            return;
+          }
+        } else if (t < w.best.t || (t == w.best.t && (int)slot < (w.best.slot & (int)kSlotMask))) {
+          w.best.t = t;
+          w.best.u = u;
+          w.best.v = v;
+          w.best.slot = (int)code;
+        }
+      }
+    }
+    if (!walk_pop<ANY, MODE>(sc, w, stack_ref, stack_t)) return;
+  }
+}
+
+// VARIANT 0: LOOP + exact slab test; 1: LOOP + FMNMX slab test for regular rays;
+// 2: rounds (inner-node phase / leaf phase) + FMNMX for regular rays.
+template <bool ANY, int VARIANT>
+__device__ __forceinline__ bool traverse_variant(const DevScene& sc, const Ray& r, float dis, Hit& best) {
+  Walk w;
+  int stack_ref[kStackSize];
+  float stack_t[kStackSize];
+  if (walk_begin(sc, w, r, dis)) {
+    if (VARIANT == 0) {
+      walk_loop<ANY, 0, false>(sc, w, stack_ref, stack_t);
+    } else if (VARIANT == 1) {
+      if (w.regular)
+        walk_loop<ANY, 0, true>(sc, w, stack_ref, stack_t);
+      else
+        walk_loop<ANY, 0, false>(sc, w, stack_ref, stack_t);
+    } else {
+      if (w.regular) {
+        while (walk_round<ANY, 0, false, true>(sc, w, stack_ref, stack_t, nullptr)) {
+        }
+      } else {
+        while (walk_round<ANY, 0, false, false>(sc, w, stack_ref, stack_t, nullptr)) {
+        }
       }
     }
   }

@@ -132,7 +132,7 @@ int fail_cuda(TutuCtx* ctx, const CudaError& e) {
 // reference walk, one 32-ray packet per warp at a time (tests only).
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_trace_closest(const DevScene sc, const float4* __restrict__ rays, unsigned long long n,
+k_trace_closest(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n,
                 TutuHit* __restrict__ out, unsigned long long* __restrict__ next) {
   auto store = [&](unsigned long long i, const Hit& h) {
     const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
@@ -171,7 +171,7 @@ k_trace_closest(const DevScene sc, const float4* __restrict__ rays, unsigned lon
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_trace_any(const DevScene sc, const float4* __restrict__ rays, unsigned long long n,
+k_trace_any(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n,
             uint8_t* __restrict__ out, unsigned long long* __restrict__ next) {
   if (MODE == 0) {
     trace_persistent<true>(
@@ -203,9 +203,38 @@ k_trace_any(const DevScene sc, const float4* __restrict__ rays, unsigned long lo
   }
 }
 
+// experimental walk flavours behind tutu_set_traversal_mode(ctx, 10 + VARIANT): 32-ray packets
+template <bool ANY, int VARIANT>
+__global__ void __launch_bounds__(256)
+k_trace_variant(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n, TutuHit* __restrict__ out,
+                uint8_t* __restrict__ out_any, unsigned long long* __restrict__ next) {
+  const unsigned lane = threadIdx.x & 31u;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(next, 32ull);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n) return;
+    const unsigned long long i = base + lane;
+    if (i < n) {
+      const float4 o = __ldg(rays + 2 * i);
+      const float4 d = __ldg(rays + 2 * i + 1);
+      Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
+      Hit h;
+      const bool any = traverse_variant<ANY, VARIANT>(sc, r, d.w, h);
+      if (ANY) {
+        out_any[i] = any ? 1 : 0;
+      } else {
+        const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
+        reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), h.t, h.u, h.v);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <bool ANY>
 __global__ void __launch_bounds__(256)
-k_trace_count(const DevScene sc, const float4* __restrict__ rays, unsigned long long n,
+k_trace_count(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n,
               unsigned long long* __restrict__ counts) {
   unsigned long long nodes = 0, prims = 0;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
@@ -243,7 +272,17 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
   unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 4;
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
-  if (ctx->traversal_mode == 1) {
+  if (ctx->traversal_mode >= 10) {
+#define TUTU_VAR_C(V)                                                                       \
+  case V: {                                                                                 \
+    int grid = persistent_grid(ctx, k_trace_variant<false, V>, 256);                        \
+    k_trace_variant<false, V><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, nullptr, next); \
+  } break;
+    switch (ctx->traversal_mode - 10) {
+      TUTU_VAR_C(0) TUTU_VAR_C(1) TUTU_VAR_C(2)
+    }
+#undef TUTU_VAR_C
+  } else if (ctx->traversal_mode == 1) {
     int grid = persistent_grid(ctx, k_trace_closest<1>, 256);
     k_trace_closest<1><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
   } else {
@@ -259,7 +298,17 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
   unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 5;
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
-  if (ctx->traversal_mode == 1) {
+  if (ctx->traversal_mode >= 10) {
+#define TUTU_VAR_A(V)                                                                      \
+  case V: {                                                                                \
+    int grid = persistent_grid(ctx, k_trace_variant<true, V>, 256);                        \
+    k_trace_variant<true, V><<<grid, 256, 0, s>>>(ctx->dev, rays, n, nullptr, d_out, next); \
+  } break;
+    switch (ctx->traversal_mode - 10) {
+      TUTU_VAR_A(0) TUTU_VAR_A(1) TUTU_VAR_A(2)
+    }
+#undef TUTU_VAR_A
+  } else if (ctx->traversal_mode == 1) {
     int grid = persistent_grid(ctx, k_trace_any<1>, 256);
     k_trace_any<1><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
   } else {
@@ -565,7 +614,8 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
 }
 
 extern "C" int tutu_set_traversal_mode(TutuCtx* ctx, int mode) {
-  if (!ctx || (mode != 0 && mode != 1)) return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument");
+  if (!ctx || !(mode == 0 || mode == 1 || (mode >= 10 && mode <= 12)))
+    return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument");
   ctx->traversal_mode = mode;
   return TUTU_OK;
 }

@@ -140,7 +140,7 @@ wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
 
 // ---- extend: IIntersectStrategy::UpdateInter -> getIntersection -------------------------------
 __global__ void __launch_bounds__(256)
-wf_extend(const DevScene sc, WfBuffers b, int cur) {
+wf_extend(const __grid_constant__ DevScene sc, WfBuffers b, int cur) {
   const unsigned n = b.ctl->n_cur;
   const float4* __restrict__ ro = b.ray_o[cur];
   const float4* __restrict__ rd = b.ray_d[cur];
@@ -160,7 +160,7 @@ wf_extend(const DevScene sc, WfBuffers b, int cur) {
 
 // ---- shadow: isShadowRayBlocked -> hasIntersection, then the deferred NEE add ------------------
 __global__ void __launch_bounds__(256)
-wf_shadow(const DevScene sc, WfBuffers b, int nxt) {
+wf_shadow(const __grid_constant__ DevScene sc, WfBuffers b, int nxt) {
   const unsigned n = b.ctl->n_shadow;
   trace_persistent<true>(
       sc, n, &b.ctl->cursor_shadow,
@@ -237,27 +237,34 @@ __device__ __forceinline__ Surf load_surface(const DevScene& sc, const Ray& r, c
   return s;
 }
 
-// textureModify + changeNormalDir, IIntegrator.hpp:27-127
-__device__ __noinline__ void texture_modify(const DevScene& sc, Surf& s) {
-  const int4 ti = __ldg(sc.leaftex + s.slot);
-  if (ti.x != -1) s.m.diffuse = tex_fetch(sc, 0, ti.x, s.tu, s.tv);
+// textureModify + changeNormalDir, IIntegrator.hpp:27-127.  By value in and out (a reference to the
+// caller's Surf would pin that whole record to local memory on the untextured path too).
+struct TexMod {
+  f3 diffuse, Ns;
+  float roughness, metallic;
+};
+__device__ __noinline__ TexMod texture_modify(const DevScene& sc, uint32_t slot, bool sphere, float tu, float tv,
+                                              f3 Ng, TexMod in) {
+  TexMod r = in;
+  const int4 ti = __ldg(sc.leaftex + slot);
+  if (ti.x != -1) r.diffuse = tex_fetch(sc, 0, ti.x, tu, tv);
   if (ti.y != -1) {
-    const f3 color = tex_fetch(sc, 1, ti.y, s.tu, s.tv);
+    const f3 color = tex_fetch(sc, 1, ti.y, tu, tv);
     f3 T, B, nDir;
-    if (!s.sphere) {
-      const float4* g = sc.geom + 3 * (size_t)s.slot;
+    if (!sphere) {
+      const float4* g = sc.geom + 3 * (size_t)slot;
       const float4 a = __ldg(g + 0), b = __ldg(g + 1), c = __ldg(g + 2);
       const f3 e1 = mk(a.w, b.x, b.y), e2 = mk(b.z, b.w, c.x);
-      const float4* sh = sc.shade + 4 * (size_t)s.slot;
+      const float4* sh = sc.shade + 4 * (size_t)slot;
       const float4 s0 = __ldg(sh + 0), s1 = __ldg(sh + 1), s2 = __ldg(sh + 2), s3 = __ldg(sh + 3);
-      nDir = normalized(s.Ns);
+      nDir = normalized(in.Ns);
       const float deltaU1 = s2.w - s0.w, deltaV1 = s3.x - s1.w;
       const float deltaU2 = s3.y - s0.w, deltaV2 = s3.z - s1.w;
       const float coef = 1 / (-deltaU1 * deltaV2 + deltaV1 * deltaU2);
       T = normalized(coef * (-deltaV2 * e1 + deltaV1 * e2));
       B = normalized(coef * (-deltaU2 * e1 + deltaU1 * e2));
     } else {
-      nDir = s.Ng;
+      nDir = Ng;
       const float q = sqrtf(nDir.x * nDir.x + nDir.y * nDir.y);
       T = mk(-nDir.y / q, nDir.x / q, 0.f);
       B = cross(nDir, T);
@@ -266,10 +273,11 @@ __device__ __noinline__ void texture_modify(const DevScene& sc, Surf& s) {
     res.x = T.x * color.x + B.x * color.y + nDir.x * color.z;
     res.y = T.y * color.x + B.y * color.y + nDir.y * color.z;
     res.z = T.z * color.x + B.z * color.y + nDir.z * color.z;
-    s.Ns = normalized(res);
+    r.Ns = normalized(res);
   }
-  if (ti.z != -1) s.m.roughness = tex_fetch(sc, 2, ti.z, s.tu, s.tv).x;
-  if (ti.w != -1) s.m.metallic = tex_fetch(sc, 3, ti.w, s.tu, s.tv).x;
+  if (ti.z != -1) r.roughness = tex_fetch(sc, 2, ti.z, tu, tv).x;
+  if (ti.w != -1) r.metallic = tex_fetch(sc, 3, ti.w, tu, tv).x;
+  return r;
 }
 
 // Object::getArea of the primitive in a leaf slot (getLightPdf, IIntegrator.hpp:155-168)
@@ -317,6 +325,12 @@ __device__ __forceinline__ LightSample sample_light(const DevScene& sc, float r_
   }
   s.pdf = 1.f / (size * area);
   return s;
+}
+
+// the rare in-kernel shadow ray of PathTracing.hpp:215 (kept out of line: it owns a traversal stack)
+__device__ __noinline__ bool shadow_blocked_inline(const DevScene& sc, const Ray r, const float dist) {
+  Hit h;
+  return traverse<true, 0, false>(sc, r, dist, h, nullptr);
 }
 
 struct ShadeOut {
@@ -445,7 +459,14 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
     return;
   }
 
-  if (s.textured) texture_modify(sc, s);
+  if (s.textured) {
+    const TexMod tm = texture_modify(sc, s.slot, s.sphere, s.tu, s.tv, s.Ng,
+                                     TexMod{s.m.diffuse, s.Ns, s.m.roughness, s.m.metallic});
+    s.m.diffuse = tm.diffuse;
+    s.Ns = tm.Ns;
+    s.m.roughness = tm.roughness;
+    s.m.metallic = tm.metallic;
+  }
   if (s.m.type == TUTU_MAT_UNLIT) {  // :161
     L = L + beta * s.m.diffuse;
     return;
@@ -484,9 +505,8 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
         if (r2 * pdfl < T_MIN_DIVISOR) {
           // :215 — an unoccluded sample this close to the light ends the whole path; the
           // decision needs the visibility now, so this rare case traces its shadow ray inline.
-          Ray sr{shadowRayOrig.x, shadowRayOrig.y, shadowRayOrig.z, sd.x, sd.y, sd.z};
-          Hit hh;
-          if (!traverse<true, 0, false>(sc, sr, dist, hh, nullptr)) return;
+          if (!shadow_blocked_inline(sc, Ray{shadowRayOrig.x, shadowRayOrig.y, shadowRayOrig.z, sd.x, sd.y, sd.z}, dist))
+            return;
         } else {
           out.shadow = true;
           out.so = shadowRayOrig;
@@ -523,7 +543,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
 #define TUTU_SHADE_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(256, TUTU_SHADE_MIN_BLOCKS)
-wf_shade(const DevScene sc, WfBuffers b, int cur, uint64_t seed) {
+wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
   const unsigned n_round = (n + 31u) & ~31u;
