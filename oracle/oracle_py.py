@@ -66,12 +66,15 @@ class OracleScene:
             raise RuntimeError("oracle_scene_create failed")
 
     def close(self):
-        if self._h:
+        if getattr(self, "_h", None):
             lib().oracle_scene_destroy(self._h)
             self._h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
 
     def bvh_export(self) -> np.ndarray:
         n = lib().oracle_bvh_node_count(self._h)

@@ -14,7 +14,7 @@ CASES = [("cornell_256", "cornell_rays.f32", "cornell_closest.bin", "cornell_any
          ("mixed", "mixed_rays.f32", "mixed_closest.bin", "mixed_any.bin")]
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("scene,rays,closest,anyf", CASES)
 def test_golden_vectors_bit_exact(api, ctx, golden, scene, rays, closest, anyf, mode):
     sc = api.Scene.load(golden / f"{scene}.tscene")
@@ -45,7 +45,7 @@ def test_random_soups_against_oracle(api, oracle, ctx, n_tris, n_spheres, dup, s
     rays = random_rays(30000, seed=seed)
     want_c, want_a = osc.trace_closest(rays), osc.trace_any(rays)
     ctx.upload(sc)
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         ctx.set_traversal_mode(mode)
         assert_hits_equal(ctx.trace_closest(rays), want_c)
         assert np.array_equal(ctx.trace_any(rays), want_a)

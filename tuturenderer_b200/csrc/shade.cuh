@@ -7,15 +7,16 @@
 //   sampleLight, getLightPdf, Triangle/Sphere::samplePoint
 //                                                    IIntegrator.hpp:155-192, Triangle.hpp:119-142,
 //                                                    Sphere.hpp:139-164
-// Shading arithmetic is ordinary fp32 (FMA contraction allowed): it feeds a Monte Carlo estimate,
-// whose parity with the reference is statistical.  Everything that selects a primitive lives in
-// trace.cuh and is exact.
+// Shading arithmetic is ordinary fp32 (FMA contraction allowed, MUFU reciprocal / rsqrt with
+// ~2 ulp instead of IEEE division / sqrt): it feeds a Monte Carlo estimate, whose parity with the
+// reference is statistical.  Everything that selects a primitive lives in trace.cuh and is exact.
 #pragma once
 #include "trace.cuh"
 
 namespace tutu {
 
 #define T_PI 3.1415926535897f /* global.hpp:15 */
+#define T_INV_PI (1.0f / 3.1415926535897f)
 #define T_EPSILON 0.0005f     /* global.hpp:16 */
 #define T_MIN_DIVISOR 0.04f   /* global.hpp:26 */
 #define T_MAX_DEPTH 6         /* PathTracing.hpp:5 */
@@ -32,16 +33,20 @@ __device__ __forceinline__ f3 operator-(f3 a) { return mk(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ f3 operator*(f3 a, f3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ f3 operator*(f3 a, float c) { return mk(a.x * c, a.y * c, a.z * c); }
 __device__ __forceinline__ f3 operator*(float c, f3 a) { return mk(a.x * c, a.y * c, a.z * c); }
-__device__ __forceinline__ f3 operator/(f3 a, float c) { return mk(a.x / c, a.y / c, a.z / c); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ f3 operator/(f3 a, float c) {
+  const float r = fdiv(1.f, c);
+  return mk(a.x * r, a.y * r, a.z * r);
+}
 __device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ float norm2(f3 a) { return dot(a, a); }
 __device__ __forceinline__ f3 cross(f3 a, f3 b) {
   return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 __device__ __forceinline__ f3 normalized(f3 v) {  // Vector.hpp:213-220
-  float mag = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
-  if (mag > 0.f) {
-    float inv = 1.f / mag;
+  const float l2 = v.x * v.x + v.y * v.y + v.z * v.z;
+  if (l2 > 0.f) {
+    const float inv = rsqrtf(l2);
     return mk(v.x * inv, v.y * inv, v.z * inv);
   }
   return v;
@@ -172,7 +177,7 @@ __device__ __forceinline__ float G_smf(f3 wi, f3 wo, f3 n, float roughness, f3 h
   return G1_wi * G1_wo;
 }
 __device__ __forceinline__ float getMisWeight(float pdf, float otherPdf) {  // :374-380
-  return (pdf * pdf) / ((pdf + otherPdf) * (pdf + otherPdf));
+  return fdiv(pdf * pdf, (pdf + otherPdf) * (pdf + otherPdf));
 }
 __device__ __forceinline__ f3 SphereLocal2world(f3 n, f3 dir) {  // :387-409
   f3 N = normalized(n);
@@ -259,11 +264,11 @@ __device__ __forceinline__ f3 BxDF(const Mat& m, f3 wi, f3 wo, f3 Ng, f3 Ns, flo
   if (m.type != TUTU_MAT_MICROFACET_T && m.type != TUTU_MAT_PERFECT_REFRACTIVE) {
     if (dot(wi, Ng) * dot(wi, Ns) <= 0 || dot(wo, Ng) * dot(wo, Ns) <= 0) return mk(0.f);
   }
-  float correctNormal = fabsf(dot(wi, Ns)) / fabsf(dot(wi, Ng));
+  float correctNormal = fdiv(fabsf(dot(wi, Ns)), fabsf(dot(wi, Ng)));
   switch (m.type) {
     case TUTU_MAT_LAMBERTIAN: {
       float cos_theta = dot(wi, Ns);
-      if (cos_theta >= 0.f) return m.diffuse / T_PI * correctNormal;
+      if (cos_theta >= 0.f) return m.diffuse * (T_INV_PI * correctNormal);
       return mk(0.f);
     }
     case TUTU_MAT_MICROFACET_R:
@@ -431,7 +436,7 @@ __device__ __noinline__ float pdf_special(const Mat m, f3 wi, f3 wo, f3 N, float
 __device__ __forceinline__ float mat_pdf_eval(const Mat& m, f3 wi, f3 wo, f3 N, float eta_i, float eta_t) {
   if (m.type == TUTU_MAT_LAMBERTIAN) {  // Material.hpp:353-360
     float c = dot(wi, N);
-    return c > 0.0f ? c / T_PI : 0.0f;
+    return c > 0.0f ? c * T_INV_PI : 0.0f;
   }
   return pdf_special(m, wi, wo, N, eta_i, eta_t);
 }

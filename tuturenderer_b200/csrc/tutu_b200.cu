@@ -128,8 +128,11 @@ int fail_cuda(TutuCtx* ctx, const CudaError& e) {
 // ---------------------------------------------------------------------------------------------
 // ray-batch kernels
 // ---------------------------------------------------------------------------------------------
-// MODE 0: persistent warps with per-lane ray refill (trace_persistent).  MODE 1: the literal
-// reference walk, one 32-ray packet per warp at a time (tests only).
+// Warps pull 32-ray packets from a global cursor (persistent threads: grid = SMs x resident blocks).
+// MODE 0: ordered + pruned walk, FMNMX slab test for regular rays (production).
+// MODE 1: the literal reference walk (tests only).
+// MODE 2: per-lane ray refill between traversal rounds (trace_persistent; measured slower than
+//         MODE 0 on every workload, kept for the record — DESIGN.md §5).
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_trace_closest(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n,
@@ -138,7 +141,7 @@ k_trace_closest(const __grid_constant__ DevScene sc, const float4* __restrict__ 
     const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
     reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), h.t, h.u, h.v);
   };
-  if (MODE == 0) {
+  if (MODE == 2) {
     trace_persistent<false>(
         sc, n, next,
         [&](unsigned long long i, Ray& r, float& dis) {
@@ -162,7 +165,10 @@ k_trace_closest(const __grid_constant__ DevScene sc, const float4* __restrict__ 
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
       Hit h;
-      traverse<false, 1, false>(sc, r, 0.f, h, nullptr);
+      if (MODE == 0)
+        traverse_variant<false, 1>(sc, r, 0.f, h);
+      else
+        traverse<false, 1, false>(sc, r, 0.f, h, nullptr);
       store(i, h);
     }
     __syncwarp();
@@ -173,7 +179,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 k_trace_any(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n,
             uint8_t* __restrict__ out, unsigned long long* __restrict__ next) {
-  if (MODE == 0) {
+  if (MODE == 2) {
     trace_persistent<true>(
         sc, n, next,
         [&](unsigned long long i, Ray& r, float& dis) {
@@ -197,7 +203,10 @@ k_trace_any(const __grid_constant__ DevScene sc, const float4* __restrict__ rays
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
       Hit h;
-      out[i] = traverse<true, 1, false>(sc, r, d.w, h, nullptr) ? 1 : 0;
+      if (MODE == 0)
+        out[i] = traverse_variant<true, 1>(sc, r, d.w, h) ? 1 : 0;
+      else
+        out[i] = traverse<true, 1, false>(sc, r, d.w, h, nullptr) ? 1 : 0;
     }
     __syncwarp();
   }
@@ -285,6 +294,9 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
   } else if (ctx->traversal_mode == 1) {
     int grid = persistent_grid(ctx, k_trace_closest<1>, 256);
     k_trace_closest<1><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+  } else if (ctx->traversal_mode == 2) {
+    int grid = persistent_grid(ctx, k_trace_closest<2>, 256);
+    k_trace_closest<2><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
   } else {
     int grid = persistent_grid(ctx, k_trace_closest<0>, 256);
     k_trace_closest<0><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
@@ -311,6 +323,9 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
   } else if (ctx->traversal_mode == 1) {
     int grid = persistent_grid(ctx, k_trace_any<1>, 256);
     k_trace_any<1><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+  } else if (ctx->traversal_mode == 2) {
+    int grid = persistent_grid(ctx, k_trace_any<2>, 256);
+    k_trace_any<2><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
   } else {
     int grid = persistent_grid(ctx, k_trace_any<0>, 256);
     k_trace_any<0><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
@@ -369,7 +384,7 @@ void wf_prepare(TutuCtx* ctx, uint64_t total_paths) {
   b.capacity = (unsigned)cap;
   if (!ctx->grid_extend) {
     ctx->grid_extend = persistent_grid(ctx, wf_extend, 256);
-    ctx->grid_shade = persistent_grid(ctx, wf_shade, 256);
+    ctx->grid_shade = persistent_grid(ctx, wf_shade, TUTU_SHADE_BLOCK);
     ctx->grid_shadow = persistent_grid(ctx, wf_shadow, 256);
     ctx->grid_raygen = persistent_grid(ctx, wf_raygen, 256);
   }
@@ -446,7 +461,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
       timer.mark(1, s);
       wf_extend<<<ctx->grid_extend, 256, 0, s>>>(ctx->dev, b, cur);
       timer.mark(2, s);
-      wf_shade<<<ctx->grid_shade, 256, 0, s>>>(ctx->dev, b, cur, seed);
+      wf_shade<<<ctx->grid_shade, TUTU_SHADE_BLOCK, 0, s>>>(ctx->dev, b, cur, seed);
       timer.mark(3, s);
       wf_shadow<<<ctx->grid_shadow, 256, 0, s>>>(ctx->dev, b, cur ^ 1);
       timer.mark(0, s);
@@ -614,7 +629,7 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
 }
 
 extern "C" int tutu_set_traversal_mode(TutuCtx* ctx, int mode) {
-  if (!ctx || !(mode == 0 || mode == 1 || (mode >= 10 && mode <= 12)))
+  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || (mode >= 10 && mode <= 12)))
     return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument");
   ctx->traversal_mode = mode;
   return TUTU_OK;

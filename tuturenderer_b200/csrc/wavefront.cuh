@@ -139,53 +139,64 @@ wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
 }
 
 // ---- extend: IIntersectStrategy::UpdateInter -> getIntersection -------------------------------
+// 32-ray packets pulled from the queue with one atomicAdd per warp (lane 0) and a shuffle
+// broadcast: a warp that drew short rays moves on to the next packet instead of idling behind the
+// slowest warp of a statically partitioned grid.
 __global__ void __launch_bounds__(256)
 wf_extend(const __grid_constant__ DevScene sc, WfBuffers b, int cur) {
   const unsigned n = b.ctl->n_cur;
   const float4* __restrict__ ro = b.ray_o[cur];
   const float4* __restrict__ rd = b.ray_d[cur];
-  float4* __restrict__ hit = b.hit;
-  trace_persistent<false>(
-      sc, n, &b.ctl->cursor_extend,
-      [&](unsigned long long i, Ray& r, float& dis) {
-        const float4 o = ro[i];
-        const float4 d = rd[i];
-        r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
-        dis = 0.f;
-      },
-      [&](unsigned long long i, const Walk& w) {
-        hit[i] = make_float4(w.best.t, w.best.u, w.best.v, __int_as_float(w.best.slot));
-      });
+  const unsigned lane = threadIdx.x & 31u;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&b.ctl->cursor_extend, 32ull);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n) return;
+    const unsigned i = (unsigned)base + lane;
+    if (i < n) {
+      const float4 o = __ldcs(ro + i);
+      const float4 d = __ldcs(rd + i);
+      Hit h;
+      traverse_variant<false, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
+      __stcs(b.hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
+    }
+    __syncwarp();
+  }
 }
 
 // ---- shadow: isShadowRayBlocked -> hasIntersection, then the deferred NEE add ------------------
 __global__ void __launch_bounds__(256)
 wf_shadow(const __grid_constant__ DevScene sc, WfBuffers b, int nxt) {
   const unsigned n = b.ctl->n_shadow;
-  trace_persistent<true>(
-      sc, n, &b.ctl->cursor_shadow,
-      [&](unsigned long long j, Ray& r, float& dis) {
-        const float4 o = b.sh_o[j];
-        const float4 d = b.sh_d[j];
-        r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
-        dis = o.w;
-      },
-      [&](unsigned long long j, const Walk& w) {
-        const bool blocked = w.best.slot >= 0;
-        const unsigned dst = __float_as_uint(b.sh_d[j].w);
-        if (dst == kShadowFinal) {
-          const float4 c = b.sh_c[j];
-          const float4 L4 = b.sh_L[j];
-          f3 L = mk(L4.x, L4.y, L4.z);
-          if (!blocked) L = L + mk(c.x, c.y, c.z);
-          accum_add(b.accum, b.ctl, __float_as_uint(c.w), L);
-        } else if (!blocked) {
-          const float4 c = b.sh_c[j];
-          float4 s = b.st2[nxt][dst];
-          s.x += c.x, s.y += c.y, s.z += c.z;
-          b.st2[nxt][dst] = s;
-        }
-      });
+  const unsigned lane = threadIdx.x & 31u;
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&b.ctl->cursor_shadow, 32ull);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n) return;
+    const unsigned j = (unsigned)base + lane;
+    if (j < n) {
+      const float4 o = __ldcs(b.sh_o + j);
+      const float4 d = __ldcs(b.sh_d + j);
+      Hit h;
+      const bool blocked = traverse_variant<true, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+      const unsigned dst = __float_as_uint(d.w);
+      if (dst == kShadowFinal) {
+        const float4 c = __ldcs(b.sh_c + j);
+        const float4 L4 = __ldcs(b.sh_L + j);
+        f3 L = mk(L4.x, L4.y, L4.z);
+        if (!blocked) L = L + mk(c.x, c.y, c.z);
+        accum_add(b.accum, b.ctl, __float_as_uint(c.w), L);
+      } else if (!blocked) {
+        const float4 c = __ldcs(b.sh_c + j);
+        float4 s = b.st2[nxt][dst];
+        s.x += c.x, s.y += c.y, s.z += c.z;
+        b.st2[nxt][dst] = s;
+      }
+    }
+    __syncwarp();
+  }
 }
 
 // ---- shade -------------------------------------------------------------------------------------
@@ -323,7 +334,7 @@ __device__ __forceinline__ LightSample sample_light(const DevScene& sc, float r_
     s.pos = w * mk(l0.x, l0.y, l0.z) + u * mk(l1.x, l1.y, l1.z) + v * mk(l2.x, l2.y, l2.z);
     s.Ns = normalized(w * mk(l3.x, l3.y, l3.z) + u * mk(l4.x, l4.y, l4.z) + v * mk(l5.x, l5.y, l5.z));
   }
-  s.pdf = 1.f / (size * area);
+  s.pdf = fdiv(1.f, size * area);
   return s;
 }
 
@@ -368,7 +379,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
     const f3 fcos = mk(st3.x, st3.y, st3.z);  // f_r * cos_theta
     const float mat_pdf = st3.w;
     float light_pdf = 0.f;
-    if (s.m.has_emission && sc.n_lights > 0) light_pdf = 1 / (sc.n_lights * slot_area(sc, s.slot, s.sphere));
+    if (s.m.has_emission && sc.n_lights > 0) light_pdf = fdiv(1.f, sc.n_lights * slot_area(sc, s.slot, s.sphere));
     bool as_light = false;
     if (light_pdf) {
       const f3 light_N = normalized(s.Ns);
@@ -376,7 +387,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
       if (cos_theta_prime > 0) {
         as_light = true;
         const float r2 = norm2(s.pos - mk(st4.x, st4.y, st4.z));
-        const float l_pdf_transformed = light_pdf * r2 / cos_theta_prime;
+        const float l_pdf_transformed = fdiv(light_pdf * r2, cos_theta_prime);
         float mis_weight_m = getMisWeight(mat_pdf, l_pdf_transformed);
         if ((flags & kFlagMirror) && mat_pdf == 1.f) mis_weight_m = 1.f;
         if (mat_pdf < T_MIN_DIVISOR) return;
@@ -495,7 +506,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
       if (cos_theta_prime > 0) {
         const float cos_theta = fabsf(dot(s.Ng, wi));
         const float pdfl = ls.pdf;
-        const float light_pdf = pdfl * r2 / cos_theta_prime;
+        const float light_pdf = fdiv(pdfl * r2, cos_theta_prime);
         const float mis_weight_l = getMisWeight(light_pdf, mat_pdf);
         const f3 f_r = BxDF(s.m, wi, wo, s.Ng, s.Ns, sc.eta);
         // isShadowRayBlocked (IIntegrator.hpp:135-153)
@@ -542,7 +553,10 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
 #ifndef TUTU_SHADE_MIN_BLOCKS
 #define TUTU_SHADE_MIN_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(256, TUTU_SHADE_MIN_BLOCKS)
+#ifndef TUTU_SHADE_BLOCK
+#define TUTU_SHADE_BLOCK 256
+#endif
+__global__ void __launch_bounds__(TUTU_SHADE_BLOCK, TUTU_SHADE_MIN_BLOCKS)
 wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
@@ -555,18 +569,20 @@ wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t see
     uint32_t pixel = 0;
     float4 s1 = make_float4(0, 0, 0, 0);
     if (valid) {
-      const float4 o = b.ray_o[cur][i];
-      const float4 d = b.ray_d[cur][i];
-      const float4 s0 = b.st0[cur][i];
-      s1 = b.st1[cur][i];
-      const float4 s2 = b.st2[cur][i];
-      const float4 hit = b.hit[i];
+      // queue records are touched once per iteration: stream them past L1/L2 residency (.cs) so
+      // the scene tables stay cached
+      const float4 o = __ldcs(b.ray_o[cur] + i);
+      const float4 d = __ldcs(b.ray_d[cur] + i);
+      const float4 s0 = __ldcs(b.st0[cur] + i);
+      s1 = __ldcs(b.st1[cur] + i);
+      const float4 s2 = __ldcs(b.st2[cur] + i);
+      const float4 hit = __ldcs(b.hit + i);
       const uint32_t dm = __float_as_uint(s2.w);
       const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
       float4 s3 = make_float4(0, 0, 0, 0), s4 = make_float4(0, 0, 0, 0);
       if (mode == kModeXInter) {
-        s3 = b.st3[cur][i];
-        s4 = b.st4[cur][i];
+        s3 = __ldcs(b.st3[cur] + i);
+        s4 = __ldcs(b.st4[cur] + i);
       }
       pixel = __float_as_uint(s0.w);
       L = mk(s2.x, s2.y, s2.z);
@@ -578,14 +594,15 @@ wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t see
     const unsigned ci = warp_append(&b.ctl->n_next, out.cont);
     const unsigned si = warp_append(&b.ctl->n_shadow, out.shadow);
     if (out.cont) {
-      b.ray_o[nxt][ci] = make_float4(out.o.x, out.o.y, out.o.z, 0.f);
-      b.ray_d[nxt][ci] = make_float4(out.d.x, out.d.y, out.d.z, 0.f);
-      b.st0[nxt][ci] = make_float4(out.beta.x, out.beta.y, out.beta.z, __uint_as_float(pixel));
-      b.st1[nxt][ci] = make_float4(out.tp.x, out.tp.y, out.tp.z, s1.w);
+      __stcs(b.ray_o[nxt] + ci, make_float4(out.o.x, out.o.y, out.o.z, 0.f));
+      __stcs(b.ray_d[nxt] + ci, make_float4(out.d.x, out.d.y, out.d.z, 0.f));
+      __stcs(b.st0[nxt] + ci, make_float4(out.beta.x, out.beta.y, out.beta.z, __uint_as_float(pixel)));
+      __stcs(b.st1[nxt] + ci, make_float4(out.tp.x, out.tp.y, out.tp.z, s1.w));
+      // st2 is read-modify-written by wf_shadow right after: keep it in L2 (default policy)
       b.st2[nxt][ci] = make_float4(L.x, L.y, L.z, __uint_as_float(out.depth_mode));
       if (((out.depth_mode >> 8) & 1u) == kModeXInter) {
-        b.st3[nxt][ci] = make_float4(out.fcos.x, out.fcos.y, out.fcos.z, out.mat_pdf);
-        b.st4[nxt][ci] = make_float4(out.prev_pos.x, out.prev_pos.y, out.prev_pos.z, 0.f);
+        __stcs(b.st3[nxt] + ci, make_float4(out.fcos.x, out.fcos.y, out.fcos.z, out.mat_pdf));
+        __stcs(b.st4[nxt] + ci, make_float4(out.prev_pos.x, out.prev_pos.y, out.prev_pos.z, 0.f));
       }
     }
     if (out.shadow) {
