@@ -385,7 +385,7 @@ void wf_prepare(TutuCtx* ctx, uint64_t total_paths) {
   b.capacity = (unsigned)cap;
   if (!ctx->grid_extend) {
     ctx->grid_extend = persistent_grid(ctx, wf_extend, 256);
-    ctx->grid_shade = persistent_grid(ctx, wf_shade, TUTU_SHADE_BLOCK, kShadeSmemBytes);
+    ctx->grid_shade = persistent_grid(ctx, wf_shade, TUTU_SHADE_BLOCK);
     ctx->grid_shadow = persistent_grid(ctx, wf_shadow, 256);
     ctx->grid_raygen = persistent_grid(ctx, wf_raygen, 256);
   }
@@ -462,7 +462,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
       timer.mark(1, s);
       wf_extend<<<ctx->grid_extend, 256, 0, s>>>(ctx->dev, b, cur);
       timer.mark(2, s);
-      wf_shade<<<ctx->grid_shade, TUTU_SHADE_BLOCK, kShadeSmemBytes, s>>>(ctx->dev, b, cur, seed);
+      wf_shade<<<ctx->grid_shade, TUTU_SHADE_BLOCK, 0, s>>>(ctx->dev, b, cur, seed);
       timer.mark(3, s);
       wf_shadow<<<ctx->grid_shadow, 256, 0, s>>>(ctx->dev, b, cur ^ 1);
       timer.mark(0, s);
