@@ -273,6 +273,9 @@ int persistent_grid(TutuCtx* ctx, K kernel, int block, size_t dyn_smem = 0) {
   if (dyn_smem) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dyn_smem));
   if (per_sm < 1) per_sm = 1;
+  if (const char* e = getenv("TUTU_GRID_DIV")) {  // experiments only: leave room for a co-running kernel
+    per_sm = std::max(1, per_sm / std::max(1, atoi(e)));
+  }
   return ctx->sm_count * per_sm;  // a multiple of the SM count: one resident wave
 }
 

@@ -556,75 +556,84 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
 #ifndef TUTU_SHADE_BLOCK
 #define TUTU_SHADE_BLOCK 256
 #endif
-
-struct ShadeIn {  // one path vertex as it sits in the queues
-  float4 o, d, s0, s1, s2, hit, s3, s4;
-};
-
-__device__ __forceinline__ void shade_load(const WfBuffers& b, int cur, unsigned i, ShadeIn& in) {
-  // queue records are touched once per iteration: stream them (.cs) so the scene tables stay cached
-  in.o = __ldcs(b.ray_o[cur] + i);
-  in.d = __ldcs(b.ray_d[cur] + i);
-  in.s0 = __ldcs(b.st0[cur] + i);
-  in.s1 = __ldcs(b.st1[cur] + i);
-  in.s2 = __ldcs(b.st2[cur] + i);
-  in.hit = __ldcs(b.hit + i);
-  in.s3 = __ldcs(b.st3[cur] + i);  // only meaningful for kModeXInter, loaded unconditionally so that
-  in.s4 = __ldcs(b.st4[cur] + i);  // all eight requests are in flight together
+// cp.async (LDGSTS) 16-byte copy global -> shared, L2 only (.cg): queue records are read once
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// Per grid-stride item: shade, then append survivors / shadow rays with warp-aggregated atomics.
-// ncu (profiles/r01_*): 23 % of this kernel's stall samples sat on the two shuffles that wait for
-// those atomicAdd results, another 14 % on the queue loads of the next item.  The loop is therefore
-// software-pipelined by hand: the atomics of item k are issued, then the loads of item k+1, and
-// only then are the atomic results consumed and item k's records stored, so both latencies overlap.
+constexpr int kShadeRecords = 8;  // ray_o, ray_d, st0, st1, st2, hit, st3, st4
+constexpr size_t kShadeSmemBytes = 2 * kShadeRecords * TUTU_SHADE_BLOCK * sizeof(float4);
+
+// The kernel is bound by the latency of its queue reads (8 float4 per path vertex, then ~1.5 k
+// dependent instructions at 128 registers = 16 warps/SM), so the records of the NEXT grid-stride
+// item are staged into shared memory with cp.async while the current item is shaded: two stages of
+// 8 x blockDim float4 (64 KB per 256-thread block).  Every thread reads back only what it copied
+// itself, so cp.async.wait_group is the only synchronisation.
 __global__ void __launch_bounds__(TUTU_SHADE_BLOCK, TUTU_SHADE_MIN_BLOCKS)
 wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
+  extern __shared__ float4 stage_mem[];  // [2][kShadeRecords][blockDim]
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
   const unsigned n_round = (n + 31u) & ~31u;
   const unsigned stride = gridDim.x * blockDim.x;
-  const unsigned lane = threadIdx.x & 31u;
+  const float4* const src[kShadeRecords] = {b.ray_o[cur], b.ray_d[cur], b.st0[cur], b.st1[cur],
+                                            b.st2[cur],   b.hit,        b.st3[cur], b.st4[cur]};
+  auto slot = [&](int st, int rec) -> float4* {
+    return stage_mem + ((size_t)(st * kShadeRecords + rec) * blockDim.x + threadIdx.x);
+  };
+  auto prefetch = [&](int st, unsigned i) {
+    if (i < n) {
+#pragma unroll
+      for (int r = 0; r < kShadeRecords; ++r) cp_async16(slot(st, r), src[r] + i);
+    }
+    cp_async_commit();
+  };
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  ShadeIn in;
-  if (i < n) shade_load(b, cur, i, in);
-  for (; i < n_round; i += stride) {
+  int st = 0;
+  prefetch(0, i);
+  for (; i < n_round; i += stride, st ^= 1) {
+    prefetch(st ^ 1, i + stride);
+    cp_async_wait<1>();  // everything but the copy just issued has landed
     const bool valid = i < n;
     ShadeOut out;
     out.cont = out.shadow = out.finished = false;
     f3 L = mk(0.f);
     uint32_t pixel = 0;
-    float sample_bits = 0.f;
+    float4 s1 = make_float4(0, 0, 0, 0);
     if (valid) {
-      const uint32_t dm = __float_as_uint(in.s2.w);
+      const float4 o = *slot(st, 0);
+      const float4 d = *slot(st, 1);
+      const float4 s0 = *slot(st, 2);
+      s1 = *slot(st, 3);
+      const float4 s2 = *slot(st, 4);
+      const float4 hit = *slot(st, 5);
+      const uint32_t dm = __float_as_uint(s2.w);
       const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
-      pixel = __float_as_uint(in.s0.w);
-      sample_bits = in.s1.w;
-      L = mk(in.s2.x, in.s2.y, in.s2.z);
-      Ray r{in.o.x, in.o.y, in.o.z, in.d.x, in.d.y, in.d.z};
-      shade_vertex(sc, seed, r, in.hit, pixel, __float_as_uint(in.s1.w), depth, mode, dm,
-                   mk(in.s0.x, in.s0.y, in.s0.z), mk(in.s1.x, in.s1.y, in.s1.z), L, in.s3, in.s4, out);
+      float4 s3 = make_float4(0, 0, 0, 0), s4 = make_float4(0, 0, 0, 0);
+      if (mode == kModeXInter) {
+        s3 = *slot(st, 6);
+        s4 = *slot(st, 7);
+      }
+      pixel = __float_as_uint(s0.w);
+      L = mk(s2.x, s2.y, s2.z);
+      Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
+      shade_vertex(sc, seed, r, hit, pixel, __float_as_uint(s1.w), depth, mode, dm, mk(s0.x, s0.y, s0.z),
+                   mk(s1.x, s1.y, s1.z), L, s3, s4, out);
     }
-    // 1) issue the two queue-append atomics (all 32 lanes of the warp arrive here together)
-    const unsigned cmask = __ballot_sync(0xFFFFFFFFu, out.cont);
-    const unsigned smask = __ballot_sync(0xFFFFFFFFu, out.shadow);
-    unsigned cbase = 0u, sbase = 0u;
-    if (lane == 0) {
-      if (cmask) cbase = atomicAdd(&b.ctl->n_next, (unsigned)__popc(cmask));
-      if (smask) sbase = atomicAdd(&b.ctl->n_shadow, (unsigned)__popc(smask));
-    }
-    // 2) start the loads of the next item while the atomics are in flight
-    const unsigned inext = i + stride;
-    if (inext < n) shade_load(b, cur, inext, in);
-    // 3) consume the atomic results and store this item's records
-    const unsigned lt = (1u << lane) - 1u;
-    const unsigned ci = __shfl_sync(0xFFFFFFFFu, cbase, 0) + (unsigned)__popc(cmask & lt);
-    const unsigned si = __shfl_sync(0xFFFFFFFFu, sbase, 0) + (unsigned)__popc(smask & lt);
+    // queue appends: all 32 lanes of the warp arrive here together
+    const unsigned ci = warp_append(&b.ctl->n_next, out.cont);
+    const unsigned si = warp_append(&b.ctl->n_shadow, out.shadow);
     if (out.cont) {
       __stcs(b.ray_o[nxt] + ci, make_float4(out.o.x, out.o.y, out.o.z, 0.f));
       __stcs(b.ray_d[nxt] + ci, make_float4(out.d.x, out.d.y, out.d.z, 0.f));
       __stcs(b.st0[nxt] + ci, make_float4(out.beta.x, out.beta.y, out.beta.z, __uint_as_float(pixel)));
-      __stcs(b.st1[nxt] + ci, make_float4(out.tp.x, out.tp.y, out.tp.z, sample_bits));
+      __stcs(b.st1[nxt] + ci, make_float4(out.tp.x, out.tp.y, out.tp.z, s1.w));
       // st2 is read-modify-written by wf_shadow right after: keep it in L2 (default policy)
       b.st2[nxt][ci] = make_float4(L.x, L.y, L.z, __uint_as_float(out.depth_mode));
       if (((out.depth_mode >> 8) & 1u) == kModeXInter) {
