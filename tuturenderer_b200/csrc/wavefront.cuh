@@ -556,50 +556,12 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
 #ifndef TUTU_SHADE_BLOCK
 #define TUTU_SHADE_BLOCK 256
 #endif
-// cp.async (LDGSTS) 16-byte copy global -> shared, L2 only (.cg): queue records are read once
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-constexpr int kShadeRecords = 8;  // ray_o, ray_d, st0, st1, st2, hit, st3, st4
-constexpr size_t kShadeSmemBytes = 2 * kShadeRecords * TUTU_SHADE_BLOCK * sizeof(float4);
-
-// The kernel is bound by the latency of its queue reads (8 float4 per path vertex, then ~1.5 k
-// dependent instructions at 128 registers = 16 warps/SM), so the records of the NEXT grid-stride
-// item are staged into shared memory with cp.async while the current item is shaded: two stages of
-// 8 x blockDim float4 (64 KB per 256-thread block).  Every thread reads back only what it copied
-// itself, so cp.async.wait_group is the only synchronisation.
 __global__ void __launch_bounds__(TUTU_SHADE_BLOCK, TUTU_SHADE_MIN_BLOCKS)
 wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
-  extern __shared__ float4 stage_mem[];  // [2][kShadeRecords][blockDim]
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
   const unsigned n_round = (n + 31u) & ~31u;
-  const unsigned stride = gridDim.x * blockDim.x;
-  const float4* const src[kShadeRecords] = {b.ray_o[cur], b.ray_d[cur], b.st0[cur], b.st1[cur],
-                                            b.st2[cur],   b.hit,        b.st3[cur], b.st4[cur]};
-  auto slot = [&](int st, int rec) -> float4* {
-    return stage_mem + ((size_t)(st * kShadeRecords + rec) * blockDim.x + threadIdx.x);
-  };
-  auto prefetch = [&](int st, unsigned i) {
-    if (i < n) {
-#pragma unroll
-      for (int r = 0; r < kShadeRecords; ++r) cp_async16(slot(st, r), src[r] + i);
-    }
-    cp_async_commit();
-  };
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  int st = 0;
-  prefetch(0, i);
-  for (; i < n_round; i += stride, st ^= 1) {
-    prefetch(st ^ 1, i + stride);
-    cp_async_wait<1>();  // everything but the copy just issued has landed
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
     const bool valid = i < n;
     ShadeOut out;
     out.cont = out.shadow = out.finished = false;
@@ -607,18 +569,20 @@ wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t see
     uint32_t pixel = 0;
     float4 s1 = make_float4(0, 0, 0, 0);
     if (valid) {
-      const float4 o = *slot(st, 0);
-      const float4 d = *slot(st, 1);
-      const float4 s0 = *slot(st, 2);
-      s1 = *slot(st, 3);
-      const float4 s2 = *slot(st, 4);
-      const float4 hit = *slot(st, 5);
+      // queue records are touched once per iteration: stream them past L1/L2 residency (.cs) so
+      // the scene tables stay cached
+      const float4 o = __ldcs(b.ray_o[cur] + i);
+      const float4 d = __ldcs(b.ray_d[cur] + i);
+      const float4 s0 = __ldcs(b.st0[cur] + i);
+      s1 = __ldcs(b.st1[cur] + i);
+      const float4 s2 = __ldcs(b.st2[cur] + i);
+      const float4 hit = __ldcs(b.hit + i);
       const uint32_t dm = __float_as_uint(s2.w);
       const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
       float4 s3 = make_float4(0, 0, 0, 0), s4 = make_float4(0, 0, 0, 0);
       if (mode == kModeXInter) {
-        s3 = *slot(st, 6);
-        s4 = *slot(st, 7);
+        s3 = __ldcs(b.st3[cur] + i);
+        s4 = __ldcs(b.st4[cur] + i);
       }
       pixel = __float_as_uint(s0.w);
       L = mk(s2.x, s2.y, s2.z);
