@@ -212,15 +212,17 @@ int tutu_trace_count_visits(TutuCtx* ctx, const float* d_rays, uint64_t n_rays, 
 int tutu_render_path(TutuCtx* ctx, uint32_t spp, uint64_t seed, float* rgb_out);
 /* Multi-GPU building block: accumulate samples [sample_begin, sample_begin+sample_count) of
  * every pixel as SUMS (NaN samples dropped) into d_accum (width*height*3 floats on the device,
- * not cleared), asynchronous on `stream`.  The caller reduces d_accum across ranks and then calls
+ * not cleared).  The work is ordered after everything already enqueued on `stream`, and `stream`
+ * is ordered after it; the call itself returns once the samples are done (it polls the wavefront).  The caller reduces d_accum across ranks and then calls
  * tutu_finalize_device with inv_spp = 1/total_spp. */
 int tutu_render_path_accumulate_device(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count,
                                        uint64_t seed, float* d_accum, void* stream);
 int tutu_finalize_device(TutuCtx* ctx, const float* d_accum, float inv_spp, float* d_rgb_out,
                          void* stream);
 int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
-/* Knobs: paths in flight (0 = default), per-stage event timing on/off. */
-int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int profile_stages);
+/* Knobs: paths in flight per wavefront lane (0 = default 4 Mi), number of interleaved wavefront
+ * lanes (0 = default 2; 1 = a single wavefront), per-stage event timing on/off. */
+int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int lanes, int profile_stages);
 
 /* ---- host-side helpers (no GPU needed) -------------------------------------------------- */
 /* Midpoint BVH with the reference's split rule (BVH.hpp:47-123).  nodes_out must hold

@@ -12,11 +12,12 @@ ctx = api.Context(0)
 sc = api.Scene.load(ROOT / "tests/golden/cornell_256.tscene").with_size(1024, 1024)
 ctx.upload(sc)
 pif = int(os.environ.get("TUTU_PIF", "0"))
-ctx.configure(pif, False)
+lanes = int(os.environ.get("TUTU_LANES", "0"))
+ctx.configure(pif, False, lanes)
 ctx.render_path(8, seed=1)
 img = ctx.render_path(spp, seed=2)
 st0 = ctx.stats()
-ctx.configure(pif, True)
+ctx.configure(pif, True, lanes)
 img = ctx.render_path(spp, seed=2)
 st = ctx.stats()
 tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("TUTU_"))

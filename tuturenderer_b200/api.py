@@ -87,7 +87,7 @@ ABI = {
     "tutu_render_path_accumulate_device": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P]),
     "tutu_finalize_device": (C.c_int, [_P, _P, C.c_float, _P, _P]),
     "tutu_render_stats": (C.c_int, [_P, C.POINTER(TutuRenderStats)]),
-    "tutu_render_configure": (C.c_int, [_P, C.c_uint64, C.c_int]),
+    "tutu_render_configure": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int]),
     "tutu_bvh_build": (C.c_int, [_P, C.c_uint32, _P, C.POINTER(C.c_uint32)]),
     "tutu_scene_file_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "tutu_scene_file_desc": (C.POINTER(TutuSceneDesc), [_P]),
@@ -373,8 +373,8 @@ class Context:
         return a.value, b.value
 
     # ---- path tracing
-    def configure(self, paths_in_flight: int = 0, profile_stages: bool = False) -> None:
-        self._ck(lib().tutu_render_configure(self._h, paths_in_flight, int(profile_stages)))
+    def configure(self, paths_in_flight: int = 0, profile_stages: bool = False, lanes: int = 0) -> None:
+        self._ck(lib().tutu_render_configure(self._h, paths_in_flight, lanes, int(profile_stages)))
 
     def render_path(self, spp: int, seed: int = 1, out: np.ndarray | None = None) -> np.ndarray:
         i = self.info()

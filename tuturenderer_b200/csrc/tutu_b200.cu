@@ -66,6 +66,34 @@ void upload_vec(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
 
 }  // namespace
 
+struct WfLane {
+  DevBuf pool, ctl;
+  WfBuffers b{};
+  uint64_t capacity = 0;
+  cudaStream_t stream = nullptr;
+  WfCtl* ctl_host = nullptr;  // pinned
+  cudaEvent_t ev_done = nullptr;
+  WfLane() = default;
+  WfLane(WfLane&& o) noexcept { *this = std::move(o); }
+  WfLane& operator=(WfLane&& o) noexcept {
+    std::swap(pool.p, o.pool.p);
+    std::swap(pool.bytes, o.pool.bytes);
+    std::swap(ctl.p, o.ctl.p);
+    std::swap(ctl.bytes, o.ctl.bytes);
+    b = o.b;
+    std::swap(capacity, o.capacity);
+    std::swap(stream, o.stream);
+    std::swap(ctl_host, o.ctl_host);
+    std::swap(ev_done, o.ev_done);
+    return *this;
+  }
+  ~WfLane() {
+    if (stream) cudaStreamDestroy(stream);
+    if (ctl_host) cudaFreeHost(ctl_host);
+    if (ev_done) cudaEventDestroy(ev_done);
+  }
+};
+
 struct TutuCtx {
   int device = 0;
   int sm_count = 148;
@@ -86,10 +114,11 @@ struct TutuCtx {
   DevBuf d_rays, d_hits, d_blocked, d_counts;
 
   // wavefront
-  DevBuf wf_pool, wf_ctl, d_accum, d_rgb;
-  WfBuffers wf{};
-  uint64_t wf_capacity = 0;
-  uint64_t paths_in_flight_cfg = 0;
+  DevBuf d_accum, d_rgb;
+  std::vector<WfLane> wf_lanes;
+  uint64_t paths_in_flight_cfg = 0;  // per lane
+  int lanes_cfg = 0;
+  int grid_lanes = 0;
   int profile_stages = 0;
   TutuRenderStats stats{};
   int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_raygen = 0;
@@ -356,19 +385,21 @@ void fill_raygen(const FlatScene& f, RayGenK* k) {
 // ---------------------------------------------------------------------------------------------
 // wavefront host loop
 // ---------------------------------------------------------------------------------------------
-void wf_prepare(TutuCtx* ctx, uint64_t total_paths) {
-  uint64_t cap = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)4 << 20;
-  cap = std::min<uint64_t>(cap, std::max<uint64_t>(total_paths, 1));
+// One wavefront "lane": its own queues, control block and stream.  Several lanes run interleaved
+// (DESIGN.md §5): wf_shade is latency bound at 16 warps/SM (128 registers) and leaves ~60 % of the
+// issue slots idle, wf_extend / wf_shadow are issue bound, so while one lane shades the other
+// traverses on the same SMs.  Each lane's grids are sized to 1/lanes of the resident-block count so
+// that both kernels fit on an SM together.
+void lane_prepare(TutuCtx* ctx, WfLane& L, uint64_t cap) {
   cap = (cap + 255) & ~(uint64_t)255;
-  if (cap > ctx->wf_capacity) {
-    // 2*(7 queues) + hit + 4 shadow arrays, float4 each
-    const size_t n_arrays = 2 * 7 + 1 + 4;
-    ctx->wf_pool.ensure(n_arrays * cap * sizeof(float4));
-    ctx->wf_capacity = cap;
+  if (cap > L.capacity) {
+    const size_t n_arrays = 2 * 7 + 1 + 4;  // 2*(7 queues) + hit + 4 shadow arrays, float4 each
+    L.pool.ensure(n_arrays * cap * sizeof(float4));
+    L.capacity = cap;
   }
-  cap = ctx->wf_capacity;
-  float4* p = ctx->wf_pool.as<float4>();
-  WfBuffers& b = ctx->wf;
+  cap = L.capacity;
+  float4* p = L.pool.as<float4>();
+  WfBuffers& b = L.b;
   for (int k = 0; k < 2; ++k) {
     b.ray_o[k] = p, p += cap;
     b.ray_d[k] = p, p += cap;
@@ -383,15 +414,12 @@ void wf_prepare(TutuCtx* ctx, uint64_t total_paths) {
   b.sh_d = p, p += cap;
   b.sh_c = p, p += cap;
   b.sh_L = p, p += cap;
-  ctx->wf_ctl.ensure(sizeof(WfCtl));
-  b.ctl = ctx->wf_ctl.as<WfCtl>();
+  L.ctl.ensure(sizeof(WfCtl));
+  b.ctl = L.ctl.as<WfCtl>();
   b.capacity = (unsigned)cap;
-  if (!ctx->grid_extend) {
-    ctx->grid_extend = persistent_grid(ctx, wf_extend, 256);
-    ctx->grid_shade = persistent_grid(ctx, wf_shade, TUTU_SHADE_BLOCK);
-    ctx->grid_shadow = persistent_grid(ctx, wf_shadow, 256);
-    ctx->grid_raygen = persistent_grid(ctx, wf_raygen, 256);
-  }
+  if (!L.stream) CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+  if (!L.ctl_host) CUDA_TRY(cudaMallocHost(&L.ctl_host, sizeof(WfCtl)));
+  if (!L.ev_done) CUDA_TRY(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
 }
 
 struct StageTimer {
@@ -399,6 +427,8 @@ struct StageTimer {
   std::vector<cudaEvent_t> ev;
   std::vector<int> tag;  // stage id of the interval that STARTS at event k
   explicit StageTimer(bool enable) : on(enable) {}
+  StageTimer(StageTimer&&) = default;
+  StageTimer(const StageTimer&) = delete;
   ~StageTimer() {
     for (auto e : ev) cudaEventDestroy(e);
   }
@@ -426,6 +456,8 @@ struct StageTimer {
 };
 
 // Accumulates samples [sample_begin, sample_begin+sample_count) of every pixel into d_accum.
+// Work is enqueued on the lanes' own streams, which are ordered after everything already on `s`;
+// `s` is ordered after the lanes when the call returns (it also blocks the host until then).
 void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint64_t seed, float* d_accum,
                cudaStream_t s) {
   const FlatScene& f = ctx->flat;
@@ -433,73 +465,126 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   const uint64_t total = npix * sample_count;
   ctx->stats = TutuRenderStats{};
   if (total == 0) return;
-  wf_prepare(ctx, total);
-  WfBuffers b = ctx->wf;
-  b.accum = d_accum;
+
+  // lanes: split the samples; a lane never gets less than ~one wavefront of paths
+  int n_lanes = ctx->lanes_cfg > 0 ? ctx->lanes_cfg : 2;
+  const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)4 << 20;
+  while (n_lanes > 1 && (sample_count < (uint32_t)n_lanes || total / n_lanes < cap_cfg / 2)) --n_lanes;
+  if ((int)ctx->wf_lanes.size() < n_lanes) ctx->wf_lanes.resize(n_lanes);
+  if (ctx->grid_lanes != n_lanes) {
+    const int div = n_lanes;
+    auto sized = [&](int full) { return ctx->sm_count * std::max(1, full / ctx->sm_count / div); };
+    ctx->grid_extend = sized(persistent_grid(ctx, wf_extend, 256));
+    ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, TUTU_SHADE_BLOCK));
+    ctx->grid_shadow = sized(persistent_grid(ctx, wf_shadow, 256));
+    ctx->grid_raygen = sized(persistent_grid(ctx, wf_raygen, 256));
+    ctx->grid_lanes = n_lanes;
+  }
   RayGenK rk;
   fill_raygen(f, &rk);
-
-  WfCtl h{};
-  h.total_paths = total;
-  CUDA_TRY(cudaMemcpyAsync(b.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, s));
 
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
-  CUDA_TRY(cudaEventRecord(e0, s));
-  StageTimer timer(ctx->profile_stages != 0);
-
-  unsigned* done_host = nullptr;
-  CUDA_TRY(cudaMallocHost(&done_host, sizeof(WfCtl)));
-  WfCtl* ctl_host = reinterpret_cast<WfCtl*>(done_host);
-  memset(ctl_host, 0, sizeof(WfCtl));
-
-  int cur = 0;
+  std::vector<StageTimer> timers;
+  struct Run {
+    uint32_t s_begin, s_count;
+    int cur = 0;
+    bool done = false;
+  };
+  std::vector<Run> runs(n_lanes);
   uint64_t launches = 0;
-  const int poll_every = 8;
   try {
+    CUDA_TRY(cudaEventRecord(e0, s));
+    for (int k = 0; k < n_lanes; ++k) {
+      WfLane& L = ctx->wf_lanes[k];
+      const uint32_t b0 = (uint32_t)((uint64_t)sample_count * k / n_lanes);
+      const uint32_t b1 = (uint32_t)((uint64_t)sample_count * (k + 1) / n_lanes);
+      runs[k].s_begin = sample_begin + b0;
+      runs[k].s_count = b1 - b0;
+      const uint64_t lane_total = npix * runs[k].s_count;
+      lane_prepare(ctx, L, std::min<uint64_t>(cap_cfg, std::max<uint64_t>(lane_total, 1)));
+      L.b.accum = d_accum;
+      CUDA_TRY(cudaStreamWaitEvent(L.stream, e0, 0));
+      WfCtl h{};
+      h.total_paths = lane_total;
+      *L.ctl_host = h;
+      CUDA_TRY(cudaMemcpyAsync(L.b.ctl, L.ctl_host, sizeof(WfCtl), cudaMemcpyHostToDevice, L.stream));
+      timers.emplace_back(ctx->profile_stages != 0);
+      runs[k].done = lane_total == 0;
+    }
+    const int poll_every = 8;
     for (uint64_t it = 0;; ++it) {
-      timer.mark(0, s);
-      wf_raygen<<<ctx->grid_raygen, 256, 0, s>>>(b, cur, rk, sample_begin);
-      wf_ctl_after_raygen<<<1, 1, 0, s>>>(b.ctl, b.capacity);
-      timer.mark(1, s);
-      wf_extend<<<ctx->grid_extend, 256, 0, s>>>(ctx->dev, b, cur);
-      timer.mark(2, s);
-      wf_shade<<<ctx->grid_shade, TUTU_SHADE_BLOCK, 0, s>>>(ctx->dev, b, cur, seed);
-      timer.mark(3, s);
-      wf_shadow<<<ctx->grid_shadow, 256, 0, s>>>(ctx->dev, b, cur ^ 1);
-      timer.mark(0, s);
-      wf_ctl_after_iter<<<1, 1, 0, s>>>(b.ctl);
-      launches += 6;
-      cur ^= 1;
+      bool any = false;
+      for (int k = 0; k < n_lanes; ++k) {
+        if (runs[k].done) continue;
+        any = true;
+        WfLane& L = ctx->wf_lanes[k];
+        cudaStream_t ls = L.stream;
+        StageTimer& timer = timers[k];
+        const int cur = runs[k].cur;
+        timer.mark(0, ls);
+        wf_raygen<<<ctx->grid_raygen, 256, 0, ls>>>(L.b, cur, rk, runs[k].s_begin);
+        wf_ctl_after_raygen<<<1, 1, 0, ls>>>(L.b.ctl, L.b.capacity);
+        timer.mark(1, ls);
+        wf_extend<<<ctx->grid_extend, 256, 0, ls>>>(ctx->dev, L.b, cur);
+        if (it == 0 && k + 1 < n_lanes) {
+          // stagger the lanes by one stage so that unlike kernels (traverse / shade) overlap
+          CUDA_TRY(cudaEventRecord(L.ev_done, ls));
+          CUDA_TRY(cudaStreamWaitEvent(ctx->wf_lanes[k + 1].stream, L.ev_done, 0));
+        }
+        timer.mark(2, ls);
+        wf_shade<<<ctx->grid_shade, TUTU_SHADE_BLOCK, 0, ls>>>(ctx->dev, L.b, cur, seed);
+        timer.mark(3, ls);
+        wf_shadow<<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, L.b, cur ^ 1);
+        timer.mark(0, ls);
+        wf_ctl_after_iter<<<1, 1, 0, ls>>>(L.b.ctl);
+        launches += 6;
+        runs[k].cur ^= 1;
+        if ((it + 1) % poll_every == 0)
+          CUDA_TRY(cudaMemcpyAsync(L.ctl_host, L.b.ctl, sizeof(WfCtl), cudaMemcpyDeviceToHost, ls));
+      }
+      if (!any) break;
       if ((it + 1) % poll_every == 0) {
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(ctl_host, b.ctl, sizeof(WfCtl), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        if (ctl_host->done) break;
+        for (int k = 0; k < n_lanes; ++k) {
+          if (runs[k].done) continue;
+          WfLane& L = ctx->wf_lanes[k];
+          CUDA_TRY(cudaStreamSynchronize(L.stream));
+          if (L.ctl_host->done) {
+            runs[k].done = true;
+            timers[k].mark(0, L.stream);
+          }
+        }
       }
     }
-    timer.mark(0, s);
+    for (int k = 0; k < n_lanes; ++k) {
+      WfLane& L = ctx->wf_lanes[k];
+      CUDA_TRY(cudaEventRecord(L.ev_done, L.stream));
+      CUDA_TRY(cudaStreamWaitEvent(s, L.ev_done, 0));
+    }
     CUDA_TRY(cudaEventRecord(e1, s));
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    ctx->stats.gpu_ms = ms;
-    ctx->stats.paths = total;
-    ctx->stats.extend_rays = ctl_host->sum_extend;
-    ctx->stats.shadow_rays = ctl_host->sum_shadow;
-    ctx->stats.shade_calls = ctl_host->sum_extend;
-    ctx->stats.nan_samples = ctl_host->nan_samples;
-    ctx->stats.iterations = ctl_host->iterations;
-    ctx->stats.kernel_launches = launches;
-    timer.resolve(&ctx->stats);
+    TutuRenderStats& st = ctx->stats;
+    st.gpu_ms = ms;
+    st.paths = total;
+    for (int k = 0; k < n_lanes; ++k) {
+      const WfCtl& c = *ctx->wf_lanes[k].ctl_host;
+      st.extend_rays += c.sum_extend;
+      st.shadow_rays += c.sum_shadow;
+      st.nan_samples += c.nan_samples;
+      st.iterations += c.iterations;
+      timers[k].resolve(&st);
+    }
+    st.shade_calls = st.extend_rays;
+    st.kernel_launches = launches;
   } catch (...) {
-    cudaFreeHost(done_host);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     throw;
   }
-  cudaFreeHost(done_host);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
 }
@@ -546,10 +631,8 @@ extern "C" int tutu_ctx_create(int device, TutuCtx** out) {
 extern "C" void tutu_ctx_destroy(TutuCtx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->stream) {
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamDestroy(ctx->stream);
-  }
+  cudaDeviceSynchronize();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
@@ -718,10 +801,13 @@ extern "C" int tutu_trace_count_visits(TutuCtx* ctx, const float* d_rays, uint64
   API_END(ctx)
 }
 
-extern "C" int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int profile_stages) {
+extern "C" int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int lanes, int profile_stages) {
   if (!ctx) return fail(nullptr, TUTU_E_INVALID, "null context");
   if (paths_in_flight > ((uint64_t)1 << 31)) return fail(ctx, TUTU_E_INVALID, "paths_in_flight too large");
+  if (lanes < 0 || lanes > 8) return fail(ctx, TUTU_E_INVALID, "lanes must be 0 (default) .. 8");
+  std::lock_guard<std::mutex> lock(ctx->mu);
   ctx->paths_in_flight_cfg = paths_in_flight;
+  ctx->lanes_cfg = lanes;
   ctx->profile_stages = profile_stages;
   return TUTU_OK;
 }

@@ -44,7 +44,7 @@ def render_distributed(accumulate: Callable[[int, int, "object"], None], accum, 
 class CudaRenderer:
     """Per-rank renderer on top of the C ABI: device accumulation buffer as a torch tensor."""
 
-    def __init__(self, scene, device: int = 0, paths_in_flight: int = 0, profile_stages: bool = False):
+    def __init__(self, scene, device: int = 0, paths_in_flight: int = 0, profile_stages: bool = False, lanes: int = 0):
         import torch
         from . import api
         self.torch = torch
@@ -53,7 +53,7 @@ class CudaRenderer:
         torch.cuda.set_device(device)
         self.ctx = api.Context(device)
         self.ctx.upload(scene)
-        self.ctx.configure(paths_in_flight, profile_stages)
+        self.ctx.configure(paths_in_flight, profile_stages, lanes)
         self.scene = scene
         n = scene.width * scene.height * 3
         self.accum = torch.zeros(n, dtype=torch.float32, device=f"cuda:{device}")
