@@ -14,7 +14,7 @@ CASES = [("cornell_256", "cornell_rays.f32", "cornell_closest.bin", "cornell_any
          ("mixed", "mixed_rays.f32", "mixed_closest.bin", "mixed_any.bin")]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 4])
 @pytest.mark.parametrize("scene,rays,closest,anyf", CASES)
 def test_golden_vectors_bit_exact(api, ctx, golden, scene, rays, closest, anyf, mode):
     sc = api.Scene.load(golden / f"{scene}.tscene")
@@ -45,7 +45,7 @@ def test_random_soups_against_oracle(api, oracle, ctx, n_tris, n_spheres, dup, s
     rays = random_rays(30000, seed=seed)
     want_c, want_a = osc.trace_closest(rays), osc.trace_any(rays)
     ctx.upload(sc)
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 4):
         ctx.set_traversal_mode(mode)
         assert_hits_equal(ctx.trace_closest(rays), want_c)
         assert np.array_equal(ctx.trace_any(rays), want_a)
@@ -74,6 +74,37 @@ def test_degenerate_rays(api, oracle, ctx, cornell):
         ctx.set_traversal_mode(mode)
         assert_hits_equal(ctx.trace_closest(rays), osc.trace_closest(rays))
         assert np.array_equal(ctx.trace_any(rays), osc.trace_any(rays))
+
+
+def test_small_scene_path_equals_tree_walk(api, oracle, ctx, cornell):
+    """Scenes with <= 32 primitives skip the tree (flat leaf-box test, trace.cuh traverse_small):
+    mode 0 uses it, mode 4 forces the BVH walk, mode 1 is the literal reference recursion."""
+    assert len(cornell.prims) == 32
+    osc = oracle.OracleScene(cornell)
+    rng = np.random.default_rng(3)
+    n = 200000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform([-50, -50, -900], [600, 600, 600], (n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 4:7] = d
+    rays[: n // 10, 4 + 1] = 0.0  # axis-degenerate directions take the fallback walk
+    rays[:, 7] = rng.uniform(1, 1500, n)
+    want_c, want_a = osc.trace_closest(rays), osc.trace_any(rays)
+    ctx.upload(cornell)
+    for mode in (0, 4, 1):
+        ctx.set_traversal_mode(mode)
+        assert_hits_equal(ctx.trace_closest(rays), want_c)
+        assert np.array_equal(ctx.trace_any(rays), want_a)
+    # spheres in a small scene
+    prims = random_soup(api, 20, 8, seed=11, dup=4)
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    osc = oracle.OracleScene(sc)
+    r2 = random_rays(50000, seed=12)
+    ctx.upload(sc)
+    ctx.set_traversal_mode(0)
+    assert_hits_equal(ctx.trace_closest(r2), osc.trace_closest(r2))
+    assert np.array_equal(ctx.trace_any(r2), osc.trace_any(r2))
 
 
 def test_any_hit_distance_rule(api, oracle, ctx, cornell):

@@ -410,6 +410,7 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
   fs->geom.resize(n);
   fs->shade.resize(n);
   fs->slot_to_prim.resize(n);
+  fs->leaf_box.resize(n);
   bool any_tex = false;
   for (uint32_t i = 0; i < n; ++i) any_tex |= desc->prims[i].tex_active != 0;
   if (any_tex) fs->leaftex.resize(n);
@@ -430,6 +431,7 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
     const uint32_t s = (uint32_t)slot_of[i];
     const TutuPrim& p = desc->prims[nd.prim];
     fs->slot_to_prim[s] = nd.prim;
+    fs->leaf_box[s] = nbox[i];
     LeafGeom& g = fs->geom[s];
     LeafShade& sh = fs->shade[s];
     memset(&g, 0, sizeof(g));

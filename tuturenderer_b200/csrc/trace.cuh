@@ -43,6 +43,7 @@ struct DevScene {
   float prune_rel;
   float prune_abs;
   int refill_min;  // persistent tracer: refill once this many lanes of a warp are idle
+  unsigned sphere_mask;  // small scenes: bit s set = leaf slot s is a sphere
 };
 
 struct Ray {
@@ -466,6 +467,73 @@ __device__ __forceinline__ bool traverse_variant(const DevScene& sc, const Ray& 
     }
   }
   best = w.best;
+  return best.slot >= 0;
+}
+
+// ---- small scenes (<= 32 primitives): no tree walk at all --------------------------------------
+// For a regular ray (every 1/d finite, so no NaN anywhere in the slab arithmetic) the slab test
+// is monotone in the box: fl((plane - o) * inv) is non-decreasing in `plane`, every inner box of
+// the reference tree is the exact fmin/fmax union of its children (BVH.hpp:65,119), hence
+// t_enter(parent) <= t_enter(child) <= t_exit(child) <= t_exit(parent): a hit leaf box implies that
+// every ancestor box is hit.  The reference's answer is therefore simply the closest primitive
+// among those whose OWN leaf box and primitive test both pass (ties: lowest DFS slot).  With 32
+// leaves that is 32 slab tests against constants read straight from the kernel-parameter bank
+// (fully convergent, no loads, no stack) followed by the primitive tests of the few set bits.
+// Irregular rays take the literal tree walk.
+constexpr int kSmallMax = 32;
+struct SmallScene {
+  int n;  // 0 = not usable (scene too large or empty)
+  float box[kSmallMax][6];  // leaf boxes in DFS slot order: lo.xyz, hi.xyz
+};
+
+template <bool ANY>
+__device__ __forceinline__ bool traverse_small(const DevScene& sc, const SmallScene& ss, const Ray& r,
+                                               float dis, Hit& best) {
+  const RayPre p = make_pre(r);
+  if (!ray_is_regular(p)) return traverse_variant<ANY, 0>(sc, r, dis, best);
+  best.t = FLT_MAX;
+  best.u = 0.f;
+  best.v = 0.f;
+  best.slot = -1;
+  unsigned mask = 0u;
+#pragma unroll
+  for (int k = 0; k < kSmallMax; ++k) {
+    if (k < ss.n) {  // uniform
+      float te;
+      if (box_test_regular(p, ss.box[k][0], ss.box[k][1], ss.box[k][2], ss.box[k][3], ss.box[k][4],
+                           ss.box[k][5], te))
+        mask |= 1u << k;
+    }
+  }
+  while (mask) {
+    const int slot = __ffs(mask) - 1;  // increasing slot order: strict '<' keeps the lowest slot on ties
+    mask &= mask - 1u;
+    const float4* g = sc.geom + 3 * slot;
+    const bool sphere = (sc.sphere_mask >> slot) & 1u;
+    float t, u = 0.f, v = 0.f;
+    bool hit;
+    if (sphere) {
+      const SphereHit sh = sphere_test(g, r);
+      hit = sh.hit;
+      t = sh.t;
+    } else {
+      hit = tri_test(g, r, t, u, v);
+    }
+    if (hit) {
+      if (ANY) {
+        if (t < dis && !(fabsf(__fsub_rn(t, dis)) < 0.0001f)) {
+          best.t = t;
+          best.slot = slot | (sphere ? (int)kSphereBit : 0);
+          return true;
+        }
+      } else if (t < best.t) {
+        best.t = t;
+        best.u = u;
+        best.v = v;
+        best.slot = slot | (sphere ? (int)kSphereBit : 0);
+      }
+    }
+  }
   return best.slot >= 0;
 }
 

@@ -105,6 +105,7 @@ struct TutuCtx {
   bool has_scene = false;
   FlatScene flat;
   DevScene dev{};
+  SmallScene small{};  // n = 0 unless the scene has <= kSmallMax primitives
   DevBuf d_inner, d_geom, d_shade, d_leaftex, d_slot_to_prim, d_materials, d_lights, d_texels;
   DevBuf d_texh[4];
   uint64_t scene_bytes = 0;
@@ -119,6 +120,7 @@ struct TutuCtx {
   uint64_t paths_in_flight_cfg = 0;  // per lane
   int lanes_cfg = 0;
   int grid_lanes = 0;
+  bool grid_small = false;
   int profile_stages = 0;
   TutuRenderStats stats{};
   int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_raygen = 0;
@@ -164,8 +166,9 @@ int fail_cuda(TutuCtx* ctx, const CudaError& e) {
 //         MODE 0 on every workload, kept for the record — DESIGN.md §5).
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_trace_closest(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n,
-                TutuHit* __restrict__ out, unsigned long long* __restrict__ next) {
+k_trace_closest(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss,
+                const float4* __restrict__ rays, unsigned long long n, TutuHit* __restrict__ out,
+                unsigned long long* __restrict__ next) {
   auto store = [&](unsigned long long i, const Hit& h) {
     const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
     reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), h.t, h.u, h.v);
@@ -194,7 +197,9 @@ k_trace_closest(const __grid_constant__ DevScene sc, const float4* __restrict__ 
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
       Hit h;
-      if (MODE == 0)
+      if (MODE == 3)
+        traverse_small<false>(sc, ss, r, 0.f, h);
+      else if (MODE == 0)
         traverse_variant<false, 1>(sc, r, 0.f, h);
       else
         traverse<false, 1, false>(sc, r, 0.f, h, nullptr);
@@ -206,8 +211,9 @@ k_trace_closest(const __grid_constant__ DevScene sc, const float4* __restrict__ 
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_trace_any(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n,
-            uint8_t* __restrict__ out, unsigned long long* __restrict__ next) {
+k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss,
+            const float4* __restrict__ rays, unsigned long long n, uint8_t* __restrict__ out,
+            unsigned long long* __restrict__ next) {
   if (MODE == 2) {
     trace_persistent<true>(
         sc, n, next,
@@ -232,7 +238,9 @@ k_trace_any(const __grid_constant__ DevScene sc, const float4* __restrict__ rays
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
       Hit h;
-      if (MODE == 0)
+      if (MODE == 3)
+        out[i] = traverse_small<true>(sc, ss, r, d.w, h) ? 1 : 0;
+      else if (MODE == 0)
         out[i] = traverse_variant<true, 1>(sc, r, d.w, h) ? 1 : 0;
       else
         out[i] = traverse<true, 1, false>(sc, r, d.w, h, nullptr) ? 1 : 0;
@@ -326,13 +334,18 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
 #undef TUTU_VAR_C
   } else if (ctx->traversal_mode == 1) {
     int grid = persistent_grid(ctx, k_trace_closest<1>, 256);
-    k_trace_closest<1><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+    k_trace_closest<1><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
   } else if (ctx->traversal_mode == 2) {
     int grid = persistent_grid(ctx, k_trace_closest<2>, 256);
-    k_trace_closest<2><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+    k_trace_closest<2><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
   } else {
-    int grid = persistent_grid(ctx, k_trace_closest<0>, 256);
-    k_trace_closest<0><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+    if (ctx->small.n > 0 && ctx->traversal_mode == 0) {
+      int grid = persistent_grid(ctx, k_trace_closest<3>, 256);
+      k_trace_closest<3><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+    } else {
+      int grid = persistent_grid(ctx, k_trace_closest<0>, 256);
+      k_trace_closest<0><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+    }
   }
   CUDA_TRY(cudaGetLastError());
 }
@@ -355,13 +368,18 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
 #undef TUTU_VAR_A
   } else if (ctx->traversal_mode == 1) {
     int grid = persistent_grid(ctx, k_trace_any<1>, 256);
-    k_trace_any<1><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+    k_trace_any<1><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
   } else if (ctx->traversal_mode == 2) {
     int grid = persistent_grid(ctx, k_trace_any<2>, 256);
-    k_trace_any<2><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+    k_trace_any<2><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
   } else {
-    int grid = persistent_grid(ctx, k_trace_any<0>, 256);
-    k_trace_any<0><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, next);
+    if (ctx->small.n > 0 && ctx->traversal_mode == 0) {
+      int grid = persistent_grid(ctx, k_trace_any<3>, 256);
+      k_trace_any<3><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+    } else {
+      int grid = persistent_grid(ctx, k_trace_any<0>, 256);
+      k_trace_any<0><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+    }
   }
   CUDA_TRY(cudaGetLastError());
 }
@@ -471,17 +489,20 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)4 << 20;
   while (n_lanes > 1 && (sample_count < (uint32_t)n_lanes || total / n_lanes < cap_cfg / 2)) --n_lanes;
   if ((int)ctx->wf_lanes.size() < n_lanes) ctx->wf_lanes.resize(n_lanes);
-  if (ctx->grid_lanes != n_lanes) {
+  if (ctx->grid_lanes != n_lanes || ctx->grid_small != (ctx->small.n > 0)) {
+    ctx->grid_small = ctx->small.n > 0;
     const int div = n_lanes;
     auto sized = [&](int full) { return ctx->sm_count * std::max(1, full / ctx->sm_count / div); };
-    ctx->grid_extend = sized(persistent_grid(ctx, wf_extend, 256));
+    const bool small = ctx->small.n > 0;
+    ctx->grid_extend = sized(small ? persistent_grid(ctx, wf_extend<true>, 256) : persistent_grid(ctx, wf_extend<false>, 256));
     ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, TUTU_SHADE_BLOCK));
-    ctx->grid_shadow = sized(persistent_grid(ctx, wf_shadow, 256));
+    ctx->grid_shadow = sized(small ? persistent_grid(ctx, wf_shadow<true>, 256) : persistent_grid(ctx, wf_shadow<false>, 256));
     ctx->grid_raygen = sized(persistent_grid(ctx, wf_raygen, 256));
     ctx->grid_lanes = n_lanes;
   }
   RayGenK rk;
   fill_raygen(f, &rk);
+  const bool small = ctx->small.n > 0;
 
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
@@ -527,7 +548,10 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         wf_raygen<<<ctx->grid_raygen, 256, 0, ls>>>(L.b, cur, rk, runs[k].s_begin);
         wf_ctl_after_raygen<<<1, 1, 0, ls>>>(L.b.ctl, L.b.capacity);
         timer.mark(1, ls);
-        wf_extend<<<ctx->grid_extend, 256, 0, ls>>>(ctx->dev, L.b, cur);
+        if (small)
+          wf_extend<true><<<ctx->grid_extend, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
+        else
+          wf_extend<false><<<ctx->grid_extend, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
         if (it == 0 && k + 1 < n_lanes) {
           // stagger the lanes by one stage so that unlike kernels (traverse / shade) overlap
           CUDA_TRY(cudaEventRecord(L.ev_done, ls));
@@ -536,7 +560,10 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         timer.mark(2, ls);
         wf_shade<<<ctx->grid_shade, TUTU_SHADE_BLOCK, 0, ls>>>(ctx->dev, L.b, cur, seed);
         timer.mark(3, ls);
-        wf_shadow<<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, L.b, cur ^ 1);
+        if (small)
+          wf_shadow<true><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
+        else
+          wf_shadow<false><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
         timer.mark(0, ls);
         wf_ctl_after_iter<<<1, 1, 0, ls>>>(L.b.ctl);
         launches += 6;
@@ -673,6 +700,16 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   d.eta = fs.eta;
   d.prune_rel = 1.0f / 1024.0f;
   d.prune_abs = fs.max_edge * (1.0f / 512.0f);
+  d.sphere_mask = 0u;
+  ctx->small = SmallScene{};
+  if (!fs.empty && fs.n_prims <= (uint32_t)kSmallMax && !getenv("TUTU_NO_SMALL")) {
+    ctx->small.n = (int)fs.n_prims;
+    for (uint32_t k = 0; k < fs.n_prims; ++k) {
+      memcpy(ctx->small.box[k] + 0, fs.leaf_box[k].lo, 12);
+      memcpy(ctx->small.box[k] + 3, fs.leaf_box[k].hi, 12);
+      if (fs.shade[k].flags & SHADE_SPHERE_BIT) d.sphere_mask |= 1u << k;
+    }
+  }
   d.refill_min = 4;
   if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);  // experiments only
@@ -716,7 +753,7 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
 }
 
 extern "C" int tutu_set_traversal_mode(TutuCtx* ctx, int mode) {
-  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || (mode >= 10 && mode <= 12)))
+  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || mode == 4 || (mode >= 10 && mode <= 12)))
     return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument");
   ctx->traversal_mode = mode;
   return TUTU_OK;

@@ -120,6 +120,7 @@ struct FlatScene {
   std::vector<LeafShade> shade;
   std::vector<LeafTex> leaftex;
   std::vector<int32_t> slot_to_prim;
+  std::vector<Box> leaf_box;  // per leaf slot (small-scene fast path)
   std::vector<DevMaterial> materials;
   std::vector<DevLight> lights;
   std::vector<TexHeader> tex_headers[4];

@@ -142,8 +142,9 @@ wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
 // 32-ray packets pulled from the queue with one atomicAdd per warp (lane 0) and a shuffle
 // broadcast: a warp that drew short rays moves on to the next packet instead of idling behind the
 // slowest warp of a statically partitioned grid.
+template <bool SMALL>
 __global__ void __launch_bounds__(256)
-wf_extend(const __grid_constant__ DevScene sc, WfBuffers b, int cur) {
+wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int cur) {
   const unsigned n = b.ctl->n_cur;
   const float4* __restrict__ ro = b.ray_o[cur];
   const float4* __restrict__ rd = b.ray_d[cur];
@@ -158,7 +159,10 @@ wf_extend(const __grid_constant__ DevScene sc, WfBuffers b, int cur) {
       const float4 o = __ldcs(ro + i);
       const float4 d = __ldcs(rd + i);
       Hit h;
-      traverse_variant<false, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
+      if (SMALL)
+        traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
+      else
+        traverse_variant<false, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
       __stcs(b.hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
     }
     __syncwarp();
@@ -166,8 +170,9 @@ wf_extend(const __grid_constant__ DevScene sc, WfBuffers b, int cur) {
 }
 
 // ---- shadow: isShadowRayBlocked -> hasIntersection, then the deferred NEE add ------------------
+template <bool SMALL>
 __global__ void __launch_bounds__(256)
-wf_shadow(const __grid_constant__ DevScene sc, WfBuffers b, int nxt) {
+wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int nxt) {
   const unsigned n = b.ctl->n_shadow;
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
@@ -180,7 +185,8 @@ wf_shadow(const __grid_constant__ DevScene sc, WfBuffers b, int nxt) {
       const float4 o = __ldcs(b.sh_o + j);
       const float4 d = __ldcs(b.sh_d + j);
       Hit h;
-      const bool blocked = traverse_variant<true, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+      const bool blocked = SMALL ? traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h)
+                                 : traverse_variant<true, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
       const unsigned dst = __float_as_uint(d.w);
       if (dst == kShadowFinal) {
         const float4 c = __ldcs(b.sh_c + j);
