@@ -13,6 +13,8 @@ ctx = api.Context(0)
 if what == "render":
     sc = api.Scene.load(ROOT / "tests/golden/cornell_256.tscene").with_size(1024, 1024)
     ctx.upload(sc)
+    import os
+    ctx.configure(0, False, int(os.environ.get("TUTU_LANES", "0")))
     img = ctx.render_path(24, seed=5)
     print("render mean", float(img.mean()), ctx.stats())
 else:
