@@ -566,8 +566,15 @@ __global__ void __launch_bounds__(TUTU_SHADE_BLOCK, TUTU_SHADE_MIN_BLOCKS)
 wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
-  const unsigned n_round = (n + 31u) & ~31u;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+  // ncu (profiles/r01_shade_stalls.txt): with one atomicAdd per WARP on the two queue counters,
+  // half of this kernel's stall samples sat on the shuffles waiting for those results — ~2 x 10^5
+  // same-address atomics per launch serialise in one L2 slice.  The counts are therefore first
+  // combined per BLOCK in shared memory (one global atomic per counter per block-iteration).
+  __shared__ unsigned s_cnt[2][TUTU_SHADE_BLOCK / 32];
+  __shared__ unsigned s_base[2];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const unsigned i = base + threadIdx.x;
     const bool valid = i < n;
     ShadeOut out;
     out.cont = out.shadow = out.finished = false;
@@ -596,9 +603,29 @@ wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t see
       shade_vertex(sc, seed, r, hit, pixel, __float_as_uint(s1.w), depth, mode, dm, mk(s0.x, s0.y, s0.z),
                    mk(s1.x, s1.y, s1.z), L, s3, s4, out);
     }
-    // queue appends: all 32 lanes of the warp arrive here together
-    const unsigned ci = warp_append(&b.ctl->n_next, out.cont);
-    const unsigned si = warp_append(&b.ctl->n_shadow, out.shadow);
+    // queue appends: warp ballots -> block prefix in shared memory -> one atomicAdd per counter
+    const unsigned cmask = __ballot_sync(0xFFFFFFFFu, out.cont);
+    const unsigned smask = __ballot_sync(0xFFFFFFFFu, out.shadow);
+    if (lane == 0) {
+      s_cnt[0][warp] = (unsigned)__popc(cmask);
+      s_cnt[1][warp] = (unsigned)__popc(smask);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      unsigned total = 0;
+#pragma unroll
+      for (int w = 0; w < TUTU_SHADE_BLOCK / 32; ++w) {
+        const unsigned c = s_cnt[threadIdx.x][w];
+        s_cnt[threadIdx.x][w] = total;  // exclusive prefix
+        total += c;
+      }
+      s_base[threadIdx.x] = total ? atomicAdd(threadIdx.x == 0 ? &b.ctl->n_next : &b.ctl->n_shadow, total) : 0u;
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned ci = s_base[0] + s_cnt[0][warp] + (unsigned)__popc(cmask & lt);
+    const unsigned si = s_base[1] + s_cnt[1][warp] + (unsigned)__popc(smask & lt);
+    __syncthreads();  // s_cnt / s_base are rewritten by the next iteration
     if (out.cont) {
       __stcs(b.ray_o[nxt] + ci, make_float4(out.o.x, out.o.y, out.o.z, 0.f));
       __stcs(b.ray_d[nxt] + ci, make_float4(out.d.x, out.d.y, out.d.z, 0.f));
