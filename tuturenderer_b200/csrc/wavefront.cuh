@@ -139,7 +139,9 @@ wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
 }
 
 // ---- extend: IIntersectStrategy::UpdateInter -> getIntersection -------------------------------
-// 32-ray packets pulled from the queue with one atomicAdd per warp (lane 0) and a shuffle
+constexpr unsigned kPacketRays = 128;  // rays per queue fetch (one same-address atomic each)
+
+// Ray packets pulled from the queue with one atomicAdd per warp (lane 0) and a shuffle
 // broadcast: a warp that drew short rays moves on to the next packet instead of idling behind the
 // slowest warp of a statically partitioned grid.
 template <bool SMALL>
@@ -151,21 +153,24 @@ wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&b.ctl->cursor_extend, 32ull);
+    if (lane == 0) base = atomicAdd(&b.ctl->cursor_extend, (unsigned long long)kPacketRays);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (base >= n) return;
-    const unsigned i = (unsigned)base + lane;
-    if (i < n) {
-      const float4 o = __ldcs(ro + i);
-      const float4 d = __ldcs(rd + i);
-      Hit h;
-      if (SMALL)
-        traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
-      else
-        traverse_variant<false, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
-      __stcs(b.hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
+#pragma unroll 1
+    for (unsigned k = 0; k < kPacketRays; k += 32u) {
+      const unsigned i = (unsigned)base + k + lane;
+      if (i < n) {
+        const float4 o = __ldcs(ro + i);
+        const float4 d = __ldcs(rd + i);
+        Hit h;
+        if (SMALL)
+          traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
+        else
+          traverse_variant<false, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
+        __stcs(b.hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -177,31 +182,34 @@ wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&b.ctl->cursor_shadow, 32ull);
+    if (lane == 0) base = atomicAdd(&b.ctl->cursor_shadow, (unsigned long long)kPacketRays);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (base >= n) return;
-    const unsigned j = (unsigned)base + lane;
-    if (j < n) {
-      const float4 o = __ldcs(b.sh_o + j);
-      const float4 d = __ldcs(b.sh_d + j);
-      Hit h;
-      const bool blocked = SMALL ? traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h)
-                                 : traverse_variant<true, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
-      const unsigned dst = __float_as_uint(d.w);
-      if (dst == kShadowFinal) {
-        const float4 c = __ldcs(b.sh_c + j);
-        const float4 L4 = __ldcs(b.sh_L + j);
-        f3 L = mk(L4.x, L4.y, L4.z);
-        if (!blocked) L = L + mk(c.x, c.y, c.z);
-        accum_add(b.accum, b.ctl, __float_as_uint(c.w), L);
-      } else if (!blocked) {
-        const float4 c = __ldcs(b.sh_c + j);
-        float4 s = b.st2[nxt][dst];
-        s.x += c.x, s.y += c.y, s.z += c.z;
-        b.st2[nxt][dst] = s;
+#pragma unroll 1
+    for (unsigned k = 0; k < kPacketRays; k += 32u) {
+      const unsigned j = (unsigned)base + k + lane;
+      if (j < n) {
+        const float4 o = __ldcs(b.sh_o + j);
+        const float4 d = __ldcs(b.sh_d + j);
+        Hit h;
+        const bool blocked = SMALL ? traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h)
+                                   : traverse_variant<true, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+        const unsigned dst = __float_as_uint(d.w);
+        if (dst == kShadowFinal) {
+          const float4 c = __ldcs(b.sh_c + j);
+          const float4 L4 = __ldcs(b.sh_L + j);
+          f3 L = mk(L4.x, L4.y, L4.z);
+          if (!blocked) L = L + mk(c.x, c.y, c.z);
+          accum_add(b.accum, b.ctl, __float_as_uint(c.w), L);
+        } else if (!blocked) {
+          const float4 c = __ldcs(b.sh_c + j);
+          float4 s = b.st2[nxt][dst];
+          s.x += c.x, s.y += c.y, s.z += c.z;
+          b.st2[nxt][dst] = s;
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
