@@ -192,7 +192,9 @@ def workload_config(args) -> dict:
                         "scene = reference src/main_cornellBox.cpp via tests/golden/cornell_256.tscene)",
             "width": WIDTH, "height": HEIGHT, "spp": args.spp, "max_depth": 6,
             "parallelism": f"spp split over {args.gpus} GPU(s), one fp32 reduce of the {WIDTH * HEIGHT * 3 * 4 / 1e6:.1f} MB accumulation buffer",
-            "l2_policy": "wavefront queues (4 Mi paths x 304 B = 1.3 GB per iteration) exceed the 126 MB L2; no flush needed"}
+            "wavefront": "2 interleaved lanes x 4 Mi paths in flight",
+            "l2_policy": "inputs larger than L2: each wavefront iteration streams 2 x 4 Mi paths x ~300 B of queue records "
+                         "(1.3 GB per lane) through the 126 MB L2; no flush needed"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -369,11 +371,13 @@ def main():
     }
     iters = max(cnt["iterations"], 1)
     ach = alg[dominant] / (stage_ms[dominant] * 1e-3) * 1e-9 if stage_ms[dominant] > 0 else 0.0
-    prof = ROOT / "profiles" / "r01_traffic.json"
+    prof = ROOT / "profiles" / "r01_traffic.json"  # dram bytes per launch from the ncu --set full capture
     traffic = None
     if prof.exists():
         traffic = json.loads(prof.read_text()).get(dominant, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "lanes_note": "stage times are summed over the 2 interleaved wavefront lanes, whose kernels co-run on the "
+                              "same SMs: a kernel's duration includes the slots it yields to the other lane",
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
                 "peak_source": "fallback 6650 GB/s" if peaks.get("fallback") else "MEASURED_PEAKS.json hbm_gbs (measured)",
                 "avg_launch_ms": stage_ms[dominant] / iters, "algorithmic_bytes_per_launch": alg[dominant] / iters,
