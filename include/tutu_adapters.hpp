@@ -7,6 +7,8 @@
 //        integrate(g) = flatten the PPMGenerator (objects in Scene::objList order, the BVHNode tree
 //        the reference itself built, textures, camera, bkgcolor, eta), tutu_scene_upload,
 //        tutu_render_path(SPP) straight into g->cam.FrameBuffer.rgb (PathTracing.hpp:501,513).
+//   CudaBdpt             : IIntegrator          (same interface; reference include/BDPT.hpp:395-674)
+//        integrate(g) = flatten + tutu_scene_upload + tutu_render_bdpt(SPP).
 //   CudaIntersectStrategy : IIntersectStrategy  (reference include/IIntersectStrategy.h:7-17)
 //        UpdateInter = one-ray tutu_trace_closest; the Intersection record is then filled by the
 //        hit object's own intersect() (same arithmetic, so the same t).  Parity tool only: a
@@ -188,6 +190,28 @@ class CudaPathTracing : public IIntegrator {
     static_assert(sizeof(Vector3f) == 3 * sizeof(float), "FrameBuffer.rgb must be packed floats");
     tutu_adapt::check(tutu_render_path(dev_.ctx(), (uint32_t)SPP, seed_, &g_->cam.FrameBuffer.rgb[0].x), dev_.ctx(),
                       "tutu_render_path");
+  }
+  TutuCtx* ctx() const { return dev_.ctx(); }
+
+ private:
+  tutu_adapt::DeviceScene dev_;
+  uint64_t seed_;
+};
+
+// IIntegrator plug-in for `integrator bdpt`: `integrator = new CudaBdpt(g, interStrategy)` where
+// Renderer.hpp:47 says `new BDPT(g, interStrategy)`.  The reference ADDS into a frame buffer that
+// Camera::initialize pre-filled with bkgcolor (Camera.hpp:28, BDPT.hpp:891); tutu_render_bdpt
+// returns bkgcolor + contributions, so the buffer is overwritten with the same value.
+class CudaBdpt : public IIntegrator {
+ public:
+  CudaBdpt(PPMGenerator* g_, IIntersectStrategy* inters, uint64_t seed = 1, int device = 0) : dev_(device), seed_(seed) {
+    this->g = g_;
+    this->interStrategy = inters;  // unused: traversal happens on the device
+  }
+  void integrate(PPMGenerator* g_) override {
+    dev_.upload(g_);
+    tutu_adapt::check(tutu_render_bdpt(dev_.ctx(), (uint32_t)SPP, seed_, &g_->cam.FrameBuffer.rgb[0].x), dev_.ctx(),
+                      "tutu_render_bdpt");
   }
   TutuCtx* ctx() const { return dev_.ctx(); }
 

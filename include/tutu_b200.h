@@ -14,6 +14,8 @@
  *   IIntegrator::integrate, PathTracing  (reference include/IIntegrator.hpp:17-24,
  *                                         PathTracing.hpp:352-475,485-516,136-279)
  *        -> tutu_render_path
+ *   IIntegrator::integrate, BDPT         (reference include/BDPT.hpp:395-674,679-900,70-390)
+ *        -> tutu_render_bdpt
  *   Scene / BVHAccel / PPMGenerator state read by the integrator
  *                                        (reference include/Scene.hpp:16-35, BVH.hpp:15-23,47-123,
  *                                         PPMGenerator.hpp:36-53,317-324, Camera.hpp:81-97)
@@ -162,7 +164,7 @@ typedef struct TutuRenderStats {
   uint64_t paths;        /* camera samples started */
   uint64_t extend_rays;  /* closest-hit rays traced */
   uint64_t shadow_rays;  /* any-hit rays traced */
-  uint64_t shade_calls;  /* shading-vertex evaluations */
+  uint64_t shade_calls;  /* shading-vertex evaluations (BDPT: sub-path vertices stored) */
   uint64_t nan_samples;  /* samples dropped by the NaN filter (PathTracing.hpp:510) */
   uint64_t kernel_launches;
   uint64_t iterations;   /* wavefront iterations */
@@ -219,6 +221,18 @@ int tutu_render_path_accumulate_device(TutuCtx* ctx, uint32_t sample_begin, uint
                                        uint64_t seed, float* d_accum, void* stream);
 int tutu_finalize_device(TutuCtx* ctx, const float* d_accum, float inv_spp, float* d_rgb_out,
                          void* stream);
+/* ---- BDPT::integrate (reference include/BDPT.hpp:395-674 -> sub_render_bdpt :679-900) -------- */
+/* Whole bidirectional render through host memory.  rgb_out = bkgcolor + sum of the weighted
+ * (s,t) strategies / spp, exactly where the reference adds them (cam.FrameBuffer.rgb, pre-filled
+ * with bkgcolor by Camera::initialize, Camera.hpp:28; BDPT.hpp:823,891).  Synchronous. */
+int tutu_render_bdpt(TutuCtx* ctx, uint32_t spp, uint64_t seed, float* rgb_out);
+/* Multi-GPU building blocks, as for the path tracer: accumulate the SUMS of samples
+ * [sample_begin, sample_begin+sample_count) into d_accum (not cleared; bkgcolor not included), then
+ * after the cross-rank reduce tutu_finalize_bdpt_device writes bkgcolor + d_accum * inv_spp. */
+int tutu_render_bdpt_accumulate_device(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count,
+                                       uint64_t seed, float* d_accum, void* stream);
+int tutu_finalize_bdpt_device(TutuCtx* ctx, const float* d_accum, float inv_spp, float* d_rgb_out,
+                              void* stream);
 int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
 /* Knobs: paths in flight per wavefront lane (0 = default 4 Mi), number of interleaved wavefront
  * lanes (0 = default 2; 1 = a single wavefront), per-stage event timing on/off. */

@@ -47,6 +47,7 @@ def lib() -> C.CDLL:
         l.oracle_trace_closest.argtypes = [P, P, C.c_uint64, P, C.c_int]
         l.oracle_trace_any.argtypes = [P, P, C.c_uint64, P, C.c_int]
         l.oracle_render_path.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, P, P, C.c_int]
+        l.oracle_render_bdpt.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, P, P, C.c_int]
         l.oracle_primary_rays.argtypes = [P, P]
         _lib = l
     return _lib
@@ -102,6 +103,15 @@ class OracleScene:
                                  cnt.ctypes.data, threads)
         return (out, cnt) if counters else out
 
+    def render_bdpt(self, spp: int, seed: int = 1, sample_begin: int = 0, total_spp: int | None = None,
+                    threads: int = 0, counters: bool = False):
+        """BDPT::integrate restated (bkgcolor + added contributions, incl. t = 1 splats)."""
+        out = np.empty((self.scene.height, self.scene.width, 3), np.float32)
+        cnt = np.zeros(3, np.uint64)
+        lib().oracle_render_bdpt(self._h, sample_begin, spp, total_spp or spp, seed, out.ctypes.data,
+                                 cnt.ctypes.data, threads)
+        return (out, cnt) if counters else out
+
     def primary_rays(self) -> np.ndarray:
         out = np.empty((self.scene.height * self.scene.width, 8), np.float32)
         lib().oracle_primary_rays(self._h, out.ctypes.data)
@@ -125,6 +135,11 @@ def _run(args: list[str], timeout: float | None = None) -> dict:
 
 def ref_dump_cornell(width: int, height: int, out_path) -> dict:
     return _run(["dump-cornell", str(REF_DIR / "model"), str(width), str(height), str(out_path)])
+
+
+def ref_dump_veach(width: int, height: int, out_path) -> dict:
+    """src/main_veach_bdpt.cpp's scene (2308 triangles) with the reference-built BVH."""
+    return _run(["dump-veach", str(REF_DIR / "model"), str(width), str(height), str(out_path)])
 
 
 def ref_export_bvh(scene, out_path=None):

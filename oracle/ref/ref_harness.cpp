@@ -18,7 +18,8 @@
 //        getIntersection / hasIntersection (BVH.hpp:145-194) per ray.
 //   ref_harness render <scene.tscene> <spp> <out.f32> [mode]
 //        PathTracing::integrate (mode "stock": N_THREAD=20 as shipped) or the reference's own
-//        sub_render_pt row worker on every host core (mode "rows").
+//        sub_render_pt row worker on every host core (mode "rows"); BDPT::integrate (mode "bdpt",
+//        BDPT.hpp:395-674) or sub_render_bdpt on every host core (mode "bdpt-rows").
 #include "ref_common.hpp"
 
 namespace {
@@ -55,6 +56,36 @@ int dump_driver_scene(const char* which, const char* model_dir, int W, int H, co
     cam.viewdir[2] = 1;
     cam.updir[1] = 1;
     cam.hfov_deg = 40;
+  } else if (!strcmp(which, "veach")) {
+    // src/main_veach_bdpt.cpp:24-86 + configs/config_veach_bdpt.txt:1-7.  The driver asks for
+    // "veach_slight.obj" (:49) while the file is veach_sLight.obj: on the author's case-insensitive
+    // file system the spot light loads (img/veach_bdpt_spp512_2.png shows it), so it is loaded here.
+    Material room, Llight, sLight, table, glass, tallLamp;
+    room.mType = LAMBERTIAN;
+    room.diffuse = {0.725f, 0.71f, 0.68f};
+    Llight.diffuse = {0.725f, 0.71f, 0.68f};
+    Llight.emission = {500.0, 500.0, 500.0};
+    Llight.emission = Llight.emission * 0.5;
+    sLight.diffuse = {0.725f, 0.71f, 0.68f};
+    sLight.emission = {6999.999881f, 5450.000167f, 3630.000055f};
+    sLight.emission = sLight.emission * 0.5;
+    table.mType = LAMBERTIAN;
+    table.diffuse = {0.32962962985, 0.257976263762, 0.150291711092};
+    glass.mType = PERFECT_REFRACTIVE;
+    glass.eta = 1.5f;
+    tallLamp.mType = MICROFACET_R;
+    tallLamp.roughness = 0.2775146484375f;
+    tallLamp.metallic = 0.5f;
+    tallLamp.diffuse = {0.32962962985, 0.257976263762, 0.150291711092};
+    specs = {{"veach_bdpt/veach_room.obj", room},         {"veach_bdpt/veach_Llight.obj", Llight},
+             {"veach_bdpt/veach_sLight.obj", sLight},     {"veach_bdpt/veach_table.obj", table},
+             {"veach_bdpt/veach_glass.obj", glass},       {"veach_bdpt/veach_tallLamp.obj", tallLamp},
+             {"veach_bdpt/veach_wallLamp.obj", room}};
+    cam.eye[0] = -0.5f, cam.eye[1] = 0, cam.eye[2] = 7.6f;
+    cam.viewdir[0] = -0.005f, cam.viewdir[2] = -1;
+    cam.updir[1] = 1;
+    cam.hfov_deg = 40;
+    integ = 3;
   } else {
     die(std::string("unknown driver scene ") + which);
   }
@@ -179,8 +210,36 @@ int trace(const char* scene, const char* rays_path, const char* kind, const char
 }
 
 // ---- render ---------------------------------------------------------------------------------
+// BDPT::integrate's ray-generation constants (BDPT.hpp:396-418)
+struct BdptFrame {
+  Vector3f ul, delta_h, delta_v, c_off_h, c_off_v, eyePos;
+};
+BdptFrame bdpt_frame(PPMGenerator* g) {
+  Camera& cam = g->cam;
+  Vector3f u = normalized(crossProduct(cam.fwdDir, cam.upDir));
+  Vector3f v = normalized(crossProduct(u, cam.fwdDir));
+  float d = cam.imagePlaneDist;
+  float width_half = fabs(tan(degree2Radians(cam.hfov / 2.f)) * d);
+  float aspect_ratio = cam.width / (float)cam.height;
+  float height_half = width_half / aspect_ratio;
+  Vector3f n = normalized(g->viewdir);
+  BdptFrame f;
+  f.eyePos = cam.position;
+  f.ul = f.eyePos + d * n - width_half * u + height_half * v;
+  Vector3f ur = f.eyePos + d * n + width_half * u + height_half * v;
+  Vector3f ll = f.eyePos + d * n - width_half * u - height_half * v;
+  f.delta_h = Vector3f(0, 0, 0);
+  f.delta_v = Vector3f(0, 0, 0);
+  if (g->width != 1) f.delta_h = (ur - f.ul) / (g->width - 1);
+  if (g->height != 1) f.delta_v = (ll - f.ul) / (g->height - 1);
+  f.c_off_h = (ur - f.ul) / (float)(g->width * 2);
+  f.c_off_v = (ll - f.ul) / (float)(g->height * 2);
+  return f;
+}
+
 int render(const char* scene, int spp, const char* out_path, const char* mode) {
-  Loaded L = load_scene(scene);
+  const bool bdpt = !strncmp(mode, "bdpt", 4);
+  Loaded L = load_scene(scene, bdpt ? 3 : 0);
   PPMGenerator* g = L.g.get();
   SPP = spp;  // mutable globals, global.hpp:19-20
   SPP_inv = 1.f / SPP;
@@ -192,7 +251,27 @@ int render(const char* scene, int spp, const char* out_path, const char* mode) {
   }
   int threads = 0;
   double sec = 0;
-  if (!strcmp(mode, "stock")) {
+  if (!strcmp(mode, "bdpt-rows")) {
+    // the reference's own row worker sub_render_bdpt (BDPT.hpp:679-900) on every host core
+    threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    BdptFrame f = bdpt_frame(g);
+    Thread_arg_bdpt arg{&f.ul, &f.delta_v, &f.delta_h, &f.c_off_h, &f.c_off_v, &f.eyePos, g,
+                        static_cast<BDPT*>(r->integrator)};
+    std::atomic<int> next{0};
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int w = 0; w < threads; ++w)
+      pool.emplace_back([&, w] {
+        for (;;) {
+          int y = next.fetch_add(1);
+          if (y >= g->height) break;
+          sub_render_bdpt(&arg, w, y, y + 1);
+        }
+      });
+    for (auto& t : pool) t.join();
+    sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  } else if (!strcmp(mode, "stock") || !strcmp(mode, "bdpt")) {
     threads = N_THREAD;
     Quiet q;
     auto t0 = std::chrono::steady_clock::now();
@@ -255,6 +334,8 @@ int main(int argc, char** argv) {
   std::string cmd = argv[1];
   if (cmd == "dump-cornell" && argc == 6)
     return dump_driver_scene("cornell", argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
+  if (cmd == "dump-veach" && argc == 6)
+    return dump_driver_scene("veach", argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
   if (cmd == "export-bvh" && argc == 4) return export_bvh(argv[2], argv[3]);
   if (cmd == "trace" && (argc == 6 || argc == 7))
     return trace(argv[2], argv[3], argv[4], argv[5], argc == 7 ? atoi(argv[6]) : 0);

@@ -1093,6 +1093,8 @@ RayGenK raygen_constants(const TutuCamera& c) {  // Camera.hpp:12-48 + PathTraci
   return k;
 }
 
+#include "tutu_oracle_bdpt.hpp"
+
 }  // namespace
 
 // =============================================================================================
@@ -1272,6 +1274,64 @@ void oracle_render_path(const OracleScene* os, uint32_t sample_begin, uint32_t s
       c2 += tr.shade_calls;
     });
   for (auto& t : pool) t.join();
+  if (counters_out) {
+    counters_out[0] = c0;
+    counters_out[1] = c1;
+    counters_out[2] = c2;
+  }
+}
+
+// BDPT::integrate (BDPT.hpp:395-674 -> sub_render_bdpt :679-900).  The frame buffer starts at
+// bkgcolor (Camera.hpp:28) and contributions are ADDED (:891); t == 1 strategies splat into other
+// pixels (:820-824), collected per thread here and summed in thread order at the end.
+// counters_out: closest-hit calls, any-hit calls, general connections attempted.
+void oracle_render_bdpt(const OracleScene* os, uint32_t sample_begin, uint32_t sample_count, uint32_t total_spp,
+                        uint64_t seed, float* rgb_out, uint64_t* counters_out, int threads) {
+  const Scene& s = os->s;
+  const int W = s.cam.width, H = s.cam.height;
+  RayGenK k = raygen_constants(s.cam);
+  const Cam cam = make_cam(s.cam);
+  const float SPP_inv = 1.f / total_spp;
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  if (threads <= 0) threads = 1;
+  std::atomic<int> next{0};
+  std::atomic<uint64_t> c0{0}, c1{0}, c2{0};
+  std::vector<std::vector<float>> splats(threads, std::vector<float>((size_t)W * H * 3, 0.f));
+  for (size_t i = 0; i < (size_t)W * H; ++i) {
+    rgb_out[3 * i] = s.bkgcolor.x, rgb_out[3 * i + 1] = s.bkgcolor.y, rgb_out[3 * i + 2] = s.bkgcolor.z;
+  }
+  std::vector<std::thread> pool;
+  for (int w = 0; w < threads; ++w)
+    pool.emplace_back([&, w] {
+      Bdpt b{s, cam, Rng{seed, 0, 0}};
+      std::vector<float>& mine = splats[w];
+      for (;;) {
+        int y = next.fetch_add(1);
+        if (y >= H) break;
+        for (int x = 0; x < W; ++x) {
+          V3 pixelPos = k.ul + (float)x * k.delta_h + (float)y * k.delta_v + k.c_off_h + k.c_off_v;  // :700
+          V3 rayDir = normalized(pixelPos - k.eye);
+          V3 estimate;
+          for (uint32_t i = 0; i < sample_count; ++i) {
+            b.rng.pixel = (uint32_t)(y * W + x);
+            b.rng.sample = sample_begin + i;
+            if (!b.sample(k.eye, pixelPos, rayDir, SPP_inv, estimate, [&](int index, const V3& v) {
+                  mine[3 * (size_t)index] += v.x, mine[3 * (size_t)index + 1] += v.y, mine[3 * (size_t)index + 2] += v.z;
+                }))
+              break;
+          }
+          V3 add = estimate * SPP_inv;  // :891
+          float* o = rgb_out + ((size_t)y * W + x) * 3;
+          o[0] += add.x, o[1] += add.y, o[2] += add.z;
+        }
+      }
+      c0 += b.closest_calls;
+      c1 += b.any_calls;
+      c2 += b.connections;
+    });
+  for (auto& t : pool) t.join();
+  for (int w = 0; w < threads; ++w)
+    for (size_t i = 0; i < (size_t)W * H * 3; ++i) rgb_out[i] += splats[w][i];
   if (counters_out) {
     counters_out[0] = c0;
     counters_out[1] = c1;

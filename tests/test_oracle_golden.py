@@ -45,3 +45,25 @@ def test_oracle_render_matches_reference_statistics(api, oracle, golden, cornell
     img256 = osc.render_path(256, seed=5)
     for c in range(3):
         assert abs(img256[..., c].mean() / stats["channel_means"][c] - 1) < 0.01
+
+
+def test_oracle_bdpt_matches_reference_statistics(api, oracle, golden, cornell):
+    """BDPT restatement (oracle/tutu_oracle_bdpt.hpp) vs the reference's BDPT (Cornell 64x64, mean of
+    4096 reference spp): same noise level at 16 spp (+-15 %), unbiased mean at 256 spp (1 %)."""
+    stats = json.loads((golden / "stats.json").read_text())["cornell_64_bdpt"]
+    ref = np.fromfile(golden / "cornell_64_bdpt_ref_mean_4096.f32", np.float32).reshape(64, 64, 3)
+    osc = oracle.OracleScene(cornell.with_size(64, 64))
+    r = np.mean([_rmse(osc.render_bdpt(16, seed=s), ref) for s in (1, 2)])
+    assert abs(r / stats["rmse_16"] - 1) < 0.15, (r, stats["rmse_16"])
+    img = osc.render_bdpt(256, seed=5)
+    for c in range(3):
+        assert abs(img[..., c].mean() / stats["channel_means"][c] - 1) < 0.01
+
+
+def test_oracle_bdpt_sample_ranges_compose(api, oracle, cornell):
+    osc = oracle.OracleScene(cornell.with_size(24, 24))
+    whole = osc.render_bdpt(5, seed=3, threads=1)
+    a = osc.render_bdpt(2, seed=3, sample_begin=0, total_spp=5, threads=1)
+    b = osc.render_bdpt(3, seed=3, sample_begin=2, total_spp=5, threads=1)
+    bkg = np.array(cornell.bkgcolor, np.float32)
+    assert np.allclose(a + b - bkg, whole, rtol=1e-5, atol=1e-6)

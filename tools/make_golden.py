@@ -11,6 +11,8 @@ Fixtures:
   hf24.tscene / hf24_*       24x24 height-field (1152 triangles) + both synthetic ray kinds
   mixed.tscene / mixed_*     spheres + triangles, every material type, 4 texture channels
   *_ref_mean_*.f32, stats.json   (with --renders) high-spp reference renders and noise statistics
+  veach_80x60.tscene, *_bdpt_ref_mean_*.f32   (with --bdpt) src/main_veach_bdpt.cpp's scene and
+                             high-spp means of the reference's BDPT integrator
 """
 import json, sys
 from pathlib import Path
@@ -107,5 +109,31 @@ def main():
         print(json.dumps(stats, indent=1))
 
 
+def bdpt_goldens():
+    """BDPT fixtures (BASELINE.json configs[4]): the Veach-room scene of src/main_veach_bdpt.cpp with
+    the reference-built BVH, and high-spp means of the reference's BDPT for Cornell and Veach."""
+    O.build(ref=True)
+    assert O.ref_available()
+    O.ref_dump_veach(80, 60, G / "veach_80x60.tscene")
+    veach = api.Scene.load(G / "veach_80x60.tscene")
+    cornell = api.Scene.load(G / "cornell_256.tscene").with_size(64, 64)
+    stats = json.loads((G / "stats.json").read_text())
+    def rmse(a, b): return float(np.sqrt(((a - b) ** 2).mean()))
+    for name, sc, spp in (("cornell_64_bdpt", cornell, 2048), ("veach_80x60_bdpt", veach, 1024)):
+        runs = [O.ref_render(sc, spp, mode="bdpt-rows")[0] for _ in range(2)]
+        mean = (runs[0] + runs[1]) * 0.5
+        mean.astype(np.float32).tofile(G / f"{name}_ref_mean_{2 * spp}.f32")
+        low = [O.ref_render(sc, 16, mode="bdpt-rows")[0] for _ in range(4)]
+        stats[name] = {"ref_spp_total": 2 * spp, "image_mean": float(mean.mean()),
+                       "channel_means": [float(x) for x in mean.mean((0, 1))],
+                       f"run_to_run_rmse_{spp}": rmse(runs[0], runs[1]),
+                       "rmse_16": float(np.mean([rmse(i, mean) for i in low]))}
+        print(name, stats[name])
+    (G / "stats.json").write_text(json.dumps(stats, indent=1))
+
+
 if __name__ == "__main__":
-    main()
+    if "--bdpt" in sys.argv:
+        bdpt_goldens()
+    else:
+        main()

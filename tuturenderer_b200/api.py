@@ -86,6 +86,9 @@ ABI = {
     "tutu_render_path": (C.c_int, [_P, C.c_uint32, C.c_uint64, _P]),
     "tutu_render_path_accumulate_device": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P]),
     "tutu_finalize_device": (C.c_int, [_P, _P, C.c_float, _P, _P]),
+    "tutu_render_bdpt": (C.c_int, [_P, C.c_uint32, C.c_uint64, _P]),
+    "tutu_render_bdpt_accumulate_device": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P]),
+    "tutu_finalize_bdpt_device": (C.c_int, [_P, _P, C.c_float, _P, _P]),
     "tutu_render_stats": (C.c_int, [_P, C.POINTER(TutuRenderStats)]),
     "tutu_render_configure": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int]),
     "tutu_bvh_build": (C.c_int, [_P, C.c_uint32, _P, C.POINTER(C.c_uint32)]),
@@ -393,6 +396,25 @@ class Context:
 
     def finalize_device(self, d_accum: int, inv_spp: float, d_out: int, stream: int = 0) -> None:
         self._ck(lib().tutu_finalize_device(self._h, d_accum, inv_spp, d_out, stream or None))
+
+    # ---- bidirectional path tracing (IIntegrator::integrate of the reference's BDPT)
+    def render_bdpt(self, spp: int, seed: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+        i = self.info()
+        if out is None:
+            out = np.empty((i.height, i.width, 3), np.float32)
+        self._ck(lib().tutu_render_bdpt(self._h, spp, seed, _ptr(out)))
+        return out
+
+    def render_bdpt_ptr(self, spp: int, seed: int, out_ptr: int) -> None:
+        self._ck(lib().tutu_render_bdpt(self._h, spp, seed, out_ptr))
+
+    def render_bdpt_accumulate_device(self, sample_begin: int, sample_count: int, seed: int, d_accum: int,
+                                      stream: int = 0) -> None:
+        self._ck(lib().tutu_render_bdpt_accumulate_device(self._h, sample_begin, sample_count, seed, d_accum,
+                                                          stream or None))
+
+    def finalize_bdpt_device(self, d_accum: int, inv_spp: float, d_out: int, stream: int = 0) -> None:
+        self._ck(lib().tutu_finalize_bdpt_device(self._h, d_accum, inv_spp, d_out, stream or None))
 
     def stats(self) -> dict:
         s = TutuRenderStats()

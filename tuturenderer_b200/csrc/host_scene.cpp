@@ -44,6 +44,7 @@ static inline V3 normalized(V3 v) {
   return v;
 }
 static inline V3 ld3(const float* p) { return {p[0], p[1], p[2]}; }
+static inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // Vector.hpp:186
 static inline void st3(float* p, V3 v) {
   p[0] = v.x;
   p[1] = v.y;
@@ -215,6 +216,106 @@ int compute_raygen(const TutuCamera* cam, RayGen* rg) {
 }
 
 // ------------------------------------------------------------------------------------------
+// BDPT camera constants — Camera.hpp:12-48, Vector.hpp:228-372, BDPT.hpp:396-418
+// ------------------------------------------------------------------------------------------
+namespace {
+struct M4 {
+  float e[16];
+  M4() {
+    for (float& v : e) v = 0.f;
+  }
+  float get(int r, int c) const { return e[c + r * 4]; }
+  void set(int r, int c, float v) { e[c + r * 4] = v; }
+  void row(int r, float a, float b, float c, float d) { e[r * 4] = a, e[r * 4 + 1] = b, e[r * 4 + 2] = c, e[r * 4 + 3] = d; }
+};
+M4 mmul(const M4& l, const M4& r) {  // Vector.hpp:337-349 (accumulates from 0, left to right)
+  M4 res;
+  for (int row = 0; row < 4; row++)
+    for (int col = 0; col < 4; col++) {
+      float acc = 0;
+      for (int i = 0; i < 4; i++) acc += l.get(row, i) * r.get(i, col);
+      res.set(row, col, acc);
+    }
+  return res;
+}
+}  // namespace
+
+int compute_bdpt_cam(const TutuCamera* cam, BdptCamConsts* out) {
+  if (cam->width <= 0 || cam->height <= 0) {
+    set_error("camera: width and height must be positive");
+    return TUTU_E_INVALID;
+  }
+  // Camera::initialize
+  V3 position = ld3(cam->eye);
+  V3 fwd = normalized(ld3(cam->viewdir));
+  V3 right = normalized(cross(fwd, ld3(cam->updir)));
+  V3 up = normalized(cross(right, fwd));
+  V3 nfwd = {-fwd.x, -fwd.y, -fwd.z};
+  V3 pos = {dot(right, position), dot(up, position), dot(nfwd, position)};
+  M4 world2Cam;
+  world2Cam.row(0, right.x, right.y, right.z, -pos.x);
+  world2Cam.row(1, up.x, up.y, up.z, -pos.y);
+  world2Cam.row(2, nfwd.x, nfwd.y, nfwd.z, -pos.z);
+  world2Cam.row(3, 0.f, 0.f, 0.f, 1.f);
+  const float aNear = 0.1f, aFar = 10000.f, aspect = (float)cam->width / cam->height;
+  M4 p2o;  // getPerspectiveMatrix, Vector.hpp:352-372
+  p2o.e[0] = aNear, p2o.e[5] = aNear, p2o.e[10] = (aNear + aFar), p2o.e[11] = aNear * aFar, p2o.e[14] = -1.0f;
+  float r = tanf(((float)cam->hfov_deg / 2) * 3.1415926535897f / 180) * aNear;
+  float l = -r;
+  float t = r / aspect;
+  float b = -t;
+  M4 orth_trans, orth_scale;
+  orth_trans.row(0, 1, 0, 0, -(r + l) / 2);
+  orth_trans.row(1, 0, 1, 0, -(t + b) / 2);
+  orth_trans.row(2, 0, 0, 1, -(aNear + aFar) / 2);
+  orth_trans.row(3, 0, 0, 0, 1);
+  orth_scale.row(0, 2 / (r - l), 0, 0, 0);
+  orth_scale.row(1, 0, 2 / -(t - b), 0, 0);
+  orth_scale.row(2, 0, 0, 2 / (aNear - aFar), 0);
+  orth_scale.row(3, 0, 0, 0, 1);
+  M4 perspective = mmul(mmul(orth_scale, orth_trans), p2o);
+  M4 world2ndc = mmul(perspective, world2Cam);
+  M4 translate;  // Mat4f::getTranslate(1,1,0)
+  translate.set(0, 3, 1.f), translate.set(1, 3, 1.f), translate.set(2, 3, 0.f);
+  translate.set(0, 0, 1), translate.set(1, 1, 1), translate.set(2, 2, 1), translate.set(3, 3, 1);
+  M4 scale;  // Mat4f::getScale(w/2, h/2, 0)
+  scale.set(3, 3, 1), scale.set(0, 0, cam->width * 0.5f), scale.set(1, 1, cam->height * 0.5f), scale.set(2, 2, 0);
+  M4 world2Raster = mmul(scale, mmul(translate, world2ndc));
+  memcpy(out->w2r, world2Raster.e, sizeof(out->w2r));
+  float tanHalfHfov = tanf(degree2Radians(cam->hfov_deg * 0.5f));
+  out->imagePlaneDist = cam->width / (2.f * tanHalfHfov);
+  out->filmPlaneAreaInv = 1.f / (cam->width * cam->height);
+  out->lensAreaInv = 1.f;
+  // BDPT::integrate (no parallel-projection override there)
+  V3 u = normalized(cross(fwd, up));
+  V3 v = normalized(cross(u, fwd));
+  float d = out->imagePlaneDist;
+  float width_half = fabsf(tanf(degree2Radians(cam->hfov_deg / 2.f)) * d);
+  float aspect_ratio = cam->width / (float)cam->height;
+  float height_half = width_half / aspect_ratio;
+  V3 n = normalized(ld3(cam->viewdir));
+  V3 base = add(position, mul(d, n));
+  V3 ul = add(sub(base, mul(width_half, u)), mul(height_half, v));
+  V3 ur = add(add(base, mul(width_half, u)), mul(height_half, v));
+  V3 ll = sub(sub(base, mul(width_half, u)), mul(height_half, v));
+  V3 delta_h = {0, 0, 0}, delta_v = {0, 0, 0};
+  if (cam->width != 1) delta_h = divs(sub(ur, ul), (float)(cam->width - 1));
+  if (cam->height != 1) delta_v = divs(sub(ll, ul), (float)(cam->height - 1));
+  V3 c_off_h = divs(sub(ur, ul), (float)(cam->width * 2));
+  V3 c_off_v = divs(sub(ll, ul), (float)(cam->height * 2));
+  st3(out->eye, position);
+  st3(out->fwd, fwd);
+  st3(out->ul, ul);
+  st3(out->dh, delta_h);
+  st3(out->dv, delta_v);
+  st3(out->coh, c_off_h);
+  st3(out->cov, c_off_v);
+  out->width = cam->width;
+  out->height = cam->height;
+  return TUTU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // flatten
 // ------------------------------------------------------------------------------------------
 static inline bool has_emission(const TutuMaterial& m) {  // Material.hpp:54-56
@@ -276,6 +377,8 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
   memcpy(fs->bkgcolor, desc->bkgcolor, sizeof(fs->bkgcolor));
   fs->eta = desc->eta;
   int rc = compute_raygen(&desc->camera, &fs->raygen);
+  if (rc != TUTU_OK) return rc;
+  rc = compute_bdpt_cam(&desc->camera, &fs->bdpt_cam);
   if (rc != TUTU_OK) return rc;
 
   // materials

@@ -93,6 +93,18 @@ __device__ __forceinline__ float draw_slot5(uint64_t seed, uint32_t pixel, uint3
   return u01(b1);
 }
 
+// one Philox block: the four values of counter (pixel, sample, depth, block)
+struct Rand4 {
+  float u[4];
+};
+__device__ __forceinline__ Rand4 draw4(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t depth, uint32_t block) {
+  uint32_t a0 = pixel, a1 = sample, a2 = depth, a3 = block;
+  philox4x32_10(a0, a1, a2, a3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  Rand4 r;
+  r.u[0] = u01(a0), r.u[1] = u01(a1), r.u[2] = u01(a2), r.u[3] = u01(a3);
+  return r;
+}
+
 // ---- global.hpp helpers ----------------------------------------------------------------------
 struct Mat {
   f3 diffuse;
@@ -259,11 +271,8 @@ __device__ __noinline__ f3 BxDF_glass(const Mat m, f3 wi, f3 wo, f3 Ns, float et
   return mk(0.f);
 }
 
-__device__ __forceinline__ f3 BxDF(const Mat& m, f3 wi, f3 wo, f3 Ng, f3 Ns, float eta_scene,
-                                   bool TIR = false) {  // Material.hpp:62-191 (adjoint = false)
-  if (m.type != TUTU_MAT_MICROFACET_T && m.type != TUTU_MAT_PERFECT_REFRACTIVE) {
-    if (dot(wi, Ng) * dot(wi, Ns) <= 0 || dot(wo, Ng) * dot(wo, Ns) <= 0) return mk(0.f);
-  }
+// Material::BxDF after its two-sidedness test and the adjoint swap (Material.hpp:74-191)
+__device__ __forceinline__ f3 BxDF_core(const Mat& m, f3 wi, f3 wo, f3 Ng, f3 Ns, float eta_scene, bool TIR) {
   float correctNormal = fdiv(fabsf(dot(wi, Ns)), fabsf(dot(wi, Ng)));
   switch (m.type) {
     case TUTU_MAT_LAMBERTIAN: {
@@ -283,6 +292,24 @@ __device__ __forceinline__ f3 BxDF(const Mat& m, f3 wi, f3 wo, f3 Ng, f3 Ns, flo
     default:
       return mk(0.f);
   }
+}
+__device__ __forceinline__ bool BxDF_sides_ok(const Mat& m, f3 wi, f3 wo, f3 Ng, f3 Ns) {  // Material.hpp:65-68
+  if (m.type != TUTU_MAT_MICROFACET_T && m.type != TUTU_MAT_PERFECT_REFRACTIVE) {
+    if (dot(wi, Ng) * dot(wi, Ns) <= 0 || dot(wo, Ng) * dot(wo, Ns) <= 0) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ f3 BxDF(const Mat& m, f3 wi, f3 wo, f3 Ng, f3 Ns, float eta_scene,
+                                   bool TIR = false) {  // Material.hpp:62-191 (adjoint = false)
+  if (!BxDF_sides_ok(m, wi, wo, Ng, Ns)) return mk(0.f);
+  return BxDF_core(m, wi, wo, Ng, Ns, eta_scene, TIR);
+}
+// adjoint = true (light sub-paths, BDPT.hpp:375,804,855): the side test sees the caller's wi/wo,
+// everything after it the swapped pair (Material.hpp:70-73)
+__device__ __forceinline__ f3 BxDF_adjoint(const Mat& m, f3 wi, f3 wo, f3 Ng, f3 Ns, float eta_scene,
+                                           bool TIR = false) {
+  if (!BxDF_sides_ok(m, wi, wo, Ng, Ns)) return mk(0.f);
+  return BxDF_core(m, wo, wi, Ng, Ns, eta_scene, TIR);
 }
 
 // GGX half-vector in the local frame, shared by MICROFACET_R/T (Material.hpp:208-221, 232-242)

@@ -13,6 +13,7 @@
 
 #include "tutu_internal.hpp"
 #include "wavefront.cuh"
+#include "bdpt.cuh"
 
 using namespace tutu;
 
@@ -113,6 +114,12 @@ struct TutuCtx {
 
   // ray batches
   DevBuf d_rays, d_hits, d_blocked, d_counts;
+
+  // BDPT
+  DevBuf bdpt_pool, bdpt_ctl;
+  BdptBuffers bdpt{};
+  uint64_t bdpt_capacity = 0;
+  BdptCtl* bdpt_ctl_host = nullptr;  // pinned
 
   // wavefront
   DevBuf d_accum, d_rgb;
@@ -616,6 +623,120 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   cudaEventDestroy(e1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// BDPT host loop (bdpt.cuh)
+// ---------------------------------------------------------------------------------------------
+void bdpt_prepare(TutuCtx* ctx, uint64_t cap) {
+  cap = (cap + 255) & ~(uint64_t)255;
+  {
+    // float4 arrays: 6 vertex arrays x 14 slots, walk queue 2 x 3 x (2 cap), hit (2 cap), shadow 3 x (7 cap)
+    const size_t n_f4 = (size_t)6 * kBdptSlots + 2 * 3 * 2 + 2 + 3 * kBdptMaxLen;
+    const size_t bytes = n_f4 * cap * sizeof(float4) + (size_t)kBdptSlots * cap * sizeof(float) + 2 * cap;
+    ctx->bdpt_pool.ensure(bytes);  // grows only; the arrays are laid out for THIS batch size
+    ctx->bdpt_capacity = cap;
+  }
+  BdptBuffers& b = ctx->bdpt;
+  float4* p = ctx->bdpt_pool.as<float4>();
+  b.vP = p, p += kBdptSlots * cap;
+  b.vNg = p, p += kBdptSlots * cap;
+  b.vNs = p, p += kBdptSlots * cap;
+  b.vT = p, p += kBdptSlots * cap;
+  b.vM = p, p += kBdptSlots * cap;
+  b.vMis = p, p += kBdptSlots * cap;
+  for (int k = 0; k < 2; ++k) {
+    b.q_o[k] = p, p += 2 * cap;
+    b.q_d[k] = p, p += 2 * cap;
+    b.q_tp[k] = p, p += 2 * cap;
+  }
+  b.hit = p, p += 2 * cap;
+  b.sh_o = p, p += kBdptMaxLen * cap;
+  b.sh_d = p, p += kBdptMaxLen * cap;
+  b.sh_c = p, p += kBdptMaxLen * cap;
+  b.vMet = reinterpret_cast<float*>(p);
+  b.nE = reinterpret_cast<unsigned char*>(b.vMet + kBdptSlots * cap);
+  b.nL = b.nE + cap;
+  ctx->bdpt_ctl.ensure(sizeof(BdptCtl));
+  b.ctl = ctx->bdpt_ctl.as<BdptCtl>();
+  b.cap = (unsigned)cap;
+  if (!ctx->bdpt_ctl_host) CUDA_TRY(cudaMallocHost(&ctx->bdpt_ctl_host, sizeof(BdptCtl)));
+}
+
+// Adds the strategy sums of samples [sample_begin, sample_begin+sample_count) of every pixel into
+// d_accum.  Everything is enqueued on `s`; the call returns after the work is done (stats readback).
+void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint64_t seed, float* d_accum,
+                 cudaStream_t s) {
+  const FlatScene& f = ctx->flat;
+  const uint64_t npix = (uint64_t)f.raygen.width * f.raygen.height;
+  const uint64_t total = npix * sample_count;
+  ctx->stats = TutuRenderStats{};
+  if (total == 0) return;
+  const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)1 << 20;
+  bdpt_prepare(ctx, std::min<uint64_t>(cap_cfg, total));
+  BdptBuffers& b = ctx->bdpt;
+  b.accum = d_accum;
+  const bool small = ctx->small.n > 0;
+  const BdptCam& cam = f.bdpt_cam;
+  const int g_start = persistent_grid(ctx, bdpt_start, 256);
+  const int g_vertex = persistent_grid(ctx, bdpt_vertex, 256);
+  const int g_connect = persistent_grid(ctx, bdpt_connect, 256);
+  const int g_extend = small ? persistent_grid(ctx, q_extend<true>, 256) : persistent_grid(ctx, q_extend<false>, 256);
+  const int g_shadow = small ? persistent_grid(ctx, q_shadow_add<true>, 256) : persistent_grid(ctx, q_shadow_add<false>, 256);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  uint64_t launches = 0;
+  try {
+    CUDA_TRY(cudaMemsetAsync(b.ctl, 0, sizeof(BdptCtl), s));
+    CUDA_TRY(cudaEventRecord(e0, s));
+    for (uint64_t first = 0; first < total; first += b.cap) {
+      const unsigned n = (unsigned)std::min<uint64_t>(b.cap, total - first);
+      bdpt_start<<<g_start, 256, 0, s>>>(ctx->dev, cam, b, first, n, sample_begin, seed);
+      bdpt_ctl_begin<<<1, 1, 0, s>>>(b.ctl, 2 * n);
+      launches += 2;
+      int cur = 0;
+      for (int it = 0; it < kBdptMaxLen; ++it) {  // vertices it+1 of both walks
+        if (small)
+          q_extend<true><<<g_extend, 256, 0, s>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+        else
+          q_extend<false><<<g_extend, 256, 0, s>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+        bdpt_vertex<<<g_vertex, 256, 0, s>>>(ctx->dev, cam, b, cur, first, sample_begin, seed);
+        bdpt_ctl_after_walk<<<1, 1, 0, s>>>(b.ctl);
+        launches += 3;
+        cur ^= 1;
+      }
+      for (int len = 1; len <= kBdptMaxLen; ++len) {
+        bdpt_connect<<<g_connect, 256, 0, s>>>(ctx->dev, cam, b, len, first, n);
+        if (small)
+          q_shadow_add<true><<<g_shadow, 256, 0, s>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+        else
+          q_shadow_add<false><<<g_shadow, 256, 0, s>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+        bdpt_ctl_after_shadow<<<1, 1, 0, s>>>(b.ctl);
+        launches += 3;
+      }
+      CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->bdpt_ctl_host, b.ctl, sizeof(BdptCtl), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    TutuRenderStats& st = ctx->stats;
+    st.gpu_ms = ms;
+    st.paths = total;
+    st.extend_rays = ctx->bdpt_ctl_host->sum_extend;
+    st.shadow_rays = ctx->bdpt_ctl_host->sum_shadow;
+    st.shade_calls = 0;
+    st.kernel_launches = launches;
+    st.iterations = (total + b.cap - 1) / b.cap;
+  } catch (...) {
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    throw;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -660,6 +781,7 @@ extern "C" void tutu_ctx_destroy(TutuCtx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->bdpt_ctl_host) cudaFreeHost(ctx->bdpt_ctl_host);
   delete ctx;
 }
 
@@ -747,7 +869,11 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
   RayGen rg;
   int rc = compute_raygen(cam, &rg);
   if (rc != TUTU_OK) return fail(ctx, rc, get_error());
+  BdptCamConsts bc;
+  rc = compute_bdpt_cam(cam, &bc);
+  if (rc != TUTU_OK) return fail(ctx, rc, get_error());
   ctx->flat.raygen = rg;
+  ctx->flat.bdpt_cam = bc;
   ctx->flat.camera = *cam;
   return TUTU_OK;
 }
@@ -883,6 +1009,51 @@ extern "C" int tutu_render_path(TutuCtx* ctx, uint32_t spp, uint64_t seed, float
   CUDA_TRY(cudaMemsetAsync(ctx->d_accum.p, 0, n * sizeof(float), s));
   wf_render(ctx, 0, spp, seed, ctx->d_accum.as<float>(), s);
   wf_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctx->d_accum.as<float>(), 1.f / (float)spp, ctx->d_rgb.as<float>(), n);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(rgb_out, ctx->d_rgb.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_render_bdpt_accumulate_device(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count,
+                                                  uint64_t seed, float* d_accum, void* stream) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (!d_accum) return fail(ctx, TUTU_E_INVALID, "tutu_render_bdpt_accumulate_device: null accumulation buffer");
+  bdpt_render(ctx, sample_begin, sample_count, seed, d_accum, stream ? (cudaStream_t)stream : ctx->stream);
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_finalize_bdpt_device(TutuCtx* ctx, const float* d_accum, float inv_spp, float* d_rgb_out,
+                                         void* stream) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (!d_accum || !d_rgb_out) return fail(ctx, TUTU_E_INVALID, "tutu_finalize_bdpt_device: null buffer");
+  const size_t npix = (size_t)ctx->flat.raygen.width * ctx->flat.raygen.height;
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  const float* bk = ctx->flat.bkgcolor;
+  bdpt_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(d_accum, inv_spp, bk[0], bk[1], bk[2], d_rgb_out, npix);
+  CUDA_TRY(cudaGetLastError());
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_render_bdpt(TutuCtx* ctx, uint32_t spp, uint64_t seed, float* rgb_out) {
+  API_BEGIN(ctx)
+  if (int rc = check_scene(ctx)) return rc;
+  if (!rgb_out || spp == 0) return fail(ctx, TUTU_E_INVALID, "tutu_render_bdpt: null output or spp == 0");
+  const size_t npix = (size_t)ctx->flat.raygen.width * ctx->flat.raygen.height;
+  const size_t n = npix * 3;
+  cudaStream_t s = ctx->stream;
+  ctx->d_accum.ensure(n * sizeof(float));
+  ctx->d_rgb.ensure(n * sizeof(float));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_accum.p, 0, n * sizeof(float), s));
+  bdpt_render(ctx, 0, spp, seed, ctx->d_accum.as<float>(), s);
+  const float* bk = ctx->flat.bkgcolor;
+  bdpt_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctx->d_accum.as<float>(), 1.f / (float)spp, bk[0], bk[1], bk[2],
+                                                  ctx->d_rgb.as<float>(), npix);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(rgb_out, ctx->d_rgb.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));

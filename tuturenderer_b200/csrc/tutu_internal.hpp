@@ -107,6 +107,14 @@ struct RayGen {
   int32_t width, height;
 };
 
+// BDPT camera constants: Camera.hpp:81-97 after initialize() + the pixel grid of BDPT.hpp:396-418
+struct BdptCamConsts {
+  float eye[3], fwd[3], ul[3], dh[3], dv[3], coh[3], cov[3];
+  float w2r[16];  // world2Raster, row major
+  float imagePlaneDist, filmPlaneAreaInv, lensAreaInv;
+  int32_t width, height;
+};
+
 struct FlatScene {
   uint32_t n_prims = 0;
   uint32_t n_ref_nodes = 0;
@@ -126,6 +134,7 @@ struct FlatScene {
   std::vector<TexHeader> tex_headers[4];
   std::vector<float> texels;  // float4 per texel (rgb + pad), all channels pooled
   RayGen raygen{};
+  BdptCamConsts bdpt_cam{};
   TutuCamera camera{};
   float bkgcolor[3] = {0, 0, 0};
   float eta = 1.f;
@@ -139,5 +148,6 @@ extern const char* (*g_ctx_error_hook)(const TutuCtx*);
 // Validates the desc, builds the BVH if none is given, flattens to device layout.
 int flatten_scene(const TutuSceneDesc* desc, FlatScene* out);
 int compute_raygen(const TutuCamera* cam, RayGen* out);
+int compute_bdpt_cam(const TutuCamera* cam, BdptCamConsts* out);
 
 }  // namespace tutu
