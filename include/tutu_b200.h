@@ -199,8 +199,10 @@ int tutu_trace_closest_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays
                               TutuHit* d_hits_out, void* stream);
 int tutu_trace_any_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays,
                           uint8_t* d_blocked_out, void* stream);
-/* Traversal variant: 0 = ordered + t-pruned (default), 1 = unpruned both-children walk that
- * mirrors the reference's recursion literally (used as a second opinion by the tests). */
+/* Traversal variant: 0 = ordered + t-pruned walk, large batches traced in a coherent order
+ * (counting sort by entry cell + direction bin; results are order independent) — the default;
+ * 3 = the same walk in the caller's ray order; 1 = unpruned both-children walk that mirrors the
+ * reference's recursion literally (used as a second opinion by the tests). */
 int tutu_set_traversal_mode(TutuCtx* ctx, int mode);
 /* Visit counters for the algorithmic-bytes figure: traces the batch with counting kernels and
  * returns total inner-node fetches and primitive tests. */

@@ -215,3 +215,26 @@ def test_full_size_properties(api, ctx):
     bary = v[:, 0] * (1 - h[:, 2:3] - h[:, 3:4]) + v[:, 1] * h[:, 2:3] + v[:, 2] * h[:, 3:4]
     assert np.abs(pos - bary).max() < 1e-4
     assert (h[:, 2] > 0).all() and (h[:, 3] > 0).all() and (1 - h[:, 2] - h[:, 3] > 0).all()
+
+
+def test_binned_order_gives_identical_results(api, oracle, ctx):
+    """Batches >= 2^16 rays are traced in a coherent order (counting sort by entry cell + direction
+    bin, tutu_b200.cu: bin_rays).  Results must not depend on the order: mode 0 (binned) == mode 3
+    (caller order) == the CPU oracle, bit for bit, for both synthetic ray kinds."""
+    prims = api.synth_heightfield(48)
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    ctx.upload(sc)
+    osc = oracle.OracleScene(sc)
+    for kind in (0, 1):
+        rays = api.synth_rays(kind, 150000, seed=77)
+        rays[::1000, 4:7] = (0, -1, 0)  # a few irregular (axis-parallel) rays inside the sorted batch
+        ctx.set_traversal_mode(0)
+        a, b = ctx.trace_closest(rays), ctx.trace_any(rays)
+        ctx.set_traversal_mode(3)
+        c, d = ctx.trace_closest(rays), ctx.trace_any(rays)
+        ctx.set_traversal_mode(0)
+        assert_hits_equal(a, c)
+        assert np.array_equal(b, d)
+        sub = slice(0, 150000, 7)
+        assert_hits_equal(np.ascontiguousarray(a[sub]), osc.trace_closest(np.ascontiguousarray(rays[sub])))
+        assert np.array_equal(b[sub], osc.trace_any(np.ascontiguousarray(rays[sub])))

@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(256)
 q_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, const float4* __restrict__ ro,
          const float4* __restrict__ rd, float4* __restrict__ hit, const unsigned* __restrict__ n_ptr,
          unsigned long long* cursor) {
+  extern __shared__ unsigned long long s_stack[];  // !SMALL: traversal stack (trace.cuh: SharedStack)
   const unsigned n = *n_ptr;
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
@@ -190,7 +191,7 @@ q_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene
           if (SMALL)
             traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
           else
-            traverse_variant<false, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
+            traverse_shared<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack);
         }
         __stcs(hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
       }
@@ -219,7 +220,7 @@ q_shadow_add(const __grid_constant__ DevScene sc, const __grid_constant__ SmallS
         const float4 d = __ldcs(sd + j);
         Hit h;
         const bool blocked = SMALL ? traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h)
-                                   : traverse_variant<true, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+                                   : traverse_variant<true, 3>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
         if (!blocked) {
           const float4 c = __ldcs(scn + j);
           float* p = accum + (size_t)__float_as_uint(d.w) * 3;

@@ -190,6 +190,26 @@ __device__ __noinline__ SphereHit sphere_test(const float4* __restrict__ g, cons
   return SphereHit{true, t};
 }
 
+// One 64-byte inner node as two 256-bit loads (LDG.E.256, sm_100+): divergent node fetches are
+// bound by L1 wavefronts (one per lane and instruction), so halving the instruction count halves them.
+#ifndef TUTU_NODE_LOAD_128
+__device__ __forceinline__ void load_node(const float4* __restrict__ n, float4& a, float4& b, float4& c, int4& k) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(n));
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w), "=r"(k.x), "=r"(k.y), "=r"(k.z), "=r"(k.w)
+               : "l"(n + 2));
+}
+#else
+__device__ __forceinline__ void load_node(const float4* __restrict__ n, float4& a, float4& b, float4& c, int4& k) {
+  a = __ldg(n + 0);
+  b = __ldg(n + 1);
+  c = __ldg(n + 2);
+  k = __ldg(reinterpret_cast<const int4*>(n + 3));
+}
+#endif
+
 struct VisitCount {
   unsigned nodes = 0, prims = 0;
 };
@@ -291,10 +311,9 @@ __device__ __forceinline__ bool walk_round(const DevScene& sc, Walk& w, int* sta
   // phase 1: inner nodes until this lane holds a leaf
   while (w.cur >= 0) {
     const float4* n = sc.inner + 4 * (size_t)w.cur;
-    const float4 a = __ldg(n + 0);
-    const float4 b = __ldg(n + 1);
-    const float4 c = __ldg(n + 2);
-    const int4 k = __ldg(reinterpret_cast<const int4*>(n + 3));
+    float4 a, b, c;
+    int4 k;
+    load_node(n, a, b, c, k);
     if (COUNT) vc->nodes++;
     float tl, tr;
     bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
@@ -381,10 +400,9 @@ __device__ __forceinline__ void walk_loop(const DevScene& sc, Walk& w, int* stac
   for (;;) {
     if (w.cur >= 0) {
       const float4* n = sc.inner + 4 * (size_t)w.cur;
-      const float4 a = __ldg(n + 0);
-      const float4 b = __ldg(n + 1);
-      const float4 c = __ldg(n + 2);
-      const int4 k = __ldg(reinterpret_cast<const int4*>(n + 3));
+      float4 a, b, c;
+      int4 k;
+      load_node(n, a, b, c, k);
       float tl, tr;
       bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
       bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
@@ -441,7 +459,234 @@ __device__ __forceinline__ void walk_loop(const DevScene& sc, Walk& w, int* stac
   }
 }
 
+
+// ---- structured walks --------------------------------------------------------------------------
+// ncu source view of walk_loop (profiles/r01_closest_lanes.txt): the node code runs with 16 of 32
+// lanes, but its four exits (`continue` out of nested ifs) reconverge only at the loop head, so
+// the stack pop runs once per exit path with 3-4 lanes, the push with 5, and a leaf test whenever a
+// single lane holds a leaf: 10 lanes per instruction on average.  Below, every iteration is
+// "one node or one leaf, then (for everybody who needs it) one pop", written as structured
+// if/else so the compiler reconverges the warp before the pop.
+template <bool ANY>
+__device__ __forceinline__ bool leaf_step(const DevScene& sc, Walk& w, int leaf_ref) {
+  const uint32_t code = ~(uint32_t)leaf_ref;
+  const uint32_t slot = code & kSlotMask;
+  const float4* g = sc.geom + 3 * (size_t)slot;
+  float t, u = 0.f, v = 0.f;
+  bool hit;
+  if (code & kSphereBit) {
+    const SphereHit sh = sphere_test(g, w.r);
+    hit = sh.hit;
+    t = sh.t;
+  } else {
+    hit = tri_test(g, w.r, t, u, v);
+  }
+  if (hit) {
+    if (ANY) {
+      if (t < w.dis && !(fabsf(__fsub_rn(t, w.dis)) < 0.0001f)) {
+        w.best.t = t;
+        w.best.slot = (int)code;
+        return true;  // blocked: the walk is over
+      }
+    } else if (t < w.best.t || (t == w.best.t && (int)slot < (w.best.slot & (int)kSlotMask))) {
+      w.best.t = t;
+      w.best.u = u;
+      w.best.v = v;
+      w.best.slot = (int)code;
+    }
+  }
+  return false;
+}
+
+// node step: returns true when the lane has to pop
+template <bool ANY, bool REGULAR>
+__device__ __forceinline__ bool node_step(const DevScene& sc, Walk& w, int* stack_ref, float* stack_t) {
+  const float4* n = sc.inner + 4 * (size_t)w.cur;
+  float4 a, b, c;
+  int4 k;
+  load_node(n, a, b, c, k);
+  float tl, tr;
+  bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
+  bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+  const float lim = prune_limit<ANY>(sc, w);
+  hl = hl && !(tl > lim);
+  hr = hr && !(tr > lim);
+  const bool swap = hr && (!hl || tr < tl);  // near child = right
+  const int near = swap ? k.y : k.x, far = swap ? k.x : k.y;
+  if (hl && hr) {
+    stack_ref[w.sp] = far;
+    stack_t[w.sp] = swap ? tl : tr;
+    ++w.sp;
+  }
+  if (hl || hr) {
+    w.cur = near;
+    return false;
+  }
+  return true;
+}
+
+template <bool ANY, bool REGULAR>
+__device__ __forceinline__ void walk_structured(const DevScene& sc, Walk& w, int* stack_ref, float* stack_t) {
+  for (;;) {
+    bool need_pop;
+    if (w.cur >= 0) {
+      need_pop = node_step<ANY, REGULAR>(sc, w, stack_ref, stack_t);
+    } else {
+      if (leaf_step<ANY>(sc, w, w.cur)) return;
+      need_pop = true;
+    }
+    if (need_pop && !walk_pop<ANY, 0>(sc, w, stack_ref, stack_t)) return;
+  }
+}
+
+// Warp-cooperative walk with postponed leaves (after Aila & Laine's speculative while-while): a lane
+// that reaches a leaf parks it and keeps walking; parked leaves are tested by all their lanes
+// together as soon as one lane cannot go on (it reached a second leaf or ran out of nodes).  All
+// 32 lanes call this together; `valid` = the lane carries a ray.
+constexpr int kNoLeaf = 0x7FFFFFFF;
+template <bool ANY>
+__device__ __forceinline__ bool traverse_warp(const DevScene& sc, const Ray& r, float dis, bool valid, Hit& best) {
+  Walk w;
+  int stack_ref[kStackSize];
+  float stack_t[kStackSize];
+  bool done = !valid || !walk_begin(sc, w, r, dis);
+  if (!valid) {
+    w.best.t = FLT_MAX, w.best.u = 0.f, w.best.v = 0.f, w.best.slot = -1;
+    w.regular = true;
+  }
+  int parked = kNoLeaf;
+  bool out_of_nodes = false;  // stack empty, only the parked leaf is left
+  const bool all_regular = __all_sync(0xFFFFFFFFu, done || w.regular);
+  while (__any_sync(0xFFFFFFFFu, !done)) {
+    // a lane is stuck when it holds a parked leaf and either stands on another leaf or has no node left
+    const bool stuck = !done && parked != kNoLeaf && (out_of_nodes || w.cur < 0);
+    if (__any_sync(0xFFFFFFFFu, stuck)) {
+      if (!done && parked != kNoLeaf) {
+        if (leaf_step<ANY>(sc, w, parked)) done = true;
+        parked = kNoLeaf;
+        if (out_of_nodes) done = true;
+      }
+      continue;
+    }
+    if (!done) {
+      bool need_pop;
+      if (w.cur >= 0) {
+        need_pop = all_regular ? node_step<ANY, true>(sc, w, stack_ref, stack_t) : node_step<ANY, false>(sc, w, stack_ref, stack_t);
+      } else {
+        parked = w.cur;  // parked == kNoLeaf here, or the lane would be stuck
+        need_pop = true;
+      }
+      if (need_pop && !walk_pop<ANY, 0>(sc, w, stack_ref, stack_t)) {
+        if (parked != kNoLeaf)
+          out_of_nodes = true;
+        else
+          done = true;
+      }
+    }
+  }
+  best = w.best;
+  return best.slot >= 0;
+}
+
+// ---- traversal stack in shared memory ------------------------------------------------------------
+// ncu (profiles/r01_rays_full.txt): the per-thread local-memory stack costs 0.44e9 of the 2.3e9 L1
+// tag-stage wavefronts of the closest-hit kernel and 41 GB of L2 sectors (3 useful bytes per
+// 32-byte sector: every lane's 4-byte slot sits in its own sector once the lanes' stack depths
+// differ).  In shared memory entry e of thread t lives at word (e * blockDim + t): any mix of
+// depths is bank-conflict free, and {ref, t_enter} travel as one 64-bit word.
+// The any-hit walk never prunes on pop (its limit is the constant `dis`, already applied when the
+// entry was pushed), so its entries are the 32-bit refs alone.
+template <bool ANY>
+struct SharedStack;
+template <>
+struct SharedStack<false> {
+  using Word = unsigned long long;
+  Word* base;  // this thread's column: base[e * stride]
+  unsigned stride;
+  int sp = 0;
+  __device__ __forceinline__ void push(int ref, float t) {
+    base[(unsigned)sp * stride] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)ref;
+    ++sp;
+  }
+  __device__ __forceinline__ void pop(int& ref, float& t) {
+    --sp;
+    const unsigned long long v = base[(unsigned)sp * stride];
+    ref = (int)(unsigned)v;
+    t = __uint_as_float((unsigned)(v >> 32));
+  }
+};
+template <>
+struct SharedStack<true> {
+  using Word = unsigned;
+  Word* base;
+  unsigned stride;
+  int sp = 0;
+  __device__ __forceinline__ void push(int ref, float) {
+    base[(unsigned)sp * stride] = (unsigned)ref;
+    ++sp;
+  }
+  __device__ __forceinline__ void pop(int& ref, float& t) {
+    --sp;
+    ref = (int)base[(unsigned)sp * stride];
+    t = 0.f;
+  }
+};
+
+template <bool ANY, bool REGULAR>
+__device__ __forceinline__ void walk_shared(const DevScene& sc, Walk& w, SharedStack<ANY>& st) {
+  for (;;) {
+    bool need_pop;
+    if (w.cur >= 0) {
+      const float4* n = sc.inner + 4 * (size_t)w.cur;
+      float4 a, b, c;
+      int4 k;
+      load_node(n, a, b, c, k);
+      float tl, tr;
+      bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
+      bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+      const float lim = prune_limit<ANY>(sc, w);
+      hl = hl && !(tl > lim);
+      hr = hr && !(tr > lim);
+      const bool swap = hr && (!hl || tr < tl);
+      if (hl && hr) st.push(swap ? k.x : k.y, swap ? tl : tr);
+      need_pop = !(hl || hr);
+      if (!need_pop) w.cur = swap ? k.y : k.x;
+    } else {
+      if (leaf_step<ANY>(sc, w, w.cur)) return;
+      need_pop = true;
+    }
+    if (need_pop) {
+      for (;;) {
+        if (st.sp == 0) return;
+        float t;
+        st.pop(w.cur, t);
+        if (!ANY && t > prune_limit<ANY>(sc, w)) continue;
+        break;
+      }
+    }
+  }
+}
+
+// whole walk of one ray with the shared-memory stack.  smem: blockDim * (tree depth + 1) words of
+// SharedStack<ANY>::Word (a ray pushes at most one entry per tree level).
+template <bool ANY>
+__device__ __forceinline__ bool traverse_shared(const DevScene& sc, const Ray& r, float dis, Hit& best, void* smem) {
+  Walk w;
+  SharedStack<ANY> st;
+  st.base = reinterpret_cast<typename SharedStack<ANY>::Word*>(smem) + threadIdx.x;
+  st.stride = blockDim.x;
+  if (walk_begin(sc, w, r, dis)) {
+    if (w.regular)
+      walk_shared<ANY, true>(sc, w, st);
+    else
+      walk_shared<ANY, false>(sc, w, st);
+  }
+  best = w.best;
+  return best.slot >= 0;
+}
+
 // VARIANT 0: LOOP + exact slab test; 1: LOOP + FMNMX slab test for regular rays;
+// 3: structured walk (walk_structured) + FMNMX slab test for regular rays;
 // 2: rounds (inner-node phase / leaf phase) + FMNMX for regular rays.
 template <bool ANY, int VARIANT>
 __device__ __forceinline__ bool traverse_variant(const DevScene& sc, const Ray& r, float dis, Hit& best) {
@@ -456,6 +701,11 @@ __device__ __forceinline__ bool traverse_variant(const DevScene& sc, const Ray& 
         walk_loop<ANY, 0, true>(sc, w, stack_ref, stack_t);
       else
         walk_loop<ANY, 0, false>(sc, w, stack_ref, stack_t);
+    } else if (VARIANT == 3) {
+      if (w.regular)
+        walk_structured<ANY, true>(sc, w, stack_ref, stack_t);
+      else
+        walk_structured<ANY, false>(sc, w, stack_ref, stack_t);
     } else {
       if (w.regular) {
         while (walk_round<ANY, 0, false, true>(sc, w, stack_ref, stack_t, nullptr)) {

@@ -114,6 +114,9 @@ struct TutuCtx {
 
   // ray batches
   DevBuf d_rays, d_hits, d_blocked, d_counts;
+  DevBuf d_bin_keys, d_bin_perm, d_bin_hist;
+  int ray_binning = 1;              // 0 = trace in the caller's order
+  uint64_t ray_binning_min = 1u << 16;
 
   // BDPT
   DevBuf bdpt_pool, bdpt_ctl;
@@ -171,11 +174,159 @@ int fail_cuda(TutuCtx* ctx, const CudaError& e) {
 // MODE 1: the literal reference walk (tests only).
 // MODE 2: per-lane ray refill between traversal rounds (trace_persistent; measured slower than
 //         MODE 0 on every workload, kept for the record — DESIGN.md §5).
+// ---- ray binning ----------------------------------------------------------------------------
+// A caller's ray batch arrives in arbitrary order; a warp of 32 unrelated rays walks 32 unrelated
+// root-to-leaf paths (ncu on the 2^24-ray batch: 10 of 32 lanes active per instruction, L1/TEX at
+// 86 % of peak from divergent 64-byte node fetches).  Large batches are therefore traced in a
+// coherent ORDER: rays are counting-sorted by a key made of the Morton code of the cell where the
+// ray enters the scene box and of an octahedral direction bin, and the tracer walks a permutation.
+// Each ray's result is computed exactly as before and written to its own slot, so the output is
+// independent of the order (tests compare sorted vs unsorted bit for bit).
+constexpr int kBinOriginBits = 5;  // per axis
+constexpr int kBinDirBits = 3;     // per octahedral axis
+constexpr int kBinKeyBits = 3 * kBinOriginBits + 2 * kBinDirBits;
+constexpr unsigned kBinCount = 1u << kBinKeyBits;
+
+__device__ __forceinline__ unsigned spread3(unsigned v) {  // 10 bits -> every third bit
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__device__ __forceinline__ unsigned ray_bin_key(const DevScene& sc, const float4 o, const float4 d) {
+  // entry point into the root box (plain fp32: ordering only, never a hit decision)
+  const float ix = 1.f / d.x, iy = 1.f / d.y, iz = 1.f / d.z;
+  const float ax = (sc.root_lo[0] - o.x) * ix, bx = (sc.root_hi[0] - o.x) * ix;
+  const float ay = (sc.root_lo[1] - o.y) * iy, by = (sc.root_hi[1] - o.y) * iy;
+  const float az = (sc.root_lo[2] - o.z) * iz, bz = (sc.root_hi[2] - o.z) * iz;
+  float te = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+  if (!(te < 3.0e38f)) te = 0.f;
+  const float px = o.x + te * d.x, py = o.y + te * d.y, pz = o.z + te * d.z;
+  const float cells = (float)(1 << kBinOriginBits);
+  auto q = [&](float p, float lo, float hi) {
+    const float w = hi - lo;
+    float u = w > 0.f ? (p - lo) / w : 0.f;
+    u = fminf(fmaxf(u, 0.f), 0.999999f);
+    return (unsigned)(u * cells);
+  };
+  const unsigned cell = spread3(q(px, sc.root_lo[0], sc.root_hi[0])) | (spread3(q(py, sc.root_lo[1], sc.root_hi[1])) << 1) |
+                        (spread3(q(pz, sc.root_lo[2], sc.root_hi[2])) << 2);
+  // octahedral direction bin
+  const float l1 = fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
+  float u = l1 > 0.f ? d.x / l1 : 0.f, v = l1 > 0.f ? d.z / l1 : 0.f;
+  if (d.y < 0.f) {
+    const float uu = (1.f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f), vv = (1.f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f);
+    u = uu, v = vv;
+  }
+  const float dcells = (float)(1 << kBinDirBits);
+  const unsigned du = (unsigned)(fminf(fmaxf(u * 0.5f + 0.5f, 0.f), 0.999999f) * dcells);
+  const unsigned dv = (unsigned)(fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 0.999999f) * dcells);
+  const unsigned dirbin = (du << kBinDirBits) | dv;
+  return (dirbin << (3 * kBinOriginBits)) | (cell & ((1u << (3 * kBinOriginBits)) - 1u));
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_count(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned n, unsigned* __restrict__ keys,
+            unsigned* __restrict__ hist) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned k = ray_bin_key(sc, __ldg(rays + 2 * (size_t)i), __ldg(rays + 2 * (size_t)i + 1));
+    keys[i] = k;
+    atomicAdd(hist + k, 1u);
+  }
+}
+
+// exclusive scan of the histogram in three coalesced passes: per-chunk totals, scan of the totals,
+// per-chunk exclusive scan + chunk offset.  A chunk = 2048 bins = 256 threads x 8 bins.
+constexpr unsigned kScanChunk = 2048u;
+constexpr unsigned kScanChunks = kBinCount / kScanChunk;
+static_assert(kScanChunks <= 1024u && kBinCount % kScanChunk == 0u, "scan layout");
+
+__device__ __forceinline__ unsigned block_exclusive_scan_256(unsigned v, unsigned* total) {
+  __shared__ unsigned ws[8];
+  const unsigned t = threadIdx.x, lane = t & 31u;
+  unsigned incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (unsigned)o) incl += y;
+  }
+  if (lane == 31u) ws[t >> 5] = incl;
+  __syncthreads();
+  unsigned before = 0, all = 0;
+  for (unsigned w = 0; w < 8; ++w) {
+    if (w < (t >> 5)) before += ws[w];
+    all += ws[w];
+  }
+  __syncthreads();
+  *total = all;
+  return before + incl - v;
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_scan_totals(const unsigned* __restrict__ hist, unsigned* __restrict__ totals) {
+  const uint4* h = reinterpret_cast<const uint4*>(hist + (size_t)blockIdx.x * kScanChunk) + 2 * threadIdx.x;
+  const uint4 a = h[0], b = h[1];
+  unsigned total;
+  block_exclusive_scan_256(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w, &total);
+  if (threadIdx.x == 0) totals[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+k_bin_scan_chunks(unsigned* __restrict__ totals) {
+  __shared__ unsigned ws[32];
+  const unsigned t = threadIdx.x, lane = t & 31u;
+  const unsigned v = t < kScanChunks ? totals[t] : 0u;
+  unsigned incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (unsigned)o) incl += y;
+  }
+  if (lane == 31u) ws[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    unsigned w = ws[t];
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+      if (t >= (unsigned)o) w += y;
+    }
+    ws[t] = w;
+  }
+  __syncthreads();
+  if (t < kScanChunks) totals[t] = incl - v + ((t >> 5) ? ws[(t >> 5) - 1] : 0u);
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_scan_apply(unsigned* __restrict__ hist, const unsigned* __restrict__ totals) {
+  uint4* h = reinterpret_cast<uint4*>(hist + (size_t)blockIdx.x * kScanChunk) + 2 * threadIdx.x;
+  const uint4 a = h[0], b = h[1];
+  unsigned total;
+  unsigned base = block_exclusive_scan_256(a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w, &total) + totals[blockIdx.x];
+  uint4 oa, ob;
+  oa.x = base, base += a.x;
+  oa.y = base, base += a.y;
+  oa.z = base, base += a.z;
+  oa.w = base, base += a.w;
+  ob.x = base, base += b.x;
+  ob.y = base, base += b.y;
+  ob.z = base, base += b.z;
+  ob.w = base;
+  h[0] = oa, h[1] = ob;
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_scatter(const unsigned* __restrict__ keys, unsigned n, unsigned* __restrict__ offsets, unsigned* __restrict__ perm) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    perm[atomicAdd(offsets + keys[i], 1u)] = i;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_trace_closest(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss,
                 const float4* __restrict__ rays, unsigned long long n, TutuHit* __restrict__ out,
-                unsigned long long* __restrict__ next) {
+                unsigned long long* __restrict__ next, const unsigned* __restrict__ perm = nullptr) {
+  extern __shared__ unsigned long long s_stack[];  // MODE 0: traversal stack (trace.cuh: SharedStack)
   auto store = [&](unsigned long long i, const Hit& h) {
     const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
     reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), h.t, h.u, h.v);
@@ -198,8 +349,9 @@ k_trace_closest(const __grid_constant__ DevScene sc, const __grid_constant__ Sma
     if (lane == 0) base = atomicAdd(next, 32ull);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (base >= n) return;
-    const unsigned long long i = base + lane;
-    if (i < n) {
+    const unsigned long long j = base + lane;
+    if (j < n) {
+      const unsigned long long i = perm ? (unsigned long long)__ldg(perm + j) : j;
       const float4 o = __ldg(rays + 2 * i);
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
@@ -207,7 +359,7 @@ k_trace_closest(const __grid_constant__ DevScene sc, const __grid_constant__ Sma
       if (MODE == 3)
         traverse_small<false>(sc, ss, r, 0.f, h);
       else if (MODE == 0)
-        traverse_variant<false, 1>(sc, r, 0.f, h);
+        traverse_shared<false>(sc, r, 0.f, h, s_stack);
       else
         traverse<false, 1, false>(sc, r, 0.f, h, nullptr);
       store(i, h);
@@ -220,7 +372,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss,
             const float4* __restrict__ rays, unsigned long long n, uint8_t* __restrict__ out,
-            unsigned long long* __restrict__ next) {
+            unsigned long long* __restrict__ next, const unsigned* __restrict__ perm = nullptr) {
   if (MODE == 2) {
     trace_persistent<true>(
         sc, n, next,
@@ -239,8 +391,9 @@ k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallSc
     if (lane == 0) base = atomicAdd(next, 32ull);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (base >= n) return;
-    const unsigned long long i = base + lane;
-    if (i < n) {
+    const unsigned long long j = base + lane;
+    if (j < n) {
+      const unsigned long long i = perm ? (unsigned long long)__ldg(perm + j) : j;
       const float4 o = __ldg(rays + 2 * i);
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
@@ -248,7 +401,7 @@ k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallSc
       if (MODE == 3)
         out[i] = traverse_small<true>(sc, ss, r, d.w, h) ? 1 : 0;
       else if (MODE == 0)
-        out[i] = traverse_variant<true, 1>(sc, r, d.w, h) ? 1 : 0;
+        out[i] = traverse_variant<true, 3>(sc, r, d.w, h) ? 1 : 0;
       else
         out[i] = traverse<true, 1, false>(sc, r, d.w, h, nullptr) ? 1 : 0;
     }
@@ -260,20 +413,54 @@ k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallSc
 template <bool ANY, int VARIANT>
 __global__ void __launch_bounds__(256)
 k_trace_variant(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n, TutuHit* __restrict__ out,
-                uint8_t* __restrict__ out_any, unsigned long long* __restrict__ next) {
+                uint8_t* __restrict__ out_any, unsigned long long* __restrict__ next, const unsigned* __restrict__ perm) {
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(next, 32ull);
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (base >= n) return;
-    const unsigned long long i = base + lane;
-    if (i < n) {
+    const unsigned long long j = base + lane;
+    const bool valid = j < n;
+    const unsigned long long i = valid ? (perm ? (unsigned long long)__ldg(perm + j) : j) : 0ull;
+    if (VARIANT == 5) {
+      extern __shared__ unsigned long long s_stack[];
+      if (valid) {
+        const float4 o = __ldg(rays + 2 * i);
+        const float4 d = __ldg(rays + 2 * i + 1);
+        Hit h;
+        const bool any = traverse_shared<ANY>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, ANY ? d.w : 0.f, h, s_stack);
+        if (ANY) {
+          out_any[i] = any ? 1 : 0;
+        } else {
+          const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
+          reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), h.t, h.u, h.v);
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    if (VARIANT == 4) {
+      float4 o = make_float4(0, 0, 0, 0), d = make_float4(1, 0, 0, 0);
+      if (valid) o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1);
+      Hit h;
+      const bool any = traverse_warp<ANY>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, ANY ? d.w : 0.f, valid, h);
+      if (valid) {
+        if (ANY) {
+          out_any[i] = any ? 1 : 0;
+        } else {
+          const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
+          reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), h.t, h.u, h.v);
+        }
+      }
+      continue;
+    }
+    if (valid) {
       const float4 o = __ldg(rays + 2 * i);
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
       Hit h;
-      const bool any = traverse_variant<ANY, VARIANT>(sc, r, d.w, h);
+      const bool any = traverse_variant<ANY, (VARIANT >= 4 ? 1 : VARIANT)>(sc, r, d.w, h);
       if (ANY) {
         out_any[i] = any ? 1 : 0;
       } else {
@@ -323,6 +510,33 @@ int persistent_grid(TutuCtx* ctx, K kernel, int block, size_t dyn_smem = 0) {
   return ctx->sm_count * per_sm;  // a multiple of the SM count: one resident wave
 }
 
+// shared-memory stack bytes for a block: one 64-bit word per thread and level; a ray pushes at
+// most one entry per tree level, +1 slack
+size_t stack_smem(const TutuCtx* ctx, int block, bool any) {
+  return (size_t)block * (ctx->flat.depth + 1) * (any ? sizeof(unsigned) : sizeof(unsigned long long));
+}
+
+// Builds the coherent traversal order of a batch (nullptr = trace in the caller's order).
+const unsigned* bin_rays(TutuCtx* ctx, const float4* rays, uint64_t n, cudaStream_t s) {
+  if (!ctx->ray_binning || !(ctx->traversal_mode == 0 || ctx->traversal_mode >= 10) || ctx->small.n > 0 || n < ctx->ray_binning_min || n >= (1ull << 32))
+    return nullptr;
+  ctx->d_bin_keys.ensure(n * sizeof(unsigned));
+  ctx->d_bin_perm.ensure(n * sizeof(unsigned));
+  ctx->d_bin_hist.ensure((size_t)(kBinCount + 1024) * sizeof(unsigned));
+  unsigned* keys = ctx->d_bin_keys.as<unsigned>();
+  unsigned* perm = ctx->d_bin_perm.as<unsigned>();
+  unsigned* hist = ctx->d_bin_hist.as<unsigned>();
+  CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)kBinCount * sizeof(unsigned), s));
+  const int grid = ctx->sm_count * 8;
+  k_bin_count<<<grid, 256, 0, s>>>(ctx->dev, rays, (unsigned)n, keys, hist);
+  k_bin_scan_totals<<<kScanChunks, 256, 0, s>>>(hist, hist + kBinCount);
+  k_bin_scan_chunks<<<1, 1024, 0, s>>>(hist + kBinCount);
+  k_bin_scan_apply<<<kScanChunks, 256, 0, s>>>(hist, hist + kBinCount);
+  k_bin_scatter<<<grid, 256, 0, s>>>(keys, (unsigned)n, hist, perm);
+  CUDA_TRY(cudaGetLastError());
+  return perm;
+}
+
 void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_out, cudaStream_t s) {
   if (n == 0) return;
   ctx->d_counts.ensure(64);
@@ -332,11 +546,13 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
   if (ctx->traversal_mode >= 10) {
 #define TUTU_VAR_C(V)                                                                       \
   case V: {                                                                                 \
-    int grid = persistent_grid(ctx, k_trace_variant<false, V>, 256);                        \
-    k_trace_variant<false, V><<<grid, 256, 0, s>>>(ctx->dev, rays, n, d_out, nullptr, next); \
+    const size_t sm = V == 5 ? stack_smem(ctx, 256, false) : 0;                             \
+    int grid = persistent_grid(ctx, k_trace_variant<false, V>, 256, sm);                    \
+    k_trace_variant<false, V><<<grid, 256, sm, s>>>(ctx->dev, rays, n, d_out, nullptr, next, perm); \
   } break;
+    const unsigned* perm = bin_rays(ctx, rays, n, s);
     switch (ctx->traversal_mode - 10) {
-      TUTU_VAR_C(0) TUTU_VAR_C(1) TUTU_VAR_C(2)
+      TUTU_VAR_C(0) TUTU_VAR_C(1) TUTU_VAR_C(2) TUTU_VAR_C(3) TUTU_VAR_C(4) TUTU_VAR_C(5)
     }
 #undef TUTU_VAR_C
   } else if (ctx->traversal_mode == 1) {
@@ -350,8 +566,10 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
       int grid = persistent_grid(ctx, k_trace_closest<3>, 256);
       k_trace_closest<3><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
     } else {
-      int grid = persistent_grid(ctx, k_trace_closest<0>, 256);
-      k_trace_closest<0><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+      const unsigned* perm = bin_rays(ctx, rays, n, s);
+      const size_t sm = stack_smem(ctx, 256, false);
+      int grid = persistent_grid(ctx, k_trace_closest<0>, 256, sm);
+      k_trace_closest<0><<<grid, 256, sm, s>>>(ctx->dev, ctx->small, rays, n, d_out, next, perm);
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -366,11 +584,13 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
   if (ctx->traversal_mode >= 10) {
 #define TUTU_VAR_A(V)                                                                      \
   case V: {                                                                                \
-    int grid = persistent_grid(ctx, k_trace_variant<true, V>, 256);                        \
-    k_trace_variant<true, V><<<grid, 256, 0, s>>>(ctx->dev, rays, n, nullptr, d_out, next); \
+    const size_t sm = V == 5 ? stack_smem(ctx, 256, true) : 0;                             \
+    int grid = persistent_grid(ctx, k_trace_variant<true, V>, 256, sm);                    \
+    k_trace_variant<true, V><<<grid, 256, sm, s>>>(ctx->dev, rays, n, nullptr, d_out, next, perm); \
   } break;
+    const unsigned* perm = bin_rays(ctx, rays, n, s);
     switch (ctx->traversal_mode - 10) {
-      TUTU_VAR_A(0) TUTU_VAR_A(1) TUTU_VAR_A(2)
+      TUTU_VAR_A(0) TUTU_VAR_A(1) TUTU_VAR_A(2) TUTU_VAR_A(3) TUTU_VAR_A(4) TUTU_VAR_A(5)
     }
 #undef TUTU_VAR_A
   } else if (ctx->traversal_mode == 1) {
@@ -384,8 +604,9 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
       int grid = persistent_grid(ctx, k_trace_any<3>, 256);
       k_trace_any<3><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
     } else {
+      const unsigned* perm = bin_rays(ctx, rays, n, s);
       int grid = persistent_grid(ctx, k_trace_any<0>, 256);
-      k_trace_any<0><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+      k_trace_any<0><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next, perm);
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -501,7 +722,8 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
     const int div = n_lanes;
     auto sized = [&](int full) { return ctx->sm_count * std::max(1, full / ctx->sm_count / div); };
     const bool small = ctx->small.n > 0;
-    ctx->grid_extend = sized(small ? persistent_grid(ctx, wf_extend<true>, 256) : persistent_grid(ctx, wf_extend<false>, 256));
+    ctx->grid_extend = sized(small ? persistent_grid(ctx, wf_extend<true>, 256)
+                                   : persistent_grid(ctx, wf_extend<false>, 256, stack_smem(ctx, 256, false)));
     ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, TUTU_SHADE_BLOCK));
     ctx->grid_shadow = sized(small ? persistent_grid(ctx, wf_shadow<true>, 256) : persistent_grid(ctx, wf_shadow<false>, 256));
     ctx->grid_raygen = sized(persistent_grid(ctx, wf_raygen, 256));
@@ -558,7 +780,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         if (small)
           wf_extend<true><<<ctx->grid_extend, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
         else
-          wf_extend<false><<<ctx->grid_extend, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
+          wf_extend<false><<<ctx->grid_extend, 256, stack_smem(ctx, 256, false), ls>>>(ctx->dev, ctx->small, L.b, cur);
         if (it == 0 && k + 1 < n_lanes) {
           // stagger the lanes by one stage so that unlike kernels (traverse / shade) overlap
           CUDA_TRY(cudaEventRecord(L.ev_done, ls));
@@ -679,7 +901,8 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
   const int g_start = persistent_grid(ctx, bdpt_start, 256);
   const int g_vertex = persistent_grid(ctx, bdpt_vertex, 256);
   const int g_connect = persistent_grid(ctx, bdpt_connect, 256);
-  const int g_extend = small ? persistent_grid(ctx, q_extend<true>, 256) : persistent_grid(ctx, q_extend<false>, 256);
+  const size_t sm_stack = stack_smem(ctx, 256, false);
+  const int g_extend = small ? persistent_grid(ctx, q_extend<true>, 256) : persistent_grid(ctx, q_extend<false>, 256, sm_stack);
   const int g_shadow = small ? persistent_grid(ctx, q_shadow_add<true>, 256) : persistent_grid(ctx, q_shadow_add<false>, 256);
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
@@ -698,7 +921,7 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
         if (small)
           q_extend<true><<<g_extend, 256, 0, s>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
         else
-          q_extend<false><<<g_extend, 256, 0, s>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+          q_extend<false><<<g_extend, 256, sm_stack, s>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
         bdpt_vertex<<<g_vertex, 256, 0, s>>>(ctx->dev, cam, b, cur, first, sample_begin, seed);
         bdpt_ctl_after_walk<<<1, 1, 0, s>>>(b.ctl);
         launches += 3;
@@ -879,8 +1102,14 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
 }
 
 extern "C" int tutu_set_traversal_mode(TutuCtx* ctx, int mode) {
-  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || mode == 4 || (mode >= 10 && mode <= 12)))
+  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || mode == 3 || mode == 4 || (mode >= 10 && mode <= 15)))
     return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument");
+  if (mode == 3) {  // production walk, caller's ray order (no binning)
+    ctx->traversal_mode = 0;
+    ctx->ray_binning = 0;
+    return TUTU_OK;
+  }
+  ctx->ray_binning = 1;
   ctx->traversal_mode = mode;
   return TUTU_OK;
 }

@@ -147,6 +147,7 @@ constexpr unsigned kPacketRays = 128;  // rays per queue fetch (one same-address
 template <bool SMALL>
 __global__ void __launch_bounds__(256)
 wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int cur) {
+  extern __shared__ unsigned long long s_stack[];  // !SMALL: traversal stack (trace.cuh: SharedStack)
   const unsigned n = b.ctl->n_cur;
   const float4* __restrict__ ro = b.ray_o[cur];
   const float4* __restrict__ rd = b.ray_d[cur];
@@ -166,7 +167,7 @@ wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
         if (SMALL)
           traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
         else
-          traverse_variant<false, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
+          traverse_shared<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack);
         __stcs(b.hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
       }
       __syncwarp();
@@ -193,7 +194,7 @@ wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
         const float4 d = __ldcs(b.sh_d + j);
         Hit h;
         const bool blocked = SMALL ? traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h)
-                                   : traverse_variant<true, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+                                   : traverse_variant<true, 3>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
         const unsigned dst = __float_as_uint(d.w);
         if (dst == kShadowFinal) {
           const float4 c = __ldcs(b.sh_c + j);
