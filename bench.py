@@ -49,6 +49,9 @@ def parse():
     p.add_argument("--spp", type=int, default=SPP)
     p.add_argument("--no-rays", action="store_true", help="skip the ray-batch microbench")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    p.add_argument("--no-extras", action="store_true", help="skip the BDPT (configs[4]) and glass (configs[3]) blocks")
+    p.add_argument("--bdpt-spp", type=int, default=512)
+    p.add_argument("--glass-spp", type=int, default=512)
     return p.parse_args()
 
 
@@ -264,6 +267,71 @@ def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict)
 
 
 # --------------------------------------------------------------------------------------------
+# BDPT (configs[4]) and the glass / textured scene (configs[3]) — extra blocks of the same line
+# --------------------------------------------------------------------------------------------
+def bdpt_bench(torch, api, do_cpu: bool, spp: int) -> dict:
+    """configs/config_veach_bdpt.txt: the Veach room of src/main_veach_bdpt.cpp, 800x600, BDPT."""
+    sc = api.Scene.load(ROOT / "tests" / "golden" / "veach_80x60.tscene").with_size(800, 600)
+    ctx = api.Context(torch.cuda.current_device())
+    ctx.upload(sc)
+    npix = 800 * 600
+    host_img = torch.empty(npix * 3, dtype=torch.float32, pin_memory=True)
+    for k in range(3):
+        ctx.render_bdpt_ptr(8, SEED + k, host_img.data_ptr())
+    t0 = time.perf_counter()
+    ctx.upload(sc)
+    ctx.render_bdpt_ptr(spp, SEED + 9, host_img.data_ptr())  # host scene in, pinned host image out
+    e2e_s = time.perf_counter() - t0
+    st = ctx.stats()
+    out = {"workload": f"veach room (2308 triangles, glass + GGX lamp + 4 emissive triangles), 800x600 @ {spp} spp, "
+                       "bidirectional path tracing (BASELINE.json configs[4])",
+           "msamples_per_s": npix * spp / st["gpu_ms"] * 1e-3, "gpu_ms": st["gpu_ms"],
+           "e2e_msamples_per_s": npix * spp / e2e_s * 1e-6,
+           "closest_rays_per_sample": st["extend_rays"] / st["paths"], "any_rays_per_sample": st["shadow_rays"] / st["paths"],
+           "kernel_launches": st["kernel_launches"], "image_mean": float(host_img.mean())}
+    ctx.close()
+    if do_cpu:
+        from oracle import oracle_py as O
+        if O.ref_available():
+            _img, info = O.ref_render(sc, 1, mode="bdpt-rows", timeout=900)
+            out["cpu_baseline"] = {"value": info["mpaths_per_s"], "unit": "Msamples/s", "cores": info["threads"],
+                                   "kind": "reference", "sample": f"800x600 @ 1 spp through the reference's sub_render_bdpt "
+                                                                  f"on {info['threads']} host threads ({info['seconds']:.1f} s)"}
+    return out
+
+
+def glass_bench(torch, api, do_cpu: bool, spp: int) -> dict:
+    """configs[3] stand-in (tools/scenes.py: glass_scene): rough-glass object + textured GGX box."""
+    sc = api.Scene.load(ROOT / "tests" / "golden" / "glass_c4.tscene").with_size(WIDTH, HEIGHT)
+    ctx = api.Context(torch.cuda.current_device())
+    ctx.upload(sc)
+    npix = WIDTH * HEIGHT
+    host_img = torch.empty(npix * 3, dtype=torch.float32, pin_memory=True)
+    for k in range(3):
+        ctx.render_path_ptr(8, SEED + k, host_img.data_ptr())
+    t0 = time.perf_counter()
+    ctx.upload(sc)
+    ctx.render_path_ptr(spp, SEED + 9, host_img.data_ptr())
+    e2e_s = time.perf_counter() - t0
+    st = ctx.stats()
+    out = {"workload": f"cornell shell + 1214-triangle MICROFACET_T glass object + textured MICROFACET_R box, "
+                       f"{WIDTH}x{HEIGHT} @ {spp} spp path tracing (BASELINE.json configs[3] stand-in)",
+           "mpaths_per_s": npix * spp / st["gpu_ms"] * 1e-3, "gpu_ms": st["gpu_ms"],
+           "e2e_mpaths_per_s": npix * spp / e2e_s * 1e-6,
+           "closest_rays_per_path": st["extend_rays"] / st["paths"], "any_rays_per_path": st["shadow_rays"] / st["paths"],
+           "nan_samples": st["nan_samples"], "image_mean": float(host_img.nan_to_num().mean())}
+    ctx.close()
+    if do_cpu:
+        from oracle import oracle_py as O
+        if O.ref_available():
+            _img, info = O.ref_render(sc.with_size(512, 512), 4, mode="rows", timeout=900)
+            out["cpu_baseline"] = {"value": info["mpaths_per_s"], "unit": "Mpaths/s", "cores": info["threads"],
+                                   "kind": "reference", "sample": f"512x512 @ 4 spp through the reference's sub_render_pt "
+                                                                  f"on {info['threads']} host threads ({info['seconds']:.1f} s)"}
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # main arm
 # --------------------------------------------------------------------------------------------
 def main():
@@ -374,7 +442,9 @@ def main():
     prof = ROOT / "profiles" / "r01_traffic.json"  # dram bytes per launch from the ncu --set full capture
     traffic = None
     if prof.exists():
-        traffic = json.loads(prof.read_text()).get(dominant, {}).get("dram_bytes_per_launch")
+        for name, rec in json.loads(prof.read_text()).items():
+            if name.split("<")[0] == dominant:  # ncu names carry the template arguments
+                traffic = rec.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "lanes_note": "stage times are summed over the 2 interleaved wavefront lanes, whose kernels co-run on the "
                               "same SMs: a kernel's duration includes the slots it yields to the other lane",
@@ -394,6 +464,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_paths_baseline(16)
+    bdpt = glass = None
+    if world == 1 and not args.no_extras:
+        bdpt = bdpt_bench(torch, api, not args.no_cpu, args.bdpt_spp)
+        glass = glass_bench(torch, api, not args.no_cpu, args.glass_spp)
 
     if rank == 0:
         line = {
@@ -409,6 +483,8 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "rays": rays,
+            "bdpt": bdpt,
+            "glass_c4": glass,
             "mrays_per_s_in_render": {"extend": ext * world / (agg["extend_ms"] * 1e-3) * 1e-6 if agg["extend_ms"] else None,
                                       "shadow": shd * world / (agg["shadow_ms"] * 1e-3) * 1e-6 if agg["shadow_ms"] else None},
             "nan_samples": cnt["nan_samples"],

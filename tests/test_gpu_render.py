@@ -91,6 +91,30 @@ def test_mixed_scene_statistics_against_reference(api, ctx, golden, mixed):
     assert rel.max() < 0.25 and rel.mean() < 0.01
 
 
+def test_glass_scene_statistics_against_reference(api, oracle, ctx, golden):
+    """BASELINE.json configs[3] stand-in (tools/scenes.py: glass_scene): 1214-triangle MICROFACET_T
+    glass object + MICROFACET_R box with all four texture channels inside the Cornell shell, against
+    the mean of 2048 reference spp (tools/make_golden.py --c4)."""
+    stats = json.loads((golden / "stats.json").read_text())["glass_c4_96"]
+    ref = np.fromfile(golden / "glass_c4_96_ref_mean_2048.f32", np.float32).reshape(96, 96, 3)
+    sc = api.Scene.load(golden / "glass_c4.tscene")
+    ctx.upload(sc)
+    img = ctx.render_path(8192, seed=2)
+    assert np.isfinite(img).all()
+    for c in range(3):  # per-channel mean within 0.5 %
+        assert abs(img[..., c].mean() / stats["channel_means"][c] - 1) < 0.005
+    assert _rmse(img, ref) < 2 * stats["run_to_run_rmse_1024"]
+    b = lambda a: a.reshape(12, 8, 12, 8, 3).mean((1, 3))  # 8x8 block means localise a wrong material
+    rel = np.abs(b(img) - b(ref)) / (b(ref) + 0.02)
+    assert rel.max() < 0.15 and rel.mean() < 0.01
+    # same Philox stream as the oracle on a small frame
+    small = sc.with_size(40, 40)
+    ctx.upload(small)
+    g = ctx.render_path(8, seed=11)
+    o = oracle.OracleScene(small).render_path(8, seed=11)
+    assert (np.abs(g - o) > 1e-3 * (1 + np.abs(o))).any(-1).mean() < 0.02
+
+
 def test_sample_ranges_compose(api, ctx, cornell):
     """Samples [0,8) rendered as one call == ranges [0,3) + [3,8) accumulated (multi-GPU split)."""
     import torch

@@ -132,8 +132,28 @@ def bdpt_goldens():
     (G / "stats.json").write_text(json.dumps(stats, indent=1))
 
 
+def c4_goldens():
+    """configs[3] stand-in (tools/scenes.py: glass_scene): reference-built BVH + a high-spp mean of the
+    reference's PathTracing."""
+    from tools.scenes import glass_scene
+    O.build(ref=True)
+    sc = O.ref_export_bvh(glass_scene(96, 96), G / "glass_c4.tscene")
+    stats = json.loads((G / "stats.json").read_text())
+    def rmse(a, b): return float(np.sqrt(((a - b) ** 2).mean()))
+    runs = [O.ref_render(sc, 1024)[0] for _ in range(2)]
+    mean = (runs[0] + runs[1]) * 0.5
+    mean.astype(np.float32).tofile(G / "glass_c4_96_ref_mean_2048.f32")
+    stats["glass_c4_96"] = {"ref_spp_total": 2048, "image_mean": float(np.nanmean(mean)),
+                            "channel_means": [float(x) for x in np.nanmean(mean, (0, 1))],
+                            "run_to_run_rmse_1024": rmse(runs[0], runs[1]), "nan_pixels": int(np.isnan(mean).any(-1).sum())}
+    print(stats["glass_c4_96"])
+    (G / "stats.json").write_text(json.dumps(stats, indent=1))
+
+
 if __name__ == "__main__":
-    if "--bdpt" in sys.argv:
+    if "--c4" in sys.argv:
+        c4_goldens()
+    elif "--bdpt" in sys.argv:
         bdpt_goldens()
     else:
         main()

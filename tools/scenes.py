@@ -147,3 +147,35 @@ def mixed_scene(width=96, height=96) -> api.Scene:
     return api.Scene(prims=prims, materials=mats, eye=(278, 273, -800), viewdir=(0, 0, 1), updir=(0, 1, 0),
                      hfov_deg=40, width=width, height=height, bkgcolor=(0.05, 0.06, 0.08), eta=1.0,
                      textures=_textures())
+
+
+def glass_scene(width=96, height=96, golden_dir=None) -> api.Scene:
+    """BASELINE.json configs[3] stand-in ("glass bunny scene with GGX microfacet transmission +
+    textured materials"; the reference ships neither a bunny nor texture files):
+    the Cornell shell, light and tall box of src/main_cornellBox.cpp, the 1214-triangle smooth-shaded
+    glass object of model/veach_bdpt/veach_glass.obj scaled x300 and moved onto the floor
+    (PPMGenerator::scaleObj / transObj arithmetic: v * s, then v + t in fp32) as MICROFACET_T
+    (eta 1.5, roughness 0.2), and a MICROFACET_R box carrying albedo / normal / roughness / metallic
+    maps.  Geometry comes from the committed fixtures (which the reference's own loader produced)."""
+    from pathlib import Path
+    g = Path(golden_dir) if golden_dir else Path(__file__).resolve().parent.parent / "tests" / "golden"
+    cornell = api.Scene.load(g / "cornell_256.tscene")
+    veach = api.Scene.load(g / "veach_80x60.tscene")
+    M = api.default_material
+    mats = np.concatenate([
+        cornell.materials,                                                        # 0 white 1 light 2 green 3 red
+        M(type=api.MAT_MICROFACET_T, eta=1.5, roughness=0.2),                     # 4 rough glass
+        M(type=api.MAT_MICROFACET_R, diffuse=(0.8, 0.6, 0.2), roughness=0.4, metallic=0.5),  # 5 textured GGX
+    ])
+    shell = cornell.prims[:22].copy()  # floor, ceiling, back wall, light, side walls, tall box
+    glass = veach.prims[veach.prims["material"] == 4].copy()
+    v = glass["v"].reshape(-1, 3, 3)
+    lo, hi = v.min((0, 1)), v.max((0, 1))
+    scale = np.float32(300.0)
+    offset = np.array([185.0, 0.5, 169.0], np.float32) - np.array([(lo[0] + hi[0]) / 2, lo[1], (lo[2] + hi[2]) / 2], np.float32) * scale
+    glass["v"] = (v * scale + offset).astype(np.float32).reshape(-1, 9)
+    glass["material"] = 4
+    tbox = np.concatenate(box((60, 0, 330), (180, 120, 450), 5, tex=(0, 0, 0, 0)))
+    prims = np.concatenate([shell, glass, tbox])
+    return api.Scene(prims=prims, materials=mats, eye=(278, 273, -800), viewdir=(0, 0, 1), updir=(0, 1, 0),
+                     hfov_deg=40, width=width, height=height, bkgcolor=(0, 0, 0), eta=1.0, textures=_textures())
