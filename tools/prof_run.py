@@ -1,5 +1,6 @@
 """Short, fixed workload for ncu (never a bench number): `render` = Cornell 1024x1024 @ 24 spp,
-`rays` = 4 Mi rays of each synthetic kind against the 999 698-triangle height-field."""
+`rays` = 4 Mi rays of each synthetic kind against the 999 698-triangle height-field, `bdpt` = the
+Veach room 800x600 @ 4 spp through tutu_render_bdpt."""
 import sys
 from pathlib import Path
 import numpy as np
@@ -17,6 +18,11 @@ if what == "render":
     ctx.configure(0, False, int(os.environ.get("TUTU_LANES", "0")))
     img = ctx.render_path(24, seed=5)
     print("render mean", float(img.mean()), ctx.stats())
+elif what == "bdpt":
+    sc = api.Scene.load(ROOT / "tests/golden/veach_80x60.tscene").with_size(800, 600)
+    ctx.upload(sc)
+    img = ctx.render_bdpt(4, seed=5)
+    print("bdpt mean", float(img.mean()), ctx.stats())
 else:
     G, N = 707, 1 << 22
     prims = api.synth_heightfield(G)

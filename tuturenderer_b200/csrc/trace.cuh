@@ -733,8 +733,32 @@ __device__ __forceinline__ bool traverse_variant(const DevScene& sc, const Ray& 
 constexpr int kSmallMax = 32;
 struct SmallScene {
   int n;  // 0 = not usable (scene too large or empty)
-  float box[kSmallMax][6];  // leaf boxes in DFS slot order: lo.xyz, hi.xyz
+  int pad;
+  float2 box[kSmallMax][3];  // leaf boxes in DFS slot order, per axis {lo, hi} (a packed-fp32 operand)
 };
+
+// Slab test for regular rays with Blackwell's packed fp32 instructions (FADD2 / FMUL2, sm_100+):
+// both planes of an axis go through one subtract and one multiply.  add.rn.f32x2(p, -o) is the IEEE
+// p - o and mul.rn.f32x2 the IEEE product, so the two t values per axis are bit-identical to
+// box_test_regular's; only the issue-slot count halves (these kernels are issue bound).
+struct RayPre2 {
+  float2 nox, noy, noz;  // (-o, -o)
+  float2 ix, iy, iz;     // (1/d, 1/d)
+};
+__device__ __forceinline__ RayPre2 make_pre2(const RayPre& p) {
+  RayPre2 q;
+  q.nox = make_float2(-p.ox, -p.ox), q.noy = make_float2(-p.oy, -p.oy), q.noz = make_float2(-p.oz, -p.oz);
+  q.ix = make_float2(p.ix, p.ix), q.iy = make_float2(p.iy, p.iy), q.iz = make_float2(p.iz, p.iz);
+  return q;
+}
+__device__ __forceinline__ bool box_test_packed(const RayPre2& q, float2 bx, float2 by, float2 bz, float& t_enter) {
+  const float2 tx = __fmul2_rn(__fadd2_rn(bx, q.nox), q.ix);
+  const float2 ty = __fmul2_rn(__fadd2_rn(by, q.noy), q.iy);
+  const float2 tz = __fmul2_rn(__fadd2_rn(bz, q.noz), q.iz);
+  t_enter = fmaxf(fminf(tx.x, tx.y), fmaxf(fminf(ty.x, ty.y), fminf(tz.x, tz.y)));
+  const float t_exit = fminf(fmaxf(tx.x, tx.y), fminf(fmaxf(ty.x, ty.y), fmaxf(tz.x, tz.y)));
+  return t_enter <= t_exit && t_exit >= 0.f;
+}
 
 template <bool ANY>
 __device__ __forceinline__ bool traverse_small(const DevScene& sc, const SmallScene& ss, const Ray& r,
@@ -746,13 +770,18 @@ __device__ __forceinline__ bool traverse_small(const DevScene& sc, const SmallSc
   best.v = 0.f;
   best.slot = -1;
   unsigned mask = 0u;
+  const RayPre2 q = make_pre2(p);
+  if (ss.n == kSmallMax) {  // uniform; the full bank (Cornell: exactly 32 triangles) needs no per-box count test
 #pragma unroll
-  for (int k = 0; k < kSmallMax; ++k) {
-    if (k < ss.n) {  // uniform
+    for (int k = 0; k < kSmallMax; ++k) {
       float te;
-      if (box_test_regular(p, ss.box[k][0], ss.box[k][1], ss.box[k][2], ss.box[k][3], ss.box[k][4],
-                           ss.box[k][5], te))
-        mask |= 1u << k;
+      if (box_test_packed(q, ss.box[k][0], ss.box[k][1], ss.box[k][2], te)) mask |= 1u << k;
+    }
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < ss.n; ++k) {
+      float te;
+      if (box_test_packed(q, ss.box[k][0], ss.box[k][1], ss.box[k][2], te)) mask |= 1u << k;
     }
   }
   while (mask) {

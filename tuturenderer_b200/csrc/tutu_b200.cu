@@ -1050,8 +1050,7 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   if (!fs.empty && fs.n_prims <= (uint32_t)kSmallMax && !getenv("TUTU_NO_SMALL")) {
     ctx->small.n = (int)fs.n_prims;
     for (uint32_t k = 0; k < fs.n_prims; ++k) {
-      memcpy(ctx->small.box[k] + 0, fs.leaf_box[k].lo, 12);
-      memcpy(ctx->small.box[k] + 3, fs.leaf_box[k].hi, 12);
+      for (int a = 0; a < 3; ++a) ctx->small.box[k][a] = make_float2(fs.leaf_box[k].lo[a], fs.leaf_box[k].hi[a]);
       if (fs.shade[k].flags & SHADE_SPHERE_BIT) d.sphere_mask |= 1u << k;
     }
   }

@@ -46,7 +46,7 @@ struct WfCtl {
 
 struct WfBuffers {
   // path queues, [2] = ping-pong
-  float4* ray_o[2];  // o.xyz, -
+  float4* ray_o[2];  // o.xyz, roulette number of the vertex that spawned the ray (Philox slot 5 of its depth)
   float4* ray_d[2];  // d.xyz, -
   float4* st0[2];    // beta.xyz, bits(pixel)
   float4* st1[2];    // tp.xyz, bits(sample)
@@ -366,16 +366,23 @@ struct ShadeOut {
   // continuation
   f3 o, d, beta, tp, fcos, prev_pos;
   float mat_pdf;
+  float rr_u;
   uint32_t depth_mode;
   // shadow
   f3 so, sd, sc;
   float sdist;
 };
 
+// SPEC bit 0: every material of the scene is LAMBERTIAN; bit 1: no primitive is textured — compile-time
+// removal of unreachable material code.  Measured: the all-Lambertian kernel still
+// needs > 80 registers (216 B of spills at 3 blocks/SM), so it buys no occupancy and only SPEC = 0 is
+// instantiated; the hook is kept for scenes where the general kernel's size matters.
+constexpr int kSpecLambertOnly = 1, kSpecNoTextures = 2;
+template <int SPEC>
 __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, const Ray& ray,
                                              const float4 hit, uint32_t pixel, uint32_t sample,
                                              uint32_t depth, uint32_t mode, uint32_t flags, f3 beta,
-                                             f3 tp, f3& L, const float4 st3, const float4 st4,
+                                             f3 tp, f3& L, const float4 st3, const float4 st4, float rr_u,
                                              ShadeOut& out) {
   out.cont = out.shadow = false;
   out.finished = true;
@@ -387,6 +394,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
     return;
   }
   Surf s = load_surface(sc, ray, hit);
+  const bool kLamb = (SPEC & kSpecLambertOnly) != 0, kNoTex = (SPEC & kSpecNoTextures) != 0;
   const f3 dir = mk(ray.dx, ray.dy, ray.dz);
 
   if (mode == kModeXInter) {
@@ -414,7 +422,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
       // jmp2: Russian roulette on tp, reset while depth <= MIN_DEPTH (:265-273)
       if (!(depth > T_MIN_DEPTH)) tp = mk(1.f);
       const float rr_prob = max3(tp);
-      if (draw_slot5(seed, pixel, sample, depth) > rr_prob) return;
+      if (rr_u > rr_prob) return;  // rr_u = slot 5 of this depth's Philox stream, drawn with the BSDF sample
       const f3 coe = fcos / (mat_pdf * rr_prob);
       if (mat_pdf * rr_prob < T_MIN_DIVISOR) return;
       tp = tp * coe;
@@ -429,7 +437,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
 
   // ---- traceRay body at `depth` with inter = this hit (:152-232) ----
   const f3 wo = -dir;
-  if (s.m.type == TUTU_MAT_PERFECT_REFRACTIVE || s.m.type == TUTU_MAT_MICROFACET_T) {
+  if (!kLamb && (s.m.type == TUTU_MAT_PERFECT_REFRACTIVE || s.m.type == TUTU_MAT_MICROFACET_T)) {
     // calcForRefractive (:80-134): no textures, no NEE, no roulette
     const Rand6 rn = draw6(seed, pixel, sample, depth);
     float eta_i = sc.eta, eta_t = s.m.eta;
@@ -480,12 +488,13 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
     out.tp = mk(1.f);
     out.fcos = mk(0.f);
     out.mat_pdf = 0.f;
+    out.rr_u = 0.f;
     out.prev_pos = s.pos;
     out.depth_mode = (depth + 1) | (kModeFresh << 8);
     return;
   }
 
-  if (s.textured) {
+  if (!kNoTex && s.textured) {
     const TexMod tm = texture_modify(sc, s.slot, s.sphere, s.tu, s.tv, s.Ng,
                                      TexMod{s.m.diffuse, s.Ns, s.m.roughness, s.m.metallic});
     s.m.diffuse = tm.diffuse;
@@ -493,7 +502,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
     s.m.roughness = tm.roughness;
     s.m.metallic = tm.metallic;
   }
-  if (s.m.type == TUTU_MAT_UNLIT) {  // :161
+  if (!kLamb && s.m.type == TUTU_MAT_UNLIT) {  // :161
     L = L + beta * s.m.diffuse;
     return;
   }
@@ -561,6 +570,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
   out.tp = tp;
   out.fcos = f_r * cos_theta;
   out.mat_pdf = mat_pdf;
+  out.rr_u = rn.u[5];
   out.prev_pos = s.pos;
   out.depth_mode = depth | (kModeXInter << 8) | (s.m.type == TUTU_MAT_PERFECT_REFLECTIVE ? kFlagMirror : 0u);
 }
@@ -571,16 +581,15 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
 #ifndef TUTU_SHADE_BLOCK
 #define TUTU_SHADE_BLOCK 256
 #endif
-__global__ void __launch_bounds__(TUTU_SHADE_BLOCK, TUTU_SHADE_MIN_BLOCKS)
-wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
+template <int SPEC>
+__device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffers& b, int cur, uint64_t seed,
+                                              unsigned (*s_cnt)[TUTU_SHADE_BLOCK / 32], unsigned* s_base) {
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
   // ncu (profiles/r01_shade_stalls.txt): with one atomicAdd per WARP on the two queue counters,
   // half of this kernel's stall samples sat on the shuffles waiting for those results — ~2 x 10^5
   // same-address atomics per launch serialise in one L2 slice.  The counts are therefore first
   // combined per BLOCK in shared memory (one global atomic per counter per block-iteration).
-  __shared__ unsigned s_cnt[2][TUTU_SHADE_BLOCK / 32];
-  __shared__ unsigned s_base[2];
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const unsigned i = base + threadIdx.x;
@@ -609,8 +618,8 @@ wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t see
       pixel = __float_as_uint(s0.w);
       L = mk(s2.x, s2.y, s2.z);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
-      shade_vertex(sc, seed, r, hit, pixel, __float_as_uint(s1.w), depth, mode, dm, mk(s0.x, s0.y, s0.z),
-                   mk(s1.x, s1.y, s1.z), L, s3, s4, out);
+      shade_vertex<SPEC>(sc, seed, r, hit, pixel, __float_as_uint(s1.w), depth, mode, dm, mk(s0.x, s0.y, s0.z),
+                   mk(s1.x, s1.y, s1.z), L, s3, s4, o.w, out);
     }
     // queue appends: warp ballots -> block prefix in shared memory -> one atomicAdd per counter
     const unsigned cmask = __ballot_sync(0xFFFFFFFFu, out.cont);
@@ -636,7 +645,7 @@ wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t see
     const unsigned si = s_base[1] + s_cnt[1][warp] + (unsigned)__popc(smask & lt);
     __syncthreads();  // s_cnt / s_base are rewritten by the next iteration
     if (out.cont) {
-      __stcs(b.ray_o[nxt] + ci, make_float4(out.o.x, out.o.y, out.o.z, 0.f));
+      __stcs(b.ray_o[nxt] + ci, make_float4(out.o.x, out.o.y, out.o.z, out.rr_u));
       __stcs(b.ray_d[nxt] + ci, make_float4(out.d.x, out.d.y, out.d.z, 0.f));
       __stcs(b.st0[nxt] + ci, make_float4(out.beta.x, out.beta.y, out.beta.z, __uint_as_float(pixel)));
       __stcs(b.st1[nxt] + ci, make_float4(out.tp.x, out.tp.y, out.tp.z, s1.w));
@@ -658,6 +667,12 @@ wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t see
   }
 }
 
+__global__ void __launch_bounds__(TUTU_SHADE_BLOCK, TUTU_SHADE_MIN_BLOCKS)
+wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
+  __shared__ unsigned s_cnt[2][TUTU_SHADE_BLOCK / 32];
+  __shared__ unsigned s_base[2];
+  wf_shade_body<0>(sc, b, cur, seed, s_cnt, s_base);
+}
 // ---- finalize: color = estimate * SPP_inv (PathTracing.hpp:513) -------------------------------
 __global__ void wf_finalize(const float* __restrict__ accum, float inv_spp, float* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
