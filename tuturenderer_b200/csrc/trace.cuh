@@ -685,6 +685,184 @@ __device__ __forceinline__ bool traverse_shared(const DevScene& sc, const Ray& r
   return best.slot >= 0;
 }
 
+// ---- persistent lanes with refill ----------------------------------------------------------------
+// ncu on incoherent queues (profiles/r01_bdpt_full.txt: 6.5 of 32 lanes active per instruction in
+// q_extend on the Veach room): a warp that walks a packet of 32 rays to completion idles behind its
+// longest ray.  Here a warp owns a chunk of the queue (one global atomic per kRefillChunk rays) and
+// hands idle lanes the next rays of the chunk whenever at least `refill_min` lanes are idle; between
+// two such checks every lane runs kStepsPerCheck single steps (one node or one leaf, then a pop).
+//   src(i, ray, dis) loads ray i;  sink(i, walk) stores its result (w.best).
+constexpr unsigned kRefillChunk = 256;
+constexpr int kStepsPerCheck = 8;
+
+// one step of walk_shared's loop; true = the walk is over
+template <bool ANY, bool REGULAR>
+__device__ __forceinline__ bool walk_step_shared(const DevScene& sc, Walk& w, SharedStack<ANY>& st) {
+  bool need_pop;
+  if (w.cur >= 0) {
+    const float4* n = sc.inner + 4 * (size_t)w.cur;
+    float4 a, b, c;
+    int4 k;
+    load_node(n, a, b, c, k);
+    float tl, tr;
+    bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
+    bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+    const float lim = prune_limit<ANY>(sc, w);
+    hl = hl && !(tl > lim);
+    hr = hr && !(tr > lim);
+    const bool swap = hr && (!hl || tr < tl);
+    if (hl && hr) st.push(swap ? k.x : k.y, swap ? tl : tr);
+    need_pop = !(hl || hr);
+    if (!need_pop) w.cur = swap ? k.y : k.x;
+  } else {
+    if (leaf_step<ANY>(sc, w, w.cur)) return true;
+    need_pop = true;
+  }
+  if (need_pop) {
+    for (;;) {
+      if (st.sp == 0) return true;
+      float t;
+      st.pop(w.cur, t);
+      if (!ANY && t > prune_limit<ANY>(sc, w)) continue;
+      break;
+    }
+  }
+  return false;
+}
+
+template <bool ANY, class Src, class Sink>
+__device__ __forceinline__ void trace_refill(const DevScene& sc, unsigned long long n, unsigned long long* cursor,
+                                             void* smem, Src src, Sink sink) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  Walk w;
+  SharedStack<ANY> st;
+  st.base = reinterpret_cast<typename SharedStack<ANY>::Word*>(smem) + threadIdx.x;
+  st.stride = blockDim.x;
+  bool active = false;
+  unsigned long long my = 0;
+  unsigned long long chunk_next = 0, chunk_end = 0;  // warp-uniform
+  bool exhausted = false;                            // warp-uniform
+  const int refill_min = sc.refill_min;
+  for (;;) {
+    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (!exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= refill_min)) {
+      if (chunk_next == chunk_end) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kRefillChunk);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        chunk_next = base < n ? base : n;
+        chunk_end = base + kRefillChunk < n ? base + kRefillChunk : n;
+        if (chunk_next >= n) exhausted = true;
+      }
+      const unsigned long long left = chunk_end - chunk_next;
+      const unsigned avail = left < 32ull ? (unsigned)left : 32u;
+      const unsigned rank = __popc(idle & lt_mask);
+      if (!active && rank < avail) {
+        my = chunk_next + rank;
+        Ray r;
+        float dis;
+        src(my, r, dis);
+        st.sp = 0;
+        if (walk_begin(sc, w, r, dis))
+          active = true;
+        else
+          sink(my, w);  // missed the scene box: w.best is the miss record
+      }
+      const unsigned want = (unsigned)__popc(idle);
+      chunk_next += want < avail ? want : avail;
+    }
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+#pragma unroll 1
+    for (int k = 0; k < kStepsPerCheck; ++k) {
+      if (active) {
+        const bool over = w.regular ? walk_step_shared<ANY, true>(sc, w, st) : walk_step_shared<ANY, false>(sc, w, st);
+        if (over) {
+          sink(my, w);
+          active = false;
+        }
+      }
+    }
+  }
+}
+
+// node part of a step with the shared-memory stack: true = the lane has to pop
+template <bool ANY, bool REGULAR>
+__device__ __forceinline__ bool node_step_shared(const DevScene& sc, Walk& w, SharedStack<ANY>& st) {
+  const float4* n = sc.inner + 4 * (size_t)w.cur;
+  float4 a, b, c;
+  int4 k;
+  load_node(n, a, b, c, k);
+  float tl, tr;
+  bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
+  bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+  const float lim = prune_limit<ANY>(sc, w);
+  hl = hl && !(tl > lim);
+  hr = hr && !(tr > lim);
+  const bool swap = hr && (!hl || tr < tl);
+  if (hl && hr) st.push(swap ? k.x : k.y, swap ? tl : tr);
+  if (hl || hr) {
+    w.cur = swap ? k.y : k.x;
+    return false;
+  }
+  return true;
+}
+
+// ---- warp walk with batched leaf tests ---------------------------------------------------------
+// ncu source view (profiles/r01_bdpt_lanes.txt, Veach room): the 85-instruction primitive test runs
+// with 2 of 32 lanes — in any one iteration few lanes stand on a leaf — and costs 36 % of the
+// issue slots; the node code runs with 12.  Here the lanes of a warp walk together: a lane that
+// reaches a leaf WAITS (it would idle through the others' node steps anyway) until at least
+// kLeafBatch lanes wait or nobody is left on an inner node; then all waiting lanes test their
+// primitives at once.  Waiting loses no pruning information, so no extra nodes are visited.
+// All 32 lanes call this together; `valid` = the lane carries a ray.
+constexpr int kLeafBatch = 8;
+template <bool ANY>
+__device__ __forceinline__ bool traverse_batched(const DevScene& sc, const Ray& r, float dis, bool valid, Hit& best,
+                                                 void* smem) {
+  Walk w;
+  SharedStack<ANY> st;
+  st.base = reinterpret_cast<typename SharedStack<ANY>::Word*>(smem) + threadIdx.x;
+  st.stride = blockDim.x;
+  w.best.t = FLT_MAX, w.best.u = 0.f, w.best.v = 0.f, w.best.slot = -1;
+  w.regular = true;
+  w.cur = 0;
+  bool done = !valid || !walk_begin(sc, w, r, dis);
+  const bool all_regular = __all_sync(0xFFFFFFFFu, done || w.regular);
+  for (;;) {
+    const unsigned at_node = __ballot_sync(0xFFFFFFFFu, !done && w.cur >= 0);
+    const unsigned at_leaf = __ballot_sync(0xFFFFFFFFu, !done && w.cur < 0);
+    if ((at_node | at_leaf) == 0u) break;
+    const int n_leaf = __popc(at_leaf), n_node = __popc(at_node);
+    bool need_pop = false;
+    if (n_leaf >= kLeafBatch || n_leaf >= n_node) {  // enough lanes wait (or nobody walks): test the leaves
+      if (!done && w.cur < 0) {
+        if (leaf_step<ANY>(sc, w, w.cur)) done = true;
+        need_pop = !done;
+      }
+    } else if (!done && w.cur >= 0) {
+      need_pop = all_regular ? node_step_shared<ANY, true>(sc, w, st) : node_step_shared<ANY, false>(sc, w, st);
+    }
+    if (need_pop) {
+      for (;;) {
+        if (st.sp == 0) {
+          done = true;
+          break;
+        }
+        float t;
+        st.pop(w.cur, t);
+        if (!ANY && t > prune_limit<ANY>(sc, w)) continue;
+        break;
+      }
+    }
+  }
+  best = w.best;
+  return best.slot >= 0;
+}
+
 // VARIANT 0: LOOP + exact slab test; 1: LOOP + FMNMX slab test for regular rays;
 // 3: structured walk (walk_structured) + FMNMX slab test for regular rays;
 // 2: rounds (inner-node phase / leaf phase) + FMNMX for regular rays.

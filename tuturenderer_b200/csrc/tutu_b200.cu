@@ -414,6 +414,28 @@ template <bool ANY, int VARIANT>
 __global__ void __launch_bounds__(256)
 k_trace_variant(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n, TutuHit* __restrict__ out,
                 uint8_t* __restrict__ out_any, unsigned long long* __restrict__ next, const unsigned* __restrict__ perm) {
+  if (VARIANT == 6) {  // persistent lanes with refill, shared-memory stack
+    extern __shared__ unsigned long long s_stack[];
+    trace_refill<ANY>(
+        sc, n, next, s_stack,
+        [&](unsigned long long j, Ray& r, float& dis) {
+          const unsigned long long i = perm ? (unsigned long long)__ldg(perm + j) : j;
+          const float4 o = __ldg(rays + 2 * i);
+          const float4 d = __ldg(rays + 2 * i + 1);
+          r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+          dis = ANY ? d.w : 0.f;
+        },
+        [&](unsigned long long j, const Walk& w) {
+          const unsigned long long i = perm ? (unsigned long long)__ldg(perm + j) : j;
+          if (ANY) {
+            out_any[i] = w.best.slot >= 0 ? 1 : 0;
+          } else {
+            const int prim = w.best.slot >= 0 ? __ldg(sc.slot_to_prim + (w.best.slot & (int)kSlotMask)) : -1;
+            reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), w.best.t, w.best.u, w.best.v);
+          }
+        });
+    return;
+  }
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     unsigned long long base = 0;
@@ -423,6 +445,22 @@ k_trace_variant(const __grid_constant__ DevScene sc, const float4* __restrict__ 
     const unsigned long long j = base + lane;
     const bool valid = j < n;
     const unsigned long long i = valid ? (perm ? (unsigned long long)__ldg(perm + j) : j) : 0ull;
+    if (VARIANT == 7) {  // warp walk with batched leaf tests
+      extern __shared__ unsigned long long s_stack[];
+      float4 o = make_float4(0, 0, 0, 0), d = make_float4(1, 0, 0, 0);
+      if (valid) o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1);
+      Hit h;
+      const bool any = traverse_batched<ANY>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, ANY ? d.w : 0.f, valid, h, s_stack);
+      if (valid) {
+        if (ANY) {
+          out_any[i] = any ? 1 : 0;
+        } else {
+          const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
+          reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), h.t, h.u, h.v);
+        }
+      }
+      continue;
+    }
     if (VARIANT == 5) {
       extern __shared__ unsigned long long s_stack[];
       if (valid) {
@@ -460,7 +498,7 @@ k_trace_variant(const __grid_constant__ DevScene sc, const float4* __restrict__ 
       const float4 d = __ldg(rays + 2 * i + 1);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
       Hit h;
-      const bool any = traverse_variant<ANY, (VARIANT >= 4 ? 1 : VARIANT)>(sc, r, d.w, h);
+      const bool any = traverse_variant<ANY, (VARIANT >= 4 ? 1 : VARIANT)>(sc, r, d.w, h);  // (4..7 return above)
       if (ANY) {
         out_any[i] = any ? 1 : 0;
       } else {
@@ -546,13 +584,13 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
   if (ctx->traversal_mode >= 10) {
 #define TUTU_VAR_C(V)                                                                       \
   case V: {                                                                                 \
-    const size_t sm = V == 5 ? stack_smem(ctx, 256, false) : 0;                             \
+    const size_t sm = V >= 5 ? stack_smem(ctx, 256, false) : 0;                             \
     int grid = persistent_grid(ctx, k_trace_variant<false, V>, 256, sm);                    \
     k_trace_variant<false, V><<<grid, 256, sm, s>>>(ctx->dev, rays, n, d_out, nullptr, next, perm); \
   } break;
     const unsigned* perm = bin_rays(ctx, rays, n, s);
     switch (ctx->traversal_mode - 10) {
-      TUTU_VAR_C(0) TUTU_VAR_C(1) TUTU_VAR_C(2) TUTU_VAR_C(3) TUTU_VAR_C(4) TUTU_VAR_C(5)
+      TUTU_VAR_C(0) TUTU_VAR_C(1) TUTU_VAR_C(2) TUTU_VAR_C(3) TUTU_VAR_C(4) TUTU_VAR_C(5) TUTU_VAR_C(6) TUTU_VAR_C(7)
     }
 #undef TUTU_VAR_C
   } else if (ctx->traversal_mode == 1) {
@@ -584,13 +622,13 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
   if (ctx->traversal_mode >= 10) {
 #define TUTU_VAR_A(V)                                                                      \
   case V: {                                                                                \
-    const size_t sm = V == 5 ? stack_smem(ctx, 256, true) : 0;                             \
+    const size_t sm = V >= 5 ? stack_smem(ctx, 256, true) : 0;                             \
     int grid = persistent_grid(ctx, k_trace_variant<true, V>, 256, sm);                    \
     k_trace_variant<true, V><<<grid, 256, sm, s>>>(ctx->dev, rays, n, nullptr, d_out, next, perm); \
   } break;
     const unsigned* perm = bin_rays(ctx, rays, n, s);
     switch (ctx->traversal_mode - 10) {
-      TUTU_VAR_A(0) TUTU_VAR_A(1) TUTU_VAR_A(2) TUTU_VAR_A(3) TUTU_VAR_A(4) TUTU_VAR_A(5)
+      TUTU_VAR_A(0) TUTU_VAR_A(1) TUTU_VAR_A(2) TUTU_VAR_A(3) TUTU_VAR_A(4) TUTU_VAR_A(5) TUTU_VAR_A(6) TUTU_VAR_A(7)
     }
 #undef TUTU_VAR_A
   } else if (ctx->traversal_mode == 1) {
@@ -1054,7 +1092,7 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
       if (fs.shade[k].flags & SHADE_SPHERE_BIT) d.sphere_mask |= 1u << k;
     }
   }
-  d.refill_min = 4;
+  d.refill_min = 8;
   if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_ABS")) d.prune_abs = (float)atof(e);
@@ -1101,7 +1139,7 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
 }
 
 extern "C" int tutu_set_traversal_mode(TutuCtx* ctx, int mode) {
-  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || mode == 3 || mode == 4 || (mode >= 10 && mode <= 15)))
+  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || mode == 3 || mode == 4 || (mode >= 10 && mode <= 17)))
     return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument");
   if (mode == 3) {  // production walk, caller's ray order (no binning)
     ctx->traversal_mode = 0;

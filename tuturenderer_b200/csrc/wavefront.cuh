@@ -15,6 +15,7 @@
 // appended through warp-aggregated atomics (one atomicAdd per warp).  Free slots are refilled by
 // raygen every iteration, so the wavefront stays full until the last samples.
 #pragma once
+#include <cstddef>
 #include "shade.cuh"
 
 namespace tutu {
@@ -31,9 +32,10 @@ struct RayGenK {
 
 struct WfCtl {
   unsigned n_cur;
+  unsigned done;
+  // n_next (low word) and n_shadow (high word) are bumped by ONE 64-bit atomicAdd per block of wf_shade
   unsigned n_next;
   unsigned n_shadow;
-  unsigned done;
   unsigned long long next_path;
   unsigned long long total_paths;
   unsigned long long sum_extend;
@@ -43,6 +45,8 @@ struct WfCtl {
   unsigned long long cursor_extend;  // ray-queue cursors of the persistent tracers
   unsigned long long cursor_shadow;
 };
+static_assert(offsetof(WfCtl, n_next) % 8 == 0 && offsetof(WfCtl, n_shadow) == offsetof(WfCtl, n_next) + 4,
+              "n_next/n_shadow must form one aligned 64-bit word");
 
 struct WfBuffers {
   // path queues, [2] = ping-pong
@@ -575,11 +579,14 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
   out.depth_mode = depth | (kModeXInter << 8) | (s.m.type == TUTU_MAT_PERFECT_REFLECTIVE ? kFlagMirror : 0u);
 }
 
+// 64-thread blocks, 8 per SM (128 registers): the block waits at two barriers for one global atomic
+// per iteration, so small blocks keep more independent groups in flight per SM.  Measured on
+// Cornell 1024^2 (Mpaths/s): 256x2 1575, 128x4 1609, 64x8 1632.
 #ifndef TUTU_SHADE_MIN_BLOCKS
-#define TUTU_SHADE_MIN_BLOCKS 2
+#define TUTU_SHADE_MIN_BLOCKS 8
 #endif
 #ifndef TUTU_SHADE_BLOCK
-#define TUTU_SHADE_BLOCK 256
+#define TUTU_SHADE_BLOCK 64
 #endif
 template <int SPEC>
 __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffers& b, int cur, uint64_t seed,
@@ -629,15 +636,19 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
       s_cnt[1][warp] = (unsigned)__popc(smask);
     }
     __syncthreads();
-    if (threadIdx.x < 2) {
-      unsigned total = 0;
+    if (threadIdx.x == 0) {
+      unsigned tc = 0, ts = 0;
 #pragma unroll
       for (int w = 0; w < TUTU_SHADE_BLOCK / 32; ++w) {
-        const unsigned c = s_cnt[threadIdx.x][w];
-        s_cnt[threadIdx.x][w] = total;  // exclusive prefix
-        total += c;
+        const unsigned c = s_cnt[0][w], d = s_cnt[1][w];
+        s_cnt[0][w] = tc, s_cnt[1][w] = ts;  // exclusive prefixes
+        tc += c, ts += d;
       }
-      s_base[threadIdx.x] = total ? atomicAdd(threadIdx.x == 0 ? &b.ctl->n_next : &b.ctl->n_shadow, total) : 0u;
+      unsigned long long base2 = 0ull;
+      if (tc | ts)  // both queue counters in one atomic: {n_shadow : n_next}
+        base2 = atomicAdd(reinterpret_cast<unsigned long long*>(&b.ctl->n_next), ((unsigned long long)ts << 32) | tc);
+      s_base[0] = (unsigned)base2;
+      s_base[1] = (unsigned)(base2 >> 32);
     }
     __syncthreads();
     const unsigned lt = (1u << lane) - 1u;
