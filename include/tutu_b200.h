@@ -240,7 +240,21 @@ int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
  * lanes (0 = default 2; 1 = a single wavefront), per-stage event timing on/off. */
 int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int lanes, int profile_stages);
 
+/* ---- output stage: PPMGenerator::writePixel (reference include/PPMGenerator.hpp:812-845) ---- */
+/* 8-bit quantisation of a linear radiance image exactly as the reference writes its PPM:
+ * out = (int)(255 * pow(clamp(0, 1, c), gamma)) per channel, gamma = GAMMA_VAL = 0.78 (global.hpp:30);
+ * gamma <= 0 selects the reference's non-gamma branch (255 * clamp).  NaN clamps to 1 like
+ * std::max(lo, std::min(hi, v)) does (global.hpp:52-55).  rgb: width*height*3 floats, out: width*height*3
+ * bytes.  Host buffers (H2D, kernel, D2H; synchronous) and device buffers (asynchronous). */
+int tutu_quantize(TutuCtx* ctx, const float* rgb, uint64_t n_pixels, float gamma, uint8_t* out);
+int tutu_quantize_device(TutuCtx* ctx, const float* d_rgb, uint64_t n_pixels, float gamma, uint8_t* d_out,
+                         void* stream);
+
 /* ---- host-side helpers (no GPU needed) -------------------------------------------------- */
+/* PPM file from 8-bit pixels: binary = 0 writes the reference's ASCII P3 byte for byte
+ * (PPMGenerator.hpp:804-809, 840-842: "P3\nW\nH\n255\n" then "r g b\n" per pixel), binary = 1
+ * writes P6 (the author's TODO, README.md:49). */
+int tutu_write_ppm(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb8, int binary);
 /* Midpoint BVH with the reference's split rule (BVH.hpp:47-123).  nodes_out must hold
  * 2*n_prims-1 entries (1 if n_prims <= 1). */
 int tutu_bvh_build(const TutuPrim* prims, uint32_t n_prims, TutuBvhNode* nodes_out,

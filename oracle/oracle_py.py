@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
         l.oracle_render_path.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, P, P, C.c_int]
         l.oracle_render_bdpt.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, P, P, C.c_int]
         l.oracle_primary_rays.argtypes = [P, P]
+        l.oracle_write_pixel.argtypes = [P, C.c_uint64, C.c_float, P]
         _lib = l
     return _lib
 
@@ -118,6 +119,14 @@ class OracleScene:
         return out
 
 
+def write_pixel(rgb: np.ndarray, gamma: float = 0.78) -> np.ndarray:
+    """PPMGenerator::writePixel's quantisation restated (oracle_write_pixel)."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    out = np.empty(rgb.shape, np.uint8)
+    lib().oracle_write_pixel(rgb.ctypes.data, rgb.size, gamma, out.ctypes.data)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # the compiled reference (oracle/_ref/ref_harness)
 # ------------------------------------------------------------------------------------------------
@@ -140,6 +149,15 @@ def ref_dump_cornell(width: int, height: int, out_path) -> dict:
 def ref_dump_veach(width: int, height: int, out_path) -> dict:
     """src/main_veach_bdpt.cpp's scene (2308 triangles) with the reference-built BVH."""
     return _run(["dump-veach", str(REF_DIR / "model"), str(width), str(height), str(out_path)])
+
+
+def ref_ppm(rgb: np.ndarray, out_path) -> None:
+    """The reference's own PPMGenerator::generate (header + writePixel) on a float image (H, W, 3)."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    with tempfile.TemporaryDirectory() as td:
+        ip = Path(td) / "in.f32"
+        rgb.tofile(ip)
+        _run(["ppm", str(rgb.shape[1]), str(rgb.shape[0]), str(ip), str(out_path)])
 
 
 def ref_export_bvh(scene, out_path=None):

@@ -16,6 +16,8 @@
 //        rebuild the objects from the file, run Scene::initializeBVH, write the tree back.
 //   ref_harness trace <scene.tscene> <rays.f32> <closest|any> <out.bin> [threads]
 //        getIntersection / hasIntersection (BVH.hpp:145-194) per ray.
+//   ref_harness ppm <W> <H> <in.f32> <out.ppm>
+//        PPMGenerator::generate (gamma 0.78 quantisation + ASCII P3, PPMGenerator.hpp:140-160,804-845)
 //   ref_harness render <scene.tscene> <spp> <out.f32> [mode]
 //        PathTracing::integrate (mode "stock": N_THREAD=20 as shipped) or the reference's own
 //        sub_render_pt row worker on every host core (mode "rows"); BDPT::integrate (mode "bdpt",
@@ -326,6 +328,36 @@ int render(const char* scene, int spp, const char* out_path, const char* mode) {
   return 0;
 }
 
+// ---- output stage -----------------------------------------------------------------------------
+// PPMGenerator::generate (PPMGenerator.hpp:140-160 -> writeHeader :804, writePixel :812) on a given
+// linear float image; the reference writes "<config path>.ppm", which is then moved to `out`.
+int ppm(int W, int H, const char* in_path, const char* out_path) {
+  TutuCamera cam;
+  memset(&cam, 0, sizeof(cam));
+  cam.viewdir[2] = 1, cam.updir[1] = 1, cam.hfov_deg = 40, cam.width = W, cam.height = H;
+  float bkg[3] = {0, 0, 0};
+  std::string cfg = write_config(cam, 0);
+  PPMGenerator g(strdup(cfg.c_str()));
+  remove(cfg.c_str());
+  apply_camera(g, cam, bkg, 1.0f);
+  std::ifstream f(in_path, std::ios::binary);
+  if (!f) die("cannot open the float image");
+  f.read((char*)g.cam.FrameBuffer.rgb.data(), (std::streamsize)((size_t)W * H * sizeof(Vector3f)));
+  {
+    Quiet q;
+    g.generate();
+  }
+  std::string produced = cfg + ".ppm";
+  if (rename(produced.c_str(), out_path) != 0) {
+    std::ifstream src(produced, std::ios::binary);
+    std::ofstream dst(out_path, std::ios::binary);
+    dst << src.rdbuf();
+    remove(produced.c_str());
+  }
+  printf("{\"width\": %d, \"height\": %d}\n", W, H);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -337,6 +369,7 @@ int main(int argc, char** argv) {
   if (cmd == "dump-veach" && argc == 6)
     return dump_driver_scene("veach", argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
   if (cmd == "export-bvh" && argc == 4) return export_bvh(argv[2], argv[3]);
+  if (cmd == "ppm" && argc == 6) return ppm(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);
   if (cmd == "trace" && (argc == 6 || argc == 7))
     return trace(argv[2], argv[3], argv[4], argv[5], argc == 7 ? atoi(argv[6]) : 0);
   if (cmd == "render" && (argc == 5 || argc == 6))

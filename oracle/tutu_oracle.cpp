@@ -1339,6 +1339,17 @@ void oracle_render_bdpt(const OracleScene* os, uint32_t sample_begin, uint32_t s
   }
 }
 
+// PPMGenerator::writePixel (PPMGenerator.hpp:812-845) with GAMMA_COORECTION (global.hpp:29-30):
+// color = 255 * pow(clamp(0, 1, color), 0.78f), written as (int)color.  `pow` on two floats is the
+// float overload (powf); clamp is std::max(lo, std::min(hi, v)) (global.hpp:52-55), so NaN -> 1.
+void oracle_write_pixel(const float* rgb, uint64_t n_values, float gamma, uint8_t* out) {
+  for (uint64_t i = 0; i < n_values; ++i) {
+    float c = clampf(0.f, 1.f, rgb[i]);
+    float v = gamma > 0.f ? 255 * powf(c, gamma) : 255 * c;
+    out[i] = (uint8_t)(int)v;
+  }
+}
+
 // primary rays exactly as sub_render_pt generates them (for ray-generation parity tests)
 void oracle_primary_rays(const OracleScene* os, float* rays_out) {
   const Scene& s = os->s;

@@ -235,6 +235,13 @@ def test_binned_order_gives_identical_results(api, oracle, ctx):
         ctx.set_traversal_mode(0)
         assert_hits_equal(a, c)
         assert np.array_equal(b, d)
+        # the other walk flavours kept in the library: structured local-stack walk,
+        # shared-stack walk, persistent lanes with refill, batched leaf tests
+        for mode in (13, 15, 16, 17):
+            ctx.set_traversal_mode(mode)
+            assert_hits_equal(ctx.trace_closest(rays), c)
+            assert np.array_equal(ctx.trace_any(rays), d)
+        ctx.set_traversal_mode(0)
         sub = slice(0, 150000, 7)
         assert_hits_equal(np.ascontiguousarray(a[sub]), osc.trace_closest(np.ascontiguousarray(rays[sub])))
         assert np.array_equal(b[sub], osc.trace_any(np.ascontiguousarray(rays[sub])))

@@ -150,8 +150,24 @@ def c4_goldens():
     (G / "stats.json").write_text(json.dumps(stats, indent=1))
 
 
+def ppm_golden():
+    """Output stage: a 64x48 float image covering [0,1] densely plus negatives, > 1, NaN and inf,
+    written by the reference's own PPMGenerator::generate."""
+    O.build(ref=True)
+    rng = np.random.default_rng(5)
+    img = rng.uniform(-0.1, 1.2, (48, 64, 3)).astype(np.float32)
+    img[0, :, 0] = np.linspace(0, 1, 64, dtype=np.float32)
+    img[1, :8, 1] = [np.nan, np.inf, -np.inf, 0.0, 1.0, -0.0, 1e-30, 0.999999]
+    img[2] = (np.arange(64 * 3, dtype=np.float32).reshape(64, 3) / 255.0) ** np.float32(1 / 0.78)  # near level boundaries
+    img.tofile(G / "ppm_in_64x48.f32")
+    O.ref_ppm(img, G / "ppm_ref_64x48.ppm")
+    print("ppm golden written")
+
+
 if __name__ == "__main__":
-    if "--c4" in sys.argv:
+    if "--ppm" in sys.argv:
+        ppm_golden()
+    elif "--c4" in sys.argv:
         c4_goldens()
     elif "--bdpt" in sys.argv:
         bdpt_goldens()

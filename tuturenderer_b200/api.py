@@ -89,6 +89,9 @@ ABI = {
     "tutu_render_bdpt": (C.c_int, [_P, C.c_uint32, C.c_uint64, _P]),
     "tutu_render_bdpt_accumulate_device": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P]),
     "tutu_finalize_bdpt_device": (C.c_int, [_P, _P, C.c_float, _P, _P]),
+    "tutu_quantize": (C.c_int, [_P, _P, C.c_uint64, C.c_float, _P]),
+    "tutu_quantize_device": (C.c_int, [_P, _P, C.c_uint64, C.c_float, _P, _P]),
+    "tutu_write_ppm": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _P, C.c_int]),
     "tutu_render_stats": (C.c_int, [_P, C.POINTER(TutuRenderStats)]),
     "tutu_render_configure": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int]),
     "tutu_bvh_build": (C.c_int, [_P, C.c_uint32, _P, C.POINTER(C.c_uint32)]),
@@ -275,6 +278,13 @@ def synth_rays(kind: int, n: int, seed: int = 12345, first: int = 0, out: np.nda
     return out
 
 
+def write_ppm(path, rgb8: np.ndarray, binary: bool = False) -> None:
+    """8-bit image (H, W, 3) -> PPM; binary=False is the reference's ASCII P3 byte for byte."""
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    h, w = rgb8.shape[:2]
+    _check(lib().tutu_write_ppm(str(path).encode(), w, h, _ptr(rgb8), int(binary)))
+
+
 def default_material(**kw) -> np.ndarray:
     """One TutuMaterial with the reference's defaults (Material.hpp:21-30)."""
     m = np.zeros(1, MATERIAL_DTYPE)
@@ -415,6 +425,16 @@ class Context:
 
     def finalize_bdpt_device(self, d_accum: int, inv_spp: float, d_out: int, stream: int = 0) -> None:
         self._ck(lib().tutu_finalize_bdpt_device(self._h, d_accum, inv_spp, d_out, stream or None))
+
+    # ---- output stage (PPMGenerator::writePixel)
+    def quantize(self, rgb: np.ndarray, gamma: float = 0.78) -> np.ndarray:
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        out = np.empty(rgb.shape, np.uint8)
+        self._ck(lib().tutu_quantize(self._h, _ptr(rgb), rgb.size // 3, gamma, _ptr(out)))
+        return out
+
+    def quantize_device(self, d_rgb: int, n_pixels: int, d_out: int, gamma: float = 0.78, stream: int = 0) -> None:
+        self._ck(lib().tutu_quantize_device(self._h, d_rgb, n_pixels, gamma, d_out, stream or None))
 
     def stats(self) -> dict:
         s = TutuRenderStats()

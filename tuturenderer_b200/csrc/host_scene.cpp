@@ -880,3 +880,40 @@ extern "C" int tutu_synth_rays(int kind, uint64_t seed, uint64_t first, uint64_t
   }
   return TUTU_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// PPM output — PPMGenerator::writeHeader / writePixel file format (PPMGenerator.hpp:804-809, 840-842)
+// ------------------------------------------------------------------------------------------
+extern "C" int tutu_write_ppm(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb8, int binary) {
+  if (!path || (!rgb8 && (size_t)width * height)) {
+    tutu::set_error("tutu_write_ppm: null argument");
+    return TUTU_E_INVALID;
+  }
+  FILE* f = fopen(path, "wb");
+  if (!f) {
+    tutu::set_error(std::string("tutu_write_ppm: cannot open ") + path);
+    return TUTU_E_IO;
+  }
+  const size_t npix = (size_t)width * height;
+  bool ok = true;
+  if (binary) {
+    ok = fprintf(f, "P6\n%u %u\n255\n", width, height) > 0;
+    ok = ok && fwrite(rgb8, 1, npix * 3, f) == npix * 3;
+  } else {
+    std::string buf;
+    buf.reserve(npix * 12 + 32);
+    buf += "P3\n" + std::to_string(width) + "\n" + std::to_string(height) + "\n255\n";
+    char tmp[16];
+    for (size_t i = 0; i < npix; ++i) {
+      int n = snprintf(tmp, sizeof(tmp), "%d %d %d\n", (int)rgb8[3 * i], (int)rgb8[3 * i + 1], (int)rgb8[3 * i + 2]);
+      buf.append(tmp, (size_t)n);
+    }
+    ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) {
+    tutu::set_error(std::string("tutu_write_ppm: write failed for ") + path);
+    return TUTU_E_IO;
+  }
+  return TUTU_OK;
+}

@@ -1327,6 +1327,37 @@ extern "C" int tutu_render_bdpt(TutuCtx* ctx, uint32_t spp, uint64_t seed, float
   API_END(ctx)
 }
 
+extern "C" int tutu_quantize_device(TutuCtx* ctx, const float* d_rgb, uint64_t n_pixels, float gamma, uint8_t* d_out,
+                                    void* stream) {
+  API_BEGIN(ctx)
+  if (n_pixels == 0) return TUTU_OK;
+  if (!d_rgb || !d_out) return fail(ctx, TUTU_E_INVALID, "tutu_quantize_device: null buffer");
+  if (((uintptr_t)d_rgb & 15u) || ((uintptr_t)d_out & 3u))
+    return fail(ctx, TUTU_E_INVALID, "tutu_quantize_device: rgb must be 16-byte and out 4-byte aligned");
+  cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+  k_quantize<<<ctx->sm_count * 8, 256, 0, s>>>(d_rgb, (size_t)n_pixels * 3, gamma, d_out);
+  CUDA_TRY(cudaGetLastError());
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_quantize(TutuCtx* ctx, const float* rgb, uint64_t n_pixels, float gamma, uint8_t* out) {
+  API_BEGIN(ctx)
+  if (n_pixels == 0) return TUTU_OK;
+  if (!rgb || !out) return fail(ctx, TUTU_E_INVALID, "tutu_quantize: null buffer");
+  const size_t n = (size_t)n_pixels * 3;
+  cudaStream_t s = ctx->stream;
+  ctx->d_rgb.ensure(n * sizeof(float));
+  ctx->d_blocked.ensure(n);
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_rgb.p, rgb, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  k_quantize<<<ctx->sm_count * 8, 256, 0, s>>>(ctx->d_rgb.as<float>(), n, gamma, ctx->d_blocked.as<uint8_t>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, ctx->d_blocked.p, n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return TUTU_OK;
+  API_END(ctx)
+}
+
 extern "C" int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out) {
   if (!ctx || !out) return fail(nullptr, TUTU_E_INVALID, "tutu_render_stats: null argument");
   *out = ctx->stats;

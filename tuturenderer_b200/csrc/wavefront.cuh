@@ -690,4 +690,36 @@ __global__ void wf_finalize(const float* __restrict__ accum, float inv_spp, floa
     out[i] = accum[i] * inv_spp;
 }
 
+
+// ---- output stage: PPMGenerator::writePixel (PPMGenerator.hpp:812-845) ---------------------------
+// (int)(255 * pow(clamp(0,1,c), gamma)).  The reference's powf (glibc) is correctly rounded in all
+// but a vanishing fraction of inputs; the double-precision pow rounded to float reproduces it.
+__device__ __forceinline__ unsigned char quantize_channel(float c, float gamma) {
+  // std::max(lo, std::min(hi, v)): NaN -> hi.  Spelled out: nvcc turns the two selects into a
+  // saturate, which sends NaN to 0.
+  const float cl = isnan(c) ? 1.f : fminf(fmaxf(c, 0.f), 1.f);
+  float v;
+  if (gamma > 0.f)
+    v = __fmul_rn(255.f, (float)pow((double)cl, (double)gamma));
+  else
+    v = __fmul_rn(255.f, cl);
+  return (unsigned char)(int)v;
+}
+__global__ void __launch_bounds__(256)
+k_quantize(const float* __restrict__ rgb, size_t n_values, float gamma, unsigned char* __restrict__ out) {
+  // 4 values (one 16-byte load, one 4-byte store) per thread and iteration
+  const size_t n4 = n_values / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(rgb) + i);
+    uchar4 q;
+    q.x = quantize_channel(v.x, gamma), q.y = quantize_channel(v.y, gamma);
+    q.z = quantize_channel(v.z, gamma), q.w = quantize_channel(v.w, gamma);
+    reinterpret_cast<uchar4*>(out)[i] = q;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n_values % 4) {
+    const size_t i = n4 * 4 + threadIdx.x;
+    out[i] = quantize_channel(rgb[i], gamma);
+  }
+}
+
 }  // namespace tutu
