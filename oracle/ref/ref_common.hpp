@@ -166,6 +166,29 @@ Loaded load_scene(const char* path, int integrator_type = 0) {
   return L;
 }
 
+// A config file parsed by the reference's own PPMGenerator (camera, inline `sphere` / `v` / `f` / `vn` /
+// `vt` geometry, `mtlcolor` / MICROFACET_* / PERFECT_* materials, `texture` / `bump` /
+// `roughnessTexture` / `metallicTexture` maps: PPMGenerator.hpp:328-482, 488-791).  The config
+// format has no emission keyword (the drivers set emission in C++, src/main_cornellBox.cpp:31-33), so
+// the Cornell ceiling light can be added the way the drivers add it: objl::Loader + loadObj.
+std::unique_ptr<PPMGenerator> load_config(const char* config_path, const char* model_dir, bool add_light) {
+  std::unique_ptr<PPMGenerator> g;
+  {
+    Quiet q;
+    g.reset(new PPMGenerator(strdup(config_path)));
+    if (add_light) {
+      Material light;
+      light.diffuse = {0.725f, 0.71f, 0.68f};
+      light.emission = {47.8348007, 38.5663986, 31.0807991};
+      objl::Loader loader;
+      std::string p = std::string(model_dir) + "/cornellBox/light.obj";
+      if (!loader.LoadFile(p)) die("cannot load " + p);
+      g->loadObj(loader, light, -1, -1);
+    }
+  }
+  return g;
+}
+
 // reference objects -> scene file (prims in objList order, materials de-duplicated)
 struct Exported {
   std::vector<TutuPrim> prims;

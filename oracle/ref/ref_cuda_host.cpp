@@ -7,6 +7,9 @@
 //
 //   ref_cuda_host render-cornell <model_dir> <W> <H> <spp> <seed> <out.f32>
 //        src/main_cornellBox.cpp's scene via objl::Loader + loadObj; CudaPathTracing::integrate
+//   ref_cuda_host render-config <config.txt> <model_dir> <spp> <seed> <out.f32>
+//        a config file parsed by the reference's PPMGenerator (+ the Cornell ceiling light) through
+//        CudaPathTracing::integrate
 //   ref_cuda_host render <scene.tscene> <spp> <seed> <out.f32>
 //   ref_cuda_host trace <scene.tscene> <rays.f32> <out.bin>
 //        every ray through CudaIntersectStrategy::UpdateInter and through BVHStrategy; writes the
@@ -71,6 +74,12 @@ int main(int argc, char** argv) {
         }
       }
       return run_integrate(g, atoi(argv[5]), strtoull(argv[6], nullptr, 10), argv[7]);
+    }
+    if (cmd == "render-config" && argc == 7) {
+      // f-2: the reference's own config parser (inline spheres / triangles, texture state machine,
+      // PPMGenerator.hpp:328-482, 584-764) feeds the flattener of include/tutu_adapters.hpp
+      std::unique_ptr<PPMGenerator> g = load_config(argv[2], argv[3], true);
+      return run_integrate(*g, atoi(argv[4]), strtoull(argv[5], nullptr, 10), argv[6]);
     }
     if (cmd == "render" && argc == 6) {
       Loaded L = load_scene(argv[2]);

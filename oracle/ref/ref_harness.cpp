@@ -16,6 +16,9 @@
 //        rebuild the objects from the file, run Scene::initializeBVH, write the tree back.
 //   ref_harness trace <scene.tscene> <rays.f32> <closest|any> <out.bin> [threads]
 //        getIntersection / hasIntersection (BVH.hpp:145-194) per ray.
+//   ref_harness render-config <config.txt> <model_dir> <spp> <out.f32> [mode]
+//        the config parsed by the reference's PPMGenerator (inline geometry, materials, P3 textures)
+//        plus the Cornell ceiling light, rendered by the reference's PathTracing
 //   ref_harness ppm <W> <H> <in.f32> <out.ppm>
 //        PPMGenerator::generate (gamma 0.78 quantisation + ASCII P3, PPMGenerator.hpp:140-160,804-845)
 //   ref_harness render <scene.tscene> <spp> <out.f32> [mode]
@@ -239,10 +242,21 @@ BdptFrame bdpt_frame(PPMGenerator* g) {
   return f;
 }
 
+int render_g(PPMGenerator* g, int spp, const char* out_path, const char* mode);
+
 int render(const char* scene, int spp, const char* out_path, const char* mode) {
   const bool bdpt = !strncmp(mode, "bdpt", 4);
   Loaded L = load_scene(scene, bdpt ? 3 : 0);
-  PPMGenerator* g = L.g.get();
+  return render_g(L.g.get(), spp, out_path, mode);
+}
+
+// config file parsed by the reference itself (+ optional Cornell ceiling light), reference PathTracing
+int render_config(const char* config, const char* model_dir, int spp, const char* out_path, const char* mode) {
+  std::unique_ptr<PPMGenerator> g = load_config(config, model_dir, true);
+  return render_g(g.get(), spp, out_path, mode);
+}
+
+int render_g(PPMGenerator* g, int spp, const char* out_path, const char* mode) {
   SPP = spp;  // mutable globals, global.hpp:19-20
   SPP_inv = 1.f / SPP;
   std::unique_ptr<Renderer> r;
@@ -369,6 +383,8 @@ int main(int argc, char** argv) {
   if (cmd == "dump-veach" && argc == 6)
     return dump_driver_scene("veach", argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
   if (cmd == "export-bvh" && argc == 4) return export_bvh(argv[2], argv[3]);
+  if (cmd == "render-config" && (argc == 6 || argc == 7))
+    return render_config(argv[2], argv[3], atoi(argv[4]), argv[5], argc == 7 ? argv[6] : "rows");
   if (cmd == "ppm" && argc == 6) return ppm(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);
   if (cmd == "trace" && (argc == 6 || argc == 7))
     return trace(argv[2], argv[3], argv[4], argv[5], argc == 7 ? atoi(argv[6]) : 0);
