@@ -29,8 +29,8 @@ using ::powf;  // Material.hpp:145 uses std::powf, which libstdc++ 13 does not d
 namespace refh {
 
 struct Quiet {  // the reference chats on std::cout
+  std::ostringstream sink;  // declared (hence constructed) before `old`, whose initialiser uses it
   std::streambuf* old;
-  std::ostringstream sink;
   Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
   ~Quiet() { std::cout.rdbuf(old); }
 };

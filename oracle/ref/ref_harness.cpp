@@ -2,7 +2,7 @@
 // $(REF)/include, compiled where they lie) on scenes given as TUTUSCN1 files.
 //
 // TEST INFRASTRUCTURE ONLY.  Built by oracle/Makefile into oracle/_ref/ (git-ignored).  Used by
-// tests/, tools/make_golden.py and bench.py's cpu_baseline / --impl reference legs; never by the
+// tests/, tests/tools/make_golden.py and bench.py's cpu_baseline / --impl reference legs; never by the
 // product library.
 //
 // The reference is a single translation unit by construction (its headers define non-inline
@@ -351,7 +351,8 @@ int ppm(int W, int H, const char* in_path, const char* out_path) {
   cam.viewdir[2] = 1, cam.updir[1] = 1, cam.hfov_deg = 40, cam.width = W, cam.height = H;
   float bkg[3] = {0, 0, 0};
   std::string cfg = write_config(cam, 0);
-  PPMGenerator g(strdup(cfg.c_str()));
+  // heap object, never destroyed: ~PPMGenerator after generate() crashes in the -O2 build
+  PPMGenerator& g = *new PPMGenerator(strdup(cfg.c_str()));
   remove(cfg.c_str());
   apply_camera(g, cam, bkg, 1.0f);
   std::ifstream f(in_path, std::ios::binary);

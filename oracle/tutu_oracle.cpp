@@ -6,7 +6,7 @@
 // Parity pin: the reference ships no tests or golden vectors, so this port is
 // pinned against the reference itself, compiled here as oracle/_ref/ref_harness
 // (oracle/Makefile): tree topology and ray-batch hits must be bit-identical, renders must agree
-// statistically (tools/make_golden.py wrote tests/golden/*, tests/test_oracle_vs_reference.py
+// statistically (tests/tools/make_golden.py wrote tests/golden/*, tests/test_oracle_vs_reference.py
 // re-checks live when oracle/_ref exists).
 //
 // Every function cites the reference lines it follows (paths relative to /root/reference).

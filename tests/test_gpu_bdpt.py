@@ -4,7 +4,7 @@ C ABI on a B200.
 * same-stream: the CPU oracle (oracle/tutu_oracle_bdpt.hpp) draws the same Philox slots, so both
   build the same eye / light sub-paths and weigh the same (s,t) strategies;
 * statistical: against high-spp means of the UNMODIFIED reference's BDPT (tests/golden/*_bdpt_*,
-  tools/make_golden.py --bdpt) on the Cornell box and on the Veach room of
+  tests/tools/make_golden.py --bdpt) on the Cornell box and on the Veach room of
   src/main_veach_bdpt.cpp (BASELINE.json configs[4]).
 Tolerances are written next to each assertion."""
 import json

@@ -94,7 +94,7 @@ def test_mixed_scene_statistics_against_reference(api, ctx, golden, mixed):
 def test_glass_scene_statistics_against_reference(api, oracle, ctx, golden):
     """BASELINE.json configs[3] stand-in (tools/scenes.py: glass_scene): 1214-triangle MICROFACET_T
     glass object + MICROFACET_R box with all four texture channels inside the Cornell shell, against
-    the mean of 2048 reference spp (tools/make_golden.py --c4)."""
+    the mean of 2048 reference spp (tests/tools/make_golden.py --c4)."""
     stats = json.loads((golden / "stats.json").read_text())["glass_c4_96"]
     ref = np.fromfile(golden / "glass_c4_96_ref_mean_2048.f32", np.float32).reshape(96, 96, 3)
     sc = api.Scene.load(golden / "glass_c4.tscene")

@@ -1,5 +1,5 @@
 """Pins the CPU oracle (oracle/tutu_oracle.cpp) against the golden vectors produced by the
-UNMODIFIED reference (tools/make_golden.py ran oracle/_ref/ref_harness in the build container)."""
+UNMODIFIED reference (tests/tools/make_golden.py ran oracle/_ref/ref_harness in the build container)."""
 import json
 
 import numpy as np

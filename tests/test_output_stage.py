@@ -1,6 +1,6 @@
 """Output stage: PPMGenerator::writePixel's gamma-0.78 quantisation and the
 ASCII P3 file, against a PPM written by the UNMODIFIED reference (tests/golden/ppm_ref_64x48.ppm,
-tools/make_golden.py --ppm)."""
+tests/tools/make_golden.py --ppm)."""
 import numpy as np
 import pytest
 

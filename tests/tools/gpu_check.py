@@ -3,7 +3,7 @@ Cornell fixture plus a first throughput reading.  Not part of the test suite."""
 import sys, time
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from tuturenderer_b200 import api
 from oracle import oracle_py as O

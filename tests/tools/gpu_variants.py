@@ -4,7 +4,7 @@ import sys, time
 from pathlib import Path
 import numpy as np
 import torch
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from tuturenderer_b200 import api
 from oracle import oracle_py as O

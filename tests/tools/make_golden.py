@@ -1,6 +1,6 @@
 """Generates tests/golden/* by running the UNMODIFIED reference (oracle/_ref/ref_harness, built by
 oracle/Makefile from /root/reference) in this container.  The fixtures travel to the GPU box,
-/root/reference does not.  Re-run:  python tools/make_golden.py [--renders]
+/root/reference does not.  Re-run:  python tests/tools/make_golden.py [--renders]
 
 Fixtures:
   cornell_256.tscene         scene of src/main_cornellBox.cpp via objl::Loader + loadObj, with the
@@ -17,7 +17,7 @@ Fixtures:
 import json, sys
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from tuturenderer_b200 import api
 from oracle import oracle_py as O

@@ -393,7 +393,7 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, const Ray& r, float
   return best.slot >= 0;
 }
 
-// ---- single-thread walk flavours (compared in tools/gpu_variants.py) ---------------------------
+// ---- single-thread walk flavours (compared in tests/tools/gpu_variants.py) ---------------------------
 // LOOP: one loop whose body handles either an inner node or a leaf (per lane).
 template <bool ANY, int MODE, bool REGULAR>
 __device__ __forceinline__ void walk_loop(const DevScene& sc, Walk& w, int* stack_ref, float* stack_t) {
