@@ -236,8 +236,8 @@ int tutu_render_bdpt_accumulate_device(TutuCtx* ctx, uint32_t sample_begin, uint
 int tutu_finalize_bdpt_device(TutuCtx* ctx, const float* d_accum, float inv_spp, float* d_rgb_out,
                               void* stream);
 int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
-/* Knobs: paths in flight per wavefront lane (0 = default 4 Mi), number of interleaved wavefront
- * lanes (0 = default 2; 1 = a single wavefront), per-stage event timing on/off. */
+/* Knobs: paths in flight per wavefront lane (0 = default 16 Mi; BDPT: samples per batch, default
+ * 1 Mi), number of interleaved wavefront lanes (0 = default 1), per-stage event timing on/off. */
 int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int lanes, int profile_stages);
 
 /* ---- output stage: PPMGenerator::writePixel (reference include/PPMGenerator.hpp:812-845) ---- */

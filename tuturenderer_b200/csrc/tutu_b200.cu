@@ -130,6 +130,8 @@ struct TutuCtx {
   uint64_t paths_in_flight_cfg = 0;  // per lane
   int lanes_cfg = 0;
   int grid_lanes = 0;
+  int shade_block = TUTU_SHADE_BLOCK;  // wavefront.cuh: kShadeBlockSimple for all-Lambertian untextured scenes
+  int grid_shade_block = 0;
   bool grid_small = false;
   int profile_stages = 0;
   TutuRenderStats stats{};
@@ -669,11 +671,9 @@ void fill_raygen(const FlatScene& f, RayGenK* k) {
 // ---------------------------------------------------------------------------------------------
 // wavefront host loop
 // ---------------------------------------------------------------------------------------------
-// One wavefront "lane": its own queues, control block and stream.  Several lanes run interleaved
-// (DESIGN.md §5): wf_shade is latency bound at 16 warps/SM (128 registers) and leaves ~60 % of the
-// issue slots idle, wf_extend / wf_shadow are issue bound, so while one lane shades the other
-// traverses on the same SMs.  Each lane's grids are sized to 1/lanes of the resident-block count so
-// that both kernels fit on an SM together.
+// One wavefront "lane": its own queues, control block and stream.  Several lanes can run interleaved
+// (tutu_render_configure): each lane's grids are then sized to 1/lanes of the resident-block count
+// so that kernels of different lanes fit on an SM together.  The default is ONE lane.
 void lane_prepare(TutuCtx* ctx, WfLane& L, uint64_t cap) {
   cap = (cap + 255) & ~(uint64_t)255;
   if (cap > L.capacity) {
@@ -751,18 +751,22 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   if (total == 0) return;
 
   // lanes: split the samples; a lane never gets less than ~one wavefront of paths
-  int n_lanes = ctx->lanes_cfg > 0 ? ctx->lanes_cfg : 2;
-  const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)4 << 20;
+  // Defaults measured on Cornell 1024^2 @ 1024 spp (tools/gpu_lanes.py, Mpaths/s): 1 lane x 4 / 8 / 16 /
+  // 32 Mi paths in flight = 1556 / 1634 / 1667 / 1680; 2 interleaved lanes = 1241 / 1316 / 1441 / 1593.
+  // (The two-lane interleave paid off only while wf_shade left most issue slots idle.)
+  int n_lanes = ctx->lanes_cfg > 0 ? ctx->lanes_cfg : 1;
+  const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)16 << 20;
   while (n_lanes > 1 && (sample_count < (uint32_t)n_lanes || total / n_lanes < cap_cfg / 2)) --n_lanes;
   if ((int)ctx->wf_lanes.size() < n_lanes) ctx->wf_lanes.resize(n_lanes);
-  if (ctx->grid_lanes != n_lanes || ctx->grid_small != (ctx->small.n > 0)) {
+  if (ctx->grid_lanes != n_lanes || ctx->grid_small != (ctx->small.n > 0) || ctx->grid_shade_block != ctx->shade_block) {
+    ctx->grid_shade_block = ctx->shade_block;
     ctx->grid_small = ctx->small.n > 0;
     const int div = n_lanes;
     auto sized = [&](int full) { return ctx->sm_count * std::max(1, full / ctx->sm_count / div); };
     const bool small = ctx->small.n > 0;
     ctx->grid_extend = sized(small ? persistent_grid(ctx, wf_extend<true>, 256)
                                    : persistent_grid(ctx, wf_extend<false>, 256, stack_smem(ctx, 256, false)));
-    ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, TUTU_SHADE_BLOCK));
+    ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, ctx->shade_block));
     ctx->grid_shadow = sized(small ? persistent_grid(ctx, wf_shadow<true>, 256) : persistent_grid(ctx, wf_shadow<false>, 256));
     ctx->grid_raygen = sized(persistent_grid(ctx, wf_raygen, 256));
     ctx->grid_lanes = n_lanes;
@@ -783,15 +787,17 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   std::vector<Run> runs(n_lanes);
   uint64_t launches = 0;
   try {
-    CUDA_TRY(cudaEventRecord(e0, s));
-    for (int k = 0; k < n_lanes; ++k) {
-      WfLane& L = ctx->wf_lanes[k];
+    for (int k = 0; k < n_lanes; ++k) {  // queue pools first: a (re)allocation is not device time of the render
       const uint32_t b0 = (uint32_t)((uint64_t)sample_count * k / n_lanes);
       const uint32_t b1 = (uint32_t)((uint64_t)sample_count * (k + 1) / n_lanes);
       runs[k].s_begin = sample_begin + b0;
       runs[k].s_count = b1 - b0;
+      lane_prepare(ctx, ctx->wf_lanes[k], std::min<uint64_t>(cap_cfg, std::max<uint64_t>(npix * runs[k].s_count, 1)));
+    }
+    CUDA_TRY(cudaEventRecord(e0, s));
+    for (int k = 0; k < n_lanes; ++k) {
+      WfLane& L = ctx->wf_lanes[k];
       const uint64_t lane_total = npix * runs[k].s_count;
-      lane_prepare(ctx, L, std::min<uint64_t>(cap_cfg, std::max<uint64_t>(lane_total, 1)));
       L.b.accum = d_accum;
       CUDA_TRY(cudaStreamWaitEvent(L.stream, e0, 0));
       WfCtl h{};
@@ -825,7 +831,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
           CUDA_TRY(cudaStreamWaitEvent(ctx->wf_lanes[k + 1].stream, L.ev_done, 0));
         }
         timer.mark(2, ls);
-        wf_shade<<<ctx->grid_shade, TUTU_SHADE_BLOCK, 0, ls>>>(ctx->dev, L.b, cur, seed);
+        wf_shade<<<ctx->grid_shade, ctx->shade_block, 0, ls>>>(ctx->dev, L.b, cur, seed);
         timer.mark(3, ls);
         if (small)
           wf_shadow<true><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
@@ -1091,6 +1097,13 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
       for (int a = 0; a < 3; ++a) ctx->small.box[k][a] = make_float2(fs.leaf_box[k].lo[a], fs.leaf_box[k].hi[a]);
       if (fs.shade[k].flags & SHADE_SPHERE_BIT) d.sphere_mask |= 1u << k;
     }
+  }
+  {
+    bool simple = true;
+    for (const DevMaterial& m : fs.materials) simple = simple && m.type == TUTU_MAT_LAMBERTIAN;
+    for (const LeafShade& ls : fs.shade) simple = simple && !(ls.flags & TEX_ACTIVE_BIT);
+    ctx->shade_block = simple ? kShadeBlockSimple : TUTU_SHADE_BLOCK;
+    if (const char* e = getenv("TUTU_SHADE_BLOCK_RT")) ctx->shade_block = atoi(e);  // experiments only
   }
   d.refill_min = 8;
   if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);  // experiments only

@@ -579,15 +579,18 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
   out.depth_mode = depth | (kModeXInter << 8) | (s.m.type == TUTU_MAT_PERFECT_REFLECTIVE ? kFlagMirror : 0u);
 }
 
-// 64-thread blocks, 8 per SM (128 registers): the block waits at two barriers for one global atomic
-// per iteration, so small blocks keep more independent groups in flight per SM.  Measured on
-// Cornell 1024^2 (Mpaths/s): 256x2 1575, 128x4 1609, 64x8 1632.
+// Compiled for up to 256 threads / 2 blocks per SM (128 registers); the launch picks the block size:
+// a block waits at two barriers for one global atomic per iteration, so small blocks keep more
+// independent groups in flight per SM, but many small blocks on different material code paths thrash
+// the instruction cache.  Measured (Mpaths/s, 1024^2): Cornell 256x2 1606 / 128x4 1652 / 64x8 1670;
+// glass + textures scene 426 / 353 / 317.  -> 64 threads for all-Lambertian untextured scenes, else 256.
 #ifndef TUTU_SHADE_MIN_BLOCKS
-#define TUTU_SHADE_MIN_BLOCKS 8
+#define TUTU_SHADE_MIN_BLOCKS 2
 #endif
 #ifndef TUTU_SHADE_BLOCK
-#define TUTU_SHADE_BLOCK 64
+#define TUTU_SHADE_BLOCK 256
 #endif
+constexpr int kShadeBlockSimple = 64;
 template <int SPEC>
 __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffers& b, int cur, uint64_t seed,
                                               unsigned (*s_cnt)[TUTU_SHADE_BLOCK / 32], unsigned* s_base) {
@@ -638,8 +641,8 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned tc = 0, ts = 0;
-#pragma unroll
-      for (int w = 0; w < TUTU_SHADE_BLOCK / 32; ++w) {
+      const int n_warps = (int)(blockDim.x >> 5);
+      for (int w = 0; w < n_warps; ++w) {
         const unsigned c = s_cnt[0][w], d = s_cnt[1][w];
         s_cnt[0][w] = tc, s_cnt[1][w] = ts;  // exclusive prefixes
         tc += c, ts += d;
