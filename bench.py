@@ -37,7 +37,7 @@ RAYS_G = 707               # 2*707^2 = 999 698 triangles
 RAYS_N = 1 << 24
 
 # queue record sizes of the wavefront (bytes), see DESIGN.md §4
-B_RAY, B_HIT, B_STATE, B_XSTATE, B_SHADOW = 32, 16, 48, 32, 48
+B_RAY, B_HIT, B_STATE, B_XSTATE, B_SHADOW = 32, 16, 48, 16, 48
 
 
 def parse():

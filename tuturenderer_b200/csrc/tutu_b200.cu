@@ -677,7 +677,7 @@ void fill_raygen(const FlatScene& f, RayGenK* k) {
 void lane_prepare(TutuCtx* ctx, WfLane& L, uint64_t cap) {
   cap = (cap + 255) & ~(uint64_t)255;
   if (cap > L.capacity) {
-    const size_t n_arrays = 2 * 7 + 1 + 4;  // 2*(7 queues) + hit + 4 shadow arrays, float4 each
+    const size_t n_arrays = 2 * 6 + 1 + 4;  // 2*(6 queues) + hit + 4 shadow arrays, float4 each
     L.pool.ensure(n_arrays * cap * sizeof(float4));
     L.capacity = cap;
   }
@@ -691,7 +691,6 @@ void lane_prepare(TutuCtx* ctx, WfLane& L, uint64_t cap) {
     b.st1[k] = p, p += cap;
     b.st2[k] = p, p += cap;
     b.st3[k] = p, p += cap;
-    b.st4[k] = p, p += cap;
   }
   b.hit = p, p += cap;
   b.sh_o = p, p += cap;

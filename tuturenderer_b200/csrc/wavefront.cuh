@@ -51,12 +51,11 @@ static_assert(offsetof(WfCtl, n_next) % 8 == 0 && offsetof(WfCtl, n_shadow) == o
 struct WfBuffers {
   // path queues, [2] = ping-pong
   float4* ray_o[2];  // o.xyz, roulette number of the vertex that spawned the ray (Philox slot 5 of its depth)
-  float4* ray_d[2];  // d.xyz, -
+  float4* ray_d[2];  // d.xyz, q = 2 (o - x_prev) . d, the cross term of |x_hit - x_prev|^2 (shade_vertex)
   float4* st0[2];    // beta.xyz, bits(pixel)
   float4* st1[2];    // tp.xyz, bits(sample)
   float4* st2[2];    // L.xyz, bits(depth | mode<<8 | flags)
   float4* st3[2];    // f_r*cos_theta of the previous vertex .xyz, mat_pdf
-  float4* st4[2];    // previous vertex position .xyz, -
   float4* hit;       // t, u, v, bits(slot code)
   // shadow queue
   float4* sh_o;  // o.xyz, dist
@@ -368,7 +367,8 @@ struct ShadeOut {
   bool shadow;    // an NEE shadow ray goes to the shadow queue
   bool finished;  // the path ended at this vertex (L must reach the frame buffer)
   // continuation
-  f3 o, d, beta, tp, fcos, prev_pos;
+  f3 o, d, beta, tp, fcos;
+  float q;  // 2 (o - x) . d for the next vertex's r^2
   float mat_pdf;
   float rr_u;
   uint32_t depth_mode;
@@ -386,7 +386,7 @@ template <int SPEC>
 __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, const Ray& ray,
                                              const float4 hit, uint32_t pixel, uint32_t sample,
                                              uint32_t depth, uint32_t mode, uint32_t flags, f3 beta,
-                                             f3 tp, f3& L, const float4 st3, const float4 st4, float rr_u,
+                                             f3 tp, f3& L, const float4 st3, float q_prev, float rr_u,
                                              ShadeOut& out) {
   out.cont = out.shadow = false;
   out.finished = true;
@@ -413,7 +413,12 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
       const float cos_theta_prime = dot(light_N, -dir);
       if (cos_theta_prime > 0) {
         as_light = true;
-        const float r2 = norm2(s.pos - mk(st4.x, st4.y, st4.z));
+        // r2 = |x_inter.pos - inter.pos|^2 (PathTracing.hpp:246) with x_inter.pos = o + t d and
+        // o = inter.pos -+ EPSILON Ns: |o - x|^2 + t^2 |d|^2 + 2 t (o - x).d.  The previous vertex
+        // passes q = 2 (o - x).d along with the ray instead of its position (16 B less per vertex in
+        // each direction); |o - x| = EPSILON |Ns| and |d| are 1 to rounding.
+        const float t_hit = hit.x;
+        const float r2 = T_EPSILON * T_EPSILON + t_hit * t_hit + q_prev * t_hit;
         const float l_pdf_transformed = fdiv(light_pdf * r2, cos_theta_prime);
         float mis_weight_m = getMisWeight(mat_pdf, l_pdf_transformed);
         if ((flags & kFlagMirror) && mat_pdf == 1.f) mis_weight_m = 1.f;
@@ -493,7 +498,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
     out.fcos = mk(0.f);
     out.mat_pdf = 0.f;
     out.rr_u = 0.f;
-    out.prev_pos = s.pos;
+    out.q = 0.f;
     out.depth_mode = (depth + 1) | (kModeFresh << 8);
     return;
   }
@@ -575,7 +580,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
   out.fcos = f_r * cos_theta;
   out.mat_pdf = mat_pdf;
   out.rr_u = rn.u[5];
-  out.prev_pos = s.pos;
+  out.q = 2.f * dot(rayOrig - s.pos, wi);
   out.depth_mode = depth | (kModeXInter << 8) | (s.m.type == TUTU_MAT_PERFECT_REFLECTIVE ? kFlagMirror : 0u);
 }
 
@@ -620,16 +625,13 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
       const float4 hit = __ldcs(b.hit + i);
       const uint32_t dm = __float_as_uint(s2.w);
       const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
-      float4 s3 = make_float4(0, 0, 0, 0), s4 = make_float4(0, 0, 0, 0);
-      if (mode == kModeXInter) {
-        s3 = __ldcs(b.st3[cur] + i);
-        s4 = __ldcs(b.st4[cur] + i);
-      }
+      float4 s3 = make_float4(0, 0, 0, 0);
+      if (mode == kModeXInter) s3 = __ldcs(b.st3[cur] + i);
       pixel = __float_as_uint(s0.w);
       L = mk(s2.x, s2.y, s2.z);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
       shade_vertex<SPEC>(sc, seed, r, hit, pixel, __float_as_uint(s1.w), depth, mode, dm, mk(s0.x, s0.y, s0.z),
-                   mk(s1.x, s1.y, s1.z), L, s3, s4, o.w, out);
+                   mk(s1.x, s1.y, s1.z), L, s3, d.w, o.w, out);
     }
     // queue appends: warp ballots -> block prefix in shared memory -> one atomicAdd per counter
     const unsigned cmask = __ballot_sync(0xFFFFFFFFu, out.cont);
@@ -660,14 +662,13 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
     __syncthreads();  // s_cnt / s_base are rewritten by the next iteration
     if (out.cont) {
       __stcs(b.ray_o[nxt] + ci, make_float4(out.o.x, out.o.y, out.o.z, out.rr_u));
-      __stcs(b.ray_d[nxt] + ci, make_float4(out.d.x, out.d.y, out.d.z, 0.f));
+      __stcs(b.ray_d[nxt] + ci, make_float4(out.d.x, out.d.y, out.d.z, out.q));
       __stcs(b.st0[nxt] + ci, make_float4(out.beta.x, out.beta.y, out.beta.z, __uint_as_float(pixel)));
       __stcs(b.st1[nxt] + ci, make_float4(out.tp.x, out.tp.y, out.tp.z, s1.w));
       // st2 is read-modify-written by wf_shadow right after: keep it in L2 (default policy)
       b.st2[nxt][ci] = make_float4(L.x, L.y, L.z, __uint_as_float(out.depth_mode));
       if (((out.depth_mode >> 8) & 1u) == kModeXInter) {
         __stcs(b.st3[nxt] + ci, make_float4(out.fcos.x, out.fcos.y, out.fcos.z, out.mat_pdf));
-        __stcs(b.st4[nxt] + ci, make_float4(out.prev_pos.x, out.prev_pos.y, out.prev_pos.z, 0.f));
       }
     }
     if (out.shadow) {
