@@ -5,6 +5,7 @@
 // Built with -ffp-contract=off: everything that feeds hit parity (bounds, centroids, E1/E2/n,
 // ray-generation constants) must round exactly like the reference's scalar float code.
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -213,6 +214,176 @@ int compute_raygen(const TutuCamera* cam, RayGen* rg) {
   rg->width = cam->width;
   rg->height = cam->height;
   return TUTU_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// traversal tree for regular rays (tutu_internal.hpp: FlatScene::inner_fast)
+// ------------------------------------------------------------------------------------------
+// For a ray whose three 1/d are finite the reference's answer depends only on the LEAF boxes and
+// the primitives (slab test monotone in the box + every reference inner box is the exact fmin/fmax
+// union of its leaves: "leaf box hit => every ancestor box hit").  Any binary tree
+// over the same leaves whose inner boxes are exact unions of their leaves' boxes therefore returns
+// bit-identical hits, and the device is free to walk a better one than the reference's
+// median-by-count split: a binned surface-area-heuristic tree (16 bins, 3 axes), depth limited so
+// that the traversal stacks stay valid.  Leaf refs keep the reference's DFS slot numbers, which is
+// what the equal-t tie rule compares.  Irregular rays keep walking the reference topology.
+namespace {
+struct FastBuilder {
+  const std::vector<Box>& lbox;
+  const std::vector<uint32_t>& code;
+  std::vector<uint32_t> idx;
+  std::vector<V3> cen;
+  InnerNode* out;
+  int max_depth;
+  uint32_t depth_seen = 0;
+
+  static float area(const Box& b) {
+    float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    return 2.f * (dx * dy + dy * dz + dz * dx);
+  }
+  static Box empty_box() {
+    Box b;
+    for (int a = 0; a < 3; ++a) b.lo[a] = FLT_MAX, b.hi[a] = -FLT_MAX;
+    return b;
+  }
+  static void grow(Box& b, const Box& o) {
+    for (int a = 0; a < 3; ++a) {
+      b.lo[a] = fminf(b.lo[a], o.lo[a]);  // fmin/fmax like BoundBox::Union (BoundBox.hpp:97-124): exact
+      b.hi[a] = fmaxf(b.hi[a], o.hi[a]);
+    }
+  }
+  static int ceil_log2(uint32_t n) {
+    int l = 0;
+    while ((1ull << l) < n) ++l;
+    return l;
+  }
+
+  // builds the subtree over idx[first, first+count); its count-1 inner nodes occupy out[base, base+count-1)
+  // in pre-order.  Returns the child ref and the exact union box.
+  int32_t build(uint32_t first, uint32_t count, uint32_t base, int depth, Box* box_out, int par_levels, uint32_t* deepest) {
+    if (count == 1) {
+      *box_out = lbox[idx[first]];
+      return (int32_t)~code[idx[first]];
+    }
+    if ((uint32_t)depth + 1 > *deepest) *deepest = (uint32_t)depth + 1;
+    uint32_t nl = count / 2;
+    bool median = (max_depth - depth) <= ceil_log2(count) + 1;
+    if (!median) {
+      Box cb = empty_box();
+      for (uint32_t k = first; k < first + count; ++k) {
+        const V3& c = cen[idx[k]];
+        cb.lo[0] = fminf(cb.lo[0], c.x), cb.hi[0] = fmaxf(cb.hi[0], c.x);
+        cb.lo[1] = fminf(cb.lo[1], c.y), cb.hi[1] = fmaxf(cb.hi[1], c.y);
+        cb.lo[2] = fminf(cb.lo[2], c.z), cb.hi[2] = fmaxf(cb.hi[2], c.z);
+      }
+      constexpr int NB = 16;
+      float best = FLT_MAX;
+      int best_axis = -1, best_split = 0;
+      for (int a = 0; a < 3; ++a) {
+        const float ext = cb.hi[a] - cb.lo[a];
+        if (!(ext > 0.f)) continue;
+        const float scale = NB / ext;
+        uint32_t cnt[NB] = {0};
+        Box bb[NB];
+        for (int b = 0; b < NB; ++b) bb[b] = empty_box();
+        for (uint32_t k = first; k < first + count; ++k) {
+          const float c = a == 0 ? cen[idx[k]].x : a == 1 ? cen[idx[k]].y : cen[idx[k]].z;
+          int b = (int)((c - cb.lo[a]) * scale);
+          b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+          cnt[b]++;
+          grow(bb[b], lbox[idx[k]]);
+        }
+        float right_area[NB];
+        uint32_t right_cnt[NB];
+        Box acc = empty_box();
+        uint32_t n = 0;
+        for (int b = NB - 1; b > 0; --b) {
+          if (cnt[b]) grow(acc, bb[b]);
+          n += cnt[b];
+          right_area[b] = n ? area(acc) : 0.f;
+          right_cnt[b] = n;
+        }
+        acc = empty_box();
+        n = 0;
+        for (int b = 0; b < NB - 1; ++b) {
+          if (cnt[b]) grow(acc, bb[b]);
+          n += cnt[b];
+          if (n == 0 || right_cnt[b + 1] == 0) continue;
+          const float cost = area(acc) * n + right_area[b + 1] * right_cnt[b + 1];
+          if (cost < best) best = cost, best_axis = a, best_split = b + 1;
+        }
+      }
+      if (best_axis >= 0) {
+        const int a = best_axis;
+        const float scale = NB / (cb.hi[a] - cb.lo[a]);
+        auto mid = std::partition(idx.begin() + first, idx.begin() + first + count, [&](uint32_t i) {
+          const float c = a == 0 ? cen[i].x : a == 1 ? cen[i].y : cen[i].z;
+          int b = (int)((c - cb.lo[a]) * scale);
+          b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+          return b < best_split;
+        });
+        nl = (uint32_t)(mid - (idx.begin() + first));
+        if (nl == 0 || nl == count) nl = count / 2;  // cannot happen; keeps the recursion well founded
+      }
+    }
+    Box bl, br;
+    int32_t lref, rref;
+    uint32_t dl = 0, dr = 0;
+    if (par_levels > 0 && count > (1u << 15)) {
+      std::thread t([&] { lref = build(first, nl, base + 1, depth + 1, &bl, par_levels - 1, &dl); });
+      rref = build(first + nl, count - nl, base + nl, depth + 1, &br, par_levels - 1, &dr);
+      t.join();
+    } else {
+      lref = build(first, nl, base + 1, depth + 1, &bl, 0, &dl);
+      rref = build(first + nl, count - nl, base + nl, depth + 1, &br, 0, &dr);
+    }
+    if (dl > *deepest) *deepest = dl;
+    if (dr > *deepest) *deepest = dr;
+    InnerNode& in = out[base];
+    memcpy(in.box + 0, bl.lo, 12);
+    memcpy(in.box + 3, bl.hi, 12);
+    memcpy(in.box + 6, br.lo, 12);
+    memcpy(in.box + 9, br.hi, 12);
+    in.left = lref;
+    in.right = rref;
+    in.pad0 = in.pad1 = 0;
+    *box_out = bl;
+    grow(*box_out, br);
+    return (int32_t)base;
+  }
+};
+}  // namespace
+
+// leaf_code[s] = slot | SPHERE_BIT.  On return fs->inner_fast / root_ref_fast / depth_fast are set;
+// when the leaf boxes are not all finite (or the tree could not respect the depth limit) the
+// reference topology is reused.
+static void build_fast_tree(FlatScene* fs, const std::vector<uint32_t>& leaf_code, int max_depth) {
+  const uint32_t n = (uint32_t)fs->leaf_box.size();
+  fs->inner_fast = fs->inner;
+  fs->root_ref_fast = fs->root_ref;
+  fs->depth_fast = fs->depth;
+  if (n < 3 || getenv("TUTU_NO_FAST_TREE")) return;
+  for (const Box& b : fs->leaf_box)
+    for (int a = 0; a < 3; ++a)
+      if (!std::isfinite(b.lo[a]) || !std::isfinite(b.hi[a])) return;
+  if (FastBuilder::ceil_log2(n) + 2 > max_depth) return;
+  std::vector<InnerNode> out(n - 1);
+  FastBuilder fb{fs->leaf_box, leaf_code, {}, {}, out.data(), max_depth};
+  fb.idx.resize(n);
+  fb.cen.resize(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    fb.idx[i] = i;
+    const Box& b = fs->leaf_box[i];
+    fb.cen[i] = {0.5f * (b.lo[0] + b.hi[0]), 0.5f * (b.lo[1] + b.hi[1]), 0.5f * (b.lo[2] + b.hi[2])};
+  }
+  Box root;
+  uint32_t deepest = 0;
+  const int32_t ref = fb.build(0, n, 0, 0, &root, 4, &deepest);
+  if ((int)deepest > max_depth) return;
+  fs->inner_fast = std::move(out);
+  fs->root_ref_fast = ref;
+  fs->depth_fast = deepest;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -608,6 +779,13 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
       L.area = sqrtf(c.x * c.x + c.y * c.y + c.z * c.z) * 0.5f;  // Triangle.hpp:109-116
     }
     fs->lights.push_back(L);
+  }
+
+  // traversal tree for regular rays (the reference topology stays in fs->inner for the others)
+  {
+    std::vector<uint32_t> leaf_code(n);
+    for (uint32_t s = 0; s < n; ++s) leaf_code[s] = s | ((fs->shade[s].flags & SHADE_SPHERE_BIT) ? SPHERE_BIT : 0u);
+    build_fast_tree(fs, leaf_code, 30);
   }
   return TUTU_OK;
 }

@@ -22,7 +22,8 @@ constexpr uint32_t kSphereBit = 1u << 30;
 constexpr uint32_t kSlotMask = kSphereBit - 1u;
 
 struct DevScene {
-  const float4* __restrict__ inner;     // 4 x float4 per inner node
+  const float4* __restrict__ inner;     // 4 x float4 per inner node, the reference's topology
+  const float4* __restrict__ inner_fast;  // SAH topology over the same leaves: regular rays (host_scene.cpp)
   const float4* __restrict__ geom;      // 3 x float4 per leaf slot
   const float4* __restrict__ shade;     // 4 x float4 per leaf slot
   const int4* __restrict__ leaftex;     // per leaf slot, or nullptr when no prim is textured
@@ -34,6 +35,7 @@ struct DevScene {
   float root_lo[3];
   float root_hi[3];
   int root_ref;
+  int root_ref_fast;
   int empty;
   int n_lights;
   float bkg[3];
@@ -244,6 +246,7 @@ __device__ __forceinline__ bool box_any(const RayPre& p, float lox, float loy, f
 // primitive code as two convergent phases instead of interleaving them lane by lane, and (b) hand
 // a finished lane a new ray between rounds (persistent threads, see trace_persistent()).
 struct Walk {
+  const float4* nodes;  // the node array this walk descends (DevScene::inner_fast for regular rays)
   Ray r;
   RayPre p;
   Hit best;
@@ -274,7 +277,8 @@ __device__ __forceinline__ float prune_limit(const DevScene& sc, const Walk& w) 
 }
 
 // Starts a walk: false when the ray cannot hit anything (empty scene / root box missed).
-__device__ __forceinline__ bool walk_begin(const DevScene& sc, Walk& w, const Ray& r, float dis) {
+// use_fast = false keeps the walk on the reference topology (literal mode).
+__device__ __forceinline__ bool walk_begin(const DevScene& sc, Walk& w, const Ray& r, float dis, bool use_fast = true) {
   w.r = r;
   w.dis = dis;
   w.best.t = FLT_MAX;
@@ -283,9 +287,14 @@ __device__ __forceinline__ bool walk_begin(const DevScene& sc, Walk& w, const Ra
   w.best.slot = -1;
   w.sp = 0;
   w.cur = sc.root_ref;
+  w.nodes = sc.inner;
   if (sc.empty) return false;
   w.p = make_pre(r);
   w.regular = ray_is_regular(w.p);
+  if (use_fast && w.regular) {
+    w.cur = sc.root_ref_fast;
+    w.nodes = sc.inner_fast;
+  }
   float te;
   return box_test(w.p, sc.root_lo[0], sc.root_lo[1], sc.root_lo[2], sc.root_hi[0], sc.root_hi[1],
                   sc.root_hi[2], te);
@@ -310,7 +319,7 @@ __device__ __forceinline__ bool walk_round(const DevScene& sc, Walk& w, int* sta
                                            VisitCount* vc) {
   // phase 1: inner nodes until this lane holds a leaf
   while (w.cur >= 0) {
-    const float4* n = sc.inner + 4 * (size_t)w.cur;
+    const float4* n = w.nodes + 4 * (size_t)w.cur;
     float4 a, b, c;
     int4 k;
     load_node(n, a, b, c, k);
@@ -380,7 +389,7 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, const Ray& r, float
   Walk w;
   int stack_ref[kStackSize];
   float stack_t[kStackSize];
-  if (walk_begin(sc, w, r, dis)) {
+  if (walk_begin(sc, w, r, dis, MODE == 0)) {
     if (w.regular) {
       while (walk_round<ANY, MODE, COUNT, true>(sc, w, stack_ref, stack_t, vc)) {
       }
@@ -399,7 +408,7 @@ template <bool ANY, int MODE, bool REGULAR>
 __device__ __forceinline__ void walk_loop(const DevScene& sc, Walk& w, int* stack_ref, float* stack_t) {
   for (;;) {
     if (w.cur >= 0) {
-      const float4* n = sc.inner + 4 * (size_t)w.cur;
+      const float4* n = w.nodes + 4 * (size_t)w.cur;
       float4 a, b, c;
       int4 k;
       load_node(n, a, b, c, k);
@@ -501,7 +510,7 @@ __device__ __forceinline__ bool leaf_step(const DevScene& sc, Walk& w, int leaf_
 // node step: returns true when the lane has to pop
 template <bool ANY, bool REGULAR>
 __device__ __forceinline__ bool node_step(const DevScene& sc, Walk& w, int* stack_ref, float* stack_t) {
-  const float4* n = sc.inner + 4 * (size_t)w.cur;
+  const float4* n = w.nodes + 4 * (size_t)w.cur;
   float4 a, b, c;
   int4 k;
   load_node(n, a, b, c, k);
@@ -637,7 +646,7 @@ __device__ __forceinline__ void walk_shared(const DevScene& sc, Walk& w, SharedS
   for (;;) {
     bool need_pop;
     if (w.cur >= 0) {
-      const float4* n = sc.inner + 4 * (size_t)w.cur;
+      const float4* n = w.nodes + 4 * (size_t)w.cur;
       float4 a, b, c;
       int4 k;
       load_node(n, a, b, c, k);
@@ -700,7 +709,7 @@ template <bool ANY, bool REGULAR>
 __device__ __forceinline__ bool walk_step_shared(const DevScene& sc, Walk& w, SharedStack<ANY>& st) {
   bool need_pop;
   if (w.cur >= 0) {
-    const float4* n = sc.inner + 4 * (size_t)w.cur;
+    const float4* n = w.nodes + 4 * (size_t)w.cur;
     float4 a, b, c;
     int4 k;
     load_node(n, a, b, c, k);
@@ -792,7 +801,7 @@ __device__ __forceinline__ void trace_refill(const DevScene& sc, unsigned long l
 // node part of a step with the shared-memory stack: true = the lane has to pop
 template <bool ANY, bool REGULAR>
 __device__ __forceinline__ bool node_step_shared(const DevScene& sc, Walk& w, SharedStack<ANY>& st) {
-  const float4* n = sc.inner + 4 * (size_t)w.cur;
+  const float4* n = w.nodes + 4 * (size_t)w.cur;
   float4 a, b, c;
   int4 k;
   load_node(n, a, b, c, k);

@@ -107,6 +107,7 @@ struct TutuCtx {
   FlatScene flat;
   DevScene dev{};
   SmallScene small{};  // n = 0 unless the scene has <= kSmallMax primitives
+  DevBuf d_inner_fast;
   DevBuf d_inner, d_geom, d_shade, d_leaftex, d_slot_to_prim, d_materials, d_lights, d_texels;
   DevBuf d_texh[4];
   uint64_t scene_bytes = 0;
@@ -553,7 +554,7 @@ int persistent_grid(TutuCtx* ctx, K kernel, int block, size_t dyn_smem = 0) {
 // shared-memory stack bytes for a block: one 64-bit word per thread and level; a ray pushes at
 // most one entry per tree level, +1 slack
 size_t stack_smem(const TutuCtx* ctx, int block, bool any) {
-  return (size_t)block * (ctx->flat.depth + 1) * (any ? sizeof(unsigned) : sizeof(unsigned long long));
+  return (size_t)block * (std::max(ctx->flat.depth, ctx->flat.depth_fast) + 1) * (any ? sizeof(unsigned) : sizeof(unsigned long long));
 }
 
 // Builds the coherent traversal order of a batch (nullptr = trace in the caller's order).
@@ -1056,10 +1057,11 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   FlatScene fs;
   int rc = flatten_scene(desc, &fs);
   if (rc != TUTU_OK) return fail(ctx, rc, get_error());
-  if (fs.depth > (uint32_t)kStackSize)
+  if (std::max(fs.depth, fs.depth_fast) > (uint32_t)kStackSize)
     return fail(ctx, TUTU_E_INVALID, "scene: BVH deeper than the traversal stack (" + std::to_string(fs.depth) + ")");
   cudaStream_t s = ctx->stream;
   upload_vec(ctx->d_inner, fs.inner, s);
+  upload_vec(ctx->d_inner_fast, fs.inner_fast, s);
   upload_vec(ctx->d_geom, fs.geom, s);
   upload_vec(ctx->d_shade, fs.shade, s);
   upload_vec(ctx->d_leaftex, fs.leaftex, s);
@@ -1071,6 +1073,8 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   CUDA_TRY(cudaStreamSynchronize(s));
   DevScene& d = ctx->dev;
   d.inner = ctx->d_inner.as<float4>();
+  d.inner_fast = ctx->d_inner_fast.as<float4>();
+  d.root_ref_fast = fs.root_ref_fast;
   d.geom = ctx->d_geom.as<float4>();
   d.shade = ctx->d_shade.as<float4>();
   d.leaftex = fs.leaftex.empty() ? nullptr : ctx->d_leaftex.as<int4>();
@@ -1108,7 +1112,7 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_ABS")) d.prune_abs = (float)atof(e);
-  ctx->scene_bytes = fs.inner.size() * sizeof(InnerNode) + fs.geom.size() * sizeof(LeafGeom) +
+  ctx->scene_bytes = (fs.inner.size() + fs.inner_fast.size()) * sizeof(InnerNode) + fs.geom.size() * sizeof(LeafGeom) +
                      fs.shade.size() * sizeof(LeafShade) + fs.leaftex.size() * sizeof(LeafTex) +
                      fs.slot_to_prim.size() * 4 + fs.materials.size() * sizeof(DevMaterial) +
                      fs.lights.size() * sizeof(DevLight) + fs.texels.size() * 4;

@@ -123,7 +123,10 @@ struct FlatScene {
   bool empty = true;
   Box root_box{};
   float max_edge = 0.f;  // longest triangle edge / sphere diameter (pruning slack)
-  std::vector<InnerNode> inner;
+  std::vector<InnerNode> inner;       // the reference's topology (irregular rays, literal walk)
+  std::vector<InnerNode> inner_fast;  // SAH topology over the same leaves (regular rays), host_scene.cpp
+  int32_t root_ref_fast = 0;
+  uint32_t depth_fast = 0;
   std::vector<LeafGeom> geom;
   std::vector<LeafShade> shade;
   std::vector<LeafTex> leaftex;
