@@ -45,6 +45,7 @@ struct DevScene {
   float prune_rel;
   float prune_abs;
   int refill_min;  // persistent tracer: refill once this many lanes of a warp are idle
+  int leaf_batch;  // traverse_batched: waiting lanes that trigger the primitive tests
   unsigned sphere_mask;  // small scenes: bit s set = leaf slot s is a sphere
 };
 
@@ -847,7 +848,7 @@ __device__ __forceinline__ bool traverse_batched(const DevScene& sc, const Ray& 
     if ((at_node | at_leaf) == 0u) break;
     const int n_leaf = __popc(at_leaf), n_node = __popc(at_node);
     bool need_pop = false;
-    if (n_leaf >= kLeafBatch || n_leaf >= n_node) {  // enough lanes wait (or nobody walks): test the leaves
+    if (n_leaf >= sc.leaf_batch || n_leaf >= n_node) {  // enough lanes wait (or nobody walks): test the leaves
       if (!done && w.cur < 0) {
         if (leaf_step<ANY>(sc, w, w.cur)) done = true;
         need_pop = !done;

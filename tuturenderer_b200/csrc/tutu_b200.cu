@@ -353,6 +353,16 @@ k_trace_closest(const __grid_constant__ DevScene sc, const __grid_constant__ Sma
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (base >= n) return;
     const unsigned long long j = base + lane;
+    if (MODE == 0) {  // production: the warp walks together, primitive tests batched (trace.cuh: traverse_batched)
+      const bool valid = j < n;
+      const unsigned long long i = valid ? (perm ? (unsigned long long)__ldg(perm + j) : j) : 0ull;
+      float4 o = make_float4(0, 0, 0, 0), d = make_float4(1, 0, 0, 0);
+      if (valid) o = __ldg(rays + 2 * i), d = __ldg(rays + 2 * i + 1);
+      Hit h;
+      traverse_batched<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, valid, h, s_stack);
+      if (valid) store(i, h);
+      continue;
+    }
     if (j < n) {
       const unsigned long long i = perm ? (unsigned long long)__ldg(perm + j) : j;
       const float4 o = __ldg(rays + 2 * i);
@@ -1109,6 +1119,8 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
     if (const char* e = getenv("TUTU_SHADE_BLOCK_RT")) ctx->shade_block = atoi(e);  // experiments only
   }
   d.refill_min = 8;
+  d.leaf_batch = kLeafBatch;
+  if (const char* e = getenv("TUTU_LEAF_BATCH")) d.leaf_batch = atoi(e);  // experiments only
   if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_ABS")) d.prune_abs = (float)atof(e);

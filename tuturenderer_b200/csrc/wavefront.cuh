@@ -169,7 +169,7 @@ wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
         Hit h;
         if (SMALL)
           traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
-        else
+        else  // incoherent queue: per-lane walk (batched primitive tests only pay on sorted batches)
           traverse_shared<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack);
         __stcs(b.hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
       }
