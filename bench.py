@@ -256,8 +256,10 @@ def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict)
                          "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": bytes_c * n_local / (res["closest"] * 1e-3) * 1e-9 / peaks["hbm_gbs"],
                          "traffic": None, "kernel": "k_trace_closest<0>",
-                         "note": "algorithmic bytes = 48 + 64*nodes + 48*prims per ray; nodes are 64-byte "
-                                 "two-child records served mostly by L1/L2, so the fraction can exceed HBM traffic"},
+                         "note": "algorithmic bytes = 48 + 64*nodes + 48*prims per ray, nodes/prims counted on this batch "
+                                 "(regular rays walk the SAH topology over the reference's leaves); 64-byte two-child "
+                                 "records are served mostly by L1/L2, so the fraction can exceed HBM traffic; the "
+                                 "timed call includes the counting sort of the batch"},
         }
         if kind == 0 and do_cpu and rank == 0:
             out["cpu_baseline"] = cpu_rays_baseline(sc, h_rays.numpy()[: 1 << 20])
