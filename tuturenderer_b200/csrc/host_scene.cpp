@@ -217,6 +217,14 @@ int compute_raygen(const TutuCamera* cam, RayGen* rg) {
 }
 
 
+// child boxes of a device inner node: per child and axis {lo, hi} pairs (trace.cuh: node_boxes)
+static inline void set_node_boxes(InnerNode& in, const Box& l, const Box& r) {
+  for (int a = 0; a < 3; ++a) {
+    in.box[2 * a] = l.lo[a], in.box[2 * a + 1] = l.hi[a];
+    in.box[6 + 2 * a] = r.lo[a], in.box[6 + 2 * a + 1] = r.hi[a];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // traversal tree for regular rays (tutu_internal.hpp: FlatScene::inner_fast)
 // ------------------------------------------------------------------------------------------
@@ -341,10 +349,7 @@ struct FastBuilder {
     if (dl > *deepest) *deepest = dl;
     if (dr > *deepest) *deepest = dr;
     InnerNode& in = out[base];
-    memcpy(in.box + 0, bl.lo, 12);
-    memcpy(in.box + 3, bl.hi, 12);
-    memcpy(in.box + 6, br.lo, 12);
-    memcpy(in.box + 9, br.hi, 12);
+    set_node_boxes(in, bl, br);
     in.left = lref;
     in.right = rref;
     in.pad0 = in.pad1 = 0;
@@ -693,10 +698,7 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
     const TutuBvhNode& nd = nodes[i];
     if (nd.left >= 0) {
       InnerNode& in = fs->inner[inner_of[i]];
-      memcpy(in.box + 0, nbox[nd.left].lo, 12);
-      memcpy(in.box + 3, nbox[nd.left].hi, 12);
-      memcpy(in.box + 6, nbox[nd.right].lo, 12);
-      memcpy(in.box + 9, nbox[nd.right].hi, 12);
+      set_node_boxes(in, nbox[nd.left], nbox[nd.right]);
       in.left = ref_of(nd.left);
       in.right = ref_of(nd.right);
       in.pad0 = in.pad1 = 0;

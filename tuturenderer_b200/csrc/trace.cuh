@@ -242,6 +242,45 @@ __device__ __forceinline__ bool box_any(const RayPre& p, float lox, float loy, f
   return box_test(p, lox, loy, loz, hix, hiy, hiz, t_enter);
 }
 
+// Slab test for regular rays with Blackwell's packed fp32 instructions (FADD2 / FMUL2, sm_100+):
+// both planes of an axis go through one subtract and one multiply.  add.rn.f32x2(p, -o) is the IEEE
+// p - o and mul.rn.f32x2 the IEEE product, so the two t values per axis are bit-identical to
+// box_test_regular's; only the issue-slot count halves (these kernels are issue bound).
+struct RayPre2 {
+  float2 nox, noy, noz;  // (-o, -o)
+  float2 ix, iy, iz;     // (1/d, 1/d)
+};
+__device__ __forceinline__ RayPre2 make_pre2(const RayPre& p) {
+  RayPre2 q;
+  q.nox = make_float2(-p.ox, -p.ox), q.noy = make_float2(-p.oy, -p.oy), q.noz = make_float2(-p.oz, -p.oz);
+  q.ix = make_float2(p.ix, p.ix), q.iy = make_float2(p.iy, p.iy), q.iz = make_float2(p.iz, p.iz);
+  return q;
+}
+__device__ __forceinline__ bool box_test_packed(const RayPre2& q, float2 bx, float2 by, float2 bz, float& t_enter) {
+  const float2 tx = __fmul2_rn(__fadd2_rn(bx, q.nox), q.ix);
+  const float2 ty = __fmul2_rn(__fadd2_rn(by, q.noy), q.iy);
+  const float2 tz = __fmul2_rn(__fadd2_rn(bz, q.noz), q.iz);
+  t_enter = fmaxf(fminf(tx.x, tx.y), fmaxf(fminf(ty.x, ty.y), fminf(tz.x, tz.y)));
+  const float t_exit = fminf(fmaxf(tx.x, tx.y), fminf(fmaxf(ty.x, ty.y), fmaxf(tz.x, tz.y)));
+  return t_enter <= t_exit && t_exit >= 0.f;
+}
+
+// Both child boxes of a 64-byte inner node.  Node layout (host_scene.cpp: set_node_boxes): per child and
+// axis {lo, hi} pairs, so that a regular ray tests an axis with one FADD2 and one FMUL2:
+//   a = {l.x.lo, l.x.hi, l.y.lo, l.y.hi}  b = {l.z.lo, l.z.hi, r.x.lo, r.x.hi}  c = {r.y.lo, r.y.hi, r.z.lo, r.z.hi}
+template <bool REGULAR>
+__device__ __forceinline__ void node_boxes(const RayPre& p, const float4 a, const float4 b, const float4 c, bool& hl,
+                                           float& tl, bool& hr, float& tr) {
+  if (REGULAR) {
+    const RayPre2 q = make_pre2(p);
+    hl = box_test_packed(q, make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), tl);
+    hr = box_test_packed(q, make_float2(b.z, b.w), make_float2(c.x, c.y), make_float2(c.z, c.w), tr);
+  } else {
+    hl = box_test(p, a.x, a.z, b.x, a.y, a.w, b.y, tl);
+    hr = box_test(p, b.z, c.x, c.z, b.w, c.y, c.w, tr);
+  }
+}
+
 // Per-ray traversal state.  The walk is cut into "rounds" (descend inner nodes until a leaf is
 // reached, test that one leaf, pop) so that a warp can (a) run the inner-node code and the
 // primitive code as two convergent phases instead of interleaving them lane by lane, and (b) hand
@@ -326,8 +365,8 @@ __device__ __forceinline__ bool walk_round(const DevScene& sc, Walk& w, int* sta
     load_node(n, a, b, c, k);
     if (COUNT) vc->nodes++;
     float tl, tr;
-    bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
-    bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+    bool hl, hr;
+    node_boxes<REGULAR>(w.p, a, b, c, hl, tl, hr, tr);
     if (MODE == 0) {
       const float lim = prune_limit<ANY>(sc, w);
       hl = hl && !(tl > lim);
@@ -414,8 +453,8 @@ __device__ __forceinline__ void walk_loop(const DevScene& sc, Walk& w, int* stac
       int4 k;
       load_node(n, a, b, c, k);
       float tl, tr;
-      bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
-      bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+      bool hl, hr;
+      node_boxes<REGULAR>(w.p, a, b, c, hl, tl, hr, tr);
       if (MODE == 0) {
         const float lim = prune_limit<ANY>(sc, w);
         hl = hl && !(tl > lim);
@@ -516,8 +555,8 @@ __device__ __forceinline__ bool node_step(const DevScene& sc, Walk& w, int* stac
   int4 k;
   load_node(n, a, b, c, k);
   float tl, tr;
-  bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
-  bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+  bool hl, hr;
+  node_boxes<REGULAR>(w.p, a, b, c, hl, tl, hr, tr);
   const float lim = prune_limit<ANY>(sc, w);
   hl = hl && !(tl > lim);
   hr = hr && !(tr > lim);
@@ -652,8 +691,8 @@ __device__ __forceinline__ void walk_shared(const DevScene& sc, Walk& w, SharedS
       int4 k;
       load_node(n, a, b, c, k);
       float tl, tr;
-      bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
-      bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+      bool hl, hr;
+      node_boxes<REGULAR>(w.p, a, b, c, hl, tl, hr, tr);
       const float lim = prune_limit<ANY>(sc, w);
       hl = hl && !(tl > lim);
       hr = hr && !(tr > lim);
@@ -715,8 +754,8 @@ __device__ __forceinline__ bool walk_step_shared(const DevScene& sc, Walk& w, Sh
     int4 k;
     load_node(n, a, b, c, k);
     float tl, tr;
-    bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
-    bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+    bool hl, hr;
+    node_boxes<REGULAR>(w.p, a, b, c, hl, tl, hr, tr);
     const float lim = prune_limit<ANY>(sc, w);
     hl = hl && !(tl > lim);
     hr = hr && !(tr > lim);
@@ -807,8 +846,8 @@ __device__ __forceinline__ bool node_step_shared(const DevScene& sc, Walk& w, Sh
   int4 k;
   load_node(n, a, b, c, k);
   float tl, tr;
-  bool hl = box_any<REGULAR>(w.p, a.x, a.y, a.z, a.w, b.x, b.y, tl);
-  bool hr = box_any<REGULAR>(w.p, b.z, b.w, c.x, c.y, c.z, c.w, tr);
+  bool hl, hr;
+  node_boxes<REGULAR>(w.p, a, b, c, hl, tl, hr, tr);
   const float lim = prune_limit<ANY>(sc, w);
   hl = hl && !(tl > lim);
   hr = hr && !(tr > lim);
@@ -924,29 +963,6 @@ struct SmallScene {
   int pad;
   float2 box[kSmallMax][3];  // leaf boxes in DFS slot order, per axis {lo, hi} (a packed-fp32 operand)
 };
-
-// Slab test for regular rays with Blackwell's packed fp32 instructions (FADD2 / FMUL2, sm_100+):
-// both planes of an axis go through one subtract and one multiply.  add.rn.f32x2(p, -o) is the IEEE
-// p - o and mul.rn.f32x2 the IEEE product, so the two t values per axis are bit-identical to
-// box_test_regular's; only the issue-slot count halves (these kernels are issue bound).
-struct RayPre2 {
-  float2 nox, noy, noz;  // (-o, -o)
-  float2 ix, iy, iz;     // (1/d, 1/d)
-};
-__device__ __forceinline__ RayPre2 make_pre2(const RayPre& p) {
-  RayPre2 q;
-  q.nox = make_float2(-p.ox, -p.ox), q.noy = make_float2(-p.oy, -p.oy), q.noz = make_float2(-p.oz, -p.oz);
-  q.ix = make_float2(p.ix, p.ix), q.iy = make_float2(p.iy, p.iy), q.iz = make_float2(p.iz, p.iz);
-  return q;
-}
-__device__ __forceinline__ bool box_test_packed(const RayPre2& q, float2 bx, float2 by, float2 bz, float& t_enter) {
-  const float2 tx = __fmul2_rn(__fadd2_rn(bx, q.nox), q.ix);
-  const float2 ty = __fmul2_rn(__fadd2_rn(by, q.noy), q.iy);
-  const float2 tz = __fmul2_rn(__fadd2_rn(bz, q.noz), q.iz);
-  t_enter = fmaxf(fminf(tx.x, tx.y), fmaxf(fminf(ty.x, ty.y), fminf(tz.x, tz.y)));
-  const float t_exit = fminf(fmaxf(tx.x, tx.y), fminf(fmaxf(ty.x, ty.y), fmaxf(tz.x, tz.y)));
-  return t_enter <= t_exit && t_exit >= 0.f;
-}
 
 template <bool ANY>
 __device__ __forceinline__ bool traverse_small(const DevScene& sc, const SmallScene& ss, const Ray& r,

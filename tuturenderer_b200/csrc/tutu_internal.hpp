@@ -21,7 +21,7 @@ struct Box {
 
 // 64-byte inner node: both child boxes + child refs (one fetch decides both children).
 struct alignas(16) InnerNode {
-  float box[12];  // [0..2] left.lo, [3..5] left.hi, [6..8] right.lo, [9..11] right.hi
+  float box[12];  // left child: {x.lo, x.hi, y.lo, y.hi, z.lo, z.hi}, then the right child likewise
   int32_t left;
   int32_t right;
   int32_t pad0;
