@@ -245,3 +245,66 @@ def test_binned_order_gives_identical_results(api, oracle, ctx):
         sub = slice(0, 150000, 7)
         assert_hits_equal(np.ascontiguousarray(a[sub]), osc.trace_closest(np.ascontiguousarray(rays[sub])))
         assert np.array_equal(b[sub], osc.trace_any(np.ascontiguousarray(rays[sub])))
+
+
+def _tri_prims(api, v):
+    """(n,3,3) vertices -> TutuPrim triangles with flat normals."""
+    v = np.asarray(v, np.float32)
+    prims = np.zeros(len(v), api.PRIM_DTYPE)
+    prims["tex_diffuse"] = prims["tex_normal"] = prims["tex_roughness"] = prims["tex_metallic"] = -1
+    prims["v"] = v.reshape(len(v), 9)
+    n = np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0])
+    n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-30)
+    prims["n"] = np.repeat(n[:, None, :], 3, 1).reshape(len(v), 9)
+    return prims
+
+
+@pytest.mark.parametrize("case", ["duplicates", "geometric_sizes", "collinear_centroids", "two", "three"])
+def test_fast_tree_edge_cases(api, oracle, ctx, case):
+    """The device walks its own SAH topology for regular rays (host_scene.cpp: build_fast_tree).
+    Scenes that stress the builder — identical primitives (no centroid extent: median fallback, equal-t
+    ties resolved by DFS slot), sizes spanning 2^-20..1 (deep SAH trees: the depth cap), collinear
+    centroids, and tiny scenes — must give the literal walk's and the oracle's hits bit for bit."""
+    rng = np.random.default_rng(3)
+    if case == "duplicates":
+        base = rng.uniform(0, 4, (3, 3, 3))
+        v = np.concatenate([np.repeat(base[k:k + 1], 40, 0) for k in range(3)])
+    elif case == "geometric_sizes":
+        k = np.arange(400)
+        s = (2.0 ** (-(k % 21)))[:, None, None]
+        c = np.stack([s[:, 0, 0] * 3, 0 * k, 0.001 * k], -1)[:, None, :]
+        v = c + s * rng.uniform(-1, 1, (400, 3, 3))
+    elif case == "collinear_centroids":
+        t = np.linspace(0, 10, 300)[:, None, None]
+        tri = np.array([[0, 0, 0], [0.3, 0, 0.1], [0, 0.3, 0.2]], np.float64)
+        tri -= tri.mean(0)
+        v = tri[None] + t * np.array([1.0, 0.5, 0.25])
+    elif case == "two":
+        v = rng.uniform(0, 4, (2, 3, 3))
+    else:
+        v = rng.uniform(0, 4, (3, 3, 3))
+    prims = _tri_prims(api, v)
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    ctx.upload(sc)
+    lo, hi = v.reshape(-1, 3).min(0), v.reshape(-1, 3).max(0)
+    n = 70000  # above the binning threshold
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(lo - 1, hi + 1, (n, 3))
+    tgt = v.reshape(-1, 3)[rng.integers(0, len(v) * 3, n)] + rng.normal(0, 0.05, (n, 3))
+    d = (tgt - rays[:, 0:3]).astype(np.float32)
+    mag = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]).astype(np.float32)
+    rays[:, 4:7] = d * (np.float32(1) / np.maximum(mag, np.float32(1e-20)))[:, None]
+    rays[:, 7] = rng.uniform(0.1, 12, n)
+    rays[::500, 4:7] = (1, 0, 0)  # irregular rays walk the reference topology
+    ctx.set_traversal_mode(0)
+    a, b = ctx.trace_closest(rays), ctx.trace_any(rays)
+    ctx.set_traversal_mode(1)
+    c, d1 = ctx.trace_closest(rays), ctx.trace_any(rays)
+    ctx.set_traversal_mode(0)
+    assert_hits_equal(a, c)
+    assert np.array_equal(b, d1)
+    sub = slice(0, n, 9)
+    osc = oracle.OracleScene(sc)
+    assert_hits_equal(np.ascontiguousarray(a[sub]), osc.trace_closest(np.ascontiguousarray(rays[sub])))
+    assert np.array_equal(b[sub], osc.trace_any(np.ascontiguousarray(rays[sub])))
+    assert (a["prim"] >= 0).mean() > 0.2
