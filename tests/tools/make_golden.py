@@ -137,16 +137,31 @@ def c4_goldens():
     reference's PathTracing."""
     from tools.scenes import glass_scene
     O.build(ref=True)
-    sc = O.ref_export_bvh(glass_scene(96, 96), G / "glass_c4.tscene")
     stats = json.loads((G / "stats.json").read_text())
     def rmse(a, b): return float(np.sqrt(((a - b) ** 2).mean()))
-    runs = [O.ref_render(sc, 1024)[0] for _ in range(2)]
-    mean = (runs[0] + runs[1]) * 0.5
-    mean.astype(np.float32).tofile(G / "glass_c4_96_ref_mean_2048.f32")
-    stats["glass_c4_96"] = {"ref_spp_total": 2048, "image_mean": float(np.nanmean(mean)),
+    if "--bdpt-only" in sys.argv:
+        sc = api.Scene.load(G / "glass_c4.tscene")
+        stats_pt = stats["glass_c4_96"]
+    else:
+        sc = O.ref_export_bvh(glass_scene(96, 96), G / "glass_c4.tscene")
+        runs = [O.ref_render(sc, 1024)[0] for _ in range(2)]
+        mean = (runs[0] + runs[1]) * 0.5
+        mean.astype(np.float32).tofile(G / "glass_c4_96_ref_mean_2048.f32")
+    stats["glass_c4_96"] = stats_pt if "--bdpt-only" in sys.argv else {"ref_spp_total": 2048, "image_mean": float(np.nanmean(mean)),
                             "channel_means": [float(x) for x in np.nanmean(mean, (0, 1))],
                             "run_to_run_rmse_1024": rmse(runs[0], runs[1]), "nan_pixels": int(np.isnan(mean).any(-1).sum())}
     print(stats["glass_c4_96"])
+    # the same scene through the reference's BDPT (64x64): MICROFACET_T / MICROFACET_R / textures in buildEyePath,
+    # buildLightPath (adjoint BSDF) and MISweight
+    sc64 = sc.with_size(64, 64)
+    runs = [O.ref_render(sc64, 512, mode="bdpt-rows")[0] for _ in range(2)]
+    mean = (runs[0] + runs[1]) * 0.5
+    mean.astype(np.float32).tofile(G / "glass_c4_64_bdpt_ref_mean_1024.f32")
+    stats["glass_c4_64_bdpt"] = {"ref_spp_total": 1024, "image_mean": float(np.nanmean(mean)),
+                                 "channel_means": [float(x) for x in np.nanmean(mean, (0, 1))],
+                                 "run_to_run_rmse_512": rmse(runs[0], runs[1]),
+                                 "median_abs_run_to_run_512": float(np.median(np.abs(runs[0] - runs[1])))}
+    print(stats["glass_c4_64_bdpt"])
     (G / "stats.json").write_text(json.dumps(stats, indent=1))
 
 
