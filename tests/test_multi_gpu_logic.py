@@ -53,6 +53,50 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
+def _worker_bdpt(rank, world, port, out_path):
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    from tuturenderer_b200 import api
+    from tuturenderer_b200.multigpu import render_distributed
+    from oracle import oracle_py
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = api.Scene.load(ROOT / "tests/golden/cornell_256.tscene").with_size(20, 20)
+    sc.bkgcolor = (0.1, 0.2, 0.3)
+    osc = oracle_py.OracleScene(sc)
+    spp = 5
+    bkg = np.array(sc.bkgcolor, np.float32)
+
+    def accumulate(begin, count, accum):
+        # the oracle returns bkgcolor + sums / total_spp; with total_spp = 1 the sums are (img - bkg)
+        img = osc.render_bdpt(count, seed=9, sample_begin=begin, total_spp=1, threads=1)
+        accum += torch.from_numpy((img - bkg).reshape(-1))
+
+    accum = torch.zeros(20 * 20 * 3, dtype=torch.float32)
+    render_distributed(accumulate, accum, spp, rank, world, dist)
+    if rank == 0:
+        np.save(out_path, (accum / spp).numpy().reshape(20, 20, 3) + bkg)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bdpt_equals_single_rank(api, oracle, tmp_path):
+    """BDPT shards the same way (t = 1 splats land in the rank's own full-frame buffer; bkgcolor is
+    added once after the reduce)."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "img.npy"
+    mp.spawn(_worker_bdpt, args=(2, port, str(out)), nprocs=2, join=True)
+    got = np.load(out)
+    sc = api.Scene.load(ROOT / "tests/golden/cornell_256.tscene").with_size(20, 20)
+    sc.bkgcolor = (0.1, 0.2, 0.3)
+    want = oracle.OracleScene(sc).render_bdpt(5, seed=9, threads=1)
+    assert np.allclose(got, want, rtol=2e-5, atol=2e-6)
+
+
 def test_two_rank_gloo_render_equals_single_rank(api, oracle, tmp_path):
     import torch.multiprocessing as mp
     with socket.socket() as s:

@@ -70,6 +70,18 @@ class CudaRenderer:
         self.ctx.finalize_device(accum.data_ptr(), 1.0 / spp, self.rgb.data_ptr(), stream)
         return self.rgb.view(self.scene.height, self.scene.width, 3)
 
+    def render_bdpt(self, spp: int, seed: int, rank: int = 0, world: int = 1):
+        """One whole BDPT frame (reference include/BDPT.hpp): ranks add the strategy sums of their sample
+        range (t = 1 splats land in the same full-frame buffer), one reduce, then bkgcolor + sum / spp."""
+        self.accum.zero_()
+        stream = lambda: self.api.stream_handle(self.torch.cuda.current_stream().cuda_stream)
+        render_distributed(lambda b, c, a: self.ctx.render_bdpt_accumulate_device(b, c, seed, a.data_ptr(), stream()),
+                           self.accum, spp, rank, world)
+        if rank == 0:
+            self.ctx.finalize_bdpt_device(self.accum.data_ptr(), 1.0 / spp, self.rgb.data_ptr(), stream())
+            return self.rgb.view(self.scene.height, self.scene.width, 3)
+        return None
+
     def render(self, spp: int, seed: int, rank: int = 0, world: int = 1):
         """One whole frame; returns the image tensor on rank 0 (None elsewhere)."""
         self.accum.zero_()
