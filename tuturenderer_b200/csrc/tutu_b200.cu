@@ -115,7 +115,10 @@ struct TutuCtx {
 
   // ray batches
   DevBuf d_rays, d_hits, d_blocked, d_counts;
-  DevBuf d_bin_keys, d_bin_perm, d_bin_hist;
+  DevBuf d_bin_keys[2], d_bin_perm[2], d_bin_hist[2];  // [pipeline slot]
+  // host-buffer ray batches are pipelined in chunks over two streams (H2D | walk | D2H overlap)
+  cudaStream_t stream2 = nullptr;
+  DevBuf d_chunk_rays[2], d_chunk_out[2];
   int ray_binning = 1;              // 0 = trace in the caller's order
   uint64_t ray_binning_min = 1u << 16;
 
@@ -568,15 +571,15 @@ size_t stack_smem(const TutuCtx* ctx, int block, bool any) {
 }
 
 // Builds the coherent traversal order of a batch (nullptr = trace in the caller's order).
-const unsigned* bin_rays(TutuCtx* ctx, const float4* rays, uint64_t n, cudaStream_t s) {
+const unsigned* bin_rays(TutuCtx* ctx, const float4* rays, uint64_t n, cudaStream_t s, int slot = 0) {
   if (!ctx->ray_binning || !(ctx->traversal_mode == 0 || ctx->traversal_mode >= 10) || ctx->small.n > 0 || n < ctx->ray_binning_min || n >= (1ull << 32))
     return nullptr;
-  ctx->d_bin_keys.ensure(n * sizeof(unsigned));
-  ctx->d_bin_perm.ensure(n * sizeof(unsigned));
-  ctx->d_bin_hist.ensure((size_t)(kBinCount + 1024) * sizeof(unsigned));
-  unsigned* keys = ctx->d_bin_keys.as<unsigned>();
-  unsigned* perm = ctx->d_bin_perm.as<unsigned>();
-  unsigned* hist = ctx->d_bin_hist.as<unsigned>();
+  ctx->d_bin_keys[slot].ensure(n * sizeof(unsigned));
+  ctx->d_bin_perm[slot].ensure(n * sizeof(unsigned));
+  ctx->d_bin_hist[slot].ensure((size_t)(kBinCount + 1024) * sizeof(unsigned));
+  unsigned* keys = ctx->d_bin_keys[slot].as<unsigned>();
+  unsigned* perm = ctx->d_bin_perm[slot].as<unsigned>();
+  unsigned* hist = ctx->d_bin_hist[slot].as<unsigned>();
   CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)kBinCount * sizeof(unsigned), s));
   const int grid = ctx->sm_count * 8;
   k_bin_count<<<grid, 256, 0, s>>>(ctx->dev, rays, (unsigned)n, keys, hist);
@@ -588,10 +591,10 @@ const unsigned* bin_rays(TutuCtx* ctx, const float4* rays, uint64_t n, cudaStrea
   return perm;
 }
 
-void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_out, cudaStream_t s) {
+void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_out, cudaStream_t s, int slot = 0) {
   if (n == 0) return;
   ctx->d_counts.ensure(64);
-  unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 4;
+  unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 4 + 2 * slot;  // cursors: [4] closest, [5] any, [6],[7] slot 1
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
   if (ctx->traversal_mode >= 10) {
@@ -601,7 +604,7 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
     int grid = persistent_grid(ctx, k_trace_variant<false, V>, 256, sm);                    \
     k_trace_variant<false, V><<<grid, 256, sm, s>>>(ctx->dev, rays, n, d_out, nullptr, next, perm); \
   } break;
-    const unsigned* perm = bin_rays(ctx, rays, n, s);
+    const unsigned* perm = bin_rays(ctx, rays, n, s, slot);
     switch (ctx->traversal_mode - 10) {
       TUTU_VAR_C(0) TUTU_VAR_C(1) TUTU_VAR_C(2) TUTU_VAR_C(3) TUTU_VAR_C(4) TUTU_VAR_C(5) TUTU_VAR_C(6) TUTU_VAR_C(7)
     }
@@ -617,7 +620,7 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
       int grid = persistent_grid(ctx, k_trace_closest<3>, 256);
       k_trace_closest<3><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
     } else {
-      const unsigned* perm = bin_rays(ctx, rays, n, s);
+      const unsigned* perm = bin_rays(ctx, rays, n, s, slot);
       const size_t sm = stack_smem(ctx, 256, false);
       int grid = persistent_grid(ctx, k_trace_closest<0>, 256, sm);
       k_trace_closest<0><<<grid, 256, sm, s>>>(ctx->dev, ctx->small, rays, n, d_out, next, perm);
@@ -626,10 +629,10 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
   CUDA_TRY(cudaGetLastError());
 }
 
-void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t s) {
+void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t s, int slot = 0) {
   if (n == 0) return;
   ctx->d_counts.ensure(64);
-  unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 5;
+  unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 5 + 2 * slot;
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
   if (ctx->traversal_mode >= 10) {
@@ -639,7 +642,7 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
     int grid = persistent_grid(ctx, k_trace_variant<true, V>, 256, sm);                    \
     k_trace_variant<true, V><<<grid, 256, sm, s>>>(ctx->dev, rays, n, nullptr, d_out, next, perm); \
   } break;
-    const unsigned* perm = bin_rays(ctx, rays, n, s);
+    const unsigned* perm = bin_rays(ctx, rays, n, s, slot);
     switch (ctx->traversal_mode - 10) {
       TUTU_VAR_A(0) TUTU_VAR_A(1) TUTU_VAR_A(2) TUTU_VAR_A(3) TUTU_VAR_A(4) TUTU_VAR_A(5) TUTU_VAR_A(6) TUTU_VAR_A(7)
     }
@@ -655,7 +658,7 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
       int grid = persistent_grid(ctx, k_trace_any<3>, 256);
       k_trace_any<3><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
     } else {
-      const unsigned* perm = bin_rays(ctx, rays, n, s);
+      const unsigned* perm = bin_rays(ctx, rays, n, s, slot);
       int grid = persistent_grid(ctx, k_trace_any<0>, 256);
       k_trace_any<0><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next, perm);
     }
@@ -1058,6 +1061,7 @@ extern "C" void tutu_ctx_destroy(TutuCtx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->bdpt_ctl_host) cudaFreeHost(ctx->bdpt_ctl_host);
   delete ctx;
 }
@@ -1199,18 +1203,42 @@ extern "C" int tutu_trace_any_device(TutuCtx* ctx, const float* d_rays, uint64_t
   API_END(ctx)
 }
 
+// Host-buffer batches: chunks of kHostChunk rays alternate between two streams, so that the H2D copy of
+// one chunk, the walk of the previous one and the D2H copy of the one before overlap (PCIe is full duplex;
+// with pinned host buffers the batch costs ~max(H2D, walk, D2H) instead of their sum).
+constexpr uint64_t kHostChunk = 1ull << 21;
+
+template <class Out, class Launch>
+static void trace_host_pipelined(TutuCtx* ctx, const float* rays, uint64_t n_rays, Out* out, Launch launch) {
+  if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  cudaStream_t st[2] = {ctx->stream, ctx->stream2};
+  const uint64_t chunk = std::min<uint64_t>(kHostChunk, n_rays);
+  const int slots = n_rays > chunk ? 2 : 1;
+  for (int k = 0; k < slots; ++k) {
+    ctx->d_chunk_rays[k].ensure(chunk * TUTU_RAY_FLOATS * sizeof(float));
+    ctx->d_chunk_out[k].ensure(chunk * sizeof(Out));
+  }
+  int k = 0;
+  for (uint64_t first = 0; first < n_rays; first += chunk, k ^= 1) {
+    const uint64_t m = std::min<uint64_t>(chunk, n_rays - first);
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_chunk_rays[k].p, rays + first * TUTU_RAY_FLOATS, m * TUTU_RAY_FLOATS * sizeof(float),
+                             cudaMemcpyHostToDevice, st[k]));
+    launch(ctx->d_chunk_rays[k].as<float>(), m, ctx->d_chunk_out[k].as<Out>(), st[k], k);
+    CUDA_TRY(cudaMemcpyAsync(out + first, ctx->d_chunk_out[k].p, m * sizeof(Out), cudaMemcpyDeviceToHost, st[k]));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st[0]));
+  if (slots > 1) CUDA_TRY(cudaStreamSynchronize(st[1]));
+}
+
 extern "C" int tutu_trace_closest(TutuCtx* ctx, const float* rays, uint64_t n_rays, TutuHit* hits_out) {
   API_BEGIN(ctx)
   if (int rc = check_scene(ctx)) return rc;
   if (n_rays == 0) return TUTU_OK;
   if (!rays || !hits_out) return fail(ctx, TUTU_E_INVALID, "tutu_trace_closest: null buffer");
-  cudaStream_t s = ctx->stream;
-  ctx->d_rays.ensure(n_rays * TUTU_RAY_FLOATS * sizeof(float));
-  ctx->d_hits.ensure(n_rays * sizeof(TutuHit));
-  CUDA_TRY(cudaMemcpyAsync(ctx->d_rays.p, rays, n_rays * TUTU_RAY_FLOATS * sizeof(float), cudaMemcpyHostToDevice, s));
-  launch_closest(ctx, ctx->d_rays.as<float>(), n_rays, ctx->d_hits.as<TutuHit>(), s);
-  CUDA_TRY(cudaMemcpyAsync(hits_out, ctx->d_hits.p, n_rays * sizeof(TutuHit), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  trace_host_pipelined<TutuHit>(ctx, rays, n_rays, hits_out,
+                                [&](const float* d_rays, uint64_t m, TutuHit* d_out, cudaStream_t s, int slot) {
+                                  launch_closest(ctx, d_rays, m, d_out, s, slot);
+                                });
   return TUTU_OK;
   API_END(ctx)
 }
@@ -1220,13 +1248,10 @@ extern "C" int tutu_trace_any(TutuCtx* ctx, const float* rays, uint64_t n_rays, 
   if (int rc = check_scene(ctx)) return rc;
   if (n_rays == 0) return TUTU_OK;
   if (!rays || !blocked_out) return fail(ctx, TUTU_E_INVALID, "tutu_trace_any: null buffer");
-  cudaStream_t s = ctx->stream;
-  ctx->d_rays.ensure(n_rays * TUTU_RAY_FLOATS * sizeof(float));
-  ctx->d_blocked.ensure(n_rays);
-  CUDA_TRY(cudaMemcpyAsync(ctx->d_rays.p, rays, n_rays * TUTU_RAY_FLOATS * sizeof(float), cudaMemcpyHostToDevice, s));
-  launch_any(ctx, ctx->d_rays.as<float>(), n_rays, ctx->d_blocked.as<uint8_t>(), s);
-  CUDA_TRY(cudaMemcpyAsync(blocked_out, ctx->d_blocked.p, n_rays, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  trace_host_pipelined<uint8_t>(ctx, rays, n_rays, blocked_out,
+                                [&](const float* d_rays, uint64_t m, uint8_t* d_out, cudaStream_t s, int slot) {
+                                  launch_any(ctx, d_rays, m, d_out, s, slot);
+                                });
   return TUTU_OK;
   API_END(ctx)
 }
