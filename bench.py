@@ -281,7 +281,7 @@ def bdpt_bench(torch, api, do_cpu: bool, spp: int) -> dict:
     npix = 800 * 600
     host_img = torch.empty(npix * 3, dtype=torch.float32, pin_memory=True)
     for k in range(3):
-        ctx.render_bdpt_ptr(8, SEED + k, host_img.data_ptr())
+        ctx.render_bdpt_ptr(16, SEED + k, host_img.data_ptr())  # 7.7 M samples: the 4 Mi-sample batch pool reaches its full size
     t0 = time.perf_counter()
     ctx.upload(sc)
     ctx.render_bdpt_ptr(spp, SEED + 9, host_img.data_ptr())  # host scene in, pinned host image out
