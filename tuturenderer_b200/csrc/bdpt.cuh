@@ -294,7 +294,7 @@ __device__ __forceinline__ MisRec light_mis(const BdptBuffers& b, unsigned i, in
 }
 
 // ---- start -------------------------------------------------------------------------------------
-// entry 2i = eye walk of sample i, entry 2i+1 = its light walk
+// entry i = eye walk of sample i (neighbouring pixels share a warp), entry n + i = its light walk
 __global__ void __launch_bounds__(256)
 bdpt_start(const __grid_constant__ DevScene sc, const __grid_constant__ BdptCam cam, BdptBuffers b,
            unsigned long long first_path, unsigned n, unsigned sample_begin, uint64_t seed) {
@@ -307,9 +307,9 @@ bdpt_start(const __grid_constant__ DevScene sc, const __grid_constant__ BdptCam 
     bdpt_pixel(cam, pixel, pixelPos, rayDir);
     float camFwd, tp0;
     bdpt_cam_pdfs(cam, pixelPos, rayDir, camFwd, tp0);
-    b.q_o[0][2 * i] = make_float4(cam.eye[0], cam.eye[1], cam.eye[2], __uint_as_float(i));
-    b.q_d[0][2 * i] = make_float4(rayDir.x, rayDir.y, rayDir.z, __uint_as_float((kKindEye << 8) | 1u));
-    b.q_tp[0][2 * i] = make_float4(tp0, tp0, tp0, 0.f);
+    b.q_o[0][i] = make_float4(cam.eye[0], cam.eye[1], cam.eye[2], __uint_as_float(i));
+    b.q_d[0][i] = make_float4(rayDir.x, rayDir.y, rayDir.z, __uint_as_float((kKindEye << 8) | 1u));
+    b.q_tp[0][i] = make_float4(tp0, tp0, tp0, 0.f);
     b.nE[i] = 0;  // becomes >= 1 once the primary ray hits (bdpt_vertex)
     b.nL[i] = 0;
     // ---- buildLightPath up to the first ray, BDPT.hpp:296-326 ----
@@ -344,9 +344,9 @@ bdpt_start(const __grid_constant__ DevScene sc, const __grid_constant__ BdptCam 
         ltp = make_float4(tp2.x, tp2.y, tp2.z, 0.f);
       }
     }
-    b.q_o[0][2 * i + 1] = lo;
-    b.q_d[0][2 * i + 1] = ld;
-    b.q_tp[0][2 * i + 1] = ltp;
+    b.q_o[0][n + i] = lo;
+    b.q_d[0][n + i] = ld;
+    b.q_tp[0][n + i] = ltp;
   }
 }
 
