@@ -195,9 +195,9 @@ def workload_config(args) -> dict:
                         "scene = reference src/main_cornellBox.cpp via tests/golden/cornell_256.tscene)",
             "width": WIDTH, "height": HEIGHT, "spp": args.spp, "max_depth": 6,
             "parallelism": f"spp split over {args.gpus} GPU(s), one fp32 reduce of the {WIDTH * HEIGHT * 3 * 4 / 1e6:.1f} MB accumulation buffer",
-            "wavefront": "1 lane x 16 Mi paths in flight",
+            "wavefront": "2 interleaved lanes x 16 Mi paths in flight",
             "l2_policy": "inputs larger than L2: each wavefront iteration streams 16 Mi paths x ~330 B of queue records "
-                         "(5 GB) through the 126 MB L2; no flush needed"}
+                         "(5 GB per lane) through the 126 MB L2; no flush needed"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -442,7 +442,16 @@ def main():
         "wf_shadow": shd * (B_SHADOW + 32),
     }
     iters = max(cnt["iterations"], 1)
-    ach = alg[dominant] / (stage_ms[dominant] * 1e-3) * 1e-9 if stage_ms[dominant] > 0 else 0.0
+    # The two wavefront lanes run on separate streams and their kernels co-run at the hand-over points, so a
+    # kernel's event-to-event time contains slots it yields to the other lane: the stage times sum to more
+    # than the wall time.  Each kernel is therefore charged its SHARE of the timed region
+    # (stage_ms / sum(stage_ms) x wall ms) — the quantity the ncu launch list checks — and the raw sums are
+    # reported next to it.
+    wall_ms = agg["gpu_ms"]
+    stage_sum = sum(stage_ms.values()) + agg["other_ms"]
+    scale = wall_ms / stage_sum if stage_sum > 0 else 1.0
+    charged_ms = {k: v * scale for k, v in stage_ms.items()}
+    ach = alg[dominant] / (charged_ms[dominant] * 1e-3) * 1e-9 if charged_ms[dominant] > 0 else 0.0
     prof = ROOT / "profiles" / "r01_traffic.json"  # dram bytes per launch from the ncu --set full capture
     traffic = None
     if prof.exists():
@@ -452,13 +461,16 @@ def main():
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
                 "peak_source": "fallback 6650 GB/s" if peaks.get("fallback") else "MEASURED_PEAKS.json hbm_gbs (measured)",
-                "avg_launch_ms": stage_ms[dominant] / iters, "algorithmic_bytes_per_launch": alg[dominant] / iters,
-                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-                "stage_gbs": {k: (alg[k] / (v * 1e-3) * 1e-9 if v > 0 else 0.0) for k, v in stage_ms.items()},
+                "avg_launch_ms": charged_ms[dominant] / iters, "algorithmic_bytes_per_launch": alg[dominant] / iters,
+                "duration_note": "lanes co-run: each kernel is charged stage_ms / sum(stage_ms) x wall ms of the timed region",
+                "stage_share": {k: v / stage_sum for k, v in stage_ms.items()},
+                "stage_ms_per_step": {k: v / args.steps for k, v in charged_ms.items()},
+                "stage_ms_per_step_raw_event_sums": {k: v / args.steps for k, v in stage_ms.items()},
+                "stage_gbs": {k: (alg[k] / (v * 1e-3) * 1e-9 if v > 0 else 0.0) for k, v in charged_ms.items()},
                 "bytes_per_path": sum(alg.values()) / max(pth, 1),
                 "rays_per_path": {"extend": ext / max(pth, 1), "shadow": shd / max(pth, 1)},
-                "note": "Cornell's BVH is 6 KB and lives in L1: the wavefront kernels are issue/latency bound, "
-                        "the HBM fraction is reported because north_star asks for it"}
+                "note": "Cornell's BVH is 6 KB and lives in the constant bank: extend / shadow are issue bound, shade is "
+                        "latency bound; the HBM fraction is reported because north_star asks for it"}
 
     rays = None
     if not args.no_rays:
@@ -487,8 +499,8 @@ def main():
             "rays": rays,
             "bdpt": bdpt,
             "glass_c4": glass,
-            "mrays_per_s_in_render": {"extend": ext * world / (agg["extend_ms"] * 1e-3) * 1e-6 if agg["extend_ms"] else None,
-                                      "shadow": shd * world / (agg["shadow_ms"] * 1e-3) * 1e-6 if agg["shadow_ms"] else None},
+            "mrays_per_s_in_render": {"extend": ext * world / (charged_ms["wf_extend"] * 1e-3) * 1e-6 if charged_ms["wf_extend"] else None,
+                                      "shadow": shd * world / (charged_ms["wf_shadow"] * 1e-3) * 1e-6 if charged_ms["wf_shadow"] else None},
             "nan_samples": cnt["nan_samples"],
         }
         print(json.dumps(line))

@@ -237,7 +237,7 @@ int tutu_finalize_bdpt_device(TutuCtx* ctx, const float* d_accum, float inv_spp,
                               void* stream);
 int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
 /* Knobs: paths in flight per wavefront lane (0 = default 16 Mi; BDPT: samples per batch, default
- * 4 Mi), number of interleaved wavefront lanes (0 = default 1), per-stage event timing on/off. */
+ * 4 Mi), number of interleaved wavefront lanes (0 = default 2), per-stage event timing on/off. */
 int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int lanes, int profile_stages);
 
 /* ---- output stage: PPMGenerator::writePixel (reference include/PPMGenerator.hpp:812-845) ---- */

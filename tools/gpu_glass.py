@@ -9,7 +9,7 @@ sc = api.Scene.load(ROOT / "tests/golden/glass_c4.tscene").with_size(1024, 1024)
 ctx = api.Context(0)
 ctx.upload(sc)
 for SPP in (128,):
-  for lanes in (1,):
+  for lanes in (1, 2):
     for pif in (16 << 20,):
         for prof in (True,):
             ctx.configure(pif, prof, lanes)

@@ -9,8 +9,8 @@ sc = api.Scene.load(ROOT / "tests/golden/cornell_256.tscene").with_size(1024, 10
 ctx = api.Context(0)
 ctx.upload(sc)
 SPP = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-for lanes in (1, 2):
-    for pif in (4 << 20, 8 << 20, 16 << 20, 32 << 20):
+for lanes in (1, 2, 3):
+    for pif in (8 << 20, 16 << 20):
         ctx.configure(pif, False, lanes)
         ctx.render_path(32, seed=1)
         best = 1e9

@@ -685,9 +685,9 @@ void fill_raygen(const FlatScene& f, RayGenK* k) {
 // ---------------------------------------------------------------------------------------------
 // wavefront host loop
 // ---------------------------------------------------------------------------------------------
-// One wavefront "lane": its own queues, control block and stream.  Several lanes can run interleaved
-// (tutu_render_configure): each lane's grids are then sized to 1/lanes of the resident-block count
-// so that kernels of different lanes fit on an SM together.  The default is ONE lane.
+// One wavefront "lane": its own queues, control block and stream.  Lanes run interleaved on separate
+// streams, staggered by one stage, every kernel at its full persistent grid; the
+// default is two lanes of 16 Mi paths.
 void lane_prepare(TutuCtx* ctx, WfLane& L, uint64_t cap) {
   cap = (cap + 255) & ~(uint64_t)255;
   if (cap > L.capacity) {
@@ -764,17 +764,18 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   if (total == 0) return;
 
   // lanes: split the samples; a lane never gets less than ~one wavefront of paths
-  // Defaults measured on Cornell 1024^2 @ 1024 spp (tools/gpu_lanes.py, Mpaths/s): 1 lane x 4 / 8 / 16 /
-  // 32 Mi paths in flight = 1556 / 1634 / 1667 / 1680; 2 interleaved lanes = 1241 / 1316 / 1441 / 1593.
-  // (The two-lane interleave paid off only while wf_shade left most issue slots idle.)
-  int n_lanes = ctx->lanes_cfg > 0 ? ctx->lanes_cfg : 1;
+  // Defaults measured on Cornell 1024^2 (tools/gpu_lanes.py, Mpaths/s): 1 lane x 4 / 8 / 16 / 32 Mi paths in
+  // flight = 1556 / 1634 / 1667 / 1680.  Two lanes with every kernel launched at its FULL persistent grid
+  // (the lanes then mostly alternate; one lane's next kernel fills the SMs that the other's draining kernel
+  // frees): 2 x 16 Mi = 1725 vs 1659 for 1 x 16 Mi.  (Grids halved per lane: 1441.)
+  int n_lanes = ctx->lanes_cfg > 0 ? ctx->lanes_cfg : 2;
   const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)16 << 20;
   while (n_lanes > 1 && (sample_count < (uint32_t)n_lanes || total / n_lanes < cap_cfg / 2)) --n_lanes;
   if ((int)ctx->wf_lanes.size() < n_lanes) ctx->wf_lanes.resize(n_lanes);
   if (ctx->grid_lanes != n_lanes || ctx->grid_small != (ctx->small.n > 0) || ctx->grid_shade_block != ctx->shade_block) {
     ctx->grid_shade_block = ctx->shade_block;
     ctx->grid_small = ctx->small.n > 0;
-    const int div = n_lanes;
+    const int div = getenv("TUTU_GRID_SPLIT") ? n_lanes : 1;  // experiments only: split the resident blocks between the lanes
     auto sized = [&](int full) { return ctx->sm_count * std::max(1, full / ctx->sm_count / div); };
     const bool small = ctx->small.n > 0;
     ctx->grid_extend = sized(small ? persistent_grid(ctx, wf_extend<true>, 256)
