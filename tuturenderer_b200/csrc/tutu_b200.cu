@@ -95,6 +95,22 @@ struct WfLane {
   }
 };
 
+struct BdptLane {
+  DevBuf pool, ctl;
+  BdptBuffers b{};
+  BdptCtl* ctl_host = nullptr;  // pinned
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_done = nullptr;
+  BdptLane() = default;
+  BdptLane(const BdptLane&) = delete;
+  BdptLane& operator=(const BdptLane&) = delete;
+  ~BdptLane() {
+    if (stream) cudaStreamDestroy(stream);
+    if (ctl_host) cudaFreeHost(ctl_host);
+    if (ev_done) cudaEventDestroy(ev_done);
+  }
+};
+
 struct TutuCtx {
   int device = 0;
   int sm_count = 148;
@@ -122,11 +138,8 @@ struct TutuCtx {
   int ray_binning = 1;              // 0 = trace in the caller's order
   uint64_t ray_binning_min = 1u << 16;
 
-  // BDPT
-  DevBuf bdpt_pool, bdpt_ctl;
-  BdptBuffers bdpt{};
-  uint64_t bdpt_capacity = 0;
-  BdptCtl* bdpt_ctl_host = nullptr;  // pinned
+  // BDPT: two lanes, batches alternate between them
+  BdptLane bdpt_lanes[2];
 
   // wavefront
   DevBuf d_accum, d_rgb;
@@ -906,17 +919,16 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
 // ---------------------------------------------------------------------------------------------
 // BDPT host loop (bdpt.cuh)
 // ---------------------------------------------------------------------------------------------
-void bdpt_prepare(TutuCtx* ctx, uint64_t cap) {
+void bdpt_prepare(TutuCtx* ctx, BdptLane& L, uint64_t cap) {
   cap = (cap + 255) & ~(uint64_t)255;
   {
     // float4 arrays: 6 vertex arrays x 14 slots, walk queue 2 x 3 x (2 cap), hit (2 cap), shadow 3 x (7 cap)
     const size_t n_f4 = (size_t)6 * kBdptSlots + 2 * 3 * 2 + 2 + 3 * kBdptMaxLen;
     const size_t bytes = n_f4 * cap * sizeof(float4) + (size_t)kBdptSlots * cap * sizeof(float) + 2 * cap;
-    ctx->bdpt_pool.ensure(bytes);  // grows only; the arrays are laid out for THIS batch size
-    ctx->bdpt_capacity = cap;
+    L.pool.ensure(bytes);  // grows only; the arrays are laid out for THIS batch size
   }
-  BdptBuffers& b = ctx->bdpt;
-  float4* p = ctx->bdpt_pool.as<float4>();
+  BdptBuffers& b = L.b;
+  float4* p = L.pool.as<float4>();
   b.vP = p, p += kBdptSlots * cap;
   b.vNg = p, p += kBdptSlots * cap;
   b.vNs = p, p += kBdptSlots * cap;
@@ -935,14 +947,19 @@ void bdpt_prepare(TutuCtx* ctx, uint64_t cap) {
   b.vMet = reinterpret_cast<float*>(p);
   b.nE = reinterpret_cast<unsigned char*>(b.vMet + kBdptSlots * cap);
   b.nL = b.nE + cap;
-  ctx->bdpt_ctl.ensure(sizeof(BdptCtl));
-  b.ctl = ctx->bdpt_ctl.as<BdptCtl>();
+  L.ctl.ensure(sizeof(BdptCtl));
+  b.ctl = L.ctl.as<BdptCtl>();
   b.cap = (unsigned)cap;
-  if (!ctx->bdpt_ctl_host) CUDA_TRY(cudaMallocHost(&ctx->bdpt_ctl_host, sizeof(BdptCtl)));
+  if (!L.ctl_host) CUDA_TRY(cudaMallocHost(&L.ctl_host, sizeof(BdptCtl)));
+  if (!L.stream) CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+  if (!L.ev_done) CUDA_TRY(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
 }
 
 // Adds the strategy sums of samples [sample_begin, sample_begin+sample_count) of every pixel into
-// d_accum.  Everything is enqueued on `s`; the call returns after the work is done (stats readback).
+// d_accum.  Batches alternate between two lanes (own pools, own streams): the late walk iterations and
+// the long path lengths of a batch carry few rays and leave most SMs idle, which the other lane's
+// batch fills.  The lanes' streams are ordered after everything already on `s`, and `s` after them;
+// the call returns once the work is done (stats readback).
 void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint64_t seed, float* d_accum,
                  cudaStream_t s) {
   const FlatScene& f = ctx->flat;
@@ -950,12 +967,14 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
   const uint64_t total = npix * sample_count;
   ctx->stats = TutuRenderStats{};
   if (total == 0) return;
-  // samples per batch (tools/gpu_bdpt_batch.py, Veach 800x600, Msamples/s): 0.5 / 1 / 2 / 4 / 8 Mi = 45.9 / 51.1 /
-  // 54.2 / 56.2 / 57.3; 4 Mi samples hold 8.2 GB of vertices and queues
+  // samples per batch (tools/gpu_bdpt_batch.py, Veach 800x600, Msamples/s, one lane): 0.5 / 1 / 2 / 4 / 8 Mi =
+  // 45.9 / 51.1 / 54.2 / 56.2 / 57.3; 4 Mi samples hold 8.2 GB of vertices and queues
   const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)4 << 20;
-  bdpt_prepare(ctx, std::min<uint64_t>(cap_cfg, total));
-  BdptBuffers& b = ctx->bdpt;
-  b.accum = d_accum;
+  const uint64_t cap = std::min<uint64_t>(cap_cfg, total);
+  const uint64_t n_batches = (total + cap - 1) / cap;
+  int n_lanes = ctx->lanes_cfg > 0 ? std::min(ctx->lanes_cfg, 2) : 2;
+  if (n_batches < 2) n_lanes = 1;
+  for (int k = 0; k < n_lanes; ++k) bdpt_prepare(ctx, ctx->bdpt_lanes[k], cap);
   const bool small = ctx->small.n > 0;
   const BdptCam& cam = f.bdpt_cam;
   const int g_start = persistent_grid(ctx, bdpt_start, 256);
@@ -969,36 +988,50 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
   CUDA_TRY(cudaEventCreate(&e1));
   uint64_t launches = 0;
   try {
-    CUDA_TRY(cudaMemsetAsync(b.ctl, 0, sizeof(BdptCtl), s));
     CUDA_TRY(cudaEventRecord(e0, s));
-    for (uint64_t first = 0; first < total; first += b.cap) {
-      const unsigned n = (unsigned)std::min<uint64_t>(b.cap, total - first);
-      bdpt_start<<<g_start, 256, 0, s>>>(ctx->dev, cam, b, first, n, sample_begin, seed);
-      bdpt_ctl_begin<<<1, 1, 0, s>>>(b.ctl, 2 * n);
+    for (int k = 0; k < n_lanes; ++k) {
+      BdptLane& L = ctx->bdpt_lanes[k];
+      L.b.accum = d_accum;
+      CUDA_TRY(cudaStreamWaitEvent(L.stream, e0, 0));
+      CUDA_TRY(cudaMemsetAsync(L.b.ctl, 0, sizeof(BdptCtl), L.stream));
+    }
+    uint64_t batch = 0;
+    for (uint64_t first = 0; first < total; first += cap, ++batch) {
+      BdptLane& L = ctx->bdpt_lanes[batch % n_lanes];
+      BdptBuffers& b = L.b;
+      cudaStream_t ls = L.stream;
+      const unsigned n = (unsigned)std::min<uint64_t>(cap, total - first);
+      bdpt_start<<<g_start, 256, 0, ls>>>(ctx->dev, cam, b, first, n, sample_begin, seed);
+      bdpt_ctl_begin<<<1, 1, 0, ls>>>(b.ctl, 2 * n);
       launches += 2;
       int cur = 0;
       for (int it = 0; it < kBdptMaxLen; ++it) {  // vertices it+1 of both walks
         if (small)
-          q_extend<true><<<g_extend, 256, 0, s>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+          q_extend<true><<<g_extend, 256, 0, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
         else
-          q_extend<false><<<g_extend, 256, sm_stack, s>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
-        bdpt_vertex<<<g_vertex, 256, 0, s>>>(ctx->dev, cam, b, cur, first, sample_begin, seed);
-        bdpt_ctl_after_walk<<<1, 1, 0, s>>>(b.ctl);
+          q_extend<false><<<g_extend, 256, sm_stack, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+        bdpt_vertex<<<g_vertex, 256, 0, ls>>>(ctx->dev, cam, b, cur, first, sample_begin, seed);
+        bdpt_ctl_after_walk<<<1, 1, 0, ls>>>(b.ctl);
         launches += 3;
         cur ^= 1;
       }
       for (int len = 1; len <= kBdptMaxLen; ++len) {
-        bdpt_connect<<<g_connect, 256, 0, s>>>(ctx->dev, cam, b, len, first, n);
+        bdpt_connect<<<g_connect, 256, 0, ls>>>(ctx->dev, cam, b, len, first, n);
         if (small)
-          q_shadow_add<true><<<g_shadow, 256, 0, s>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+          q_shadow_add<true><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
         else
-          q_shadow_add<false><<<g_shadow, 256, 0, s>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
-        bdpt_ctl_after_shadow<<<1, 1, 0, s>>>(b.ctl);
+          q_shadow_add<false><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+        bdpt_ctl_after_shadow<<<1, 1, 0, ls>>>(b.ctl);
         launches += 3;
       }
       CUDA_TRY(cudaGetLastError());
     }
-    CUDA_TRY(cudaMemcpyAsync(ctx->bdpt_ctl_host, b.ctl, sizeof(BdptCtl), cudaMemcpyDeviceToHost, s));
+    for (int k = 0; k < n_lanes; ++k) {
+      BdptLane& L = ctx->bdpt_lanes[k];
+      CUDA_TRY(cudaMemcpyAsync(L.ctl_host, L.b.ctl, sizeof(BdptCtl), cudaMemcpyDeviceToHost, L.stream));
+      CUDA_TRY(cudaEventRecord(L.ev_done, L.stream));
+      CUDA_TRY(cudaStreamWaitEvent(s, L.ev_done, 0));
+    }
     CUDA_TRY(cudaEventRecord(e1, s));
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0;
@@ -1006,11 +1039,13 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
     TutuRenderStats& st = ctx->stats;
     st.gpu_ms = ms;
     st.paths = total;
-    st.extend_rays = ctx->bdpt_ctl_host->sum_extend;
-    st.shadow_rays = ctx->bdpt_ctl_host->sum_shadow;
+    for (int k = 0; k < n_lanes; ++k) {
+      st.extend_rays += ctx->bdpt_lanes[k].ctl_host->sum_extend;
+      st.shadow_rays += ctx->bdpt_lanes[k].ctl_host->sum_shadow;
+    }
     st.shade_calls = 0;
     st.kernel_launches = launches;
-    st.iterations = (total + b.cap - 1) / b.cap;
+    st.iterations = n_batches;
   } catch (...) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -1065,7 +1100,6 @@ extern "C" void tutu_ctx_destroy(TutuCtx* ctx) {
   cudaDeviceSynchronize();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-  if (ctx->bdpt_ctl_host) cudaFreeHost(ctx->bdpt_ctl_host);
   delete ctx;
 }
 
