@@ -68,7 +68,7 @@ void upload_vec(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
 }  // namespace
 
 struct WfLane {
-  DevBuf pool, ctl;
+  DevBuf pool, ctl, class_perm;
   WfBuffers b{};
   uint64_t capacity = 0;
   cudaStream_t stream = nullptr;
@@ -81,6 +81,8 @@ struct WfLane {
     std::swap(pool.bytes, o.pool.bytes);
     std::swap(ctl.p, o.ctl.p);
     std::swap(ctl.bytes, o.ctl.bytes);
+    std::swap(class_perm.p, o.class_perm.p);
+    std::swap(class_perm.bytes, o.class_perm.bytes);
     b = o.b;
     std::swap(capacity, o.capacity);
     std::swap(stream, o.stream);
@@ -147,6 +149,7 @@ struct TutuCtx {
   uint64_t paths_in_flight_cfg = 0;  // per lane
   int lanes_cfg = 0;
   int grid_lanes = 0;
+  bool sort_by_class = false;  // wavefront.cuh: wf_classify (scenes with more than one shading class)
   int shade_block = TUTU_SHADE_BLOCK;  // wavefront.cuh: kShadeBlockSimple for all-Lambertian untextured scenes
   int grid_shade_block = 0;
   bool grid_small = false;
@@ -727,6 +730,11 @@ void lane_prepare(TutuCtx* ctx, WfLane& L, uint64_t cap) {
   L.ctl.ensure(sizeof(WfCtl));
   b.ctl = L.ctl.as<WfCtl>();
   b.capacity = (unsigned)cap;
+  b.class_perm = nullptr;
+  if (ctx->sort_by_class) {
+    L.class_perm.ensure((size_t)kShadeClasses * cap * sizeof(unsigned));
+    b.class_perm = L.class_perm.as<unsigned>();
+  }
   if (!L.stream) CUDA_TRY(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
   if (!L.ctl_host) CUDA_TRY(cudaMallocHost(&L.ctl_host, sizeof(WfCtl)));
   if (!L.ev_done) CUDA_TRY(cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
@@ -858,6 +866,10 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
           CUDA_TRY(cudaStreamWaitEvent(ctx->wf_lanes[k + 1].stream, L.ev_done, 0));
         }
         timer.mark(2, ls);
+        if (L.b.class_perm) {
+          wf_classify<<<ctx->sm_count * 8, 256, 0, ls>>>(ctx->dev, L.b);
+          launches += 1;
+        }
         wf_shade<<<ctx->grid_shade, ctx->shade_block, 0, ls>>>(ctx->dev, L.b, cur, seed);
         timer.mark(3, ls);
         if (small)
@@ -1157,6 +1169,7 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
     for (const DevMaterial& m : fs.materials) simple = simple && m.type == TUTU_MAT_LAMBERTIAN;
     for (const LeafShade& ls : fs.shade) simple = simple && !(ls.flags & TEX_ACTIVE_BIT);
     ctx->shade_block = simple ? kShadeBlockSimple : TUTU_SHADE_BLOCK;
+    ctx->sort_by_class = !simple && !getenv("TUTU_NO_CLASS_SORT");
     if (const char* e = getenv("TUTU_SHADE_BLOCK_RT")) ctx->shade_block = atoi(e);  // experiments only
   }
   d.refill_min = 8;

@@ -44,6 +44,7 @@ struct WfCtl {
   unsigned long long iterations;
   unsigned long long cursor_extend;  // ray-queue cursors of the persistent tracers
   unsigned long long cursor_shadow;
+  unsigned class_count[8];  // wf_classify: queue entries per shading class (kShadeClasses)
 };
 static_assert(offsetof(WfCtl, n_next) % 8 == 0 && offsetof(WfCtl, n_shadow) == offsetof(WfCtl, n_next) + 4,
               "n_next/n_shadow must form one aligned 64-bit word");
@@ -65,6 +66,9 @@ struct WfBuffers {
   WfCtl* ctl;
   float* accum;  // width*height*3 sums
   unsigned capacity;
+  // shading-class order of the current queue (wf_classify), kShadeClasses lists of `capacity` entries;
+  // nullptr = shade in queue order (scenes with one shading class)
+  unsigned* class_perm;
 };
 
 __device__ __forceinline__ void accum_add(float* accum, WfCtl* ctl, uint32_t pixel, f3 L) {
@@ -103,6 +107,7 @@ __global__ void wf_ctl_after_raygen(WfCtl* ctl, unsigned capacity) {
   ctl->cursor_extend = 0;
   ctl->cursor_shadow = 0;
   ctl->sum_extend += ctl->n_cur;
+  for (int c = 0; c < 8; ++c) ctl->class_count[c] = 0;
 }
 __global__ void wf_ctl_after_iter(WfCtl* ctl) {
   ctl->sum_shadow += ctl->n_shadow;
@@ -214,6 +219,58 @@ wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
       }
       __syncwarp();
     }
+  }
+}
+
+// ---- shading classes ----------------------------------------------------------------------------
+// ncu on the glass / texture scene (profiles/r01_glass_shade_lanes.txt): wf_shade runs with 8.9 of 32
+// lanes per instruction — the GGX / glass / texture code (1500+ instructions) executes for the one or
+// two lanes of a warp that hit such a material while the Lambertian lanes wait.  On scenes with more
+// than one class the queue is therefore ordered by the hit's shading class between extend and shade:
+// wf_classify appends every queue index to its class's list (block-aggregated atomics, one per class and
+// block iteration; warp-contiguous runs keep the Lambertian majority's loads coalesced) and wf_shade
+// walks the lists back to back.  Path results do not depend on the order (every path writes its own
+// continuation / frame-buffer sample), only the float summation order of the atomics changes.
+constexpr int kShadeClasses = 8;  // 0 miss | 1 + MaterialType (Lambertian .. UNLIT) | 7 textured Lambertian
+__device__ __forceinline__ int shade_class(const DevScene& sc, const float4 hit) {
+  const int code = __float_as_int(hit.w);
+  if (code < 0) return 0;
+  const uint32_t flags = __float_as_uint(__ldg(sc.shade + 4 * (size_t)((uint32_t)code & kSlotMask) + 3).w);
+  const int type = __float_as_int(__ldg(sc.materials + 4 * (size_t)(flags & 0x3FFFFFFFu)).w);
+  if (type == TUTU_MAT_LAMBERTIAN && (flags & 0x80000000u)) return 7;
+  return 1 + (type < 0 ? 0 : (type > 5 ? 5 : type));
+}
+
+__global__ void __launch_bounds__(256)
+wf_classify(const __grid_constant__ DevScene sc, WfBuffers b) {
+  const unsigned n = b.ctl->n_cur;
+  __shared__ unsigned s_cnt[kShadeClasses][8];  // [class][warp] -> exclusive prefix within the block
+  __shared__ unsigned s_base[kShadeClasses];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const unsigned i = base + threadIdx.x;
+    const int c = i < n ? shade_class(sc, __ldg(b.hit + i)) : -1;
+    unsigned my_mask = 0u;
+#pragma unroll
+    for (int k = 0; k < kShadeClasses; ++k) {
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, c == k);
+      if (lane == 0) s_cnt[k][warp] = (unsigned)__popc(m);
+      if (c == k) my_mask = m;
+    }
+    __syncthreads();
+    if (threadIdx.x < kShadeClasses) {
+      unsigned total = 0;
+      for (int w = 0; w < 8; ++w) {
+        const unsigned v = s_cnt[threadIdx.x][w];
+        s_cnt[threadIdx.x][w] = total;
+        total += v;
+      }
+      s_base[threadIdx.x] = total ? atomicAdd(&b.ctl->class_count[threadIdx.x], total) : 0u;
+    }
+    __syncthreads();
+    if (c >= 0)
+      b.class_perm[(size_t)c * b.capacity + s_base[c] + s_cnt[c][warp] + (unsigned)__popc(my_mask & ((1u << lane) - 1u))] = i;
+    __syncthreads();
   }
 }
 
@@ -598,7 +655,7 @@ __device__ __forceinline__ void shade_vertex(const DevScene& sc, uint64_t seed, 
 constexpr int kShadeBlockSimple = 64;
 template <int SPEC>
 __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffers& b, int cur, uint64_t seed,
-                                              unsigned (*s_cnt)[TUTU_SHADE_BLOCK / 32], unsigned* s_base) {
+                                              unsigned (*s_cnt)[TUTU_SHADE_BLOCK / 32], unsigned* s_base, unsigned* s_pref) {
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
   // ncu (profiles/r01_shade_stalls.txt): with one atomicAdd per WARP on the two queue counters,
@@ -606,9 +663,30 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
   // same-address atomics per launch serialise in one L2 slice.  The counts are therefore first
   // combined per BLOCK in shared memory (one global atomic per counter per block-iteration).
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  // class lists (wf_classify): entry j of the concatenated lists -> queue index
+  if (b.class_perm) {
+    if (threadIdx.x == 0) {
+      unsigned acc = 0u;
+      for (int c = 0; c < kShadeClasses; ++c) {
+        s_pref[c] = acc;
+        acc += b.ctl->class_count[c];
+      }
+    }
+    __syncthreads();
+  }
   for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    const unsigned i = base + threadIdx.x;
-    const bool valid = i < n;
+    const unsigned j = base + threadIdx.x;
+    const bool valid = j < n;
+    unsigned i = j;
+    if (b.class_perm && valid) {
+      unsigned c = 0u, start = 0u;
+#pragma unroll
+      for (int k = 1; k < kShadeClasses; ++k) {
+        const unsigned p = s_pref[k];
+        if (j >= p) c = (unsigned)k, start = p;
+      }
+      i = b.class_perm[(size_t)c * b.capacity + (j - start)];
+    }
     ShadeOut out;
     out.cont = out.shadow = out.finished = false;
     f3 L = mk(0.f);
@@ -686,7 +764,8 @@ __global__ void __launch_bounds__(TUTU_SHADE_BLOCK, TUTU_SHADE_MIN_BLOCKS)
 wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
   __shared__ unsigned s_cnt[2][TUTU_SHADE_BLOCK / 32];
   __shared__ unsigned s_base[2];
-  wf_shade_body<0>(sc, b, cur, seed, s_cnt, s_base);
+  __shared__ unsigned s_pref[kShadeClasses];
+  wf_shade_body<0>(sc, b, cur, seed, s_cnt, s_base, s_pref);
 }
 // ---- finalize: color = estimate * SPP_inv (PathTracing.hpp:513) -------------------------------
 __global__ void wf_finalize(const float* __restrict__ accum, float inv_spp, float* __restrict__ out, size_t n) {
