@@ -239,6 +239,12 @@ int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
 /* Knobs: paths in flight per wavefront lane (0 = default 16 Mi; BDPT: samples per batch, default
  * 4 Mi), number of interleaved wavefront lanes (0 = default 2), per-stage event timing on/off. */
 int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int lanes, int profile_stages);
+/* Path-tracing pipeline: 0 = automatic (default), 1 = wavefront (queues in HBM, any scene), 2 =
+ * register-resident persistent kernel (scenes of <= 32 primitives, whose geometry fits the kernel's
+ * constant bank; a render on a larger scene then fails with TUTU_E_STATE).  Automatic picks 2 where it
+ * applies.  Both evaluate the same per-path arithmetic with the same random numbers; only the float
+ * summation order in the frame buffer differs. */
+int tutu_render_pipeline(TutuCtx* ctx, int pipeline);
 
 /* ---- output stage: PPMGenerator::writePixel (reference include/PPMGenerator.hpp:812-845) ---- */
 /* 8-bit quantisation of a linear radiance image exactly as the reference writes its PPM:

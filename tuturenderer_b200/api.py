@@ -94,6 +94,7 @@ ABI = {
     "tutu_write_ppm": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _P, C.c_int]),
     "tutu_render_stats": (C.c_int, [_P, C.POINTER(TutuRenderStats)]),
     "tutu_render_configure": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int]),
+    "tutu_render_pipeline": (C.c_int, [_P, C.c_int]),
     "tutu_bvh_build": (C.c_int, [_P, C.c_uint32, _P, C.POINTER(C.c_uint32)]),
     "tutu_scene_file_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "tutu_scene_file_desc": (C.POINTER(TutuSceneDesc), [_P]),
@@ -388,6 +389,13 @@ class Context:
     # ---- path tracing
     def configure(self, paths_in_flight: int = 0, profile_stages: bool = False, lanes: int = 0) -> None:
         self._ck(lib().tutu_render_configure(self._h, paths_in_flight, lanes, int(profile_stages)))
+
+    PIPELINES = {"auto": 0, "wavefront": 1, "resident": 2}
+
+    def pipeline(self, name: str = "auto") -> None:
+        """Path-tracing pipeline: 'auto' (register-resident kernel when the scene has <= 32 primitives, else the
+        wavefront), 'wavefront', or 'resident' (renders then fail on larger scenes)."""
+        self._ck(lib().tutu_render_pipeline(self._h, self.PIPELINES[name]))
 
     def render_path(self, spp: int, seed: int = 1, out: np.ndarray | None = None) -> np.ndarray:
         i = self.info()

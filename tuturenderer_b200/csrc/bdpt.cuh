@@ -454,7 +454,7 @@ bdpt_vertex(const __grid_constant__ DevScene sc, const __grid_constant__ BdptCam
 
 // ---- MISweight, BDPT.hpp:70-222 ----------------------------------------------------------------
 // sEnd / tEnd are lpverts[s-1] / epverts[t-1] (ignored when s == 0 / t == 1 respectively).
-__device__ __noinline__ float bdpt_mis_weight(const DevScene& sc, const BdptCam& cam, const BdptBuffers& b, unsigned i,
+static __device__ __noinline__ float bdpt_mis_weight(const DevScene& sc, const BdptCam& cam, const BdptBuffers& b, unsigned i,
                                               int s, int t, const Vtx sEnd, const Vtx tEnd, float camFwd) {
   if (s + t == 2) return 1.f;
   float pdf_tEndFwd = 0.f, pdf_tEndRev = 0.f, pdf_sEndFwd = 0.f, pdf_sEndRev = 0.f, G_connect = 0.f;

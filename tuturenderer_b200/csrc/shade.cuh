@@ -202,7 +202,7 @@ __device__ __forceinline__ f3 SphereLocal2world(f3 n, f3 dir) {  // :387-409
 // ---- Material.hpp ----------------------------------------------------------------------------
 // (__noinline__ helpers take everything by value: a reference parameter would pin the caller's
 // material / direction registers to local memory on the common Lambertian path as well)
-__device__ __noinline__ f3 BxDF_microfacet(const Mat m, f3 wi, f3 wo, f3 Ns, float eta_scene,
+static __device__ __noinline__ f3 BxDF_microfacet(const Mat m, f3 wi, f3 wo, f3 Ns, float eta_scene,
                                            bool TIR, float correctNormal) {
   if (m.type == TUTU_MAT_MICROFACET_R) {  // Material.hpp:87-108
     f3 h = normalized(wi + wo);
@@ -251,7 +251,7 @@ __device__ __noinline__ f3 BxDF_microfacet(const Mat m, f3 wi, f3 wo, f3 Ns, flo
   return mk(numerator / denominator * correctNormal);
 }
 
-__device__ __noinline__ f3 BxDF_glass(const Mat m, f3 wi, f3 wo, f3 Ns, float eta_scene, bool TIR,
+static __device__ __noinline__ f3 BxDF_glass(const Mat m, f3 wi, f3 wo, f3 Ns, float eta_scene, bool TIR,
                                       float correctNormal) {  // Material.hpp:159-186
   f3 refDir = normalized(getReflectionDir(wo, Ns));
   float eta_i = eta_scene, eta_t = m.eta;
@@ -327,7 +327,7 @@ struct DirSample {
   int flags;  // bit0 = success, bit1 = TIR ("special event")
 };
 // ra, rb, rc = getRandomFloat() calls in order.
-__device__ __noinline__ DirSample sampleDirection_special(const Mat m, f3 wo, f3 N, float eta_i,
+static __device__ __noinline__ DirSample sampleDirection_special(const Mat m, f3 wo, f3 N, float eta_i,
                                                           float ra, float rb, float rc) {
   f3 out = mk(0.f);
   const int flags = [&]() -> int {
@@ -405,7 +405,7 @@ __device__ __forceinline__ int sampleDirection(const Mat& m, f3 wo, f3 N, f3& ou
   return ds.flags;
 }
 
-__device__ __noinline__ float pdf_special(const Mat m, f3 wi, f3 wo, f3 N, float eta_i, float eta_t) {
+static __device__ __noinline__ float pdf_special(const Mat m, f3 wi, f3 wo, f3 N, float eta_i, float eta_t) {
   switch (m.type) {
     case TUTU_MAT_MICROFACET_R: {  // Material.hpp:362-373
       f3 h = normalized(wo + wi);

@@ -148,7 +148,7 @@ struct SphereHit {
 };
 // by-value arguments and result: a __noinline__ callee taking references would force the caller's
 // ray and walk state into local memory
-__device__ __noinline__ SphereHit sphere_test(const float4* __restrict__ g, const Ray r) {
+static __device__ __noinline__ SphereHit sphere_test(const float4* __restrict__ g, const Ray r) {
   float t = 0.f;
   const float4 a = __ldg(g + 0);  // centre.xyz, radius
   const float ocx = __fsub_rn(r.ox, a.x), ocy = __fsub_rn(r.oy, a.y), ocz = __fsub_rn(r.oz, a.z);
@@ -959,10 +959,27 @@ __device__ __forceinline__ bool traverse_variant(const DevScene& sc, const Ray& 
 // Irregular rays take the literal tree walk.
 constexpr int kSmallMax = 32;
 struct SmallScene {
-  int n;  // 0 = not usable (scene too large or empty)
-  int pad;
-  float2 box[kSmallMax][3];  // leaf boxes in DFS slot order, per axis {lo, hi} (a packed-fp32 operand)
+  int n;        // primitives; 0 = not usable (scene too large or empty)
+  int n_boxes;  // distinct leaf boxes (bitwise): the two triangles of a quad have the same bounds, so the
+                // Cornell box's 32 leaves are 16 slab tests
+  float2 box[kSmallMax][3];  // distinct leaf boxes, per axis {lo, hi} (a packed-fp32 operand)
+  unsigned slots[kSmallMax]; // DFS slots of the primitives that own box k (0 for the unused tail)
 };
+
+// one group of 8 distinct boxes, indices known at compile time (operands straight from the constant bank)
+template <bool ANY, int K0>
+__device__ __forceinline__ unsigned small_box_group(const SmallScene& ss, const RayPre2& q, float lim) {
+  unsigned mask = 0u;
+#pragma unroll
+  for (int k = K0; k < K0 + 8; ++k) {
+    float te;
+    const bool hit = box_test_packed(q, ss.box[k][0], ss.box[k][1], ss.box[k][2], te);
+    // any-hit: a blocker needs t < dis, so a box entered beyond dis (+ the pruning slack of the tree
+    // walk, prune_limit) cannot hold one
+    if (hit && (!ANY || te <= lim)) mask |= ss.slots[k];
+  }
+  return mask;
+}
 
 template <bool ANY>
 __device__ __forceinline__ bool traverse_small(const DevScene& sc, const SmallScene& ss, const Ray& r,
@@ -973,21 +990,12 @@ __device__ __forceinline__ bool traverse_small(const DevScene& sc, const SmallSc
   best.u = 0.f;
   best.v = 0.f;
   best.slot = -1;
-  unsigned mask = 0u;
   const RayPre2 q = make_pre2(p);
-  if (ss.n == kSmallMax) {  // uniform; the full bank (Cornell: exactly 32 triangles) needs no per-box count test
-#pragma unroll
-    for (int k = 0; k < kSmallMax; ++k) {
-      float te;
-      if (box_test_packed(q, ss.box[k][0], ss.box[k][1], ss.box[k][2], te)) mask |= 1u << k;
-    }
-  } else {
-#pragma unroll 4
-    for (int k = 0; k < ss.n; ++k) {
-      float te;
-      if (box_test_packed(q, ss.box[k][0], ss.box[k][1], ss.box[k][2], te)) mask |= 1u << k;
-    }
-  }
+  const float lim = ANY ? fmaf(dis, sc.prune_rel, dis + sc.prune_abs) : 0.f;
+  unsigned mask = small_box_group<ANY, 0>(ss, q, lim);  // n_boxes is uniform: whole groups are skipped
+  if (ss.n_boxes > 8) mask |= small_box_group<ANY, 8>(ss, q, lim);
+  if (ss.n_boxes > 16) mask |= small_box_group<ANY, 16>(ss, q, lim);
+  if (ss.n_boxes > 24) mask |= small_box_group<ANY, 24>(ss, q, lim);
   while (mask) {
     const int slot = __ffs(mask) - 1;  // increasing slot order: strict '<' keeps the lowest slot on ties
     mask &= mask - 1u;

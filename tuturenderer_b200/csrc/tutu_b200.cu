@@ -14,6 +14,7 @@
 #include "tutu_internal.hpp"
 #include "wavefront.cuh"
 #include "bdpt.cuh"
+#include "resident.cuh"
 
 using namespace tutu;
 
@@ -154,6 +155,11 @@ struct TutuCtx {
   int grid_shade_block = 0;
   bool grid_small = false;
   int profile_stages = 0;
+  // 0 = automatic (register-resident kernel when the scene fits the constant bank, else wavefront),
+  // 1 = wavefront, 2 = register-resident (fails on scenes that do not fit)
+  int pipeline_cfg = 0;
+  DevBuf d_resident_ctl;
+  int grid_resident = 0;
   TutuRenderStats stats{};
   int grid_extend = 0, grid_shade = 0, grid_shadow = 0, grid_raygen = 0;
 };
@@ -686,6 +692,11 @@ int check_scene(TutuCtx* ctx) {
   if (!ctx->has_scene) return fail(ctx, TUTU_E_STATE, "no scene uploaded (call tutu_scene_upload first)");
   return TUTU_OK;
 }
+int check_pipeline(TutuCtx* ctx) {
+  if (ctx->pipeline_cfg == 2 && ctx->small.n <= 0)
+    return fail(ctx, TUTU_E_STATE, "the register-resident pipeline needs a scene of at most 32 primitives");
+  return TUTU_OK;
+}
 
 void fill_raygen(const FlatScene& f, RayGenK* k) {
   memcpy(k->eye, f.raygen.eye, 12);
@@ -773,11 +784,72 @@ struct StageTimer {
   }
 };
 
+// resident.cuh: the whole render is one persistent launch on `s` (plus the 40-byte control block).
+void resident_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint64_t seed, float* d_accum,
+                     cudaStream_t s) {
+  const FlatScene& f = ctx->flat;
+  const uint64_t npix = (uint64_t)f.raygen.width * f.raygen.height;
+  ctx->stats = TutuRenderStats{};
+  if (npix * sample_count == 0) return;
+  if (!ctx->grid_resident) {
+    CUDA_TRY(pt_resident_grid(ctx->sm_count, &ctx->grid_resident));
+  }
+  const uint64_t threads = (uint64_t)ctx->grid_resident * TUTU_RESIDENT_BLOCK;
+  // samples per work item: 64, less when the frame is too small to give every lane ~4 items
+  uint32_t chunk = 64;
+  if (const char* e = getenv("TUTU_RESIDENT_CHUNK")) chunk = (uint32_t)std::max(1, atoi(e));
+  while (chunk > 1 && npix * ((sample_count + chunk - 1) / chunk) < 4 * threads) chunk /= 2;
+  chunk = std::min(chunk, sample_count);
+  ResidentArgs a{};
+  fill_raygen(f, &a.rk);
+  a.sample_begin = sample_begin;
+  a.sample_count = sample_count;
+  a.chunk = chunk;
+  a.n_items = npix * ((sample_count + chunk - 1) / chunk);
+  a.seed = seed;
+  a.accum = d_accum;
+  ctx->d_resident_ctl.ensure(sizeof(ResidentCtl));
+  a.ctl = ctx->d_resident_ctl.as<ResidentCtl>();
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  try {
+    CUDA_TRY(cudaEventRecord(e0, s));
+    CUDA_TRY(cudaMemsetAsync(a.ctl, 0, sizeof(ResidentCtl), s));
+    const uint64_t want = (a.n_items + TUTU_RESIDENT_BLOCK - 1) / TUTU_RESIDENT_BLOCK;
+    const int grid = (int)std::min<uint64_t>((uint64_t)ctx->grid_resident, std::max<uint64_t>(want, 1));
+    CUDA_TRY(pt_resident_launch(grid, s, ctx->dev, ctx->small, a));
+    ResidentCtl h{};
+    CUDA_TRY(cudaMemcpyAsync(&h, a.ctl, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    TutuRenderStats& st = ctx->stats;
+    st.gpu_ms = ms;
+    st.paths = npix * sample_count;
+    st.extend_rays = h.sum_extend;
+    st.shadow_rays = h.sum_shadow;
+    st.shade_calls = h.sum_extend;
+    st.nan_samples = h.nan_samples;
+    st.iterations = h.iterations;
+    st.kernel_launches = 1;
+    if (ctx->profile_stages) st.shade_ms = ms;  // one kernel: all stages in one
+  } catch (...) {
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    throw;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
 // Accumulates samples [sample_begin, sample_begin+sample_count) of every pixel into d_accum.
 // Work is enqueued on the lanes' own streams, which are ordered after everything already on `s`;
 // `s` is ordered after the lanes when the call returns (it also blocks the host until then).
 void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint64_t seed, float* d_accum,
                cudaStream_t s) {
+  if (ctx->pipeline_cfg == 2 && ctx->small.n > 0) return resident_render(ctx, sample_begin, sample_count, seed, d_accum, s);
   const FlatScene& f = ctx->flat;
   const uint64_t npix = (uint64_t)f.raygen.width * f.raygen.height;
   const uint64_t total = npix * sample_count;
@@ -1159,10 +1231,20 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   ctx->small = SmallScene{};
   if (!fs.empty && fs.n_prims <= (uint32_t)kSmallMax && !getenv("TUTU_NO_SMALL")) {
     ctx->small.n = (int)fs.n_prims;
+    SmallScene& sm = ctx->small;
     for (uint32_t k = 0; k < fs.n_prims; ++k) {
-      for (int a = 0; a < 3; ++a) ctx->small.box[k][a] = make_float2(fs.leaf_box[k].lo[a], fs.leaf_box[k].hi[a]);
+      float2 b[3];
+      for (int a = 0; a < 3; ++a) b[a] = make_float2(fs.leaf_box[k].lo[a], fs.leaf_box[k].hi[a]);
+      int j = 0;  // bitwise-identical bounds share one slab test
+      while (j < sm.n_boxes && memcmp(sm.box[j], b, sizeof(b)) != 0) ++j;
+      if (j == sm.n_boxes || getenv("TUTU_NO_BOX_DEDUPE")) {
+        j = sm.n_boxes++;
+        memcpy(sm.box[j], b, sizeof(b));
+      }
+      sm.slots[j] |= 1u << k;
       if (fs.shade[k].flags & SHADE_SPHERE_BIT) d.sphere_mask |= 1u << k;
     }
+    for (int j = sm.n_boxes; j < kSmallMax; ++j) memcpy(sm.box[j], sm.box[0], sizeof(sm.box[0]));  // slots = 0
   }
   {
     bool simple = true;
@@ -1344,11 +1426,20 @@ extern "C" int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int
   return TUTU_OK;
 }
 
+extern "C" int tutu_render_pipeline(TutuCtx* ctx, int pipeline) {
+  if (!ctx) return fail(nullptr, TUTU_E_INVALID, "null context");
+  if (pipeline < 0 || pipeline > 2) return fail(ctx, TUTU_E_INVALID, "pipeline must be 0 (automatic), 1 (wavefront) or 2 (register-resident)");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->pipeline_cfg = pipeline;
+  return TUTU_OK;
+}
+
 extern "C" int tutu_render_path_accumulate_device(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count,
                                                   uint64_t seed, float* d_accum, void* stream) {
   API_BEGIN(ctx)
   if (int rc = check_scene(ctx)) return rc;
   if (!d_accum) return fail(ctx, TUTU_E_INVALID, "tutu_render_path_accumulate_device: null accumulation buffer");
+  if (int rc = check_pipeline(ctx)) return rc;
   wf_render(ctx, sample_begin, sample_count, seed, d_accum, stream ? (cudaStream_t)stream : ctx->stream);
   return TUTU_OK;
   API_END(ctx)
@@ -1371,6 +1462,7 @@ extern "C" int tutu_render_path(TutuCtx* ctx, uint32_t spp, uint64_t seed, float
   API_BEGIN(ctx)
   if (int rc = check_scene(ctx)) return rc;
   if (!rgb_out || spp == 0) return fail(ctx, TUTU_E_INVALID, "tutu_render_path: null output or spp == 0");
+  if (int rc = check_pipeline(ctx)) return rc;
   const size_t n = (size_t)ctx->flat.raygen.width * ctx->flat.raygen.height * 3;
   cudaStream_t s = ctx->stream;
   ctx->d_accum.ensure(n * sizeof(float));
