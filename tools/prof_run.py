@@ -16,7 +16,7 @@ if what == "render":
     ctx.upload(sc)
     import os
     ctx.configure(0, False, int(os.environ.get("TUTU_LANES", "0")))
-    img = ctx.render_path(24, seed=5)
+    img = ctx.render_path(int(os.environ.get("TUTU_PROF_SPP", "24")), seed=5)
     print("render mean", float(img.mean()), ctx.stats())
 elif what == "bdpt":
     sc = api.Scene.load(ROOT / "tests/golden/veach_80x60.tscene").with_size(800, 600)

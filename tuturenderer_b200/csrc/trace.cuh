@@ -966,12 +966,12 @@ struct SmallScene {
   unsigned slots[kSmallMax]; // DFS slots of the primitives that own box k (0 for the unused tail)
 };
 
-// one group of 8 distinct boxes, indices known at compile time (operands straight from the constant bank)
+// one group of 4 distinct boxes, indices known at compile time (operands straight from the constant bank)
 template <bool ANY, int K0>
 __device__ __forceinline__ unsigned small_box_group(const SmallScene& ss, const RayPre2& q, float lim) {
   unsigned mask = 0u;
 #pragma unroll
-  for (int k = K0; k < K0 + 8; ++k) {
+  for (int k = K0; k < K0 + 4; ++k) {
     float te;
     const bool hit = box_test_packed(q, ss.box[k][0], ss.box[k][1], ss.box[k][2], te);
     // any-hit: a blocker needs t < dis, so a box entered beyond dis (+ the pruning slack of the tree
@@ -979,6 +979,57 @@ __device__ __forceinline__ unsigned small_box_group(const SmallScene& ss, const 
     if (hit && (!ANY || te <= lim)) mask |= ss.slots[k];
   }
   return mask;
+}
+
+// Candidate mask of a regular ray: DFS slots of the primitives whose leaf box the ray hits.
+template <bool ANY>
+__device__ __forceinline__ unsigned small_candidates(const DevScene& sc, const SmallScene& ss, const RayPre& p, float dis) {
+  const RayPre2 q = make_pre2(p);
+  const float lim = ANY ? fmaf(dis, sc.prune_rel, dis + sc.prune_abs) : 0.f;
+  unsigned mask = small_box_group<ANY, 0>(ss, q, lim);  // n_boxes is uniform: whole groups are skipped
+  if (ss.n_boxes > 4) mask |= small_box_group<ANY, 4>(ss, q, lim);
+  if (ss.n_boxes > 8) mask |= small_box_group<ANY, 8>(ss, q, lim);
+  if (ss.n_boxes > 12) mask |= small_box_group<ANY, 12>(ss, q, lim);
+  if (ss.n_boxes > 16) mask |= small_box_group<ANY, 16>(ss, q, lim);
+  if (ss.n_boxes > 20) mask |= small_box_group<ANY, 20>(ss, q, lim);
+  if (ss.n_boxes > 24) mask |= small_box_group<ANY, 24>(ss, q, lim);
+  if (ss.n_boxes > 28) mask |= small_box_group<ANY, 28>(ss, q, lim);
+  return mask;
+}
+
+// Primitive test of the lowest candidate.  Candidates are taken in increasing slot order: strict '<'
+// keeps the lowest slot on ties.  Returns true when an any-hit ray is blocked (mask is then cleared).
+template <bool ANY>
+__device__ __forceinline__ bool small_test_next(const DevScene& sc, const Ray& r, float dis, unsigned& mask, Hit& best) {
+  const int slot = __ffs(mask) - 1;
+  mask &= mask - 1u;
+  const float4* g = sc.geom + 3 * slot;
+  const bool sphere = (sc.sphere_mask >> slot) & 1u;
+  float t, u = 0.f, v = 0.f;
+  bool hit;
+  if (sphere) {
+    const SphereHit sh = sphere_test(g, r);
+    hit = sh.hit;
+    t = sh.t;
+  } else {
+    hit = tri_test(g, r, t, u, v);
+  }
+  if (hit) {
+    if (ANY) {
+      if (t < dis && !(fabsf(__fsub_rn(t, dis)) < 0.0001f)) {
+        best.t = t;
+        best.slot = slot | (sphere ? (int)kSphereBit : 0);
+        mask = 0u;
+        return true;
+      }
+    } else if (t < best.t) {
+      best.t = t;
+      best.u = u;
+      best.v = v;
+      best.slot = slot | (sphere ? (int)kSphereBit : 0);
+    }
+  }
+  return false;
 }
 
 template <bool ANY>
@@ -990,42 +1041,99 @@ __device__ __forceinline__ bool traverse_small(const DevScene& sc, const SmallSc
   best.u = 0.f;
   best.v = 0.f;
   best.slot = -1;
-  const RayPre2 q = make_pre2(p);
-  const float lim = ANY ? fmaf(dis, sc.prune_rel, dis + sc.prune_abs) : 0.f;
-  unsigned mask = small_box_group<ANY, 0>(ss, q, lim);  // n_boxes is uniform: whole groups are skipped
-  if (ss.n_boxes > 8) mask |= small_box_group<ANY, 8>(ss, q, lim);
-  if (ss.n_boxes > 16) mask |= small_box_group<ANY, 16>(ss, q, lim);
-  if (ss.n_boxes > 24) mask |= small_box_group<ANY, 24>(ss, q, lim);
-  while (mask) {
-    const int slot = __ffs(mask) - 1;  // increasing slot order: strict '<' keeps the lowest slot on ties
-    mask &= mask - 1u;
-    const float4* g = sc.geom + 3 * slot;
-    const bool sphere = (sc.sphere_mask >> slot) & 1u;
-    float t, u = 0.f, v = 0.f;
-    bool hit;
-    if (sphere) {
-      const SphereHit sh = sphere_test(g, r);
-      hit = sh.hit;
-      t = sh.t;
-    } else {
-      hit = tri_test(g, r, t, u, v);
-    }
-    if (hit) {
-      if (ANY) {
-        if (t < dis && !(fabsf(__fsub_rn(t, dis)) < 0.0001f)) {
-          best.t = t;
-          best.slot = slot | (sphere ? (int)kSphereBit : 0);
-          return true;
-        }
-      } else if (t < best.t) {
-        best.t = t;
-        best.u = u;
-        best.v = v;
-        best.slot = slot | (sphere ? (int)kSphereBit : 0);
-      }
-    }
-  }
+  unsigned mask = small_candidates<ANY>(sc, ss, p, dis);
+  while (mask)
+    if (small_test_next<ANY>(sc, r, dis, mask, best)) return true;
   return best.slot >= 0;
+}
+
+// Two-phase form for the queue kernels (wavefront.cuh).  ncu on the Cornell box (profiles/r01e_resident_*):
+// the primitive loop above runs 8.8 rounds per warp with 10 of 32 lanes — 88 % of the rays have the two
+// candidates of one wall quad, but nearly every warp holds a ray that crosses a block's bounds and has
+// 6-10.  So a warp tests at most kSmallFirst candidates per ray in its first pass, parks the rays that
+// still have candidates (state in shared memory, warp-private, no atomics) and finishes 32 parked rays
+// at a time with all lanes busy.
+constexpr int kSmallFirst = 2;
+constexpr unsigned kParkCap = 64;  // a warp parks at most 31 + 32 rays before it drains 32
+struct SmallPark {                 // per warp
+  float4 o[kParkCap];              // o.xyz, dis
+  float4 d[kParkCap];              // d.xyz, bits(queue index)
+  float4 best[kParkCap];           // t, u, v, bits(slot)
+  unsigned mask[kParkCap];
+};
+
+// begin: candidate mask + first pass.  Returns true when the ray is finished (result in best / blocked).
+template <bool ANY>
+__device__ __forceinline__ bool small_first_pass(const DevScene& sc, const SmallScene& ss, const Ray& r, float dis,
+                                                 Hit& best, unsigned& mask, bool& blocked) {
+  const RayPre p = make_pre(r);
+  mask = 0u;
+  if (!ray_is_regular(p)) {
+    blocked = traverse_variant<ANY, 0>(sc, r, dis, best);
+    return true;
+  }
+  best.t = FLT_MAX;
+  best.u = 0.f;
+  best.v = 0.f;
+  best.slot = -1;
+  blocked = false;
+  mask = small_candidates<ANY>(sc, ss, p, dis);
+#pragma unroll
+  for (int k = 0; k < kSmallFirst; ++k)
+    if (mask && small_test_next<ANY>(sc, r, dis, mask, best)) blocked = true;
+  return mask == 0u;
+}
+
+// Warp-collective: lanes with `more` append their ray to the warp's park; returns the new count.
+__device__ __forceinline__ unsigned small_park_push(SmallPark& pk, unsigned cnt, bool more, const Ray& r, float dis,
+                                                    unsigned index, const Hit& best, unsigned mask) {
+  const unsigned bal = __ballot_sync(0xFFFFFFFFu, more);
+  if (more) {
+    const unsigned pos = cnt + (unsigned)__popc(bal & ((1u << (threadIdx.x & 31u)) - 1u));
+    pk.o[pos] = make_float4(r.ox, r.oy, r.oz, dis);
+    pk.d[pos] = make_float4(r.dx, r.dy, r.dz, __uint_as_float(index));
+    pk.best[pos] = make_float4(best.t, best.u, best.v, __int_as_float(best.slot));
+    pk.mask[pos] = mask;
+  }
+  __syncwarp();
+  return cnt + (unsigned)__popc(bal);
+}
+
+// Warp-collective: the last min(cnt, 32) parked rays get kSmallNext more tests each (all their remaining
+// candidates when `finish`); finished rays go to sink(index, ray, dis, best, blocked), the others are
+// parked again.  Returns the new count.
+constexpr int kSmallNext = 2;
+template <bool ANY, class Sink>
+__device__ __forceinline__ unsigned small_park_drain(const DevScene& sc, SmallPark& pk, unsigned cnt, bool finish,
+                                                     Sink sink) {
+  const unsigned take = cnt < 32u ? cnt : 32u;
+  const unsigned lane = threadIdx.x & 31u;
+  const bool mine = lane < take;
+  Ray r{};
+  Hit best{};
+  unsigned mask = 0u, index = 0u;
+  float dis = 0.f;
+  if (mine) {
+    const unsigned e = cnt - take + lane;
+    const float4 o = pk.o[e], d = pk.d[e], b = pk.best[e];
+    mask = pk.mask[e];
+    r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+    dis = o.w;
+    index = __float_as_uint(d.w);
+    best = Hit{b.x, b.y, b.z, __float_as_int(b.w)};
+    bool blocked = false;
+    if (finish) {
+      while (mask)
+        if (small_test_next<ANY>(sc, r, dis, mask, best)) blocked = true;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kSmallNext; ++k)
+        if (mask && small_test_next<ANY>(sc, r, dis, mask, best)) blocked = true;
+    }
+    if (mask == 0u) sink(index, r, dis, best, ANY ? blocked : best.slot >= 0);
+  }
+  __syncwarp();  // every lane has read its entry before the survivors are written back
+  return small_park_push(pk, cnt - take, mine && mask != 0u, r, dis, index, best, mask);
 }
 
 // Persistent-thread tracer: every warp owns a chunk of the ray queue (one global atomicAdd per

@@ -871,10 +871,10 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
     const int div = getenv("TUTU_GRID_SPLIT") ? n_lanes : 1;  // experiments only: split the resident blocks between the lanes
     auto sized = [&](int full) { return ctx->sm_count * std::max(1, full / ctx->sm_count / div); };
     const bool small = ctx->small.n > 0;
-    ctx->grid_extend = sized(small ? persistent_grid(ctx, wf_extend<true>, 256)
+    ctx->grid_extend = sized(small ? persistent_grid(ctx, wf_extend_small, kSmallBlock)
                                    : persistent_grid(ctx, wf_extend<false>, 256, stack_smem(ctx, 256, false)));
     ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, ctx->shade_block));
-    ctx->grid_shadow = sized(small ? persistent_grid(ctx, wf_shadow<true>, 256) : persistent_grid(ctx, wf_shadow<false>, 256));
+    ctx->grid_shadow = sized(small ? persistent_grid(ctx, wf_shadow_small, kSmallBlock) : persistent_grid(ctx, wf_shadow<false>, 256));
     ctx->grid_raygen = sized(persistent_grid(ctx, wf_raygen, 256));
     ctx->grid_lanes = n_lanes;
   }
@@ -929,7 +929,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         wf_ctl_after_raygen<<<1, 1, 0, ls>>>(L.b.ctl, L.b.capacity);
         timer.mark(1, ls);
         if (small)
-          wf_extend<true><<<ctx->grid_extend, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
+          wf_extend_small<<<ctx->grid_extend, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
         else
           wf_extend<false><<<ctx->grid_extend, 256, stack_smem(ctx, 256, false), ls>>>(ctx->dev, ctx->small, L.b, cur);
         if (it == 0 && k + 1 < n_lanes) {
@@ -945,7 +945,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         wf_shade<<<ctx->grid_shade, ctx->shade_block, 0, ls>>>(ctx->dev, L.b, cur, seed);
         timer.mark(3, ls);
         if (small)
-          wf_shadow<true><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
+          wf_shadow_small<<<ctx->grid_shadow, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
         else
           wf_shadow<false><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
         timer.mark(0, ls);

@@ -212,6 +212,98 @@ wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
   }
 }
 
+// ---- small scenes: two-phase flat tests (trace.cuh: SmallPark) ----------------------------------
+constexpr int kSmallBlock = 256;
+__global__ void __launch_bounds__(kSmallBlock)
+wf_extend_small(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int cur) {
+  __shared__ SmallPark s_park[kSmallBlock / 32];
+  SmallPark& pk = s_park[threadIdx.x >> 5];
+  const unsigned n = b.ctl->n_cur;
+  const float4* __restrict__ ro = b.ray_o[cur];
+  const float4* __restrict__ rd = b.ray_d[cur];
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned parked = 0u;  // warp-uniform
+  auto sink = [&](unsigned i, const Ray&, float, const Hit& h, bool) {
+    __stcs(b.hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
+  };
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&b.ctl->cursor_extend, (unsigned long long)kPacketRays);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n) break;
+#pragma unroll 1
+    for (unsigned k = 0; k < kPacketRays; k += 32u) {
+      const unsigned i = (unsigned)base + k + lane;
+      bool more = false;
+      Ray r{};
+      Hit h{};
+      unsigned mask = 0u;
+      if (i < n) {
+        const float4 o = __ldcs(ro + i);
+        const float4 d = __ldcs(rd + i);
+        r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+        bool blocked;
+        more = !small_first_pass<false>(sc, ss, r, 0.f, h, mask, blocked);
+        if (!more) sink(i, r, 0.f, h, false);
+      }
+      parked = small_park_push(pk, parked, more, r, 0.f, i, h, mask);
+      while (parked >= 32u) parked = small_park_drain<false>(sc, pk, parked, false, sink);
+    }
+  }
+  while (parked) parked = small_park_drain<false>(sc, pk, parked, parked <= 32u, sink);
+}
+
+__global__ void __launch_bounds__(kSmallBlock)
+wf_shadow_small(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int nxt) {
+  __shared__ SmallPark s_park[kSmallBlock / 32];
+  SmallPark& pk = s_park[threadIdx.x >> 5];
+  const unsigned n = b.ctl->n_shadow;
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned parked = 0u;
+  auto sink = [&](unsigned j, const Ray&, float, const Hit&, bool blocked) {
+    const unsigned dst = __float_as_uint(__ldcs(b.sh_d + j).w);
+    if (dst == kShadowFinal) {
+      const float4 c = __ldcs(b.sh_c + j);
+      const float4 L4 = __ldcs(b.sh_L + j);
+      f3 L = mk(L4.x, L4.y, L4.z);
+      if (!blocked) L = L + mk(c.x, c.y, c.z);
+      accum_add(b.accum, b.ctl, __float_as_uint(c.w), L);
+    } else if (!blocked) {
+      const float4 c = __ldcs(b.sh_c + j);
+      float4 s = b.st2[nxt][dst];
+      s.x += c.x, s.y += c.y, s.z += c.z;
+      b.st2[nxt][dst] = s;
+    }
+  };
+  for (;;) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&b.ctl->cursor_shadow, (unsigned long long)kPacketRays);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n) break;
+#pragma unroll 1
+    for (unsigned k = 0; k < kPacketRays; k += 32u) {
+      const unsigned j = (unsigned)base + k + lane;
+      bool more = false;
+      Ray r{};
+      Hit h{};
+      unsigned mask = 0u;
+      float dis = 0.f;
+      if (j < n) {
+        const float4 o = __ldcs(b.sh_o + j);
+        const float4 d = __ldcs(b.sh_d + j);
+        r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+        dis = o.w;
+        bool blocked;
+        more = !small_first_pass<true>(sc, ss, r, dis, h, mask, blocked);
+        if (!more) sink(j, r, dis, h, blocked);
+      }
+      parked = small_park_push(pk, parked, more, r, dis, j, h, mask);
+      while (parked >= 32u) parked = small_park_drain<true>(sc, pk, parked, false, sink);
+    }
+  }
+  while (parked) parked = small_park_drain<true>(sc, pk, parked, parked <= 32u, sink);
+}
+
 // ---- shading classes ----------------------------------------------------------------------------
 // ncu on the glass / texture scene (profiles/r01_glass_shade_lanes.txt): wf_shade runs with 8.9 of 32
 // lanes per instruction — the GGX / glass / texture code (1500+ instructions) executes for the one or
@@ -276,6 +368,7 @@ wf_classify(const __grid_constant__ DevScene sc, WfBuffers b) {
 #define TUTU_SHADE_BLOCK 256
 #endif
 constexpr int kShadeBlockSimple = 64;
+
 template <int SPEC>
 __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffers& b, int cur, uint64_t seed,
                                               unsigned (*s_cnt)[TUTU_SHADE_BLOCK / 32], unsigned* s_base, unsigned* s_pref) {
