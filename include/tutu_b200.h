@@ -241,9 +241,9 @@ int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
 int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int lanes, int profile_stages);
 /* Path-tracing pipeline: 0 = automatic (default), 1 = wavefront (queues in HBM, any scene), 2 =
  * register-resident persistent kernel (scenes of <= 32 primitives, whose geometry fits the kernel's
- * constant bank; a render on a larger scene then fails with TUTU_E_STATE).  Automatic picks 2 where it
- * applies.  Both evaluate the same per-path arithmetic with the same random numbers; only the float
- * summation order in the frame buffer differs. */
+ * constant bank; a render on a larger scene then fails with TUTU_E_STATE).  Automatic is the wavefront
+ * (measured faster on a B200).  Both run the same vertex code on the same random numbers:
+ * images agree to float noise (frame-buffer summation order, FMA contraction per translation unit). */
 int tutu_render_pipeline(TutuCtx* ctx, int pipeline);
 
 /* ---- output stage: PPMGenerator::writePixel (reference include/PPMGenerator.hpp:812-845) ---- */

@@ -16,9 +16,16 @@
 //                 `estimate = estimate + res`, PathTracing.hpp:507-511, NaN filter per sample) and
 //                 adds the sum once (3 atomics per `chunk` paths).
 //
-// Every path draws the Philox slots (seed; pixel, sample, depth) it draws in the wavefront, so the two
-// pipelines produce the same per-path radiance; only the float summation order of the frame buffer
-// differs.  HBM traffic: the 12 MB frame buffer.
+// Every path draws the Philox slots (seed; pixel, sample, depth) it draws in the wavefront and runs the
+// same shade_vertex / flat tests, so the two pipelines agree to float noise (frame-buffer summation order;
+// FMA contraction is decided per translation unit).  HBM traffic: the 12 MB frame buffer.
+//
+// Measured on a B200 (Cornell 1024^2, tools/gpu_resident.py): 1313 Mpaths/s against the wavefront's 1950.
+// ncu (profiles/r01e_resident_*): 128 registers -> 16 warps per SM, 29 % of the stall samples are
+// instruction-cache misses (flat tests + shading = one 10 000-instruction loop that warps run out of
+// phase), 17 of 32 lanes per instruction (a lane cannot be parked and refilled the way a queue entry
+// can).  It is therefore opt-in (tutu_render_pipeline = 2): one launch, no queue pools — the low-latency
+// choice for small frames.
 #pragma once
 #include "vertex.cuh"
 
