@@ -312,7 +312,7 @@ def glass_bench(torch, api, do_cpu: bool, spp: int) -> dict:
     npix = WIDTH * HEIGHT
     host_img = torch.empty(npix * 3, dtype=torch.float32, pin_memory=True)
     for k in range(3):
-        ctx.render_path_ptr(16, SEED + k, host_img.data_ptr())  # 16 spp = 16 Mi paths: the queue pool reaches its full size
+        ctx.render_path_ptr(32, SEED + k, host_img.data_ptr())  # 32 spp = 2 lanes x 16 Mi paths: both queue pools reach their full size
     t0 = time.perf_counter()
     ctx.upload(sc)
     ctx.render_path_ptr(spp, SEED + 9, host_img.data_ptr())

@@ -244,3 +244,15 @@ def test_pipelines_give_the_same_paths(api, ctx, cornell, mixed):
         ctx.render_path(2)
     ctx.pipeline("auto")
     assert np.isfinite(ctx.render_path(2)).all()
+
+
+def test_scene_switch_between_trees_of_different_depth(api, ctx, golden):
+    """The cached launch configuration of the wavefront depends on the traversal-stack size: a context that
+    rendered one tree must render a deeper one (regression: CUDA 'invalid argument' on the second scene)."""
+    means = []
+    for name in ("glass_c4", "veach_80x60", "mixed", "glass_c4"):
+        ctx.upload(api.Scene.load(golden / f"{name}.tscene").with_size(24, 24))
+        img = ctx.render_path(2, seed=3)
+        assert np.isfinite(img).all()
+        means.append(float(img.mean()))
+    assert means[0] == pytest.approx(means[3], rel=1e-5)

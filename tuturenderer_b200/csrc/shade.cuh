@@ -45,11 +45,8 @@ __device__ __forceinline__ f3 cross(f3 a, f3 b) {
 }
 __device__ __forceinline__ f3 normalized(f3 v) {  // Vector.hpp:213-220
   const float l2 = v.x * v.x + v.y * v.y + v.z * v.z;
-  if (l2 > 0.f) {
-    const float inv = rsqrtf(l2);
-    return mk(v.x * inv, v.y * inv, v.z * inv);
-  }
-  return v;
+  const float inv = l2 > 0.f ? rsqrtf(l2) : 1.f;  // a select, not a branch: v * 1 is v (mag == 0 and NaN included)
+  return mk(v.x * inv, v.y * inv, v.z * inv);
 }
 __device__ __forceinline__ bool FLOAT_EQUAL(float x, float y) { return fabsf(x - y) < 0.0001f; }
 __device__ __forceinline__ float max3(f3 a) { return fmaxf(a.x, fmaxf(a.y, a.z)); }

@@ -114,6 +114,7 @@ struct BdptLane {
   }
 };
 
+constexpr int kHostSlotsMax = 4;  // host-buffer ray batches: chunks in flight (trace_host_pipelined)
 struct TutuCtx {
   int device = 0;
   int sm_count = 148;
@@ -134,10 +135,10 @@ struct TutuCtx {
 
   // ray batches
   DevBuf d_rays, d_hits, d_blocked, d_counts;
-  DevBuf d_bin_keys[2], d_bin_perm[2], d_bin_hist[2];  // [pipeline slot]
+  DevBuf d_bin_keys[kHostSlotsMax], d_bin_perm[kHostSlotsMax], d_bin_hist[kHostSlotsMax];  // [pipeline slot]
   // host-buffer ray batches are pipelined in chunks over two streams (H2D | walk | D2H overlap)
-  cudaStream_t stream2 = nullptr;
-  DevBuf d_chunk_rays[2], d_chunk_out[2];
+  cudaStream_t slot_streams[kHostSlotsMax] = {};  // [0] unused (slot 0 runs on `stream`)
+  DevBuf d_chunk_rays[kHostSlotsMax], d_chunk_out[kHostSlotsMax];
   int ray_binning = 1;              // 0 = trace in the caller's order
   uint64_t ray_binning_min = 1u << 16;
 
@@ -153,6 +154,7 @@ struct TutuCtx {
   bool sort_by_class = false;  // wavefront.cuh: wf_classify (scenes with more than one shading class)
   int shade_block = TUTU_SHADE_BLOCK;  // wavefront.cuh: kShadeBlockSimple for all-Lambertian untextured scenes
   int grid_shade_block = 0;
+  size_t grid_stack_smem = 0;
   bool grid_small = false;
   int profile_stages = 0;
   // 0 = automatic (register-resident kernel when the scene fits the constant bank, else wavefront),
@@ -615,7 +617,7 @@ const unsigned* bin_rays(TutuCtx* ctx, const float4* rays, uint64_t n, cudaStrea
 
 void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_out, cudaStream_t s, int slot = 0) {
   if (n == 0) return;
-  ctx->d_counts.ensure(64);
+  ctx->d_counts.ensure(256);
   unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 4 + 2 * slot;  // cursors: [4] closest, [5] any, [6],[7] slot 1
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
@@ -653,7 +655,7 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
 
 void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t s, int slot = 0) {
   if (n == 0) return;
-  ctx->d_counts.ensure(64);
+  ctx->d_counts.ensure(256);
   unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 5 + 2 * slot;
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
@@ -865,7 +867,11 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)16 << 20;
   while (n_lanes > 1 && (sample_count < (uint32_t)n_lanes || total / n_lanes < cap_cfg / 2)) --n_lanes;
   if ((int)ctx->wf_lanes.size() < n_lanes) ctx->wf_lanes.resize(n_lanes);
-  if (ctx->grid_lanes != n_lanes || ctx->grid_small != (ctx->small.n > 0) || ctx->grid_shade_block != ctx->shade_block) {
+  // the cached grids depend on the scene through the kernel variants and the traversal-stack size
+  const size_t want_stack = ctx->small.n > 0 ? 0 : stack_smem(ctx, 256, false);
+  if (ctx->grid_lanes != n_lanes || ctx->grid_small != (ctx->small.n > 0) || ctx->grid_shade_block != ctx->shade_block ||
+      ctx->grid_stack_smem != want_stack) {
+    ctx->grid_stack_smem = want_stack;
     ctx->grid_shade_block = ctx->shade_block;
     ctx->grid_small = ctx->small.n > 0;
     const int div = getenv("TUTU_GRID_SPLIT") ? n_lanes : 1;  // experiments only: split the resident blocks between the lanes
@@ -1183,7 +1189,8 @@ extern "C" void tutu_ctx_destroy(TutuCtx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
-  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  for (cudaStream_t st : ctx->slot_streams)
+    if (st) cudaStreamDestroy(st);
   delete ctx;
 }
 
@@ -1335,31 +1342,39 @@ extern "C" int tutu_trace_any_device(TutuCtx* ctx, const float* d_rays, uint64_t
   API_END(ctx)
 }
 
-// Host-buffer batches: chunks of kHostChunk rays alternate between two streams, so that the H2D copy of
+// Host-buffer batches: chunks of kHostChunk rays rotate over kHostSlots streams, so that the H2D copy of
 // one chunk, the walk of the previous one and the D2H copy of the one before overlap (PCIe is full duplex;
-// with pinned host buffers the batch costs ~max(H2D, walk, D2H) instead of their sum).
-constexpr uint64_t kHostChunk = 1ull << 21;
+// with pinned host buffers the batch costs ~max(H2D, walk, D2H) instead of their sum).  Measured on 2^24
+// rays vs the 999 698-triangle height-field (tools/gpu_e2e.py, Mrays/s): 2 slots x 2 Mi 1223, 2 x 1 Mi 1213,
+// 3 x 2 Mi 1386, 3 x 1 Mi 1523, 4 x 1 Mi 1524 (the H2D copy alone allows ~1700).
+constexpr uint64_t kHostChunk = 1ull << 20;
+constexpr int kHostSlots = 3;
 
 template <class Out, class Launch>
 static void trace_host_pipelined(TutuCtx* ctx, const float* rays, uint64_t n_rays, Out* out, Launch launch) {
-  if (!ctx->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-  cudaStream_t st[2] = {ctx->stream, ctx->stream2};
-  const uint64_t chunk = std::min<uint64_t>(kHostChunk, n_rays);
-  const int slots = n_rays > chunk ? 2 : 1;
+  static const int slots_cfg = getenv("TUTU_HOST_SLOTS") ? std::min(kHostSlotsMax, std::max(1, atoi(getenv("TUTU_HOST_SLOTS")))) : kHostSlots;
+  static const uint64_t chunk_cfg = getenv("TUTU_HOST_CHUNK_LOG2") ? 1ull << atoi(getenv("TUTU_HOST_CHUNK_LOG2")) : kHostChunk;
+  const uint64_t chunk = std::min<uint64_t>(chunk_cfg, n_rays);
+  const int slots = (int)std::min<uint64_t>((uint64_t)slots_cfg, (n_rays + chunk - 1) / chunk);
+  cudaStream_t st[kHostSlotsMax];
+  st[0] = ctx->stream;
+  for (int k = 1; k < slots; ++k) {
+    if (!ctx->slot_streams[k]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->slot_streams[k], cudaStreamNonBlocking));
+    st[k] = ctx->slot_streams[k];
+  }
   for (int k = 0; k < slots; ++k) {
     ctx->d_chunk_rays[k].ensure(chunk * TUTU_RAY_FLOATS * sizeof(float));
     ctx->d_chunk_out[k].ensure(chunk * sizeof(Out));
   }
   int k = 0;
-  for (uint64_t first = 0; first < n_rays; first += chunk, k ^= 1) {
+  for (uint64_t first = 0; first < n_rays; first += chunk, k = (k + 1) % slots) {
     const uint64_t m = std::min<uint64_t>(chunk, n_rays - first);
     CUDA_TRY(cudaMemcpyAsync(ctx->d_chunk_rays[k].p, rays + first * TUTU_RAY_FLOATS, m * TUTU_RAY_FLOATS * sizeof(float),
                              cudaMemcpyHostToDevice, st[k]));
     launch(ctx->d_chunk_rays[k].as<float>(), m, ctx->d_chunk_out[k].as<Out>(), st[k], k);
     CUDA_TRY(cudaMemcpyAsync(out + first, ctx->d_chunk_out[k].p, m * sizeof(Out), cudaMemcpyDeviceToHost, st[k]));
   }
-  CUDA_TRY(cudaStreamSynchronize(st[0]));
-  if (slots > 1) CUDA_TRY(cudaStreamSynchronize(st[1]));
+  for (int j = 0; j < slots; ++j) CUDA_TRY(cudaStreamSynchronize(st[j]));
 }
 
 extern "C" int tutu_trace_closest(TutuCtx* ctx, const float* rays, uint64_t n_rays, TutuHit* hits_out) {
@@ -1394,7 +1409,7 @@ extern "C" int tutu_trace_count_visits(TutuCtx* ctx, const float* d_rays, uint64
   if (int rc = check_scene(ctx)) return rc;
   if (!nodes_out || !prims_out || (n_rays && !d_rays)) return fail(ctx, TUTU_E_INVALID, "tutu_trace_count_visits: null argument");
   cudaStream_t s = ctx->stream;
-  ctx->d_counts.ensure(64);
+  ctx->d_counts.ensure(256);
   unsigned long long* c = ctx->d_counts.as<unsigned long long>();
   CUDA_TRY(cudaMemsetAsync(c, 0, 16, s));
   if (n_rays) {
