@@ -972,11 +972,15 @@ __device__ __forceinline__ unsigned small_box_group(const SmallScene& ss, const 
   unsigned mask = 0u;
 #pragma unroll
   for (int k = K0; k < K0 + 4; ++k) {
-    float te;
-    const bool hit = box_test_packed(q, ss.box[k][0], ss.box[k][1], ss.box[k][2], te);
-    // any-hit: a blocker needs t < dis, so a box entered beyond dis (+ the pruning slack of the tree
-    // walk, prune_limit) cannot hold one
-    if (hit && (!ANY || te <= lim)) mask |= ss.slots[k];
+    // box_test_packed with the two comparisons folded: t_enter <= t_exit && t_exit >= 0  <=>
+    // max(t_enter, 0) <= t_exit (no NaN for a regular ray); any-hit: ... && t_enter <= lim
+    const float2 tx = __fmul2_rn(__fadd2_rn(ss.box[k][0], q.nox), q.ix);
+    const float2 ty = __fmul2_rn(__fadd2_rn(ss.box[k][1], q.noy), q.iy);
+    const float2 tz = __fmul2_rn(__fadd2_rn(ss.box[k][2], q.noz), q.iz);
+    const float te = fmaxf(fminf(tx.x, tx.y), fmaxf(fminf(ty.x, ty.y), fminf(tz.x, tz.y)));
+    float t_exit = fminf(fmaxf(tx.x, tx.y), fminf(fmaxf(ty.x, ty.y), fmaxf(tz.x, tz.y)));
+    if (ANY) t_exit = te <= lim ? t_exit : -1.f;  // beyond the limit: cannot hold a blocker
+    if (fmaxf(te, 0.f) <= t_exit) mask |= ss.slots[k];
   }
   return mask;
 }
@@ -1053,7 +1057,13 @@ __device__ __forceinline__ bool traverse_small(const DevScene& sc, const SmallSc
 // 6-10.  So a warp tests at most kSmallFirst candidates per ray in its first pass, parks the rays that
 // still have candidates (state in shared memory, warp-private, no atomics) and finishes 32 parked rays
 // at a time with all lanes busy.
-constexpr int kSmallFirst = 2;
+#ifndef TUTU_SMALL_FIRST
+#define TUTU_SMALL_FIRST 2
+#endif
+#ifndef TUTU_SMALL_NEXT
+#define TUTU_SMALL_NEXT 2
+#endif
+constexpr int kSmallFirst = TUTU_SMALL_FIRST;
 constexpr unsigned kParkCap = 64;  // a warp parks at most 31 + 32 rays before it drains 32
 struct SmallPark {                 // per warp
   float4 o[kParkCap];              // o.xyz, dis
@@ -1102,7 +1112,7 @@ __device__ __forceinline__ unsigned small_park_push(SmallPark& pk, unsigned cnt,
 // Warp-collective: the last min(cnt, 32) parked rays get kSmallNext more tests each (all their remaining
 // candidates when `finish`); finished rays go to sink(index, ray, dis, best, blocked), the others are
 // parked again.  Returns the new count.
-constexpr int kSmallNext = 2;
+constexpr int kSmallNext = TUTU_SMALL_NEXT;
 template <bool ANY, class Sink>
 __device__ __forceinline__ unsigned small_park_drain(const DevScene& sc, SmallPark& pk, unsigned cnt, bool finish,
                                                      Sink sink) {
