@@ -186,6 +186,8 @@ V3 SphereLocal2world(const V3& n, const V3& dir) {  // :387-409
 // ---------------------------------------------------------------------------------------------
 // random numbers: Philox4x32-10, counter (pixel, sample, depth, block), key = seed
 // slots per depth: 0 light index, 1-2 light point, 3-4 BSDF, 5 third BSDF draw / roulette
+// Path tracing (packed6): the six numbers of a vertex are the six 21-bit fields of ONE block's 128 bits
+// (u = field * 2^-21), the GPU's draw6; BDPT keeps one 24-bit number per 32-bit word (draw4).
 // ---------------------------------------------------------------------------------------------
 inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
   for (int r = 0; r < 10; ++r) {
@@ -203,7 +205,20 @@ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 struct Rng {
   uint64_t seed;
   uint32_t pixel, sample;
+  bool packed6 = false;
   float get(int depth, int slot) const {
+    if (packed6) {
+      uint32_t c[4] = {pixel, sample, (uint32_t)depth, 0u};
+      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      const uint32_t hi = c[slot < 3 ? 0 : 2], lo = c[slot < 3 ? 1 : 3];
+      uint32_t f;
+      switch (slot % 3) {
+        case 0: f = hi >> 11; break;
+        case 1: f = ((hi & 0x7FFu) << 10) | (lo >> 22); break;
+        default: f = (lo >> 1) & 0x1FFFFFu; break;
+      }
+      return (float)f * (1.0f / 2097152.0f);
+    }
     uint32_t c[4] = {pixel, sample, (uint32_t)depth, (uint32_t)(slot >> 2)};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     return (float)(c[slot & 3] >> 8) * (1.0f / 16777216.0f);
@@ -1250,7 +1265,7 @@ void oracle_render_path(const OracleScene* os, uint32_t sample_begin, uint32_t s
   std::vector<std::thread> pool;
   for (int w = 0; w < threads; ++w)
     pool.emplace_back([&] {
-      Tracer tr{s, Rng{seed, 0, 0}};
+      Tracer tr{s, Rng{seed, 0, 0, true}};
       for (;;) {
         int y = next.fetch_add(1);
         if (y >= H) break;

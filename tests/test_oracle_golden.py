@@ -37,7 +37,10 @@ def test_oracle_render_matches_reference_statistics(api, oracle, golden, cornell
     sc = cornell.with_size(128, 128)
     osc = oracle.OracleScene(sc)
     img = osc.render_path(64, seed=11)
-    assert np.array_equal((img == 0).all(-1), (ref == 0).all(-1)), "background mask differs"
+    # background pixels are exactly 0 at any spp; at 64 spp a few deeply shadowed pixels (reference mean
+    # 0.016 at 4096 spp) may also have drawn 64 zeros
+    zero, ref_zero = (img == 0).all(-1), (ref == 0).all(-1)
+    assert (zero >= ref_zero).all() and (zero & ~ref_zero).sum() <= 8, "background mask differs"
     light = np.array([47.8348007, 38.5663986, 31.0807991], np.float32)
     assert np.array_equal((img == light).all(-1), (ref == light).all(-1)), "emission mask differs"
     r = _rmse(img, ref)

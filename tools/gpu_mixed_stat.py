@@ -1,0 +1,14 @@
+import sys, json
+sys.path.insert(0, '/root/repo')
+import numpy as np
+from tuturenderer_b200 import api
+g = '/root/repo/tests/golden/'
+ref = np.fromfile(g + 'mixed_96_ref_mean_2048.f32', np.float32).reshape(96, 96, 3)
+sc = api.Scene.load(g + 'mixed.tscene')
+ctx = api.Context(0); ctx.upload(sc)
+b = lambda a: a.reshape(12, 8, 12, 8, 3).mean((1, 3))
+for seed in (1, 2, 3, 4, 5, 6):
+    img = ctx.render_path(8192, seed=seed)
+    rel = np.abs(b(img) - b(ref)) / (b(ref) + 0.02)
+    k = np.unravel_index(rel.argmax(), rel.shape)
+    print(seed, 'max', rel.max(), 'at', k, 'mean', rel.mean(), 'img', b(img)[k], 'ref', b(ref)[k], 'chan means', [float(img[..., c].mean() / ref[..., c].mean()) for c in range(3)])

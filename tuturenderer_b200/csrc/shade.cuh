@@ -74,20 +74,21 @@ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32
   }
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// The six numbers of a path-tracing vertex: the six 21-bit fields of ONE Philox block (u = field * 2^-21,
+// exact in fp32).  One block instead of two: Philox is ~13 % of wf_shade's instructions, and that kernel's
+// time follows its instruction count.  The tests' CPU restatement draws the same fields.
 __device__ __forceinline__ Rand6 draw6(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t depth) {
   Rand6 r;
   uint32_t a0 = pixel, a1 = sample, a2 = depth, a3 = 0u;
   philox4x32_10(a0, a1, a2, a3, (uint32_t)seed, (uint32_t)(seed >> 32));
-  uint32_t b0 = pixel, b1 = sample, b2 = depth, b3 = 1u;
-  philox4x32_10(b0, b1, b2, b3, (uint32_t)seed, (uint32_t)(seed >> 32));
-  r.u[0] = u01(a0), r.u[1] = u01(a1), r.u[2] = u01(a2), r.u[3] = u01(a3);
-  r.u[4] = u01(b0), r.u[5] = u01(b1);
+  const float s = 1.0f / 2097152.0f;
+  r.u[0] = (float)(a0 >> 11) * s;
+  r.u[1] = (float)(((a0 & 0x7FFu) << 10) | (a1 >> 22)) * s;
+  r.u[2] = (float)((a1 >> 1) & 0x1FFFFFu) * s;
+  r.u[3] = (float)(a2 >> 11) * s;
+  r.u[4] = (float)(((a2 & 0x7FFu) << 10) | (a3 >> 22)) * s;
+  r.u[5] = (float)((a3 >> 1) & 0x1FFFFFu) * s;
   return r;
-}
-__device__ __forceinline__ float draw_slot5(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t depth) {
-  uint32_t b0 = pixel, b1 = sample, b2 = depth, b3 = 1u;
-  philox4x32_10(b0, b1, b2, b3, (uint32_t)seed, (uint32_t)(seed >> 32));
-  return u01(b1);
 }
 
 // one Philox block: the four values of counter (pixel, sample, depth, block)
