@@ -261,3 +261,23 @@ def test_scene_switch_between_trees_of_different_depth(api, ctx, golden):
         assert np.isfinite(img).all()
         means.append(float(img.mean()))
     assert means[0] == pytest.approx(means[3], rel=1e-5)
+
+
+def test_small_scene_kernels_equal_the_tree_walk_at_full_size(api, ctx, cornell, monkeypatch):
+    """BASELINE size (1024x1024): the flat small-scene kernels (distinct-box slab tests, parked rays) and the
+    general stack walk over the same tree must find the same hit for every one of the 10^7 queued rays, so
+    the two renders trace the same paths: equal ray counts, images equal up to the order of the float
+    atomics."""
+    sc = cornell.with_size(1024, 1024)
+    ctx.upload(sc)
+    a = ctx.render_path(2, seed=13)
+    sa = ctx.stats()
+    monkeypatch.setenv("TUTU_NO_SMALL", "1")  # read by tutu_scene_upload
+    ctx.upload(sc)
+    b = ctx.render_path(2, seed=13)
+    sb = ctx.stats()
+    monkeypatch.delenv("TUTU_NO_SMALL")
+    ctx.upload(sc)
+    for k in ("paths", "extend_rays", "shadow_rays", "nan_samples"):
+        assert sa[k] == sb[k], k
+    assert np.allclose(a, b, rtol=2e-5, atol=1e-6)
