@@ -137,7 +137,10 @@ wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
 }
 
 // ---- extend: IIntersectStrategy::UpdateInter -> getIntersection -------------------------------
-constexpr unsigned kPacketRays = 128;  // rays per queue fetch (one same-address atomic each)
+#ifndef TUTU_PACKET_RAYS
+#define TUTU_PACKET_RAYS 128
+#endif
+constexpr unsigned kPacketRays = TUTU_PACKET_RAYS;  // rays per queue fetch (one same-address atomic each)
 
 // Ray packets pulled from the queue with one atomicAdd per warp (lane 0) and a shuffle
 // broadcast: a warp that drew short rays moves on to the next packet instead of idling behind the
@@ -213,8 +216,11 @@ wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
 }
 
 // ---- small scenes: two-phase flat tests (trace.cuh: SmallPark) ----------------------------------
+#ifndef TUTU_SMALL_MIN_BLOCKS
+#define TUTU_SMALL_MIN_BLOCKS 1
+#endif
 constexpr int kSmallBlock = 256;
-__global__ void __launch_bounds__(kSmallBlock)
+__global__ void __launch_bounds__(kSmallBlock, TUTU_SMALL_MIN_BLOCKS)
 wf_extend_small(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int cur) {
   __shared__ SmallPark s_park[kSmallBlock / 32];
   SmallPark& pk = s_park[threadIdx.x >> 5];
@@ -253,7 +259,7 @@ wf_extend_small(const __grid_constant__ DevScene sc, const __grid_constant__ Sma
   while (parked) parked = small_park_drain<false>(sc, pk, parked, parked <= 32u, sink);
 }
 
-__global__ void __launch_bounds__(kSmallBlock)
+__global__ void __launch_bounds__(kSmallBlock, TUTU_SMALL_MIN_BLOCKS)
 wf_shadow_small(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int nxt) {
   __shared__ SmallPark s_park[kSmallBlock / 32];
   SmallPark& pk = s_park[threadIdx.x >> 5];
