@@ -954,7 +954,7 @@ __device__ __forceinline__ bool traverse_variant(const DevScene& sc, const Ray& 
 // t_enter(parent) <= t_enter(child) <= t_exit(child) <= t_exit(parent): a hit leaf box implies that
 // every ancestor box is hit.  The reference's answer is therefore simply the closest primitive
 // among those whose OWN leaf box and primitive test both pass (ties: lowest DFS slot).  With 32
-// leaves that is 32 slab tests against constants read straight from the kernel-parameter bank
+// leaves that is at most 32 slab tests (one per distinct box) against constants read straight from the kernel-parameter bank
 // (fully convergent, no loads, no stack) followed by the primitive tests of the few set bits.
 // Irregular rays take the literal tree walk.
 constexpr int kSmallMax = 32;

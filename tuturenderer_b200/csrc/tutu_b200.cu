@@ -136,7 +136,7 @@ struct TutuCtx {
   // ray batches
   DevBuf d_rays, d_hits, d_blocked, d_counts;
   DevBuf d_bin_keys[kHostSlotsMax], d_bin_perm[kHostSlotsMax], d_bin_hist[kHostSlotsMax];  // [pipeline slot]
-  // host-buffer ray batches are pipelined in chunks over two streams (H2D | walk | D2H overlap)
+  // host-buffer ray batches are pipelined in chunks over kHostSlots streams (H2D | walk | D2H overlap)
   cudaStream_t slot_streams[kHostSlotsMax] = {};  // [0] unused (slot 0 runs on `stream`)
   DevBuf d_chunk_rays[kHostSlotsMax], d_chunk_out[kHostSlotsMax];
   int ray_binning = 1;              // 0 = trace in the caller's order
