@@ -241,9 +241,11 @@ int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
 int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int lanes, int profile_stages);
 /* Path-tracing pipeline: 0 = automatic (default), 1 = wavefront (queues in HBM, any scene), 2 =
  * register-resident persistent kernel (scenes of <= 32 primitives, whose geometry fits the kernel's
- * constant bank; a render on a larger scene then fails with TUTU_E_STATE).  Automatic is the wavefront
- * (measured faster on a B200).  Both run the same vertex code on the same random numbers:
- * images agree to float noise (frame-buffer summation order, FMA contraction per translation unit). */
+ * constant bank; a render on a larger scene then fails with TUTU_E_STATE).  Automatic takes 2 for renders
+ * of fewer than 768 Ki paths on such scenes (one launch, no queue pools: 3.4x faster at 64x64 @ 16 spp) and
+ * the wavefront otherwise (1.5x faster once its queues fill).  Both run the same vertex code
+ * on the same random numbers: images agree to float noise (frame-buffer summation order, FMA contraction
+ * per translation unit). */
 int tutu_render_pipeline(TutuCtx* ctx, int pipeline);
 
 /* ---- output stage: PPMGenerator::writePixel (reference include/PPMGenerator.hpp:812-845) ---- */

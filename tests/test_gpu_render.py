@@ -17,6 +17,16 @@ pytestmark = pytest.mark.gpu
 LIGHT = np.array([47.8348007, 38.5663986, 31.0807991], np.float32)
 
 
+@pytest.fixture(params=["auto", "wavefront"])
+def ctx(api, request):
+    """Every test of this module runs with the automatic pipeline choice (small renders of the Cornell scenes
+    take the register-resident kernel) and with the wavefront forced."""
+    c = api.Context(0)
+    c.pipeline(request.param)
+    yield c
+    c.close()
+
+
 def _rmse(a, b):
     return float(np.sqrt(((a - b) ** 2).mean()))
 

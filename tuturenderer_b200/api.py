@@ -393,8 +393,9 @@ class Context:
     PIPELINES = {"auto": 0, "wavefront": 1, "resident": 2}
 
     def pipeline(self, name: str = "auto") -> None:
-        """Path-tracing pipeline: 'auto' (= 'wavefront'), 'wavefront', or 'resident' (one persistent kernel with
-        the path state in registers; scenes of <= 32 primitives only, renders fail on larger ones)."""
+        """Path-tracing pipeline: 'auto' (the resident kernel for renders below 768 Ki paths of scenes with <= 32
+        primitives, else the wavefront), 'wavefront', or 'resident' (one persistent kernel with the path state
+        in registers; scenes of <= 32 primitives only, renders fail on larger ones)."""
         self._ck(lib().tutu_render_pipeline(self._h, self.PIPELINES[name]))
 
     def render_path(self, spp: int, seed: int = 1, out: np.ndarray | None = None) -> np.ndarray:

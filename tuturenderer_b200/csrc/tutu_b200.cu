@@ -157,8 +157,8 @@ struct TutuCtx {
   size_t grid_stack_smem = 0;
   bool grid_small = false;
   int profile_stages = 0;
-  // 0 = automatic (register-resident kernel when the scene fits the constant bank, else wavefront),
-  // 1 = wavefront, 2 = register-resident (fails on scenes that do not fit)
+  // 0 = automatic (register-resident kernel for small renders of scenes that fit the constant bank, else
+  // wavefront), 1 = wavefront, 2 = register-resident (fails on scenes that do not fit)
   int pipeline_cfg = 0;
   DevBuf d_resident_ctl;
   int grid_resident = 0;
@@ -851,7 +851,13 @@ void resident_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count,
 // `s` is ordered after the lanes when the call returns (it also blocks the host until then).
 void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint64_t seed, float* d_accum,
                cudaStream_t s) {
-  if (ctx->pipeline_cfg == 2 && ctx->small.n > 0) return resident_render(ctx, sample_begin, sample_count, seed, d_accum, s);
+  // Automatic choice: the register-resident kernel is one launch with no queue pools, the wavefront is faster
+  // per path once its queues fill.  Measured on Cornell (tools/gpu_small_frames.py, device ms wavefront /
+  // resident): 0.07 M paths 0.44 / 0.13, 0.26 M 0.57 / 0.27, 1.05 M 0.92 / 0.92, 4.2 M 2.4 / 3.4.
+  constexpr uint64_t kResidentBelowPaths = 768u << 10;
+  if (ctx->small.n > 0 && (ctx->pipeline_cfg == 2 || (ctx->pipeline_cfg == 0 &&
+                                                       (uint64_t)ctx->flat.raygen.width * ctx->flat.raygen.height * sample_count < kResidentBelowPaths)))
+    return resident_render(ctx, sample_begin, sample_count, seed, d_accum, s);
   const FlatScene& f = ctx->flat;
   const uint64_t npix = (uint64_t)f.raygen.width * f.raygen.height;
   const uint64_t total = npix * sample_count;
