@@ -519,7 +519,7 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
     }
     for (uint32_t i = 0; i < desc->n_tex[c]; ++i) {
       const TutuTexture& t = desc->tex[c][i];
-      if (t.width < 0 || t.height < 0 || ((size_t)t.width * t.height && !t.rgb)) {
+      if (t.width < 0 || t.height < 0 || ((size_t)t.width * t.height != 0 && !t.rgb)) {
         set_error("scene: malformed texture");
         return TUTU_E_INVALID;
       }
@@ -1065,7 +1065,7 @@ extern "C" int tutu_synth_rays(int kind, uint64_t seed, uint64_t first, uint64_t
 // PPM output — PPMGenerator::writeHeader / writePixel file format (PPMGenerator.hpp:804-809, 840-842)
 // ------------------------------------------------------------------------------------------
 extern "C" int tutu_write_ppm(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb8, int binary) {
-  if (!path || (!rgb8 && (size_t)width * height)) {
+  if (!path || (!rgb8 && (size_t)width * height != 0)) {
     tutu::set_error("tutu_write_ppm: null argument");
     return TUTU_E_INVALID;
   }
