@@ -179,6 +179,10 @@ def test_render_errors(api, cornell):
     c.upload(cornell.with_size(8, 8))
     with pytest.raises(api.TutuError):
         c.render_path(0)
+    # pipeline knob: 0..2 only; the setting survives a failed call
+    assert api.lib().tutu_render_pipeline(c._h, 3) != 0
+    assert api.lib().tutu_render_pipeline(c._h, -1) != 0
+    assert np.isfinite(c.render_path(1)).all()
     c.close()
 
 
