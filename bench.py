@@ -35,6 +35,8 @@ SEED = 20261018
 PUBLISHED_MPATHS = 0.283  # README's "spp512_1900sec" 1024x1024 Cornell render
 RAYS_G = 707               # 2*707^2 = 999 698 triangles
 RAYS_N = 1 << 24
+CORNELL_FILE = ROOT / "tests" / "golden" / "cornell_256.tscene"  # dumped from the reference driver's scene
+REF_SPP_PER_STEP = 4  # --impl reference: bounded sample per step
 
 # queue record sizes of the wavefront (bytes), see DESIGN.md §4
 B_RAY, B_HIT, B_STATE, B_XSTATE, B_SHADOW = 32, 16, 48, 16, 48
@@ -57,7 +59,7 @@ def parse():
 
 def cornell_scene(width=WIDTH, height=HEIGHT):
     from tuturenderer_b200 import api
-    return api.Scene.load(ROOT / "tests" / "golden" / "cornell_256.tscene").with_size(width, height)
+    return api.Scene.load(CORNELL_FILE).with_size(width, height)
 
 
 # --------------------------------------------------------------------------------------------
@@ -115,59 +117,81 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU legs (the reference compiled from its own sources; oracle port only if that is missing)
 # --------------------------------------------------------------------------------------------
-def cpu_paths_baseline(spp: int, modes=("rows", "stock")) -> dict:
+def cpu_paths_baseline(spp: int, modes=("rows", "stock")):
+    """Returns (cpu_baseline dict, the reference's linear float image of its fastest mode)."""
     from oracle import oracle_py as O
-    sc = cornell_scene()
     cores = os.cpu_count() or 1
     if O.ref_available():
-        best = None
+        best = best_img = None
         for mode in modes:
-            _img, info = O.ref_render(sc, spp, mode=mode, timeout=600)
+            img, info = O.ref_render_file(CORNELL_FILE, spp, mode=mode, width=WIDTH, height=HEIGHT, timeout=600)
             if best is None or info["mpaths_per_s"] > best["mpaths_per_s"]:
-                best = info
+                best, best_img = info, img
         return {"value": best["mpaths_per_s"], "unit": "Mpaths/s", "cores": min(best["threads"], cores),
                 "threads": best["threads"], "kind": "reference",
                 "sample": f"Cornell {WIDTH}x{HEIGHT} @ {spp} spp ({WIDTH * HEIGHT * spp / 1e6:.1f} Mpaths), "
                           f"reference PathTracing via oracle/_ref/ref_harness mode={best['mode']} "
-                          f"({best['seconds']:.1f} s); modes tried: {','.join(modes)}"}
+                          f"({best['seconds']:.1f} s); modes tried: {','.join(modes)}"}, best_img
+    sc = cornell_scene()
     t = time.perf_counter()
-    O.OracleScene(sc).render_path(spp, seed=1)
+    img = O.OracleScene(sc).render_path(spp, seed=1)
     dt = time.perf_counter() - t
     return {"value": WIDTH * HEIGHT * spp / dt * 1e-6, "unit": "Mpaths/s", "cores": cores, "kind": "port",
-            "sample": f"Cornell {WIDTH}x{HEIGHT} @ {spp} spp, oracle port ({dt:.1f} s); oracle/_ref not built"}
+            "sample": f"Cornell {WIDTH}x{HEIGHT} @ {spp} spp, oracle port ({dt:.1f} s); oracle/_ref not built"}, img
 
 
-def cpu_rays_baseline(scene, rays: np.ndarray) -> dict:
+def image_parity(ref_n: np.ndarray, gpu_n: np.ndarray, gpu_hi: np.ndarray, n: int, hi: int) -> dict:
+    """Headline-step parity figure: the reference's own n-spp render and the GPU's n-spp render, both against a
+    GPU render at `hi` spp with another seed.  Unbiased and equally noisy <=> mean ratios ~ 1 and RMSE ratio ~ 1
+    (tests/test_gpu_render.py holds the gates; this is the measured figure of THIS run)."""
+    ref_n, gpu_n, gpu_hi = (np.nan_to_num(a.reshape(-1, 3).astype(np.float64)) for a in (ref_n, gpu_n, gpu_hi))
+    rmse = lambda a, b: float(np.sqrt(((a - b) ** 2).mean()))
+    relmse = lambda a, b: float((((a - b) ** 2) / (b * b + 1e-2)).mean())
+    r_ref, r_gpu = rmse(ref_n, gpu_hi), rmse(gpu_n, gpu_hi)
+    return {"compared": f"reference @ {n} spp and GPU @ {n} spp, each against GPU @ {hi} spp (independent seed), "
+                        f"{WIDTH}x{HEIGHT} linear float frame buffers",
+            "channel_mean_ratio_ref_over_gpu": [float(ref_n[:, c].mean() / gpu_hi[:, c].mean()) for c in range(3)],
+            "rmse_reference": r_ref, "rmse_gpu": r_gpu, "rmse_ratio_gpu_over_reference": r_gpu / r_ref,
+            "relmse_reference": relmse(ref_n, gpu_hi), "relmse_gpu": relmse(gpu_n, gpu_hi),
+            "background_mask_equal": bool(np.array_equal((ref_n == 0).all(1), (gpu_hi == 0).all(1)))}
+
+
+def cpu_rays_baseline(scene, rays: np.ndarray, scene_path):
+    """Returns (cpu_baseline dict, reference hits, reference any-hit booleans) for the given rays."""
     from oracle import oracle_py as O
     cores = os.cpu_count() or 1
     if O.ref_available():
-        _h, info = O.ref_trace(scene, rays, "closest", threads=cores)
-        _a, info_a = O.ref_trace(scene, rays, "any", threads=cores)
+        h, info = O.ref_trace(scene, rays, "closest", threads=cores, scene_path=scene_path)
+        a, info_a = O.ref_trace(scene, rays, "any", threads=cores, scene_path=scene_path)
         return {"value": info["rays"] / info["seconds"] * 1e-6, "any_value": info_a["rays"] / info_a["seconds"] * 1e-6,
                 "unit": "Mrays/s", "cores": cores, "kind": "reference",
                 "sample": f"first {len(rays)} of the {RAYS_N} rays, reference getIntersection/hasIntersection "
-                          f"on {cores} std::threads ({info['seconds']:.1f} s + {info_a['seconds']:.1f} s)"}
+                          f"on {cores} std::threads ({info['seconds']:.1f} s + {info_a['seconds']:.1f} s)"}, h, a
     osc = O.OracleScene(scene)
     t = time.perf_counter()
-    osc.trace_closest(rays)
+    h = osc.trace_closest(rays)
     dt = time.perf_counter() - t
     return {"value": len(rays) / dt * 1e-6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-            "sample": f"first {len(rays)} rays, oracle port"}
+            "sample": f"first {len(rays)} rays, oracle port"}, h, osc.trace_any(rays)
 
 
 def run_reference(args) -> None:
+    """--impl reference: the UNMODIFIED reference's PathTracing on the host cores.  Nothing of the product
+    package is imported here: the golden scene file goes straight to oracle/_ref/ref_harness."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle_py as O
-    spp = 4  # bounded sample per step: 1024x1024 @ 4 spp = 4.2 Mpaths
-    sc = cornell_scene()
+    spp = REF_SPP_PER_STEP
     cores = os.cpu_count() or 1
     times = []
     mode = "rows"
+    if not O.ref_available():
+        # the oracle port (CPU restatement) stands in; it takes the scene through the product's POD mirror
+        sc = cornell_scene()
     for i in range(args.warmup + args.steps):
         if O.ref_available():
-            _img, info = O.ref_render(sc, spp, mode=mode, timeout=900)
+            _img, info = O.ref_render_file(CORNELL_FILE, spp, mode=mode, width=WIDTH, height=HEIGHT, timeout=900)
             dt, kind, threads = info["seconds"], "reference", info["threads"]
         else:
             t = time.perf_counter()
@@ -183,7 +207,12 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": value / PUBLISHED_MPATHS, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args),
+        "data": "synthetic",
+        "config": {"workload": f"cornell_box_{WIDTH}x{HEIGHT}_path_tracing_nee_mis (BASELINE.json configs[2]; scene = reference "
+                               "src/main_cornellBox.cpp via tests/golden/cornell_256.tscene), bounded sample per step",
+                   "width": WIDTH, "height": HEIGHT, "spp_per_step": spp, "max_depth": 6,
+                   "parallelism": f"{threads} host threads, rows handed out dynamically (no GPU)",
+                   "note": "Mpaths/s of the reference does not depend on spp (cpu_baseline of the GPU arm runs 16 spp)"},
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": min(threads, cores), "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -200,20 +229,43 @@ def workload_config(args) -> dict:
                          "(5 GB per lane) through the 126 MB L2; no flush needed"}
 
 
+def profile_record(kernel: str) -> dict | None:
+    """ncu --set full figures of `kernel` from this round's capture (profiles/r02_traffic.json, written by
+    tools/ncu_summary.py from the committed .txt summaries): DRAM bytes per launch, L1/TEX and DRAM
+    throughput %.  Static evidence of the same code, not a live measurement."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        f = ROOT / "profiles" / name
+        if not f.exists():
+            continue
+        for k, rec in json.loads(f.read_text()).items():
+            if k.split("<")[0] == kernel.split("<")[0] and (("<" not in kernel) or k == kernel):
+                return dict(rec, source=f"profiles/{name}")
+    return None
+
+
 # --------------------------------------------------------------------------------------------
 # ray-batch microbench (configs[1])
 # --------------------------------------------------------------------------------------------
 def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict) -> dict:
     from tuturenderer_b200 import api
     prims = api.synth_heightfield(RAYS_G)
-    nodes = api.bvh_build(prims)
+    t0 = time.perf_counter()
+    nodes = api.bvh_build(prims)  # the reference's midpoint tree (host; irregular rays and the literal walk need it)
+    ref_tree_ms = (time.perf_counter() - t0) * 1e3
     sc = api.Scene(prims=prims, materials=api.default_material(), bvh_nodes=nodes)
     ctx = ctx_cls(torch.cuda.current_device())
     ctx.upload(sc)
+    t0 = time.perf_counter()
+    ctx.upload(sc)  # second upload: device buffers exist, what is left is flatten + traversal-tree build + H2D
+    upload_ms = (time.perf_counter() - t0) * 1e3
     n_local = RAYS_N // world
     first = rank * n_local
-    out = {}
+    out = {"upload_ms": upload_ms, "reference_tree_build_ms": ref_tree_ms,
+           "upload_note": "tutu_scene_upload of the 999 698-triangle scene with the reference tree given: host flatten + "
+                          "traversal-tree build + H2D, wall clock; reference_tree_build_ms = tutu_bvh_build (host, the "
+                          "reference's std::sort split rule) for hosts that do not hand over the reference's own tree"}
     stream = api.stream_handle(torch.cuda.current_stream().cuda_stream)
+    scene_path = None
     for kind, label in ((0, "coherent_topdown"), (1, "incoherent_inside")):
         h_rays = torch.empty((n_local, 8), dtype=torch.float32, pin_memory=True)
         api.synth_rays(kind, n_local, first=first, out=h_rays.numpy())
@@ -236,14 +288,17 @@ def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict)
             res[name] = e0.elapsed_time(e1) / reps
         nodes_c, prims_c = ctx.count_visits(d_rays.data_ptr(), n_local, False)
         nodes_a, prims_a = ctx.count_visits(d_rays.data_ptr(), n_local, True)
-        bytes_c = 32 + 16 + 64 * nodes_c / n_local + 48 * prims_c / n_local
-        bytes_a = 32 + 1 + 64 * nodes_a / n_local + 48 * prims_a / n_local
+        nb = ctx.node_bytes()
+        bytes_c = 32 + 16 + nb["node"] * nodes_c / n_local + nb["leaf"] * prims_c / n_local
+        bytes_a = 32 + 1 + nb["node"] * nodes_a / n_local + nb["leaf"] * prims_a / n_local
         # end to end through the host-buffer entry point (pinned buffers): H2D + kernel + D2H
         ctx.trace_closest_ptr(h_rays.data_ptr(), 1 << 16, h_hits.data_ptr())  # first call allocates the staging buffers
         ctx.trace_closest_ptr(h_rays.data_ptr(), n_local, h_hits.data_ptr())
         t0 = time.perf_counter()
         ctx.trace_closest_ptr(h_rays.data_ptr(), n_local, h_hits.data_ptr())
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        ach = bytes_c * n_local / (res["closest"] * 1e-3) * 1e-9
+        prof = profile_record("k_trace_closest")
         out[label] = {
             "closest_mrays_s": n_local * world / res["closest"] * 1e-3, "any_mrays_s": n_local * world / res["any"] * 1e-3,
             "closest_ms": res["closest"], "any_ms": res["any"],
@@ -252,18 +307,39 @@ def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict)
             "bytes_per_ray": bytes_c, "any_bytes_per_ray": bytes_a,
             "e2e_closest_mrays_s": n_local * world / e2e_ms * 1e-3,
             "e2e_h2d_bytes": n_local * 32, "e2e_d2h_bytes": n_local * 16,
-            "roofline": {"bound": "hbm", "achieved": bytes_c * n_local / (res["closest"] * 1e-3) * 1e-9,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": bytes_c * n_local / (res["closest"] * 1e-3) * 1e-9 / peaks["hbm_gbs"],
-                         "traffic": None, "kernel": "k_trace_closest<0>",
-                         "note": "algorithmic bytes = 48 + 64*nodes + 48*prims per ray, nodes/prims counted on this batch "
-                                 "(regular rays walk the SAH topology over the reference's leaves); 64-byte two-child "
-                                 "records are served mostly by L1/L2, so the fraction can exceed HBM traffic; the "
-                                 "timed call includes the counting sort of the batch"},
+            "roofline": {"bound": "hbm", "limiter": "l1tex", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / peaks["hbm_gbs"],
+                         "traffic": prof.get("dram_bytes_per_launch") if prof and kind == 0 else None,
+                         "ncu": prof if kind == 0 else None, "kernel": "k_trace_closest",
+                         "note": f"algorithmic bytes = 48 + {nb['node']}*nodes + {nb['leaf']}*leaf records per ray, counted on this batch by "
+                                 "tutu_trace_count_visits over the tree the kernel walks; node records are served mostly by "
+                                 "L1/L2 (the tree is L2 resident), so this fraction is NOT an HBM utilisation: the DRAM "
+                                 "counter of the ncu capture (ncu.dram_bytes_per_launch / avg launch time) is the HBM "
+                                 "figure and the kernel's limiter is the L1/TEX data path (ncu.l1tex_pct); the timed call "
+                                 "includes the counting sort of the batch"},
         }
-        if kind == 0 and do_cpu and rank == 0:
-            out["cpu_baseline"] = cpu_rays_baseline(sc, h_rays.numpy()[: 1 << 20])
+        if do_cpu and rank == 0:
+            n_cmp = 1 << 20
+            if scene_path is None:
+                scene_path = Path(tempfile.mkdtemp()) / "c2.tscene"
+                sc.save(scene_path)
+            cpu, want_h, want_a = cpu_rays_baseline(sc, h_rays.numpy()[:n_cmp], scene_path)
+            got_h = d_hits[:n_cmp].cpu().numpy().view(np.uint8).reshape(n_cmp, 16)
+            got_a = d_any[:n_cmp].cpu().numpy()
+            bad_h = int((got_h != want_h.view(np.uint8).reshape(n_cmp, 16)).any(1).sum())
+            out[label]["parity"] = {"compared": n_cmp, "mismatches": bad_h, "any_mismatches": int((got_a != want_a).sum()),
+                                    "against": f"{cpu['kind']}: getIntersection / hasIntersection on the first {n_cmp} rays of the "
+                                               "timed batch; {prim,t,u,v} compared byte for byte, any-hit booleans exactly"}
+            out[label]["cpu_baseline"] = cpu
+            if kind == 0:
+                out["cpu_baseline"] = cpu
         del d_rays, d_hits, d_any, h_rays, h_hits
+    if scene_path is not None:
+        scene_path.unlink(missing_ok=True)
+    if "coherent_topdown" in out and "parity" in out["coherent_topdown"]:
+        out["parity"] = {"compared": sum(out[k]["parity"]["compared"] for k in ("coherent_topdown", "incoherent_inside")),
+                         "mismatches": sum(out[k]["parity"]["mismatches"] + out[k]["parity"]["any_mismatches"]
+                                           for k in ("coherent_topdown", "incoherent_inside"))}
     out["workload"] = (f"{len(prims)} triangle height-field ({RAYS_G}x{RAYS_G} quads), midpoint BVH {len(nodes)} nodes, "
                        f"{RAYS_N} rays per batch (BASELINE.json configs[1])")
     ctx.close()
@@ -273,28 +349,71 @@ def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict)
 # --------------------------------------------------------------------------------------------
 # BDPT (configs[4]) and the glass / textured scene (configs[3]) — extra blocks of the same line
 # --------------------------------------------------------------------------------------------
-def bdpt_bench(torch, api, do_cpu: bool, spp: int) -> dict:
-    """configs/config_veach_bdpt.txt: the Veach room of src/main_veach_bdpt.cpp, 800x600, BDPT."""
+def stage_roofline(st: dict, alg: dict, peaks: dict, kernels: dict) -> dict:
+    """Roofline of the dominant stage of a profiled render (CUDA events between the stages on one stream)."""
+    stage_ms = {k: st[f"{k}_ms"] for k in ("extend", "shade", "shadow")}
+    dom = max(stage_ms, key=stage_ms.get)
+    ach = alg[dom] / (stage_ms[dom] * 1e-3) * 1e-9 if stage_ms[dom] > 0 else 0.0
+    prof = profile_record(kernels[dom])
+    total = sum(stage_ms.values()) + st["other_ms"]
+    return {"bound": "hbm", "limiter": "l1tex" if dom != "shade" else "latency", "kernel": kernels[dom], "achieved": ach,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+            "traffic": prof.get("dram_bytes_per_launch") if prof else None, "ncu": prof,
+            "stage_share": {k: v / total for k, v in stage_ms.items()},
+            "algorithmic_bytes": alg[dom], "stage_ms": stage_ms[dom],
+            "note": "queue records only (the tree is L1/L2 resident); stage times from a profiled one-lane pass"}
+
+
+def bdpt_bench(torch, api, rank: int, world: int, do_cpu: bool, spp: int, peaks: dict) -> dict:
+    """configs/config_veach_bdpt.txt: the Veach room of src/main_veach_bdpt.cpp, 800x600, BDPT.  Samples are split
+    over the ranks and the strategy sums reduced onto rank 0 (multigpu.CudaRenderer.render_bdpt)."""
+    import torch.distributed as dist
+    from tuturenderer_b200.multigpu import CudaRenderer
     sc = api.Scene.load(ROOT / "tests" / "golden" / "veach_80x60.tscene").with_size(800, 600)
-    ctx = api.Context(torch.cuda.current_device())
-    ctx.upload(sc)
+    r = CudaRenderer(sc, torch.cuda.current_device())
     npix = 800 * 600
-    host_img = torch.empty(npix * 3, dtype=torch.float32, pin_memory=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for k in range(3):
-        ctx.render_bdpt_ptr(16, SEED + k, host_img.data_ptr())  # 7.7 M samples: the 4 Mi-sample batch pool reaches its full size
-    t0 = time.perf_counter()
-    ctx.upload(sc)
-    ctx.render_bdpt_ptr(spp, SEED + 9, host_img.data_ptr())  # host scene in, pinned host image out
-    e2e_s = time.perf_counter() - t0
-    st = ctx.stats()
+        r.render_bdpt(16 * world, SEED + k, rank, world)  # 7.7 M samples per rank: the 4 Mi-sample batch pools reach their size
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    img = r.render_bdpt(spp, SEED + 9, rank, world)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    gpu_ms = float(ms.item())
+    st = r.ctx.stats()
     out = {"workload": f"veach room (2308 triangles, glass + GGX lamp + 4 emissive triangles), 800x600 @ {spp} spp, "
-                       "bidirectional path tracing (BASELINE.json configs[4])",
-           "msamples_per_s": npix * spp / st["gpu_ms"] * 1e-3, "gpu_ms": st["gpu_ms"],
-           "e2e_msamples_per_s": npix * spp / e2e_s * 1e-6,
-           "closest_rays_per_sample": st["extend_rays"] / st["paths"], "any_rays_per_sample": st["shadow_rays"] / st["paths"],
-           "kernel_launches": st["kernel_launches"], "image_mean": float(host_img.mean())}
-    ctx.close()
-    if do_cpu:
+                       f"bidirectional path tracing (BASELINE.json configs[4]), samples split over {world} GPU(s)",
+           "msamples_per_s": npix * spp / gpu_ms * 1e-3, "gpu_ms": gpu_ms, "n_gpus": world,
+           "closest_rays_per_sample": st["extend_rays"] / max(st["paths"], 1), "any_rays_per_sample": st["shadow_rays"] / max(st["paths"], 1),
+           "kernel_launches": st["kernel_launches"]}
+    if rank == 0:
+        out["image_mean"] = float(img.mean())
+    if world == 1:
+        host_img = torch.empty(npix * 3, dtype=torch.float32, pin_memory=True)
+        t0 = time.perf_counter()
+        r.ctx.upload(sc)
+        r.ctx.render_bdpt_ptr(spp, SEED + 9, host_img.data_ptr())  # host scene in, pinned host image out
+        out["e2e_msamples_per_s"] = npix * spp / (time.perf_counter() - t0) * 1e-6
+        # walk-queue roofline: 48 B per queued closest-hit ray + 112 B per stored vertex + 48 B per shadow ray
+        ach = (st["extend_rays"] * (32 + 16 + 112) + st["shadow_rays"] * 48) / (st["gpu_ms"] * 1e-3) * 1e-9
+        prof = profile_record("q_extend")
+        out["roofline"] = {"bound": "hbm", "limiter": "l1tex+issue", "kernel": "q_extend", "achieved": ach,
+                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                           "traffic": prof.get("dram_bytes_per_launch") if prof else None, "ncu": prof,
+                           "note": "whole-render queue + vertex traffic over the whole render time (the BDPT kernels of a "
+                                   "batch are not timed individually); the 4.6 k-node tree is L1/L2 resident"}
+    r.ctx.close()
+    if do_cpu and rank == 0:
         from oracle import oracle_py as O
         if O.ref_available():
             _img, info = O.ref_render(sc, 1, mode="bdpt-rows", timeout=900)
@@ -304,7 +423,7 @@ def bdpt_bench(torch, api, do_cpu: bool, spp: int) -> dict:
     return out
 
 
-def glass_bench(torch, api, do_cpu: bool, spp: int) -> dict:
+def glass_bench(torch, api, do_cpu: bool, spp: int, peaks: dict) -> dict:
     """configs[3] stand-in (tools/scenes.py: glass_scene): rough-glass object + textured GGX box."""
     sc = api.Scene.load(ROOT / "tests" / "golden" / "glass_c4.tscene").with_size(WIDTH, HEIGHT)
     ctx = api.Context(torch.cuda.current_device())
@@ -324,6 +443,17 @@ def glass_bench(torch, api, do_cpu: bool, spp: int) -> dict:
            "e2e_mpaths_per_s": npix * spp / e2e_s * 1e-6,
            "closest_rays_per_path": st["extend_rays"] / st["paths"], "any_rays_per_path": st["shadow_rays"] / st["paths"],
            "nan_samples": st["nan_samples"], "image_mean": float(host_img.nan_to_num().mean())}
+    # stage shares + roofline of the dominant stage: one profiled one-lane pass
+    ctx.configure(0, True, 1)
+    ctx.render_path_ptr(max(32, spp // 8), SEED + 11, host_img.data_ptr())
+    ps = ctx.stats()
+    ctx.configure(0, False, 0)
+    ext, shd, pth = ps["extend_rays"], ps["shadow_rays"], ps["paths"]
+    cont = max(ext - pth, 0)
+    alg = {"extend": ext * (B_RAY + B_HIT),
+           "shade": ext * (B_RAY + B_STATE + B_HIT + 4) + cont * B_XSTATE + cont * (B_RAY + B_STATE + B_XSTATE) + shd * B_SHADOW + pth * 12,
+           "shadow": shd * (B_SHADOW + 32)}
+    out["roofline"] = stage_roofline(ps, alg, peaks, {"extend": "wf_extend", "shade": "wf_shade", "shadow": "wf_shadow"})
     ctx.close()
     if do_cpu:
         from oracle import oracle_py as O
@@ -332,6 +462,38 @@ def glass_bench(torch, api, do_cpu: bool, spp: int) -> dict:
             out["cpu_baseline"] = {"value": info["mpaths_per_s"], "unit": "Mpaths/s", "cores": info["threads"],
                                    "kind": "reference", "sample": f"512x512 @ 4 spp through the reference's sub_render_pt "
                                                                   f"on {info['threads']} host threads ({info['seconds']:.1f} s)"}
+    return out
+
+
+def c1_bench(torch, api) -> dict:
+    """BASELINE.json configs[0] as written: configs/config_cornellBox.txt, 256x256 @ 16 spp.  The reference runs
+    its stock driver path (PathTracing::integrate, N_THREAD 20 row bands, global.hpp:24); the GPU renders the same
+    frame through tutu_render_path (host scene in, pinned host image out; the automatic pipeline choice)."""
+    from oracle import oracle_py as O
+    out = {"workload": "configs/config_cornellBox.txt, 256x256 @ 16 spp path tracing (BASELINE.json configs[0])"}
+    sc = cornell_scene(256, 256)
+    ctx = api.Context(torch.cuda.current_device())
+    host_img = torch.empty(256 * 256 * 3, dtype=torch.float32, pin_memory=True)
+    ctx.upload(sc)
+    for k in range(3):
+        ctx.render_path_ptr(16, SEED + k, host_img.data_ptr())
+    reps = 20
+    t0 = time.perf_counter()
+    for k in range(reps):
+        ctx.upload(sc)
+        ctx.render_path_ptr(16, SEED + 10 + k, host_img.data_ptr())
+    gpu_s = (time.perf_counter() - t0) / reps
+    st = ctx.stats()
+    gpu_img = host_img.numpy().reshape(256, 256, 3).copy()
+    ctx.close()
+    out.update({"gpu_ms_e2e": gpu_s * 1e3, "gpu_ms_device": st["gpu_ms"], "gpu_mpaths_per_s_e2e": 256 * 256 * 16 / gpu_s * 1e-6,
+                "kernel_launches": st["kernel_launches"]})
+    if O.ref_available():
+        ref_img, info = O.ref_render_file(CORNELL_FILE, 16, mode="stock", width=256, height=256, timeout=600)
+        out["reference"] = {"seconds": info["seconds"], "mpaths_per_s": info["mpaths_per_s"], "threads": info["threads"],
+                            "mode": "stock: PathTracing::integrate as shipped (N_THREAD 20 static row bands)"}
+        out["speedup_e2e"] = info["seconds"] / gpu_s
+        out["channel_mean_ratio_ref_over_gpu"] = [float(ref_img[..., c].mean() / gpu_img[..., c].mean()) for c in range(3)]
     return out
 
 
@@ -385,8 +547,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    last_img = None
     for k in range(args.steps):
-        step(SEED + 100 + k)
+        last_img = step(SEED + 100 + k)
         st = r.ctx.stats()
         for key in agg:
             agg[key] += st[key]
@@ -404,6 +567,7 @@ def main():
     total_ms = float(ms.item())
     paths_per_step = npix * args.spp
     value = paths_per_step * args.steps / total_ms * 1e-3  # Mpaths/s, whole job
+    hi_img = last_img.cpu().numpy().copy() if (rank == 0 and last_img is not None) else None  # the timed step's own image
 
     # ---- stage shares: one profiled pass, one lane, this rank's sample share (not part of any timed region)
     prof_spp = max(32, args.spp // 4)
@@ -459,18 +623,14 @@ def main():
     stage_sum = sum(stage_ms.values()) + prof_stats["other_ms"]
     charged_ms = {k: v / stage_sum * wall_ms for k, v in stage_ms.items()}
     ach = alg[dominant] / (charged_ms[dominant] * 1e-3) * 1e-9 if charged_ms[dominant] > 0 else 0.0
-    prof = ROOT / "profiles" / "r01_traffic.json"  # dram bytes per launch from the ncu --set full capture
-    traffic = None
-    if prof.exists():
-        for name, rec in json.loads(prof.read_text()).items():
-            if name.split("<")[0] == dominant:  # ncu names carry the template arguments
-                traffic = rec.get("dram_bytes_per_launch")
+    prof = profile_record(dominant)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+                "frac": ach / peaks["hbm_gbs"], "traffic": prof.get("dram_bytes_per_launch") if prof else None, "ncu": prof,
                 "peak_source": "fallback 6650 GB/s" if peaks.get("fallback") else "MEASURED_PEAKS.json hbm_gbs (measured)",
                 "avg_launch_ms": charged_ms[dominant] / iters, "algorithmic_bytes_per_launch": alg[dominant] / iters,
                 "duration_note": f"stage shares from a profiled one-lane pass of {prof_spp} spp (CUDA events between the kernels on "
-                                 "one stream); each kernel is charged share x wall ms of the timed two-lane region",
+                                 "one stream); each kernel is charged share x wall ms of the timed two-lane region "
+                                 "(attribution, checked against the ncu launch list under profiles/)",
                 "stage_share": {k: v / stage_sum for k, v in stage_ms.items()},
                 "stage_ms_per_step": {k: v / args.steps for k, v in charged_ms.items()},
                 "stage_ms_in_profiled_pass": dict(stage_ms, other=prof_stats["other_ms"], gpu_ms=prof_stats["gpu_ms"]),
@@ -483,13 +643,19 @@ def main():
     rays = None
     if not args.no_rays:
         rays = rays_bench(torch, api.Context, rank, world, do_cpu=(not args.no_cpu and world == 1), peaks=peaks)
-    cpu = None
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_paths_baseline(16)
-    bdpt = glass = None
-    if world == 1 and not args.no_extras:
-        bdpt = bdpt_bench(torch, api, not args.no_cpu, args.bdpt_spp)
-        glass = glass_bench(torch, api, not args.no_cpu, args.glass_spp)
+        cpu, ref_img = cpu_paths_baseline(16)
+        r.ctx.upload(sc)
+        gpu16 = r.ctx.render_path(16, seed=SEED + 300)
+        parity = image_parity(ref_img, gpu16, hi_img, 16, args.spp)
+    bdpt = glass = c1 = None
+    if not args.no_extras:
+        bdpt = bdpt_bench(torch, api, rank, world, not args.no_cpu and world == 1, args.bdpt_spp, peaks)
+        if world == 1:
+            glass = glass_bench(torch, api, not args.no_cpu, args.glass_spp, peaks)
+            if not args.no_cpu:
+                c1 = c1_bench(torch, api)
 
     if rank == 0:
         line = {
@@ -504,9 +670,11 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity": parity,
             "rays": rays,
             "bdpt": bdpt,
             "glass_c4": glass,
+            "c1": c1,
             "mrays_per_s_in_render": {"extend": ext * world / (charged_ms["wf_extend"] * 1e-3) * 1e-6 if charged_ms["wf_extend"] else None,
                                       "shadow": shd * world / (charged_ms["wf_shadow"] * 1e-3) * 1e-6 if charged_ms["wf_shadow"] else None},
             "nan_samples": cnt["nan_samples"],

@@ -171,17 +171,64 @@ def ref_export_bvh(scene, out_path=None):
         return Scene.load(dst)
 
 
-def ref_trace(scene, rays: np.ndarray, kind: str = "closest", threads: int = 0):
-    """getIntersection / hasIntersection of the reference; returns (result, info)."""
-    from tuturenderer_b200.api import HIT_DTYPE
+HIT_DTYPE = np.dtype([("prim", "<i4"), ("t", "<f4"), ("u", "<f4"), ("v", "<f4")])  # TutuHit, include/tutu_b200.h
+
+
+def ref_trace(scene, rays: np.ndarray, kind: str = "closest", threads: int = 0, scene_path=None):
+    """getIntersection / hasIntersection of the reference; returns (result, info).  `scene_path`: an
+    already saved .tscene of `scene` (big scenes traced several times are written once)."""
     rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
     with tempfile.TemporaryDirectory() as td:
         sp, rp, op = Path(td) / "s.tscene", Path(td) / "r.f32", Path(td) / "o.bin"
-        scene.save(sp)
+        if scene_path is not None:
+            sp = Path(scene_path)
+        else:
+            scene.save(sp)
         rays.tofile(rp)
         info = _run(["trace", str(sp), str(rp), kind, str(op), str(threads)])
         out = np.fromfile(op, dtype=np.uint8 if kind == "any" else HIT_DTYPE)
     return out, info
+
+
+def ref_postprocess(rgb: np.ndarray, mode: str, **kw):
+    """The reference's Postprocessor (Postprocessor.hpp:29-197) on a linear float image (H, W, 3).
+    mode: "bloom" (extract -> blur -> add), "extract", "blur", "hdr" (exposure tone map);
+    kw: threshold, kernel (odd), sigma, exposure."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    h, w = rgb.shape[:2]
+    with tempfile.TemporaryDirectory() as td:
+        ip, op = Path(td) / "in.f32", Path(td) / "out.f32"
+        rgb.tofile(ip)
+        _run(["postprocess", mode, str(w), str(h), str(ip), str(op), str(kw.get("threshold", 1.0)),
+              str(kw.get("kernel", 15)), str(kw.get("sigma", 5.0)), str(kw.get("exposure", 1.0))])
+        return np.fromfile(op, np.float32).reshape(h, w, 3)
+
+
+# TUTUSCN1 header (tuturenderer_b200/csrc/host_scene.cpp: FileHeader): magic[8], version, n_prims, n_materials,
+# n_bvh_nodes, n_tex[4], TutuCamera{eye[3], viewdir[3], updir[3], hfov, width, height, parallel}, bkg[3], eta
+_HDR_WIDTH_OFFSET = 8 + 4 + 12 + 16 + 36 + 4
+
+
+def ref_render_file(scene_file, spp: int, mode: str = "rows", width: int | None = None, height: int | None = None,
+                    timeout: float | None = None):
+    """PathTracing::integrate of the reference on a .tscene FILE, optionally at another frame size
+    (the header's width/height are patched in a scratch copy).  Uses nothing of the product package:
+    this is what bench.py --impl reference runs."""
+    raw = bytearray(Path(scene_file).read_bytes())
+    if raw[:8] != b"TUTUSCN1":
+        raise RuntimeError(f"{scene_file} is not a TUTUSCN1 file")
+    wh = np.frombuffer(raw, np.int32, 2, _HDR_WIDTH_OFFSET)
+    if width is not None:
+        wh[0] = width
+    if height is not None:
+        wh[1] = height
+    w, h = int(wh[0]), int(wh[1])
+    with tempfile.TemporaryDirectory() as td:
+        sp, op = Path(td) / "s.tscene", Path(td) / "o.f32"
+        sp.write_bytes(raw)
+        info = _run(["render", str(sp), str(spp), str(op), mode], timeout=timeout)
+        img = np.fromfile(op, dtype=np.float32).reshape(h, w, 3)
+    return img, info
 
 
 def ref_render(scene, spp: int, mode: str = "rows", timeout: float | None = None):

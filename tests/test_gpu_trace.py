@@ -217,6 +217,43 @@ def test_full_size_properties(api, ctx):
     assert (h[:, 2] > 0).all() and (h[:, 3] > 0).all() and (1 - h[:, 2] - h[:, 3] > 0).all()
 
 
+@pytest.fixture(scope="module")
+def full_size_scene(api, tmp_path_factory):
+    """BASELINE.json configs[1]: the 999 698-triangle height-field, saved once for the reference harness."""
+    from oracle import oracle_py as O
+    assert O.ref_available(), "oracle/_ref/ref_harness is missing: the full-size parity test needs the compiled reference"
+    prims = api.synth_heightfield(707)
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    path = tmp_path_factory.mktemp("c2") / "hf707.tscene"
+    sc.save(path)
+    return sc, path
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_full_size_against_the_reference(api, ctx, full_size_scene, kind):
+    """configs[1] at BASELINE size against the REFERENCE ITSELF (BVH.hpp:145-194 through
+    oracle/_ref/ref_harness trace: the reference's own recursiveBuild tree, getIntersection and
+    hasIntersection): 2^20 rays of each kind, {prim, t, u, v} byte for byte and the any-hit booleans,
+    for the production walk (mode 0) and the literal walk (mode 1).  The 2^20 rays are a strided
+    sample of the 2^24-ray batch bench.py times, so the compared rays cover the whole batch."""
+    from oracle import oracle_py as O
+    sc, path = full_size_scene
+    n = 1 << 20
+    # every 16th ray of the bench's batch (tutu_synth_rays is a pure function of the ray index)
+    rays = np.concatenate([api.synth_rays(kind, 1 << 16, first=f) for f in range(0, 1 << 24, 1 << 20)])
+    assert len(rays) == n
+    want_c, info_c = O.ref_trace(sc, rays, "closest", scene_path=path)
+    want_a, info_a = O.ref_trace(sc, rays, "any", scene_path=path)
+    assert info_c["rays"] == n and info_a["rays"] == n
+    ctx.upload(sc)
+    for mode in (0, 1):
+        ctx.set_traversal_mode(mode)
+        assert_hits_equal(ctx.trace_closest(rays), want_c)
+        assert np.array_equal(ctx.trace_any(rays), want_a)
+    ctx.set_traversal_mode(0)
+    assert (want_c["prim"] >= 0).mean() > (0.9 if kind == 0 else 0.3)
+
+
 def test_binned_order_gives_identical_results(api, oracle, ctx):
     """Batches >= 2^16 rays are traced in a coherent order (counting sort by entry cell + direction
     bin, tutu_b200.cu: bin_rays).  Results must not depend on the order: mode 0 (binned) == mode 3

@@ -43,6 +43,21 @@ def test_large_builder_is_threaded_and_consistent(api, oracle):
     assert np.array_equal(api.bvh_build(prims), oracle.OracleScene(sc).bvh_export())
 
 
+def test_full_size_tree_equals_the_reference(api, tmp_path):
+    """BASELINE.json configs[1]: the 999 698-triangle height-field.  tutu_bvh_build's tree equals the tree
+    the reference's own BVHAccel::recursiveBuild (BVH.hpp:47-123) builds for the same objList, node for
+    node (1 999 395 nodes; the unstable std::sort at every level included)."""
+    from oracle import oracle_py as O
+    assert O.ref_available(), "oracle/_ref/ref_harness is missing"
+    prims = api.synth_heightfield(707)
+    assert len(prims) == 999698
+    mine = api.bvh_build(prims)
+    ref = O.ref_export_bvh(api.Scene(prims=prims, materials=api.default_material()), tmp_path / "ref.tscene")
+    assert len(mine) == 2 * 999698 - 1
+    assert np.array_equal(ref.prims, prims)
+    assert np.array_equal(mine, ref.bvh_nodes)
+
+
 def test_scene_file_roundtrip(api, mixed, tmp_path):
     p = tmp_path / "m.tscene"
     mixed.save(p)

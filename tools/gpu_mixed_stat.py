@@ -12,3 +12,8 @@ for seed in (1, 2, 3, 4, 5, 6):
     rel = np.abs(b(img) - b(ref)) / (b(ref) + 0.02)
     k = np.unravel_index(rel.argmax(), rel.shape)
     print(seed, 'max', rel.max(), 'at', k, 'mean', rel.mean(), 'img', b(img)[k], 'ref', b(ref)[k], 'chan means', [float(img[..., c].mean() / ref[..., c].mean()) for c in range(3)])
+# per-pixel outliers of the last render (the deterministic mirror-silhouette pixels masked in tests/test_gpu_render.py)
+d = np.abs(img - ref).max(-1)
+for idx in np.argsort(d.ravel())[::-1][:6]:
+    y, x = divmod(int(idx), 96)
+    print('pixel', (y, x), 'gpu', img[y, x], 'ref', ref[y, x], 'absdiff', d[y, x])
