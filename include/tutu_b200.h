@@ -258,6 +258,33 @@ int tutu_quantize(TutuCtx* ctx, const float* rgb, uint64_t n_pixels, float gamma
 int tutu_quantize_device(TutuCtx* ctx, const float* d_rgb, uint64_t n_pixels, float gamma, uint8_t* d_out,
                          void* stream);
 
+/* ---- output stage: Postprocessor (reference include/Postprocessor.hpp:29-197) ----------------- */
+/* The reference's bloom / exposure post-process on a linear radiance image (its call is commented out in
+ * every driver, src/main_cornellBox.cpp:82-84; the class is complete).  Parameters = the reference's
+ * #defines (Postprocessor.hpp:10-14) and the literal in getEmmisiveTexture (:141). */
+typedef struct TutuPostParams {
+  float emissive_norm;    /* pixels with |rgb| > 3.f count as emissive (Postprocessor.hpp:141) */
+  float strength;         /* STRENGTH 2: the brightest channel of an emissive pixel is rescaled to this */
+  int32_t gaussian_loops; /* GAUSSIANLOOP 1: the extract is blurred 1 + gaussian_loops times */
+  int32_t kernel_size;    /* KERNELSIZE 10: taps start at (int)(-kernel_size * 0.5), so 10 taps are -5..4 */
+  float stddev;           /* STDDEV 30 */
+  float exposure;         /* EXPOSURE 1.5 */
+} TutuPostParams;
+void tutu_post_params_default(TutuPostParams* out);
+#define TUTU_POST_EXTRACT 1   /* getEmmisiveTexture */
+#define TUTU_POST_BLUR 2      /* getGaussianBlurTexture, once (vertical pass, then horizontal) */
+#define TUTU_POST_BLOOM 3     /* extract, 1 + loops blurs, add to the source (performPostProcess under BLOOM_ONLY) */
+#define TUTU_POST_HDR 4       /* getHDRtexture: 1 - exp(-c * exposure) (performPostProcess under HDR_ONLY) */
+#define TUTU_POST_HDR_BLOOM 5 /* bloom, then the tone map (performPostProcess under HDR_BLOOM) */
+/* rgb, rgb_out: width*height*3 floats (rgb_out may equal rgb for the host entry point).  params = NULL takes
+ * the reference's constants.  Host buffers (H2D, kernels, D2H; synchronous) and device buffers (asynchronous on
+ * `stream`; d_rgb_out must not alias d_rgb).  Every read goes through Texture::getRGBat's index arithmetic
+ * (Texture.hpp:18-39) exactly as in the reference, including its u == 0 wrap-around. */
+int tutu_postprocess(TutuCtx* ctx, const float* rgb, uint32_t width, uint32_t height, int mode,
+                     const TutuPostParams* params, float* rgb_out);
+int tutu_postprocess_device(TutuCtx* ctx, const float* d_rgb, uint32_t width, uint32_t height, int mode,
+                            const TutuPostParams* params, float* d_rgb_out, void* stream);
+
 /* ---- host-side helpers (no GPU needed) -------------------------------------------------- */
 /* PPM file from 8-bit pixels: binary = 0 writes the reference's ASCII P3 byte for byte
  * (PPMGenerator.hpp:804-809, 840-842: "P3\nW\nH\n255\n" then "r g b\n" per pixel), binary = 1

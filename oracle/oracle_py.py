@@ -50,6 +50,8 @@ def lib() -> C.CDLL:
         l.oracle_render_bdpt.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, P, P, C.c_int]
         l.oracle_primary_rays.argtypes = [P, P]
         l.oracle_write_pixel.argtypes = [P, C.c_uint64, C.c_float, P]
+        l.oracle_postprocess.restype = C.c_int
+        l.oracle_postprocess.argtypes = [P, C.c_int, C.c_int, C.c_int, P, P]
         _lib = l
     return _lib
 
@@ -127,6 +129,21 @@ def write_pixel(rgb: np.ndarray, gamma: float = 0.78) -> np.ndarray:
     return out
 
 
+POST_MODES = {"extract": 1, "blur": 2, "bloom": 3, "hdr": 4, "full": 5}  # TUTU_POST_* of include/tutu_b200.h
+
+
+def postprocess(rgb: np.ndarray, mode: str, params=None) -> np.ndarray:
+    """The reference's Postprocessor restated (oracle_postprocess); `params` = a tuturenderer_b200.api.TutuPostParams
+    or None for the reference's #define constants."""
+    rgb = np.ascontiguousarray(rgb, np.float32)
+    out = np.empty_like(rgb)
+    rc = lib().oracle_postprocess(rgb.ctypes.data, rgb.shape[1], rgb.shape[0], POST_MODES[mode],
+                                  C.byref(params) if params is not None else None, out.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"oracle_postprocess: bad mode {mode}")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # the compiled reference (oracle/_ref/ref_harness)
 # ------------------------------------------------------------------------------------------------
@@ -190,18 +207,17 @@ def ref_trace(scene, rays: np.ndarray, kind: str = "closest", threads: int = 0, 
     return out, info
 
 
-def ref_postprocess(rgb: np.ndarray, mode: str, **kw):
-    """The reference's Postprocessor (Postprocessor.hpp:29-197) on a linear float image (H, W, 3).
-    mode: "bloom" (extract -> blur -> add), "extract", "blur", "hdr" (exposure tone map);
-    kw: threshold, kernel (odd), sigma, exposure."""
+def ref_postprocess(rgb: np.ndarray, mode: str):
+    """The reference's Postprocessor (Postprocessor.hpp:29-197, its own #define constants) on a linear float
+    image (H, W, 3).  mode: "extract", "blur", "bloom", "hdr" or "full" (= performPostProcess under HDR_BLOOM).
+    Returns (image, info)."""
     rgb = np.ascontiguousarray(rgb, np.float32)
     h, w = rgb.shape[:2]
     with tempfile.TemporaryDirectory() as td:
         ip, op = Path(td) / "in.f32", Path(td) / "out.f32"
         rgb.tofile(ip)
-        _run(["postprocess", mode, str(w), str(h), str(ip), str(op), str(kw.get("threshold", 1.0)),
-              str(kw.get("kernel", 15)), str(kw.get("sigma", 5.0)), str(kw.get("exposure", 1.0))])
-        return np.fromfile(op, np.float32).reshape(h, w, 3)
+        info = _run(["postprocess", mode, str(w), str(h), str(ip), str(op)])
+        return np.fromfile(op, np.float32).reshape(h, w, 3), info
 
 
 # TUTUSCN1 header (tuturenderer_b200/csrc/host_scene.cpp: FileHeader): magic[8], version, n_prims, n_materials,

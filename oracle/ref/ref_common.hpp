@@ -14,6 +14,11 @@ using ::powf;  // Material.hpp:145 uses std::powf, which libstdc++ 13 does not d
 #include "Object.hpp"
 #include "Renderer.hpp"
 #include "OBJ_Loader.h"
+// Postprocessor::performPostProcess has no return statement unless one of HDR_ONLY / BLOOM_ONLY /
+// HDR_BLOOM is defined (Postprocessor.hpp:29-60); HDR_BLOOM selects the whole chain (bloom, then the
+// exposure tone map).  Nothing in the reference's drivers defines any of them (the call is commented out).
+#define HDR_BLOOM
+#include "Postprocessor.hpp"
 
 #include <atomic>
 #include <chrono>

@@ -21,6 +21,12 @@
 //        plus the Cornell ceiling light, rendered by the reference's PathTracing
 //   ref_harness ppm <W> <H> <in.f32> <out.ppm>
 //        PPMGenerator::generate (gamma 0.78 quantisation + ASCII P3, PPMGenerator.hpp:140-160,804-845)
+//   ref_harness postprocess <mode> <W> <H> <in.f32> <out.f32>
+//        the reference's Postprocessor (Postprocessor.hpp:29-197) on a linear float image with its own
+//        constants (STRENGTH 2, GAUSSIANLOOP 1, KERNELSIZE 10, STDDEV 30, EXPOSURE 1.5): mode "extract"
+//        (getEmmisiveTexture), "blur" (getGaussianBlurTexture once), "bloom" (the chain of
+//        performPostProcess before the tone map: extract, 1 + GAUSSIANLOOP blurs, add), "hdr"
+//        (getHDRtexture) or "full" (performPostProcess itself, compiled with HDR_BLOOM)
 //   ref_harness render <scene.tscene> <spp> <out.f32> [mode]
 //        PathTracing::integrate (mode "stock": N_THREAD=20 as shipped) or the reference's own
 //        sub_render_pt row worker on every host core (mode "rows"); BDPT::integrate (mode "bdpt",
@@ -373,6 +379,49 @@ int ppm(int W, int H, const char* in_path, const char* out_path) {
   return 0;
 }
 
+// ---- Postprocessor ----------------------------------------------------------------------------
+int postprocess(const char* mode, int W, int H, const char* in_path, const char* out_path) {
+  Texture src;
+  src.width = W;
+  src.height = H;
+  src.rgb.resize((size_t)W * H);
+  std::ifstream f(in_path, std::ios::binary);
+  if (!f) die("cannot open the float image");
+  f.read((char*)src.rgb.data(), (std::streamsize)((size_t)W * H * sizeof(Vector3f)));
+  Postprocessor p(&src);
+  Texture out;
+  auto t0 = std::chrono::steady_clock::now();
+  if (!strcmp(mode, "extract")) {
+    out = p.getEmmisiveTexture(&src);
+  } else if (!strcmp(mode, "blur")) {
+    out = p.getGaussianBlurTexture(&src, KERNELSIZE, STDDEV);
+  } else if (!strcmp(mode, "hdr")) {
+    out = p.getHDRtexture(&src);
+  } else if (!strcmp(mode, "bloom")) {
+    // Postprocessor.hpp:37-50, statement for statement, without the final tone map
+    p.renderTextures[1] = p.getEmmisiveTexture(&p.renderTextures[0]);
+    int index = 2;
+    p.renderTextures[index] = p.getGaussianBlurTexture(&p.renderTextures[1], KERNELSIZE, STDDEV);
+    index = 3;
+    for (int i = 0; i < GAUSSIANLOOP; i++) {
+      p.renderTextures[index] = p.getGaussianBlurTexture(&p.renderTextures[index == 2 ? 3 : 2], KERNELSIZE, STDDEV);
+      index = index == 2 ? 3 : 2;
+    }
+    index = index == 2 ? 3 : 2;
+    out = p.add(&p.renderTextures[0], &p.renderTextures[index]);
+  } else if (!strcmp(mode, "full")) {
+    out = p.performPostProcess();
+  } else {
+    die(std::string("unknown postprocess mode ") + mode);
+  }
+  double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (out.width != W || out.height != H || out.rgb.size() != (size_t)W * H) die("postprocess: unexpected output size");
+  std::ofstream of(out_path, std::ios::binary);
+  of.write((const char*)out.rgb.data(), (std::streamsize)(out.rgb.size() * sizeof(Vector3f)));
+  printf("{\"width\": %d, \"height\": %d, \"mode\": \"%s\", \"seconds\": %.6f}\n", W, H, mode, sec);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -386,6 +435,7 @@ int main(int argc, char** argv) {
   if (cmd == "export-bvh" && argc == 4) return export_bvh(argv[2], argv[3]);
   if (cmd == "render-config" && (argc == 6 || argc == 7))
     return render_config(argv[2], argv[3], atoi(argv[4]), argv[5], argc == 7 ? argv[6] : "rows");
+  if (cmd == "postprocess" && argc == 7) return postprocess(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argv[6]);
   if (cmd == "ppm" && argc == 6) return ppm(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);
   if (cmd == "trace" && (argc == 6 || argc == 7))
     return trace(argv[2], argv[3], argv[4], argv[5], argc == 7 ? atoi(argv[6]) : 0);

@@ -1365,6 +1365,147 @@ void oracle_write_pixel(const float* rgb, uint64_t n_values, float gamma, uint8_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Postprocessor (Postprocessor.hpp:29-197) restated.  mode: 1 getEmmisiveTexture (:131-156), 2
+// getGaussianBlurTexture (:64-128), 3 the bloom chain of performPostProcess (:37-50), 4 getHDRtexture
+// (:182-207), 5 bloom then tone map (performPostProcess under HDR_BLOOM).  Constants are the reference's
+// #defines (:10-14); every texel read goes through Texture::getRGBat (Texture.hpp:18-39) as there.
+// ---------------------------------------------------------------------------------------------
+namespace pp {
+struct Tex {
+  int width = 0, height = 0;
+  std::vector<V3> rgb;
+  V3 getRGBat(float u, float v) const {  // Texture.hpp:18-39
+    if (width == 0 && height == 0) return V3();
+    if (u > 0)
+      u = u - (int)u;
+    else
+      u = 1 - (std::fabs(u) - (int)std::fabs(u));
+    if (v > 0)
+      v = v - (int)v;
+    else
+      v = 1 - (std::fabs(v) - (int)std::fabs(v));
+    int x = u * width;
+    int y = v * height;
+    long long index = (long long)y * width + x;
+    if (index < 0) index = 0;
+    if (index >= (long long)rgb.size()) index = (long long)rgb.size() - 1;
+    return rgb[(size_t)index];
+  }
+};
+Tex like(const Tex& s) {
+  Tex r;
+  r.width = s.width, r.height = s.height;
+  r.rgb.assign((size_t)s.width * s.height, V3());
+  return r;
+}
+float rescale(float input, float originMax, float originMin, float targetMax, float targetMin) {  // global.hpp:66-68
+  return targetMin + ((targetMax - targetMin) * (input - originMin) / (originMax - originMin));
+}
+Tex emissive(const Tex& src, float threshold, float strength) {  // :131-156
+  Tex res = like(src);
+  int h = res.height, w = res.width;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      V3& color = res.rgb[(size_t)y * w + x];
+      float U = (float)x / w, V = (float)y / h;
+      V3 col = src.getRGBat(clampf(0, 0.999f, U), clampf(0, 0.999f, V));
+      if (sqrtf(col.x * col.x + col.y * col.y + col.z * col.z) > threshold) {
+        float mx = col.x > col.y ? col.x : col.y;
+        mx = mx > col.z ? mx : col.z;
+        color.x = rescale(col.x, mx, 0.f, strength, 0.f);
+        color.y = rescale(col.y, mx, 0.f, strength, 0.f);
+        color.z = rescale(col.z, mx, 0.f, strength, 0.f);
+      }
+    }
+  return res;
+}
+Tex blur(const Tex& img, int kernelSize, float stddev) {  // :64-128
+  Tex src = img;
+  Tex res = like(src);
+  int h = res.height, w = res.width;
+  const float E = 2.7182818f;
+  const float PI_F = 3.1415926535897f;  // global.hpp:15
+  auto gaussian = [&](int inputX, float standardDev) -> float {
+    return (1 / sqrtf(2 * PI_F * standardDev)) * powf(E, -(inputX * inputX) / (2 * standardDev * standardDev));
+  };
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      V3& color = res.rgb[(size_t)y * w + x];
+      int startY = -kernelSize * 0.5;
+      V3 col;
+      float kernelSum = 0;
+      for (int i = 0; i < kernelSize; i++) {
+        float U = (float)x / w;
+        float V = (float)(y + i + startY) / h;
+        float gauss = gaussian(startY + i, stddev);
+        col = col + src.getRGBat(clampf(0, 0.999f, U), clampf(0, 0.999f, V)) * gauss;
+        kernelSum += gauss;
+      }
+      color = V3(col.x / kernelSum, col.y / kernelSum, col.z / kernelSum);
+    }
+  src = res;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      V3& color = res.rgb[(size_t)y * w + x];
+      int startX = -kernelSize * 0.5;
+      V3 col;
+      float kernelSum = 0;
+      for (int i = 0; i < kernelSize; i++) {
+        float U = (float)(x + i + startX) / w;
+        float V = (float)y / h;
+        float gauss = gaussian(startX + i, stddev);
+        col = col + src.getRGBat(clampf(0, 0.999f, U), clampf(0, 0.999f, V)) * gauss;
+        kernelSum += gauss;
+      }
+      color = V3(col.x / kernelSum, col.y / kernelSum, col.z / kernelSum);
+    }
+  return res;
+}
+Tex add(const Tex& a, const Tex& b) {  // :158-175
+  Tex res = a;
+  for (size_t i = 0; i < res.rgb.size(); ++i) res.rgb[i] = V3(res.rgb[i].x + b.rgb[i].x, res.rgb[i].y + b.rgb[i].y, res.rgb[i].z + b.rgb[i].z);
+  return res;
+}
+Tex hdr(const Tex& src, float exposure) {  // :182-207
+  Tex dst = like(src);
+  for (int y = 0; y < dst.height; y++)
+    for (int x = 0; x < dst.width; x++) {
+      float U = (float)x / dst.width, V = (float)y / dst.height;
+      V3 c = src.getRGBat(clampf(0, 0.999f, U), clampf(0, 0.999f, V));
+      dst.rgb[(size_t)y * src.width + x] = V3(1 - expf(-c.x * exposure), 1 - expf(-c.y * exposure), 1 - expf(-c.z * exposure));
+    }
+  return dst;
+}
+}  // namespace pp
+
+int oracle_postprocess(const float* rgb, int width, int height, int mode, const TutuPostParams* params, float* out) {
+  TutuPostParams p{3.f, 2.f, 1, 10, 30.f, 1.5f};  // Postprocessor.hpp:10-14, :141
+  if (params) p = *params;
+  pp::Tex src;
+  src.width = width, src.height = height;
+  src.rgb.resize((size_t)width * height);
+  for (size_t i = 0; i < src.rgb.size(); ++i) src.rgb[i] = V3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+  pp::Tex res;
+  if (mode == TUTU_POST_EXTRACT) {
+    res = pp::emissive(src, p.emissive_norm, p.strength);
+  } else if (mode == TUTU_POST_BLUR) {
+    res = pp::blur(src, p.kernel_size, p.stddev);
+  } else if (mode == TUTU_POST_HDR) {
+    res = pp::hdr(src, p.exposure);
+  } else if (mode == TUTU_POST_BLOOM || mode == TUTU_POST_HDR_BLOOM) {
+    pp::Tex e = pp::emissive(src, p.emissive_norm, p.strength);
+    pp::Tex b = pp::blur(e, p.kernel_size, p.stddev);
+    for (int i = 0; i < p.gaussian_loops; ++i) b = pp::blur(b, p.kernel_size, p.stddev);
+    res = pp::add(src, b);
+    if (mode == TUTU_POST_HDR_BLOOM) res = pp::hdr(res, p.exposure);
+  } else {
+    return -1;
+  }
+  for (size_t i = 0; i < res.rgb.size(); ++i) out[3 * i] = res.rgb[i].x, out[3 * i + 1] = res.rgb[i].y, out[3 * i + 2] = res.rgb[i].z;
+  return 0;
+}
+
 // primary rays exactly as sub_render_pt generates them (for ray-generation parity tests)
 void oracle_primary_rays(const OracleScene* os, float* rays_out) {
   const Scene& s = os->s;

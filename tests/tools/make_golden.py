@@ -179,8 +179,44 @@ def ppm_golden():
     print("ppm golden written")
 
 
+def post_inputs():
+    """Postprocessor fixtures' inputs: (a) 40 rows x 48 columns with emissive patches (|rgb| > 3) in the interior, in
+    the corners (the u == 0 / v == 0 wrap-around of Texture::getRGBat) and values around the tone map's
+    cancellation range; (b) an 8 x 1030 strip: frames wider than 1000 pixels reach clamp(0, 0.999, u)."""
+    rng = np.random.default_rng(7)
+    a = rng.uniform(0, 1.2, (40, 48, 3)).astype(np.float32)
+    a[10:14, 20:26] = [10, 8, 6]
+    a[0, 0] = [5, 5, 5]
+    a[39, 47] = [0, 9, 0]
+    a[5, 0] = [4, 0, 0]
+    a[30, 40:44] = [1.8, 1.8, 1.7]  # norm just above / below 3
+    a[31, 40:44] = [1.7, 1.7, 1.7]
+    a[20, :7, 0] = [0, 1e-4, 3e-3, 1e-6, 0.5, 2.9, 1.74]
+    b = rng.uniform(0, 1.0, (8, 1030, 3)).astype(np.float32)
+    b[3, 1020:1030] = [6, 6, 6]
+    b[7, 0:3] = [0, 0, 7]
+    return a, b
+
+
+def post_golden():
+    """Output stage, Postprocessor.hpp:29-197 run by the UNMODIFIED reference (ref_harness postprocess)."""
+    O.build(ref=True)
+    a, b = post_inputs()
+    a.tofile(G / "post_in_48x40.f32")
+    b.tofile(G / "post_in_1030x8.f32")
+    for mode in ("extract", "blur", "bloom", "hdr", "full"):
+        out, _ = O.ref_postprocess(a, mode)
+        out.tofile(G / f"post_ref_48x40_{mode}.f32")
+    for mode in ("blur", "full"):
+        out, _ = O.ref_postprocess(b, mode)
+        out.tofile(G / f"post_ref_1030x8_{mode}.f32")
+    print("postprocess goldens written")
+
+
 if __name__ == "__main__":
-    if "--ppm" in sys.argv:
+    if "--post" in sys.argv:
+        post_golden()
+    elif "--ppm" in sys.argv:
         ppm_golden()
     elif "--c4" in sys.argv:
         c4_goldens()

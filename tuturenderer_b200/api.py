@@ -67,6 +67,13 @@ class TutuRenderStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class TutuPostParams(C.Structure):
+    _fields_ = [("emissive_norm", C.c_float), ("strength", C.c_float), ("gaussian_loops", C.c_int32),
+                ("kernel_size", C.c_int32), ("stddev", C.c_float), ("exposure", C.c_float)]
+
+
+POST_MODES = {"extract": 1, "blur": 2, "bloom": 3, "hdr": 4, "hdr_bloom": 5, "full": 5}
+
 # every symbol include/tutu_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 ABI = {
@@ -91,6 +98,9 @@ ABI = {
     "tutu_finalize_bdpt_device": (C.c_int, [_P, _P, C.c_float, _P, _P]),
     "tutu_quantize": (C.c_int, [_P, _P, C.c_uint64, C.c_float, _P]),
     "tutu_quantize_device": (C.c_int, [_P, _P, C.c_uint64, C.c_float, _P, _P]),
+    "tutu_post_params_default": (None, [C.POINTER(TutuPostParams)]),
+    "tutu_postprocess": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(TutuPostParams), _P]),
+    "tutu_postprocess_device": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(TutuPostParams), _P, _P]),
     "tutu_write_ppm": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _P, C.c_int]),
     "tutu_render_stats": (C.c_int, [_P, C.POINTER(TutuRenderStats)]),
     "tutu_render_configure": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int]),
@@ -286,6 +296,15 @@ def write_ppm(path, rgb8: np.ndarray, binary: bool = False) -> None:
     _check(lib().tutu_write_ppm(str(path).encode(), w, h, _ptr(rgb8), int(binary)))
 
 
+def post_params(**kw) -> TutuPostParams:
+    """The reference's Postprocessor constants (Postprocessor.hpp:10-14), optionally overridden."""
+    p = TutuPostParams()
+    lib().tutu_post_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
 def default_material(**kw) -> np.ndarray:
     """One TutuMaterial with the reference's defaults (Material.hpp:21-30)."""
     m = np.zeros(1, MATERIAL_DTYPE)
@@ -444,6 +463,20 @@ class Context:
 
     def quantize_device(self, d_rgb: int, n_pixels: int, d_out: int, gamma: float = 0.78, stream: int = 0) -> None:
         self._ck(lib().tutu_quantize_device(self._h, d_rgb, n_pixels, gamma, d_out, stream or None))
+
+    # ---- output stage (Postprocessor: bloom / exposure tone map)
+    def postprocess(self, rgb: np.ndarray, mode: str = "hdr_bloom", params: TutuPostParams | None = None) -> np.ndarray:
+        """Host image (H, W, 3) through the reference's Postprocessor stages; params=None = its #define constants."""
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        out = np.empty_like(rgb)
+        self._ck(lib().tutu_postprocess(self._h, _ptr(rgb), rgb.shape[1], rgb.shape[0], POST_MODES[mode],
+                                        C.byref(params) if params is not None else None, _ptr(out)))
+        return out
+
+    def postprocess_device(self, d_rgb: int, width: int, height: int, d_out: int, mode: str = "hdr_bloom",
+                           params: TutuPostParams | None = None, stream: int = 0) -> None:
+        self._ck(lib().tutu_postprocess_device(self._h, d_rgb, width, height, POST_MODES[mode],
+                                               C.byref(params) if params is not None else None, d_out, stream or None))
 
     def stats(self) -> dict:
         s = TutuRenderStats()

@@ -492,6 +492,25 @@ int compute_bdpt_cam(const TutuCamera* cam, BdptCamConsts* out) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Postprocessor::getGaussianBlurTexture's weights (Postprocessor.hpp:75-79): the lambda
+//   (1 / sqrt(2 * M_PI * standardDev)) * pow(E, -(inputX * inputX) / (2 * standardDev * standardDev))
+// with M_PI = 3.1415926535897f (global.hpp:15) and static float E = 2.7182818f: every operand is a float, so
+// the C++ overloads are the float ones (sqrtf, powf).  kernelSum adds the taps in tap order.
+// ------------------------------------------------------------------------------------------
+void post_gaussian_weights(int kernel_size, float stddev, float* g, float* sum, int* start) {
+  const float E = 2.7182818f;
+  const int s0 = (int)(-kernel_size * 0.5);  // int startY = -kernelSize * 0.5;
+  float acc = 0;
+  for (int i = 0; i < kernel_size; ++i) {
+    const int x = s0 + i;
+    g[i] = (1 / sqrtf(2 * TUTU_M_PI * stddev)) * powf(E, -(x * x) / (2 * stddev * stddev));
+    acc += g[i];
+  }
+  *sum = acc;
+  *start = s0;
+}
+
+// ------------------------------------------------------------------------------------------
 // flatten
 // ------------------------------------------------------------------------------------------
 static inline bool has_emission(const TutuMaterial& m) {  // Material.hpp:54-56
@@ -800,6 +819,16 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
 using namespace tutu;
 
 extern "C" int tutu_abi_version(void) { return TUTU_ABI_VERSION; }
+
+extern "C" void tutu_post_params_default(TutuPostParams* out) {  // Postprocessor.hpp:10-14, :141
+  if (!out) return;
+  out->emissive_norm = 3.f;
+  out->strength = 2.f;
+  out->gaussian_loops = 1;
+  out->kernel_size = 10;
+  out->stddev = 30.f;
+  out->exposure = 1.5f;
+}
 
 namespace tutu {
 const char* (*g_ctx_error_hook)(const TutuCtx*) = nullptr;  // installed by tutu_b200.cu

@@ -15,6 +15,7 @@
 #include "wavefront.cuh"
 #include "bdpt.cuh"
 #include "resident.cuh"
+#include "postprocess.cuh"
 
 using namespace tutu;
 
@@ -144,6 +145,9 @@ struct TutuCtx {
 
   // BDPT: two lanes, batches alternate between them
   BdptLane bdpt_lanes[2];
+
+  // Postprocessor scratch: [0..2] intermediates, [3],[4] staging of the host entry point
+  DevBuf d_post[5];
 
   // wavefront
   DevBuf d_accum, d_rgb;
@@ -1569,6 +1573,99 @@ extern "C" int tutu_quantize(TutuCtx* ctx, const float* rgb, uint64_t n_pixels, 
   k_quantize<<<ctx->sm_count * 8, 256, 0, s>>>(ctx->d_rgb.as<float>(), n, gamma, ctx->d_blocked.as<uint8_t>());
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(out, ctx->d_blocked.p, n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+// ---- Postprocessor (postprocess.cuh) ---------------------------------------------------------------
+namespace {
+// Enqueues `mode` on `s`: src -> dst (both device, width*height*3 floats, not aliased); scratch buffers are
+// the ctx's.  The kernel sequence is the statement sequence of Postprocessor::performPostProcess (:37-58).
+void post_enqueue(TutuCtx* ctx, const float* src, uint32_t width, uint32_t height, int mode, const TutuPostParams& p,
+                  float* dst, cudaStream_t s) {
+  const size_t bytes = (size_t)width * height * 3 * sizeof(float);
+  const int w = (int)width, h = (int)height;
+  const int grid = ctx->sm_count * 8;
+  PostWeights pw{};
+  if (mode == TUTU_POST_BLUR || mode == TUTU_POST_BLOOM || mode == TUTU_POST_HDR_BLOOM) {
+    pw.n = p.kernel_size;
+    post_gaussian_weights(p.kernel_size, p.stddev, pw.g, &pw.sum, &pw.start);
+  }
+  auto blur = [&](const float* in, float* tmp, float* out) {  // vertical pass, then horizontal (src = res between)
+    pp_blur<true><<<grid, 256, 0, s>>>(in, w, h, pw, tmp);
+    pp_blur<false><<<grid, 256, 0, s>>>(tmp, w, h, pw, out);
+  };
+  switch (mode) {
+    case TUTU_POST_EXTRACT:
+      pp_extract<<<grid, 256, 0, s>>>(src, w, h, p.emissive_norm, p.strength, dst);
+      break;
+    case TUTU_POST_BLUR:
+      ctx->d_post[0].ensure(bytes);
+      blur(src, ctx->d_post[0].as<float>(), dst);
+      break;
+    case TUTU_POST_HDR:
+      pp_combine<true><<<grid, 256, 0, s>>>(src, nullptr, w, h, p.exposure, dst);
+      break;
+    case TUTU_POST_BLOOM:
+    case TUTU_POST_HDR_BLOOM: {
+      for (int k = 0; k < 3; ++k) ctx->d_post[k].ensure(bytes);
+      float* a = ctx->d_post[0].as<float>();
+      float* b = ctx->d_post[1].as<float>();
+      float* tmp = ctx->d_post[2].as<float>();
+      pp_extract<<<grid, 256, 0, s>>>(src, w, h, p.emissive_norm, p.strength, a);
+      for (int k = 0; k < 1 + p.gaussian_loops; ++k) {
+        blur(a, tmp, b);
+        std::swap(a, b);
+      }
+      if (mode == TUTU_POST_BLOOM)
+        pp_combine<false><<<grid, 256, 0, s>>>(src, a, w, h, p.exposure, dst);
+      else
+        pp_combine<true><<<grid, 256, 0, s>>>(src, a, w, h, p.exposure, dst);
+    } break;
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
+int post_check(TutuCtx* ctx, const void* in, const void* out, uint32_t width, uint32_t height, int mode, const TutuPostParams* params,
+               TutuPostParams* p) {
+  if (!in || !out) return fail(ctx, TUTU_E_INVALID, "tutu_postprocess: null buffer");
+  if (width == 0 || height == 0 || (uint64_t)width * height > (1ull << 30))
+    return fail(ctx, TUTU_E_INVALID, "tutu_postprocess: bad image size");
+  if (mode < TUTU_POST_EXTRACT || mode > TUTU_POST_HDR_BLOOM) return fail(ctx, TUTU_E_INVALID, "tutu_postprocess: unknown mode");
+  if (params)
+    *p = *params;
+  else
+    tutu_post_params_default(p);
+  if (p->kernel_size < 1 || p->kernel_size > kPostMaxKernel || p->gaussian_loops < 0 || p->gaussian_loops > 64 || !(p->stddev > 0.f))
+    return fail(ctx, TUTU_E_INVALID, "tutu_postprocess: kernel_size must be 1..64, gaussian_loops 0..64, stddev > 0");
+  return TUTU_OK;
+}
+}  // namespace
+
+extern "C" int tutu_postprocess_device(TutuCtx* ctx, const float* d_rgb, uint32_t width, uint32_t height, int mode,
+                                       const TutuPostParams* params, float* d_rgb_out, void* stream) {
+  API_BEGIN(ctx)
+  TutuPostParams p;
+  if (int rc = post_check(ctx, d_rgb, d_rgb_out, width, height, mode, params, &p)) return rc;
+  if (d_rgb == d_rgb_out) return fail(ctx, TUTU_E_INVALID, "tutu_postprocess_device: output must not alias the input");
+  post_enqueue(ctx, d_rgb, width, height, mode, p, d_rgb_out, stream ? (cudaStream_t)stream : ctx->stream);
+  return TUTU_OK;
+  API_END(ctx)
+}
+
+extern "C" int tutu_postprocess(TutuCtx* ctx, const float* rgb, uint32_t width, uint32_t height, int mode,
+                                const TutuPostParams* params, float* rgb_out) {
+  API_BEGIN(ctx)
+  TutuPostParams p;
+  if (int rc = post_check(ctx, rgb, rgb_out, width, height, mode, params, &p)) return rc;
+  const size_t bytes = (size_t)width * height * 3 * sizeof(float);
+  cudaStream_t s = ctx->stream;
+  ctx->d_post[3].ensure(bytes);
+  ctx->d_post[4].ensure(bytes);
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_post[3].p, rgb, bytes, cudaMemcpyHostToDevice, s));
+  post_enqueue(ctx, ctx->d_post[3].as<float>(), width, height, mode, p, ctx->d_post[4].as<float>(), s);
+  CUDA_TRY(cudaMemcpyAsync(rgb_out, ctx->d_post[4].p, bytes, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return TUTU_OK;
   API_END(ctx)

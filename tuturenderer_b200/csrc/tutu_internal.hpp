@@ -143,6 +143,10 @@ struct FlatScene {
   float eta = 1.f;
 };
 
+// Gaussian taps of Postprocessor::getGaussianBlurTexture (Postprocessor.hpp:77-79, 86-97), evaluated on the
+// host with the reference's own float expression.  g must hold kernel_size floats.
+void post_gaussian_weights(int kernel_size, float stddev, float* g, float* sum, int* start);
+
 // Error plumbing (thread-local message, mirrored into the ctx by the callers in tutu_b200.cu).
 void set_error(const std::string& msg);
 const std::string& get_error();
