@@ -290,6 +290,15 @@ int tutu_postprocess_device(TutuCtx* ctx, const float* d_rgb, uint32_t width, ui
  * (PPMGenerator.hpp:804-809, 840-842: "P3\nW\nH\n255\n" then "r g b\n" per pixel), binary = 1
  * writes P6 (the author's TODO, README.md:49). */
 int tutu_write_ppm(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb8, int binary);
+int tutu_write_png(const char* path, uint32_t width, uint32_t height, const uint8_t* rgb8); /* 8-bit RGB PNG */
+/* Texture files for TutuTexture.rgb (scene authoring).  ASCII P3 is read exactly as the
+ * reference's PPMGenerator::loadTexture does (PPMGenerator.hpp:1027-1084: texel = (r/max, g/max, b/max) in
+ * fp32, rows top to bottom); binary P6 (maxval <= 65535) and PNG (grey, grey+alpha, RGB, RGBA at 8/16 bits,
+ * grey at 1/2/4 bits, palette; alpha ignored; no Adam7) are what it cannot read (:1050).  normal_map != 0
+ * applies the reference's `bump` recovery c * 2 - 1 (PPMGenerator.hpp:714-720).  *rgb_out holds
+ * width*height*3 floats and is released with tutu_texture_free. */
+int tutu_texture_load(const char* path, int normal_map, float** rgb_out, int32_t* width, int32_t* height);
+void tutu_texture_free(float* rgb);
 /* Midpoint BVH with the reference's split rule (BVH.hpp:47-123).  nodes_out must hold
  * 2*n_prims-1 entries (1 if n_prims <= 1). */
 int tutu_bvh_build(const TutuPrim* prims, uint32_t n_prims, TutuBvhNode* nodes_out,

@@ -194,6 +194,55 @@ std::unique_ptr<PPMGenerator> load_config(const char* config_path, const char* m
   return g;
 }
 
+// f-2 authoring path: the Cornell shell of src/main_cornellBox.cpp plus model/veach_bdpt/veach_glass.obj
+// (1214 smooth-shaded triangles) placed with the reference's OWN object transforms, in the order a driver
+// would call them: PPMGenerator::scaleObj, rotateObj, transObj (PPMGenerator.hpp:210-270), then loadObj.
+struct Xform {
+  float sx, sy, sz;
+  int axis;
+  float degree;
+  float tx, ty, tz;
+};
+std::unique_ptr<PPMGenerator> load_xform_scene(const char* model_dir, int W, int H, const Xform& x) {
+  TutuCamera cam;
+  memset(&cam, 0, sizeof(cam));
+  cam.eye[0] = 278, cam.eye[1] = 273, cam.eye[2] = -800;  // configs/config_cornellBox.txt
+  cam.viewdir[2] = 1, cam.updir[1] = 1, cam.hfov_deg = 40;
+  cam.width = W, cam.height = H;
+  float bkg[3] = {0, 0, 0};
+  std::string cfg = write_config(cam, 0);
+  std::unique_ptr<PPMGenerator> g(new PPMGenerator(strdup(cfg.c_str())));
+  remove(cfg.c_str());
+  apply_camera(*g, cam, bkg, 1.0f);
+  Material white, light, green, red, glass;
+  white.mType = LAMBERTIAN, white.diffuse = {0.725f, 0.71f, 0.68f};
+  light.diffuse = {0.725f, 0.71f, 0.68f}, light.emission = {47.8348007, 38.5663986, 31.0807991};
+  green.mType = LAMBERTIAN, green.diffuse = {0.14f, 0.45f, 0.091f};
+  red.mType = LAMBERTIAN, red.diffuse = {0.63f, 0.065f, 0.05f};
+  glass.mType = MICROFACET_T, glass.eta = 1.5f, glass.roughness = 0.2f;
+  const std::pair<const char*, Material*> shell[] = {{"floor", &white}, {"light", &light}, {"right", &green},
+                                                     {"left", &red}, {"tallbox", &white}};
+  Quiet q;
+  for (auto& s : shell) {
+    objl::Loader loader;
+    std::string p = std::string(model_dir) + "/cornellBox/" + s.first + ".obj";
+    if (!loader.LoadFile(p)) die("cannot load " + p);
+    g->loadObj(loader, *s.second, -1, -1);
+  }
+  objl::Loader loader;
+  std::string p = std::string(model_dir) + "/veach_bdpt/veach_glass.obj";
+  if (!loader.LoadFile(p)) die("cannot load " + p);
+  g->scaleObj(loader, x.sx, x.sy, x.sz);
+  g->rotateObj(loader, x.axis, x.degree);
+  g->transObj(loader, x.tx, x.ty, x.tz);
+  g->loadObj(loader, glass, -1, -1);
+  return g;
+}
+inline Xform parse_xform(char** a) {
+  return Xform{(float)atof(a[0]), (float)atof(a[1]), (float)atof(a[2]), atoi(a[3]), (float)atof(a[4]),
+               (float)atof(a[5]), (float)atof(a[6]), (float)atof(a[7])};
+}
+
 // reference objects -> scene file (prims in objList order, materials de-duplicated)
 struct Exported {
   std::vector<TutuPrim> prims;

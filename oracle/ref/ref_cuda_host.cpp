@@ -10,6 +10,9 @@
 //   ref_cuda_host render-config <config.txt> <model_dir> <spp> <seed> <out.f32>
 //        a config file parsed by the reference's PPMGenerator (+ the Cornell ceiling light) through
 //        CudaPathTracing::integrate
+//   ref_cuda_host render-xform <model_dir> <W> <H> <spp> <seed> <out.f32> <sx> <sy> <sz> <axis> <deg> <tx> <ty> <tz>
+//        Cornell shell + veach_glass.obj placed by the reference's own scaleObj / rotateObj / transObj
+//        (PPMGenerator.hpp:210-270) before loadObj; the adapter flattens what the host authored
 //   ref_cuda_host render <scene.tscene> <spp> <seed> <out.f32>
 //   ref_cuda_host trace <scene.tscene> <rays.f32> <out.bin>
 //        every ray through CudaIntersectStrategy::UpdateInter and through BVHStrategy; writes the
@@ -80,6 +83,10 @@ int main(int argc, char** argv) {
       // PPMGenerator.hpp:328-482, 584-764) feeds the flattener of include/tutu_adapters.hpp
       std::unique_ptr<PPMGenerator> g = load_config(argv[2], argv[3], true);
       return run_integrate(*g, atoi(argv[4]), strtoull(argv[5], nullptr, 10), argv[6]);
+    }
+    if (cmd == "render-xform" && argc == 16) {
+      std::unique_ptr<PPMGenerator> g = load_xform_scene(argv[2], atoi(argv[3]), atoi(argv[4]), parse_xform(argv + 8));
+      return run_integrate(*g, atoi(argv[5]), strtoull(argv[6], nullptr, 10), argv[7]);
     }
     if (cmd == "render" && argc == 6) {
       Loaded L = load_scene(argv[2]);

@@ -19,6 +19,12 @@
 //   ref_harness render-config <config.txt> <model_dir> <spp> <out.f32> [mode]
 //        the config parsed by the reference's PPMGenerator (inline geometry, materials, P3 textures)
 //        plus the Cornell ceiling light, rendered by the reference's PathTracing
+//   ref_harness render-xform <model_dir> <W> <H> <spp> <out.f32> <sx> <sy> <sz> <axis> <deg> <tx> <ty> <tz>
+//   ref_harness dump-xform   <model_dir> <W> <H> <out.tscene>     <sx> <sy> <sz> <axis> <deg> <tx> <ty> <tz>
+//        Cornell shell + veach_glass.obj placed by the reference's own scaleObj / rotateObj / transObj
+//        (PPMGenerator.hpp:210-270), rendered by the reference's PathTracing / exported with its BVH
+//   ref_harness load-texture <file.ppm> <out.f32>
+//        PPMGenerator::loadTexture (ASCII P3, PPMGenerator.hpp:1027-1084): prints width/height, dumps the texels
 //   ref_harness ppm <W> <H> <in.f32> <out.ppm>
 //        PPMGenerator::generate (gamma 0.78 quantisation + ASCII P3, PPMGenerator.hpp:140-160,804-845)
 //   ref_harness postprocess <mode> <W> <H> <in.f32> <out.f32>
@@ -379,6 +385,46 @@ int ppm(int W, int H, const char* in_path, const char* out_path) {
   return 0;
 }
 
+// ---- f-2 authoring paths ----------------------------------------------------------------------
+int dump_xform(const char* model_dir, int W, int H, const char* out, const Xform& x) {
+  std::unique_ptr<PPMGenerator> g = load_xform_scene(model_dir, W, H, x);
+  {
+    Quiet q;
+    g->scene.initializeBVH();
+  }
+  Exported e;
+  export_objects(*g, e);
+  export_tree(*g, e);
+  TutuSceneDesc like;
+  memset(&like, 0, sizeof(like));
+  like.camera.eye[0] = 278, like.camera.eye[1] = 273, like.camera.eye[2] = -800;
+  like.camera.viewdir[2] = 1, like.camera.updir[1] = 1, like.camera.hfov_deg = 40;
+  like.camera.width = W, like.camera.height = H;
+  like.eta = 1.0f;
+  save(e, like, out);
+  printf("{\"prims\": %zu, \"materials\": %zu, \"nodes\": %zu}\n", e.prims.size(), e.mats.size(), e.nodes.size());
+  return 0;
+}
+
+int load_texture(const char* file, const char* out) {
+  TutuCamera cam;
+  memset(&cam, 0, sizeof(cam));
+  cam.viewdir[2] = 1, cam.updir[1] = 1, cam.hfov_deg = 40, cam.width = 4, cam.height = 4;
+  std::string cfg = write_config(cam, 0);
+  PPMGenerator& g = *new PPMGenerator(strdup(cfg.c_str()));
+  remove(cfg.c_str());
+  {
+    Quiet q;
+    g.loadTexture(file, g.diffuseMaps);
+  }
+  if (g.diffuseMaps.empty()) die("loadTexture loaded nothing");
+  Texture* t = g.diffuseMaps.back();
+  std::ofstream of(out, std::ios::binary);
+  of.write((const char*)t->rgb.data(), (std::streamsize)(t->rgb.size() * sizeof(Vector3f)));
+  printf("{\"width\": %d, \"height\": %d, \"texels\": %zu}\n", t->width, t->height, t->rgb.size());
+  return 0;
+}
+
 // ---- Postprocessor ----------------------------------------------------------------------------
 int postprocess(const char* mode, int W, int H, const char* in_path, const char* out_path) {
   Texture src;
@@ -435,6 +481,12 @@ int main(int argc, char** argv) {
   if (cmd == "export-bvh" && argc == 4) return export_bvh(argv[2], argv[3]);
   if (cmd == "render-config" && (argc == 6 || argc == 7))
     return render_config(argv[2], argv[3], atoi(argv[4]), argv[5], argc == 7 ? argv[6] : "rows");
+  if (cmd == "render-xform" && argc == 15) {
+    std::unique_ptr<PPMGenerator> g = load_xform_scene(argv[2], atoi(argv[3]), atoi(argv[4]), parse_xform(argv + 7));
+    return render_g(g.get(), atoi(argv[5]), argv[6], "rows");
+  }
+  if (cmd == "dump-xform" && argc == 14) return dump_xform(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], parse_xform(argv + 6));
+  if (cmd == "load-texture" && argc == 4) return load_texture(argv[2], argv[3]);
   if (cmd == "postprocess" && argc == 7) return postprocess(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argv[6]);
   if (cmd == "ppm" && argc == 6) return ppm(atoi(argv[2]), atoi(argv[3]), argv[4], argv[5]);
   if (cmd == "trace" && (argc == 6 || argc == 7))

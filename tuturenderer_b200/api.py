@@ -102,6 +102,9 @@ ABI = {
     "tutu_postprocess": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(TutuPostParams), _P]),
     "tutu_postprocess_device": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(TutuPostParams), _P, _P]),
     "tutu_write_ppm": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _P, C.c_int]),
+    "tutu_write_png": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _P]),
+    "tutu_texture_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "tutu_texture_free": (None, [C.POINTER(C.c_float)]),
     "tutu_render_stats": (C.c_int, [_P, C.POINTER(TutuRenderStats)]),
     "tutu_render_configure": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int]),
     "tutu_render_pipeline": (C.c_int, [_P, C.c_int]),
@@ -294,6 +297,24 @@ def write_ppm(path, rgb8: np.ndarray, binary: bool = False) -> None:
     rgb8 = np.ascontiguousarray(rgb8, np.uint8)
     h, w = rgb8.shape[:2]
     _check(lib().tutu_write_ppm(str(path).encode(), w, h, _ptr(rgb8), int(binary)))
+
+
+def write_png(path, rgb8: np.ndarray) -> None:
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    h, w = rgb8.shape[:2]
+    _check(lib().tutu_write_png(str(path).encode(), w, h, _ptr(rgb8)))
+
+
+def load_texture(path, normal_map: bool = False) -> np.ndarray:
+    """Texture file (ASCII P3 as the reference reads it, binary P6, PNG) -> (H, W, 3) float32 texels for
+    Scene.textures; normal_map applies the reference's `bump` recovery c * 2 - 1."""
+    p = C.POINTER(C.c_float)()
+    w, h = C.c_int32(0), C.c_int32(0)
+    _check(lib().tutu_texture_load(str(path).encode(), int(normal_map), C.byref(p), C.byref(w), C.byref(h)))
+    try:
+        return np.ctypeslib.as_array(p, (h.value, w.value, 3)).copy()
+    finally:
+        lib().tutu_texture_free(p)
 
 
 def post_params(**kw) -> TutuPostParams:

@@ -16,8 +16,8 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libtutu_b200.so"
 
-SOURCES = [CSRC / "tutu_b200.cu", CSRC / "resident.cu", CSRC / "host_scene.cpp"]
-HEADERS = [CSRC / "trace.cuh", CSRC / "shade.cuh", CSRC / "vertex.cuh", CSRC / "wavefront.cuh", CSRC / "resident.cuh", CSRC / "bdpt.cuh", CSRC / "tutu_internal.hpp",
+SOURCES = [CSRC / "tutu_b200.cu", CSRC / "resident.cu", CSRC / "host_scene.cpp", CSRC / "host_image.cpp"]
+HEADERS = [CSRC / "trace.cuh", CSRC / "shade.cuh", CSRC / "vertex.cuh", CSRC / "wavefront.cuh", CSRC / "resident.cuh", CSRC / "bdpt.cuh", CSRC / "postprocess.cuh", CSRC / "tutu_internal.hpp",
            ROOT / "include" / "tutu_b200.h"]
 
 
@@ -38,6 +38,7 @@ def nvcc_command(out: Path = LIB, extra: list[str] | None = None) -> list[str]:
         "-shared", "-o", str(out),
         *(extra or []),
         *map(str, SOURCES),
+        "-lz",  # host_image.cpp: PNG inflate / deflate
     ]
 
 
