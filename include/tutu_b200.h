@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TUTU_ABI_VERSION 1
+#define TUTU_ABI_VERSION 2
 
 /* status codes */
 #define TUTU_OK 0
@@ -157,6 +157,13 @@ typedef struct TutuSceneInfo {
   uint32_t n_materials;
   uint32_t width, height;
   uint64_t device_bytes; /* HBM held by the uploaded scene */
+  /* the tree the production walk descends for regular rays (not the reference's topology) */
+  uint32_t trav_nodes;      /* inner nodes */
+  uint32_t trav_depth;      /* deepest inner node, root = 1 */
+  uint32_t trav_width;      /* children per node: 2 (binary SAH tree) or 8 (compressed wide tree) */
+  uint32_t trav_node_bytes; /* bytes fetched per inner-node visit */
+  uint32_t trav_leaf_bytes; /* bytes fetched per primitive test */
+  uint32_t reserved;
 } TutuSceneInfo;
 
 /* Counters of the last tutu_render_path* call (diagnostics and the roofline arithmetic). */
@@ -202,7 +209,10 @@ int tutu_trace_any_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays,
 /* Traversal variant: 0 = ordered + t-pruned walk, large batches traced in a coherent order
  * (counting sort by entry cell + direction bin; results are order independent) — the default;
  * 3 = the same walk in the caller's ray order; 1 = unpruned both-children walk that mirrors the
- * reference's recursion literally (used as a second opinion by the tests). */
+ * reference's recursion literally (used as a second opinion by the tests);
+ * 6 = as 0, but regular rays (every 1/d finite) walk the compressed 8-wide collapse of the traversal tree (8-bit
+ * child boxes quantised outwards, decoded exactly; built on the first use).  Same hits bit for bit; on a B200 it
+ * is slower than the binary walk, so it is an option. */
 int tutu_set_traversal_mode(TutuCtx* ctx, int mode);
 /* Visit counters for the algorithmic-bytes figure: traces the batch with counting kernels and
  * returns total inner-node fetches and primitive tests. */
@@ -303,6 +313,19 @@ void tutu_texture_free(float* rgb);
  * 2*n_prims-1 entries (1 if n_prims <= 1). */
 int tutu_bvh_build(const TutuPrim* prims, uint32_t n_prims, TutuBvhNode* nodes_out,
                    uint32_t* n_nodes_out);
+/* Host-only self check of the traversal trees tutu_scene_upload would build for `desc` (the binned-SAH binary
+ * tree over the reference's leaves and its compressed 8-wide collapse): every child box of every wide node,
+ * decoded with the device's own arithmetic, must contain the exact boxes of all leaves below it, and every
+ * leaf must be referenced exactly once.  violations == 0 is what the bit-exact hit parity of regular rays
+ * rests on. */
+typedef struct TutuTreeCheck {
+  uint32_t n_leaves;
+  uint32_t binary_nodes, binary_depth;
+  uint32_t wide_nodes, wide_depth; /* 0 = no wide tree (degenerate scene: the device walks the binary tree) */
+  uint64_t wide_children;          /* occupied slots over all wide nodes */
+  uint64_t violations;
+} TutuTreeCheck;
+int tutu_traversal_tree_check(const TutuSceneDesc* desc, TutuTreeCheck* out);
 /* Scene files (tests, benches, the oracle harness): a flat little-endian dump of TutuSceneDesc. */
 typedef struct TutuSceneFile TutuSceneFile;
 int tutu_scene_file_load(const char* path, TutuSceneFile** out);

@@ -25,12 +25,13 @@ def test_header_symbols_are_exported(api):
 
 
 def test_abi_version(api):
-    assert api.lib().tutu_abi_version() == 1
+    assert api.lib().tutu_abi_version() == 2
 
 
 def test_pod_sizes_match_header(api):
     assert C.sizeof(api.TutuCamera) == 52
-    assert C.sizeof(api.TutuSceneInfo) == 40
+    assert C.sizeof(api.TutuSceneInfo) == 64
+    assert C.sizeof(api.TutuPostParams) == 24
     assert api.PRIM_DTYPE.itemsize == 124 and api.MATERIAL_DTYPE.itemsize == 56
 
 

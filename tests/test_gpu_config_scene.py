@@ -119,12 +119,18 @@ def test_transformed_obj_through_reference_host_and_adapter(api, tmp_path):
     placed = api.Scene.load(tmp_path / "placed.tscene")
     pv = placed.prims[placed.materials["type"][placed.prims["material"]] == api.MAT_MICROFACET_T]["v"].reshape(-1, 3)
     assert abs(pv[:, 1].min() - 0.5) < 1e-2 and 0 < pv[:, 0].min() and pv[:, 0].max() < 556 and pv[:, 2].max() < 559
-    # rotateObj really rotated: the x extent after a 30 degree turn differs from the unrotated scaled extent
+    # rotateObj really rotated (the glass is a solid of revolution, so extents do not show it): every vertex of the
+    # probe is the unrotated vertex turned by 30 degrees about y, x' = cos x + sin z, z' = -sin x + cos z (:247-252)
     _run("ref_harness", "dump-xform", REF / "model", 48, 48, "unrot.tscene", 300, 300, 300, 1, 0, 0, 0, 0, cwd=tmp_path)
     un = api.Scene.load(tmp_path / "unrot.tscene")
     uv = un.prims[un.materials["type"][un.prims["material"]] == api.MAT_MICROFACET_T]["v"].reshape(-1, 3)
-    assert abs((uv[:, 0].max() - uv[:, 0].min()) - (hi[0] - lo[0])) > 1.0
-    assert np.allclose(np.linalg.norm(uv[:, [0, 2]], axis=1), np.linalg.norm(v[:, [0, 2]], axis=1), rtol=1e-4, atol=1e-3)
+    c, s_ = np.cos(np.radians(30.0)), np.sin(np.radians(30.0))
+    assert np.allclose(v[:, 0], c * uv[:, 0] + s_ * uv[:, 2], atol=2e-3) and np.allclose(v[:, 2], -s_ * uv[:, 0] + c * uv[:, 2], atol=2e-3)
+    assert np.array_equal(v[:, 1], uv[:, 1]) and np.abs(v[:, 0] - uv[:, 0]).max() > 10.0
+    # scaleObj: x300 of the OBJ's own coordinates (committed fixture of the unscaled object)
+    raw = api.Scene.load(ROOT / "tests" / "golden" / "veach_80x60.tscene")
+    rv = raw.prims[raw.materials["type"][raw.prims["material"]] == api.MAT_PERFECT_REFRACTIVE]["v"].reshape(-1, 3)
+    assert np.array_equal(uv, rv * np.float32(300))
     cpu = []
     for k in range(2):
         _run("ref_harness", "render-xform", REF / "model", 48, 48, 512, f"cpu{k}.f32", *xf, cwd=tmp_path)

@@ -95,15 +95,19 @@ def test_mixed_scene_statistics_against_reference(api, ctx, golden, mixed):
     for c in range(3):
         assert abs(img[..., c].mean() / ref[..., c].mean() - 1) < 0.01
     assert _rmse(img, ref) < 2 * stats["run_to_run_rmse_1024"]
-    # block means (8x8) localise a wrong material: mean deviation below 1 % (+0.02 absolute), worst block
-    # below 30 %.  The worst block (0.24-0.26 for any seed, tools/gpu_mixed_stat.py) holds two pixels on
-    # the silhouette of the PERFECT_REFLECTIVE sphere: their specular chain is deterministic, so a last-place
-    # difference in the grazing reflection (FMA / rsqrt vs libm) flips every sample of the pixel at once
-    # (0.63 and 0.40 where the reference has 0 and 0.13); the other 9213 pixels agree with the same-stream
-    # CPU render to 2 %.
+    # block means (8x8) localise a wrong material.  Four pixels are excluded by name: they sit on the silhouettes of
+    # the PERFECT_REFLECTIVE and PERFECT_REFRACTIVE spheres, where the camera ray (no pixel jitter) starts a
+    # deterministic specular chain; a last-place difference in the grazing reflection (FMA contraction / rsqrt in the
+    # shading code vs the reference's libm build) sends EVERY sample of such a pixel to another surface (e.g. 0.08 where
+    # the reference has 0.35; tools/gpu_mixed_stat.py lists them, identical for every seed).  All other 9212 pixels
+    # are gated: worst 8x8 block below 10 %, mean block deviation below 1 % (+0.02 absolute).
+    CHAIN_PIXELS = [(42, 39), (70, 69), (40, 46), (57, 47)]
+    img_m, ref_m = img.copy(), ref.copy()
+    for y, x in CHAIN_PIXELS:
+        img_m[y, x] = ref_m[y, x] = 0
     b = lambda a: a.reshape(12, 8, 12, 8, 3).mean((1, 3))
-    rel = np.abs(b(img) - b(ref)) / (b(ref) + 0.02)
-    assert rel.max() < 0.30 and rel.mean() < 0.01
+    rel = np.abs(b(img_m) - b(ref_m)) / (b(ref_m) + 0.02)
+    assert rel.max() < 0.10 and rel.mean() < 0.01, (rel.max(), rel.mean())
 
 
 def test_glass_scene_statistics_against_reference(api, oracle, ctx, golden):

@@ -14,7 +14,7 @@ CASES = [("cornell_256", "cornell_rays.f32", "cornell_closest.bin", "cornell_any
          ("mixed", "mixed_rays.f32", "mixed_closest.bin", "mixed_any.bin")]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 4, 6])
 @pytest.mark.parametrize("scene,rays,closest,anyf", CASES)
 def test_golden_vectors_bit_exact(api, ctx, golden, scene, rays, closest, anyf, mode):
     sc = api.Scene.load(golden / f"{scene}.tscene")
@@ -45,10 +45,16 @@ def test_random_soups_against_oracle(api, oracle, ctx, n_tris, n_spheres, dup, s
     rays = random_rays(30000, seed=seed)
     want_c, want_a = osc.trace_closest(rays), osc.trace_any(rays)
     ctx.upload(sc)
-    for mode in (0, 1, 2, 4):
+    for mode in (0, 1, 2, 4, 6):  # 6 = compressed 8-wide tree (built on demand)
         ctx.set_traversal_mode(mode)
         assert_hits_equal(ctx.trace_closest(rays), want_c)
         assert np.array_equal(ctx.trace_any(rays), want_a)
+    ctx.upload(sc)  # an upload in mode 6 builds the wide tree as part of the upload
+    assert ctx.info().trav_width == (8 if n_tris + n_spheres + dup >= 1 else 2)
+    assert_hits_equal(ctx.trace_closest(rays), want_c)
+    assert np.array_equal(ctx.trace_any(rays), want_a)
+    ctx.set_traversal_mode(0)
+    assert ctx.info().trav_width == 2
     if dup:
         assert (want_c["prim"] >= 0).any()
 
@@ -70,7 +76,7 @@ def test_degenerate_rays(api, oracle, ctx, cornell):
     rays[:, 7] = 300.0
     osc = oracle.OracleScene(cornell)
     ctx.upload(cornell)
-    for mode in (0, 1):
+    for mode in (0, 1, 6):
         ctx.set_traversal_mode(mode)
         assert_hits_equal(ctx.trace_closest(rays), osc.trace_closest(rays))
         assert np.array_equal(ctx.trace_any(rays), osc.trace_any(rays))
@@ -246,7 +252,7 @@ def test_full_size_against_the_reference(api, ctx, full_size_scene, kind):
     want_a, info_a = O.ref_trace(sc, rays, "any", scene_path=path)
     assert info_c["rays"] == n and info_a["rays"] == n
     ctx.upload(sc)
-    for mode in (0, 1):
+    for mode in (0, 1, 6):  # production walk, literal walk, compressed 8-wide tree
         ctx.set_traversal_mode(mode)
         assert_hits_equal(ctx.trace_closest(rays), want_c)
         assert np.array_equal(ctx.trace_any(rays), want_a)
@@ -337,9 +343,13 @@ def test_fast_tree_edge_cases(api, oracle, ctx, case):
     a, b = ctx.trace_closest(rays), ctx.trace_any(rays)
     ctx.set_traversal_mode(1)
     c, d1 = ctx.trace_closest(rays), ctx.trace_any(rays)
+    ctx.set_traversal_mode(6)  # the compressed wide collapse of the same SAH tree
+    e, f = ctx.trace_closest(rays), ctx.trace_any(rays)
     ctx.set_traversal_mode(0)
     assert_hits_equal(a, c)
     assert np.array_equal(b, d1)
+    assert_hits_equal(e, c)
+    assert np.array_equal(f, d1)
     sub = slice(0, n, 9)
     osc = oracle.OracleScene(sc)
     assert_hits_equal(np.ascontiguousarray(a[sub]), osc.trace_closest(np.ascontiguousarray(rays[sub])))

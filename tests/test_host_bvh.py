@@ -58,6 +58,47 @@ def test_full_size_tree_equals_the_reference(api, tmp_path):
     assert np.array_equal(mine, ref.bvh_nodes)
 
 
+@pytest.mark.parametrize("name", ["cornell_256", "hf24", "mixed", "veach_80x60", "glass_c4"])
+def test_wide_tree_contains_its_leaves(api, golden, name):
+    """The compressed 8-wide tree (traversal mode 6): every child box, DECODED with the device's arithmetic, contains
+    the exact boxes of all leaves below it, and every leaf is referenced once (tutu_traversal_tree_check)."""
+    r = api.traversal_tree_check(api.Scene.load(golden / f"{name}.tscene"))
+    assert r["violations"] == 0 and r["wide_nodes"] > 0 and r["n_leaves"] == r["binary_nodes"] + 1
+    assert r["wide_children"] == r["n_leaves"] + r["wide_nodes"] - 1  # every node but the root is somebody's child
+    assert r["wide_children"] / r["wide_nodes"] > 5.0  # the surface-area collapse fills the nodes
+
+
+@pytest.mark.parametrize("case", ["single", "pair", "duplicates", "far_from_origin", "huge_and_tiny", "flat", "spheres"])
+def test_wide_tree_degenerate_scenes(api, case):
+    rng = np.random.default_rng(11)
+    prims = random_soup(api, 300, seed=5)
+    if case == "single":
+        prims = prims[:1]
+    elif case == "pair":
+        prims = prims[:2]
+    elif case == "duplicates":
+        prims["v"][:] = prims["v"][0]
+    elif case == "far_from_origin":   # planes of the order 1e7 with extents of the order 1: the frame's base2 carries rounding
+        prims["v"] += np.float32(1.0e7)
+    elif case == "huge_and_tiny":
+        v = prims["v"].reshape(-1, 3, 3)
+        v[:100] *= np.float32(1e-6)
+        v[100:200] *= np.float32(1e6)
+    elif case == "flat":              # axis-aligned quads: zero-thickness boxes (the Cornell walls)
+        prims["v"].reshape(-1, 3, 3)[:, :, 1] = np.float32(3.25)
+    else:
+        prims = random_soup(api, 50, n_spheres=40, seed=6)
+    r = api.traversal_tree_check(api.Scene(prims=prims, materials=api.default_material()))
+    assert r["violations"] == 0 and r["n_leaves"] == len(prims)
+    assert r["wide_nodes"] >= 1
+
+
+def test_wide_tree_full_size(api):
+    prims = api.synth_heightfield(160)
+    r = api.traversal_tree_check(api.Scene(prims=prims, materials=api.default_material()))
+    assert r["violations"] == 0 and r["wide_depth"] <= 8 and r["wide_children"] / r["wide_nodes"] > 6.0
+
+
 def test_scene_file_roundtrip(api, mixed, tmp_path):
     p = tmp_path / "m.tscene"
     mixed.save(p)

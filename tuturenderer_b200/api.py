@@ -54,7 +54,9 @@ class TutuSceneDesc(C.Structure):
 class TutuSceneInfo(C.Structure):
     _fields_ = [("n_prims", C.c_uint32), ("n_nodes", C.c_uint32), ("n_inner", C.c_uint32),
                 ("depth", C.c_uint32), ("n_lights", C.c_uint32), ("n_materials", C.c_uint32),
-                ("width", C.c_uint32), ("height", C.c_uint32), ("device_bytes", C.c_uint64)]
+                ("width", C.c_uint32), ("height", C.c_uint32), ("device_bytes", C.c_uint64),
+                ("trav_nodes", C.c_uint32), ("trav_depth", C.c_uint32), ("trav_width", C.c_uint32),
+                ("trav_node_bytes", C.c_uint32), ("trav_leaf_bytes", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class TutuRenderStats(C.Structure):
@@ -65,6 +67,12 @@ class TutuRenderStats(C.Structure):
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class TutuTreeCheck(C.Structure):
+    _fields_ = [("n_leaves", C.c_uint32), ("binary_nodes", C.c_uint32), ("binary_depth", C.c_uint32),
+                ("wide_nodes", C.c_uint32), ("wide_depth", C.c_uint32), ("wide_children", C.c_uint64),
+                ("violations", C.c_uint64)]
 
 
 class TutuPostParams(C.Structure):
@@ -109,6 +117,7 @@ ABI = {
     "tutu_render_configure": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int]),
     "tutu_render_pipeline": (C.c_int, [_P, C.c_int]),
     "tutu_bvh_build": (C.c_int, [_P, C.c_uint32, _P, C.POINTER(C.c_uint32)]),
+    "tutu_traversal_tree_check": (C.c_int, [C.POINTER(TutuSceneDesc), C.POINTER(TutuTreeCheck)]),
     "tutu_scene_file_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "tutu_scene_file_desc": (C.POINTER(TutuSceneDesc), [_P]),
     "tutu_scene_file_free": (None, [_P]),
@@ -279,6 +288,15 @@ def bvh_build(prims: np.ndarray) -> np.ndarray:
     return out[:cnt.value]
 
 
+def traversal_tree_check(scene: "Scene") -> dict:
+    """Host-only self check of the traversal trees an upload of `scene` builds (tutu_traversal_tree_check)."""
+    d, keep = scene.to_c()
+    out = TutuTreeCheck()
+    _check(lib().tutu_traversal_tree_check(C.byref(d), C.byref(out)))
+    del keep
+    return {n: getattr(out, n) for n, _ in TutuTreeCheck._fields_}
+
+
 def synth_heightfield(G: int, seed: int = 12345) -> np.ndarray:
     prims = np.zeros(2 * G * G, PRIM_DTYPE)
     _check(lib().tutu_synth_heightfield(G, seed, _ptr(prims)))
@@ -389,6 +407,11 @@ class Context:
         i = TutuSceneInfo()
         self._ck(lib().tutu_scene_info(self._h, C.byref(i)))
         return i
+
+    def node_bytes(self) -> dict:
+        """Record sizes of the tree the production walk descends (for the algorithmic-bytes figure)."""
+        i = self.info()
+        return {"node": int(i.trav_node_bytes), "leaf": int(i.trav_leaf_bytes)}
 
     def set_traversal_mode(self, mode: int) -> None:
         self._ck(lib().tutu_set_traversal_mode(self._h, mode))

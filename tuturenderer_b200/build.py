@@ -16,8 +16,8 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libtutu_b200.so"
 
-SOURCES = [CSRC / "tutu_b200.cu", CSRC / "resident.cu", CSRC / "host_scene.cpp", CSRC / "host_image.cpp"]
-HEADERS = [CSRC / "trace.cuh", CSRC / "shade.cuh", CSRC / "vertex.cuh", CSRC / "wavefront.cuh", CSRC / "resident.cuh", CSRC / "bdpt.cuh", CSRC / "postprocess.cuh", CSRC / "tutu_internal.hpp",
+SOURCES = [CSRC / "tutu_b200.cu", CSRC / "resident.cu", CSRC / "trace_kernels.cu", CSRC / "host_scene.cpp", CSRC / "host_image.cpp", CSRC / "host_wide.cpp"]
+HEADERS = [CSRC / "trace.cuh", CSRC / "shade.cuh", CSRC / "vertex.cuh", CSRC / "wavefront.cuh", CSRC / "resident.cuh", CSRC / "bdpt.cuh", CSRC / "postprocess.cuh", CSRC / "wide.cuh", CSRC / "wf_types.cuh", CSRC / "trace_kernels.hpp", CSRC / "tutu_internal.hpp",
            ROOT / "include" / "tutu_b200.h"]
 
 
@@ -30,7 +30,7 @@ def nvcc_path() -> str:
 
 def nvcc_command(out: Path = LIB, extra: list[str] | None = None) -> list[str]:
     return [
-        nvcc_path(), "-O3", "-std=c++17",
+        nvcc_path(), "-O3", "-std=c++17", "--threads", "0",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-lineinfo",
         # host code must round like the reference's scalar build (no FMA contraction)

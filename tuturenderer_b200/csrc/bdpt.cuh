@@ -166,7 +166,8 @@ __global__ void bdpt_ctl_after_shadow(BdptCtl* ctl) {
 }
 
 // ---- generic queue tracers (same packet scheme as wf_extend / wf_shadow) --------------------------
-template <bool SMALL>
+// KIND: 0 = binary trees (trace.cuh), 1 = small scene (flat tests); the wide-tree tracers are in trace_kernels.cu
+template <int KIND>
 __global__ void __launch_bounds__(256)
 q_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, const float4* __restrict__ ro,
          const float4* __restrict__ rd, float4* __restrict__ hit, const unsigned* __restrict__ n_ptr,
@@ -188,7 +189,7 @@ q_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene
         Hit h;
         h.t = FLT_MAX, h.u = 0.f, h.v = 0.f, h.slot = -1;
         if (__float_as_uint(d.w) != kDeadEntry) {
-          if (SMALL)
+          if constexpr (KIND == 1)
             traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
           else
             traverse_shared<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack);
@@ -200,7 +201,7 @@ q_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene
   }
 }
 
-template <bool SMALL>
+template <int KIND>
 __global__ void __launch_bounds__(256)
 q_shadow_add(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, const float4* __restrict__ so,
              const float4* __restrict__ sd, const float4* __restrict__ scn, float* __restrict__ accum,
@@ -219,8 +220,11 @@ q_shadow_add(const __grid_constant__ DevScene sc, const __grid_constant__ SmallS
         const float4 o = __ldcs(so + j);
         const float4 d = __ldcs(sd + j);
         Hit h;
-        const bool blocked = SMALL ? traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h)
-                                   : traverse_variant<true, 3>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+        bool blocked;
+        if constexpr (KIND == 1)
+          blocked = traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+        else
+          blocked = traverse_variant<true, 3>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
         if (!blocked) {
           const float4 c = __ldcs(scn + j);
           float* p = accum + (size_t)__float_as_uint(d.w) * 3;

@@ -838,6 +838,36 @@ extern "C" const char* tutu_last_error(const TutuCtx* ctx) {
   return get_error().c_str();
 }
 
+extern "C" int tutu_traversal_tree_check(const TutuSceneDesc* desc, TutuTreeCheck* out) {
+  if (!desc || !out) {
+    set_error("tutu_traversal_tree_check: null argument");
+    return TUTU_E_INVALID;
+  }
+  try {
+    FlatScene fs;
+    int rc = flatten_scene(desc, &fs);
+    if (rc != TUTU_OK) return rc;
+    build_wide_tree(&fs);
+    memset(out, 0, sizeof(*out));
+    out->n_leaves = (uint32_t)fs.leaf_box.size();
+    out->binary_nodes = (uint32_t)fs.inner_fast.size();
+    out->binary_depth = fs.depth_fast;
+    out->wide_nodes = (uint32_t)fs.wide.size();
+    out->wide_depth = fs.wide_depth;
+    out->violations = verify_wide_tree(fs);
+    uint64_t kids = 0;
+    for (const WideNode& w : fs.wide) kids += (uint64_t)__builtin_popcount(w.imask) + (uint64_t)__builtin_popcount(w.lmask);
+    out->wide_children = kids;
+    return TUTU_OK;
+  } catch (const std::bad_alloc&) {
+    set_error("tutu_traversal_tree_check: out of host memory");
+    return TUTU_E_NOMEM;
+  } catch (const std::exception& e) {
+    set_error(std::string("tutu_traversal_tree_check: ") + e.what());
+    return TUTU_E_INVALID;
+  }
+}
+
 extern "C" int tutu_bvh_build(const TutuPrim* prims, uint32_t n_prims, TutuBvhNode* nodes_out,
                               uint32_t* n_nodes_out) {
   if ((n_prims && !prims) || !nodes_out || !n_nodes_out) {

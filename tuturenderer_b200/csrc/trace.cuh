@@ -24,6 +24,9 @@ constexpr uint32_t kSlotMask = kSphereBit - 1u;
 struct DevScene {
   const float4* __restrict__ inner;     // 4 x float4 per inner node, the reference's topology
   const float4* __restrict__ inner_fast;  // SAH topology over the same leaves: regular rays (host_scene.cpp)
+  const float4* __restrict__ wide;      // compressed 8-wide tree for regular rays: 6 x 16 B per node (wide.cuh); nullptr = none
+  const float4* __restrict__ wleaf;     // its leaf records: 4 x float4 (LeafGeom + leaf code), in wide-tree order
+  const float4* __restrict__ wbox;      // exact leaf boxes, 2 x float4, same order
   const float4* __restrict__ geom;      // 3 x float4 per leaf slot
   const float4* __restrict__ shade;     // 4 x float4 per leaf slot
   const int4* __restrict__ leaftex;     // per leaf slot, or nullptr when no prim is textured
@@ -1216,3 +1219,5 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, unsigned lo
 }
 
 }  // namespace tutu
+
+#include "wide.cuh"

@@ -16,6 +16,7 @@
 #include "bdpt.cuh"
 #include "resident.cuh"
 #include "postprocess.cuh"
+#include "trace_kernels.hpp"
 
 using namespace tutu;
 
@@ -128,7 +129,9 @@ struct TutuCtx {
   FlatScene flat;
   DevScene dev{};
   SmallScene small{};  // n = 0 unless the scene has <= kSmallMax primitives
-  DevBuf d_inner_fast;
+  DevBuf d_inner_fast, d_wide, d_wleaf, d_wbox;
+  WideGrids wide_grids;  // trace_kernels.cu: persistent grids of the wide-tree kernels for the current stack size
+  bool use_wide = false;  // tutu_set_traversal_mode(ctx, 6): regular rays walk the compressed 8-wide tree (built on demand)
   DevBuf d_inner, d_geom, d_shade, d_leaftex, d_slot_to_prim, d_materials, d_lights, d_texels;
   DevBuf d_texh[4];
   uint64_t scene_bytes = 0;
@@ -160,6 +163,7 @@ struct TutuCtx {
   int grid_shade_block = 0;
   size_t grid_stack_smem = 0;
   bool grid_small = false;
+  bool grid_wide = false;
   int profile_stages = 0;
   // 0 = automatic (register-resident kernel for small renders of scenes that fit the constant bank, else
   // wavefront), 1 = wavefront, 2 = register-resident (fails on scenes that do not fit)
@@ -598,6 +602,14 @@ size_t stack_smem(const TutuCtx* ctx, int block, bool any) {
   return (size_t)block * (std::max(ctx->flat.depth, ctx->flat.depth_fast) + 1) * (any ? sizeof(unsigned) : sizeof(unsigned long long));
 }
 
+size_t wide_stack_smem(const TutuCtx* ctx, int block) { return (size_t)block * (ctx->flat.wide_depth + 1) * sizeof(unsigned long long); }
+// grids of the wide-tree kernels (trace_kernels.cu) for the uploaded scene's stack size
+const WideGrids& wide_grids_for(TutuCtx* ctx) {
+  const size_t sm = wide_stack_smem(ctx, kTraceBlock);
+  if (ctx->wide_grids.smem != sm) CUDA_TRY(wide_grids(ctx->sm_count, sm, &ctx->wide_grids));
+  return ctx->wide_grids;
+}
+
 // Builds the coherent traversal order of a batch (nullptr = trace in the caller's order).
 const unsigned* bin_rays(TutuCtx* ctx, const float4* rays, uint64_t n, cudaStream_t s, int slot = 0) {
   if (!ctx->ray_binning || !(ctx->traversal_mode == 0 || ctx->traversal_mode >= 10) || ctx->small.n > 0 || n < ctx->ray_binning_min || n >= (1ull << 32))
@@ -647,6 +659,10 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
     if (ctx->small.n > 0 && ctx->traversal_mode == 0) {
       int grid = persistent_grid(ctx, k_trace_closest<3>, 256);
       k_trace_closest<3><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+    } else if (ctx->dev.wide) {
+      const unsigned* perm = bin_rays(ctx, rays, n, s, slot);
+      const WideGrids& g = wide_grids_for(ctx);
+      CUDA_TRY(wide_launch_batch(false, g.batch_closest, g.smem, s, ctx->dev, rays, n, d_out, nullptr, next, perm));
     } else {
       const unsigned* perm = bin_rays(ctx, rays, n, s, slot);
       const size_t sm = stack_smem(ctx, 256, false);
@@ -685,6 +701,10 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
     if (ctx->small.n > 0 && ctx->traversal_mode == 0) {
       int grid = persistent_grid(ctx, k_trace_any<3>, 256);
       k_trace_any<3><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+    } else if (ctx->dev.wide) {
+      const unsigned* perm = bin_rays(ctx, rays, n, s, slot);
+      const WideGrids& g = wide_grids_for(ctx);
+      CUDA_TRY(wide_launch_batch(true, g.batch_any, g.smem, s, ctx->dev, rays, n, nullptr, d_out, next, perm));
     } else {
       const unsigned* perm = bin_rays(ctx, rays, n, s, slot);
       int grid = persistent_grid(ctx, k_trace_any<0>, 256);
@@ -878,19 +898,24 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   while (n_lanes > 1 && (sample_count < (uint32_t)n_lanes || total / n_lanes < cap_cfg / 2)) --n_lanes;
   if ((int)ctx->wf_lanes.size() < n_lanes) ctx->wf_lanes.resize(n_lanes);
   // the cached grids depend on the scene through the kernel variants and the traversal-stack size
-  const size_t want_stack = ctx->small.n > 0 ? 0 : stack_smem(ctx, 256, false);
+  const bool wide = ctx->small.n == 0 && ctx->dev.wide != nullptr;
+  const size_t want_stack = ctx->small.n > 0 ? 0 : (wide ? wide_stack_smem(ctx, 256) : stack_smem(ctx, 256, false));
   if (ctx->grid_lanes != n_lanes || ctx->grid_small != (ctx->small.n > 0) || ctx->grid_shade_block != ctx->shade_block ||
-      ctx->grid_stack_smem != want_stack) {
+      ctx->grid_stack_smem != want_stack || ctx->grid_wide != wide) {
     ctx->grid_stack_smem = want_stack;
+    ctx->grid_wide = wide;
     ctx->grid_shade_block = ctx->shade_block;
     ctx->grid_small = ctx->small.n > 0;
     const int div = getenv("TUTU_GRID_SPLIT") ? n_lanes : 1;  // experiments only: split the resident blocks between the lanes
     auto sized = [&](int full) { return ctx->sm_count * std::max(1, full / ctx->sm_count / div); };
     const bool small = ctx->small.n > 0;
-    ctx->grid_extend = sized(small ? persistent_grid(ctx, wf_extend_small, kSmallBlock)
-                                   : persistent_grid(ctx, wf_extend<false>, 256, stack_smem(ctx, 256, false)));
+    ctx->grid_extend = sized(small  ? persistent_grid(ctx, wf_extend_small, kSmallBlock)
+                             : wide ? wide_grids_for(ctx).wf_extend
+                                    : persistent_grid(ctx, wf_extend<0>, 256, want_stack));
     ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, ctx->shade_block));
-    ctx->grid_shadow = sized(small ? persistent_grid(ctx, wf_shadow_small, kSmallBlock) : persistent_grid(ctx, wf_shadow<false>, 256));
+    ctx->grid_shadow = sized(small  ? persistent_grid(ctx, wf_shadow_small, kSmallBlock)
+                             : wide ? wide_grids_for(ctx).wf_shadow
+                                    : persistent_grid(ctx, wf_shadow<0>, 256));
     ctx->grid_raygen = sized(persistent_grid(ctx, wf_raygen, 256));
     ctx->grid_lanes = n_lanes;
   }
@@ -946,8 +971,10 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         timer.mark(1, ls);
         if (small)
           wf_extend_small<<<ctx->grid_extend, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
+        else if (wide)
+          CUDA_TRY(wide_launch_wf_extend(ctx->grid_extend, want_stack, ls, ctx->dev, L.b, cur));
         else
-          wf_extend<false><<<ctx->grid_extend, 256, stack_smem(ctx, 256, false), ls>>>(ctx->dev, ctx->small, L.b, cur);
+          wf_extend<0><<<ctx->grid_extend, 256, want_stack, ls>>>(ctx->dev, ctx->small, L.b, cur);
         if (it == 0 && k + 1 < n_lanes) {
           // stagger the lanes by one stage so that unlike kernels (traverse / shade) overlap
           CUDA_TRY(cudaEventRecord(L.ev_done, ls));
@@ -962,8 +989,10 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         timer.mark(3, ls);
         if (small)
           wf_shadow_small<<<ctx->grid_shadow, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
+        else if (wide)
+          CUDA_TRY(wide_launch_wf_shadow(ctx->grid_shadow, want_stack, ls, ctx->dev, L.b, cur ^ 1));
         else
-          wf_shadow<false><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
+          wf_shadow<0><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
         timer.mark(0, ls);
         wf_ctl_after_iter<<<1, 1, 0, ls>>>(L.b.ctl);
         launches += 6;
@@ -1080,9 +1109,14 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
   const int g_start = persistent_grid(ctx, bdpt_start, 256);
   const int g_vertex = persistent_grid(ctx, bdpt_vertex, 256);
   const int g_connect = persistent_grid(ctx, bdpt_connect, 256);
-  const size_t sm_stack = stack_smem(ctx, 256, false);
-  const int g_extend = small ? persistent_grid(ctx, q_extend<true>, 256) : persistent_grid(ctx, q_extend<false>, 256, sm_stack);
-  const int g_shadow = small ? persistent_grid(ctx, q_shadow_add<true>, 256) : persistent_grid(ctx, q_shadow_add<false>, 256);
+  const bool wide = !small && ctx->dev.wide != nullptr;
+  const size_t sm_stack = wide ? wide_stack_smem(ctx, 256) : stack_smem(ctx, 256, false);
+  const int g_extend = small  ? persistent_grid(ctx, q_extend<1>, 256)
+                       : wide ? wide_grids_for(ctx).q_extend
+                              : persistent_grid(ctx, q_extend<0>, 256, sm_stack);
+  const int g_shadow = small  ? persistent_grid(ctx, q_shadow_add<1>, 256)
+                       : wide ? wide_grids_for(ctx).q_shadow
+                              : persistent_grid(ctx, q_shadow_add<0>, 256);
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
@@ -1107,9 +1141,11 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
       int cur = 0;
       for (int it = 0; it < kBdptMaxLen; ++it) {  // vertices it+1 of both walks
         if (small)
-          q_extend<true><<<g_extend, 256, 0, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+          q_extend<1><<<g_extend, 256, 0, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+        else if (wide)
+          CUDA_TRY(wide_launch_q_extend(g_extend, sm_stack, ls, ctx->dev, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend));
         else
-          q_extend<false><<<g_extend, 256, sm_stack, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+          q_extend<0><<<g_extend, 256, sm_stack, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
         bdpt_vertex<<<g_vertex, 256, 0, ls>>>(ctx->dev, cam, b, cur, first, sample_begin, seed);
         bdpt_ctl_after_walk<<<1, 1, 0, ls>>>(b.ctl);
         launches += 3;
@@ -1118,9 +1154,11 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
       for (int len = 1; len <= kBdptMaxLen; ++len) {
         bdpt_connect<<<g_connect, 256, 0, ls>>>(ctx->dev, cam, b, len, first, n);
         if (small)
-          q_shadow_add<true><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+          q_shadow_add<1><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+        else if (wide)
+          CUDA_TRY(wide_launch_q_shadow_add(g_shadow, sm_stack, ls, ctx->dev, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow));
         else
-          q_shadow_add<false><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+          q_shadow_add<0><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
         bdpt_ctl_after_shadow<<<1, 1, 0, ls>>>(b.ctl);
         launches += 3;
       }
@@ -1209,11 +1247,15 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   FlatScene fs;
   int rc = flatten_scene(desc, &fs);
   if (rc != TUTU_OK) return fail(ctx, rc, get_error());
+  if (ctx->use_wide) build_wide_tree(&fs);
   if (std::max(fs.depth, fs.depth_fast) > (uint32_t)kStackSize)
     return fail(ctx, TUTU_E_INVALID, "scene: BVH deeper than the traversal stack (" + std::to_string(fs.depth) + ")");
   cudaStream_t s = ctx->stream;
   upload_vec(ctx->d_inner, fs.inner, s);
   upload_vec(ctx->d_inner_fast, fs.inner_fast, s);
+  upload_vec(ctx->d_wide, fs.wide, s);
+  upload_vec(ctx->d_wleaf, fs.wleaf, s);
+  upload_vec(ctx->d_wbox, fs.wbox, s);
   upload_vec(ctx->d_geom, fs.geom, s);
   upload_vec(ctx->d_shade, fs.shade, s);
   upload_vec(ctx->d_leaftex, fs.leaftex, s);
@@ -1227,6 +1269,9 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   d.inner = ctx->d_inner.as<float4>();
   d.inner_fast = ctx->d_inner_fast.as<float4>();
   d.root_ref_fast = fs.root_ref_fast;
+  d.wide = (fs.wide.empty() || !ctx->use_wide) ? nullptr : ctx->d_wide.as<float4>();
+  d.wleaf = ctx->d_wleaf.as<float4>();
+  d.wbox = ctx->d_wbox.as<float4>();
   d.geom = ctx->d_geom.as<float4>();
   d.shade = ctx->d_shade.as<float4>();
   d.leaftex = fs.leaftex.empty() ? nullptr : ctx->d_leaftex.as<int4>();
@@ -1278,6 +1323,7 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);  // experiments only
   if (const char* e = getenv("TUTU_PRUNE_ABS")) d.prune_abs = (float)atof(e);
   ctx->scene_bytes = (fs.inner.size() + fs.inner_fast.size()) * sizeof(InnerNode) + fs.geom.size() * sizeof(LeafGeom) +
+                     fs.wide.size() * sizeof(WideNode) + fs.wleaf.size() * sizeof(WideLeaf) + fs.wbox.size() * sizeof(WideLeafBox) +
                      fs.shade.size() * sizeof(LeafShade) + fs.leaftex.size() * sizeof(LeafTex) +
                      fs.slot_to_prim.size() * 4 + fs.materials.size() * sizeof(DevMaterial) +
                      fs.lights.size() * sizeof(DevLight) + fs.texels.size() * 4;
@@ -1300,6 +1346,13 @@ extern "C" int tutu_scene_info(const TutuCtx* ctx, TutuSceneInfo* out) {
   out->width = (uint32_t)f.raygen.width;
   out->height = (uint32_t)f.raygen.height;
   out->device_bytes = ctx->scene_bytes;
+  const bool wide = ctx->dev.wide != nullptr;
+  out->trav_nodes = wide ? (uint32_t)f.wide.size() : (uint32_t)f.inner_fast.size();
+  out->trav_depth = wide ? f.wide_depth : f.depth_fast;
+  out->trav_width = wide ? 8 : 2;
+  out->trav_node_bytes = wide ? (uint32_t)sizeof(WideNode) : (uint32_t)sizeof(InnerNode);
+  out->trav_leaf_bytes = wide ? (uint32_t)sizeof(WideLeaf) : (uint32_t)sizeof(LeafGeom);
+  out->reserved = 0;
   return TUTU_OK;
 }
 
@@ -1320,8 +1373,38 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
 }
 
 extern "C" int tutu_set_traversal_mode(TutuCtx* ctx, int mode) {
-  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || mode == 3 || mode == 4 || (mode >= 10 && mode <= 17)))
+  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || mode == 3 || mode == 4 || mode == 6 || (mode >= 10 && mode <= 17)))
     return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (mode == 6) {
+    // Regular rays walk the compressed 8-wide collapse of the SAH tree (wide.cuh).  Bit-identical hits; measured
+    // SLOWER than the binary walk on a B200 (the exact plane decode makes a node visit ~210
+    // instructions and these kernels are issue bound), so it is an option, not the default.
+    try {
+      CUDA_TRY(cudaSetDevice(ctx->device));
+      ctx->use_wide = true;
+      if (ctx->has_scene && ctx->flat.wide.empty()) {
+        CUDA_TRY(cudaDeviceSynchronize());  // nothing may still read the buffers that are replaced below
+        build_wide_tree(&ctx->flat);
+        upload_vec(ctx->d_wide, ctx->flat.wide, ctx->stream);
+        upload_vec(ctx->d_wleaf, ctx->flat.wleaf, ctx->stream);
+        upload_vec(ctx->d_wbox, ctx->flat.wbox, ctx->stream);
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->dev.wleaf = ctx->d_wleaf.as<float4>();
+        ctx->dev.wbox = ctx->d_wbox.as<float4>();
+      }
+      if (ctx->has_scene) ctx->dev.wide = ctx->flat.wide.empty() ? nullptr : ctx->d_wide.as<float4>();
+    } catch (const CudaError& e) {
+      return fail_cuda(ctx, e);
+    } catch (const std::exception& e) {
+      return fail(ctx, TUTU_E_NOMEM, std::string("tutu_set_traversal_mode: ") + e.what());
+    }
+    ctx->ray_binning = 1;
+    ctx->traversal_mode = 0;
+    return TUTU_OK;
+  }
+  ctx->use_wide = false;
+  ctx->dev.wide = nullptr;
   if (mode == 3) {  // production walk, caller's ray order (no binning)
     ctx->traversal_mode = 0;
     ctx->ray_binning = 0;
@@ -1425,7 +1508,10 @@ extern "C" int tutu_trace_count_visits(TutuCtx* ctx, const float* d_rays, uint64
   if (n_rays) {
     const float4* rays = reinterpret_cast<const float4*>(d_rays);
     const int grid = ctx->sm_count * 8;
-    if (any_hit)
+    if (ctx->dev.wide) {  // visits of the tree the production walk descends (irregular rays are not counted)
+      const WideGrids& g = wide_grids_for(ctx);
+      CUDA_TRY(wide_launch_count(any_hit != 0, grid, g.smem, s, ctx->dev, rays, n_rays, c));
+    } else if (any_hit)
       k_trace_count<true><<<grid, 256, 0, s>>>(ctx->dev, rays, n_rays, c);
     else
       k_trace_count<false><<<grid, 256, 0, s>>>(ctx->dev, rays, n_rays, c);

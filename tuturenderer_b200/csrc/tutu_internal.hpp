@@ -38,6 +38,44 @@ struct alignas(16) LeafGeom {
 };
 static_assert(sizeof(LeafGeom) == 48, "LeafGeom must be 48 bytes");
 
+// Compressed 8-wide node of the traversal tree for regular rays (host_wide.cpp builds it, wide.cuh walks it).
+// 96 bytes = three 32-byte sectors = three LDG.E.256:
+//   [ 0,32)  base2.xyz, scale.xyz, child_base, leaf_base
+//   [32,64)  imask, lmask, 6 pad bytes, qlo[x][8], qlo[y][8], qlo[z][8]
+//   [64,96)  qhi[x][8], qhi[y][8], qhi[z][8], 8 pad bytes
+// Plane decode (bit-identical on host and device): dec(q) = fma(as_float(0x4B000000 | q), scale, base2).
+// Slot s holds an inner child (imask bit s; node child_base + rank of s in imask), a leaf (lmask bit s; leaf record
+// leaf_base + rank of s in lmask) or nothing (inverted box qlo = 255 > qhi = 0).
+struct alignas(32) WideNode {
+  float base2[3];
+  float scale[3];
+  uint32_t child_base;
+  uint32_t leaf_base;
+  uint8_t imask;
+  uint8_t lmask;
+  uint8_t pad0[6];
+  uint8_t qlo[3][8];
+  uint8_t qhi[3][8];
+  uint8_t pad1[8];
+};
+static_assert(sizeof(WideNode) == 96, "WideNode must be 96 bytes");
+
+// Leaf record of the wide tree, in the order the wide nodes reference them: the LeafGeom of the primitive plus
+// its leaf code (DFS slot | sphere bit: the tie rule and the result are in terms of the reference's DFS slots).
+struct alignas(32) WideLeaf {
+  float f[12];
+  uint32_t code;
+  uint32_t pad[3];
+};
+static_assert(sizeof(WideLeaf) == 64, "WideLeaf must be 64 bytes");
+// exact leaf box (the reference tests it before the primitive, BVH.hpp:148,173), same order as WideLeaf
+struct alignas(32) WideLeafBox {
+  float lo[3];
+  float hi[3];
+  float pad[2];
+};
+static_assert(sizeof(WideLeafBox) == 32, "WideLeafBox must be 32 bytes");
+
 // 64-byte shading record per leaf slot:
 // {n0.xyz, uv0.x} {n1.xyz, uv0.y} {n2.xyz, uv1.x} {uv1.y, uv2.x, uv2.y, bits(flags)}
 // flags: material index | TEX_ACTIVE_BIT | SPHERE flag bit 30
@@ -127,6 +165,10 @@ struct FlatScene {
   std::vector<InnerNode> inner_fast;  // SAH topology over the same leaves (regular rays), host_scene.cpp
   int32_t root_ref_fast = 0;
   uint32_t depth_fast = 0;
+  std::vector<WideNode> wide;      // compressed 8-wide collapse of inner_fast (empty: the device walks inner_fast)
+  std::vector<WideLeaf> wleaf;
+  std::vector<WideLeafBox> wbox;
+  uint32_t wide_depth = 0;         // levels of wide nodes, root = 1
   std::vector<LeafGeom> geom;
   std::vector<LeafShade> shade;
   std::vector<LeafTex> leaftex;
@@ -154,6 +196,9 @@ extern const char* (*g_ctx_error_hook)(const TutuCtx*);
 
 // Validates the desc, builds the BVH if none is given, flattens to device layout.
 int flatten_scene(const TutuSceneDesc* desc, FlatScene* out);
+// host_wide.cpp
+void build_wide_tree(FlatScene* fs);
+uint64_t verify_wide_tree(const FlatScene& fs);
 int compute_raygen(const TutuCamera* cam, RayGen* out);
 int compute_bdpt_cam(const TutuCamera* cam, BdptCamConsts* out);
 

@@ -17,73 +17,9 @@
 #pragma once
 #include <cstddef>
 #include "vertex.cuh"
+#include "wf_types.cuh"
 
 namespace tutu {
-
-struct WfCtl {
-  unsigned n_cur;
-  unsigned done;
-  // n_next (low word) and n_shadow (high word) are bumped by ONE 64-bit atomicAdd per block of wf_shade
-  unsigned n_next;
-  unsigned n_shadow;
-  unsigned long long next_path;
-  unsigned long long total_paths;
-  unsigned long long sum_extend;
-  unsigned long long sum_shadow;
-  unsigned long long nan_samples;
-  unsigned long long iterations;
-  unsigned long long cursor_extend;  // ray-queue cursors of the persistent tracers
-  unsigned long long cursor_shadow;
-  unsigned class_count[8];  // wf_classify: queue entries per shading class (kShadeClasses)
-};
-static_assert(offsetof(WfCtl, n_next) % 8 == 0 && offsetof(WfCtl, n_shadow) == offsetof(WfCtl, n_next) + 4,
-              "n_next/n_shadow must form one aligned 64-bit word");
-
-struct WfBuffers {
-  // path queues, [2] = ping-pong
-  float4* ray_o[2];  // o.xyz, roulette number of the vertex that spawned the ray (Philox slot 5 of its depth)
-  float4* ray_d[2];  // d.xyz, q = 2 (o - x_prev) . d, the cross term of |x_hit - x_prev|^2 (shade_vertex)
-  float4* st0[2];    // beta.xyz, bits(pixel)
-  float4* st1[2];    // tp.xyz, bits(sample)
-  float4* st2[2];    // L.xyz, bits(depth | mode<<8 | flags)
-  float4* st3[2];    // f_r*cos_theta of the previous vertex .xyz, mat_pdf
-  float4* hit;       // t, u, v, bits(slot code)
-  // shadow queue
-  float4* sh_o;  // o.xyz, dist
-  float4* sh_d;  // d.xyz, bits(destination index in the next path queue | kShadowFinal)
-  float4* sh_c;  // beta * NEE term .xyz, bits(pixel)
-  float4* sh_L;  // L.xyz of a path that already ended (only for kShadowFinal)
-  WfCtl* ctl;
-  float* accum;  // width*height*3 sums
-  unsigned capacity;
-  // shading-class order of the current queue (wf_classify), kShadeClasses lists of `capacity` entries;
-  // nullptr = shade in queue order (scenes with one shading class)
-  unsigned* class_perm;
-};
-
-__device__ __forceinline__ void accum_add(float* accum, WfCtl* ctl, uint32_t pixel, f3 L) {
-  // PathTracing.hpp:510-511: a sample with any NaN component is dropped (still divided by SPP)
-  if (any_nan(L)) {
-    atomicAdd(&ctl->nan_samples, 1ull);
-    return;
-  }
-  float* p = accum + (size_t)pixel * 3;
-  atomicAdd(p + 0, L.x);
-  atomicAdd(p + 1, L.y);
-  atomicAdd(p + 2, L.z);
-}
-
-// warp-aggregated append: one atomicAdd per warp, lanes take consecutive slots
-__device__ __forceinline__ unsigned warp_append(unsigned* counter, bool want) {
-  const unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
-  if (mask == 0u) return 0u;
-  const unsigned lane = threadIdx.x & 31u;
-  const int leader = __ffs(mask) - 1;
-  unsigned base = 0u;
-  if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
-  base = __shfl_sync(0xFFFFFFFFu, base, leader);
-  return base + (unsigned)__popc(mask & ((1u << lane) - 1u));
-}
 
 // ---- control ---------------------------------------------------------------------------------
 __global__ void wf_ctl_after_raygen(WfCtl* ctl, unsigned capacity) {
@@ -137,15 +73,11 @@ wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
 }
 
 // ---- extend: IIntersectStrategy::UpdateInter -> getIntersection -------------------------------
-#ifndef TUTU_PACKET_RAYS
-#define TUTU_PACKET_RAYS 128
-#endif
-constexpr unsigned kPacketRays = TUTU_PACKET_RAYS;  // rays per queue fetch (one same-address atomic each)
-
 // Ray packets pulled from the queue with one atomicAdd per warp (lane 0) and a shuffle
 // broadcast: a warp that drew short rays moves on to the next packet instead of idling behind the
 // slowest warp of a statically partitioned grid.
-template <bool SMALL>
+// KIND: 0 = binary trees (trace.cuh), 1 = small scene (flat tests); the wide-tree tracers are in trace_kernels.cu
+template <int KIND>
 __global__ void __launch_bounds__(256)
 wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int cur) {
   extern __shared__ unsigned long long s_stack[];  // !SMALL: traversal stack (trace.cuh: SharedStack)
@@ -165,7 +97,7 @@ wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
         const float4 o = __ldcs(ro + i);
         const float4 d = __ldcs(rd + i);
         Hit h;
-        if (SMALL)
+        if constexpr (KIND == 1)
           traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
         else  // incoherent queue: per-lane walk (batched primitive tests only pay on sorted batches)
           traverse_shared<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack);
@@ -177,7 +109,7 @@ wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
 }
 
 // ---- shadow: isShadowRayBlocked -> hasIntersection, then the deferred NEE add ------------------
-template <bool SMALL>
+template <int KIND>
 __global__ void __launch_bounds__(256)
 wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int nxt) {
   const unsigned n = b.ctl->n_shadow;
@@ -194,8 +126,11 @@ wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
         const float4 o = __ldcs(b.sh_o + j);
         const float4 d = __ldcs(b.sh_d + j);
         Hit h;
-        const bool blocked = SMALL ? traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h)
-                                   : traverse_variant<true, 3>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+        bool blocked;
+        if constexpr (KIND == 1)
+          blocked = traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+        else
+          blocked = traverse_variant<true, 3>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
         const unsigned dst = __float_as_uint(d.w);
         if (dst == kShadowFinal) {
           const float4 c = __ldcs(b.sh_c + j);
