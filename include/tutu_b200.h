@@ -201,7 +201,9 @@ int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam);
 int tutu_trace_closest(TutuCtx* ctx, const float* rays, uint64_t n_rays, TutuHit* hits_out);
 int tutu_trace_any(TutuCtx* ctx, const float* rays, uint64_t n_rays, uint8_t* blocked_out);
 /* Device buffers (CUDA device pointers valid on the ctx's device), asynchronous on `stream`
- * (a cudaStream_t / CUstream passed as void*, NULL = the ctx's own stream). */
+ * (a cudaStream_t / CUstream passed as void*, NULL = the ctx's own stream).  Batches may be enqueued on
+ * different streams: the context's work cursor and binning scratch are handed from one batch to the next with
+ * an event, so batches of one context run one after the other on the device. */
 int tutu_trace_closest_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays,
                               TutuHit* d_hits_out, void* stream);
 int tutu_trace_any_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays,
@@ -209,7 +211,8 @@ int tutu_trace_any_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays,
 /* Traversal variant: 0 = ordered + t-pruned walk, large batches traced in a coherent order
  * (counting sort by entry cell + direction bin; results are order independent) — the default;
  * 3 = the same walk in the caller's ray order; 1 = unpruned both-children walk that mirrors the
- * reference's recursion literally (used as a second opinion by the tests);
+ * reference's recursion literally (used as a second opinion by the tests); 4 = the general tree walk also on scenes
+ * of <= 32 primitives, for ray batches and renders (otherwise their flat leaf-box kernels are used);
  * 6 = as 0, but regular rays (every 1/d finite) walk the compressed 8-wide collapse of the traversal tree (8-bit
  * child boxes quantised outwards, decoded exactly; built on the first use).  Same hits bit for bit; on a B200 it
  * is slower than the binary walk, so it is an option. */

@@ -218,7 +218,7 @@ def test_small_scene_with_spheres_same_stream(api, oracle, ctx, cornell):
     d = np.abs(g - o)
     # <= 3 % of the pixels (12 paths each) hold a path that took another branch: the spheres fill a third
     # of the frame and Sphere::intersect / the normalisations differ from libm in the last place.  The
-    # tree walk (TUTU_NO_SMALL=1) gives the same 2.3 % and the same ray counts as the flat kernels.
+    # tree walk (traversal mode 4) gives the same 2.3 % and the same ray counts as the flat kernels.
     assert (d > 1e-3 * (1 + np.abs(o))).any(-1).mean() < 0.03
     assert np.median(d) < 1e-6
     assert abs(g.mean() / o.mean() - 1) < 5e-3
@@ -281,7 +281,7 @@ def test_scene_switch_between_trees_of_different_depth(api, ctx, golden):
     assert means[0] == pytest.approx(means[3], rel=1e-5)
 
 
-def test_small_scene_kernels_equal_the_tree_walk_at_full_size(api, ctx, cornell, monkeypatch):
+def test_small_scene_kernels_equal_the_tree_walk_at_full_size(api, ctx, cornell):
     """BASELINE size (1024x1024): the flat small-scene kernels (distinct-box slab tests, parked rays) and the
     general stack walk over the same tree must find the same hit for every one of the 10^7 queued rays, so
     the two renders trace the same paths: equal ray counts, images equal up to the order of the float
@@ -290,12 +290,10 @@ def test_small_scene_kernels_equal_the_tree_walk_at_full_size(api, ctx, cornell,
     ctx.upload(sc)
     a = ctx.render_path(2, seed=13)
     sa = ctx.stats()
-    monkeypatch.setenv("TUTU_NO_SMALL", "1")  # read by tutu_scene_upload
-    ctx.upload(sc)
+    ctx.set_traversal_mode(4)  # the general tree walk instead of the small-scene kernels
     b = ctx.render_path(2, seed=13)
     sb = ctx.stats()
-    monkeypatch.delenv("TUTU_NO_SMALL")
-    ctx.upload(sc)
+    ctx.set_traversal_mode(0)
     for k in ("paths", "extend_rays", "shadow_rays", "nan_samples"):
         assert sa[k] == sb[k], k
     assert np.allclose(a, b, rtol=2e-5, atol=1e-6)

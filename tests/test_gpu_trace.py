@@ -290,6 +290,37 @@ def test_binned_order_gives_identical_results(api, oracle, ctx):
         assert np.array_equal(b[sub], osc.trace_any(np.ascontiguousarray(rays[sub])))
 
 
+def test_batches_on_different_streams_do_not_share_a_cursor(api, ctx):
+    """tutu_trace_*_device is asynchronous on the caller's stream, and the context's work cursor and binning scratch
+    are shared: batches enqueued back to back on DIFFERENT streams must still each trace all of their rays."""
+    import torch
+    prims = api.synth_heightfield(96)
+    ctx.upload(api.Scene(prims=prims, materials=api.default_material()))
+    n = 1 << 18
+    rays = [torch.from_numpy(api.synth_rays(k % 2, n, seed=100 + k)).cuda() for k in range(4)]
+    want_h, want_a = [], []
+    for r in rays:  # serial reference on one stream
+        h = torch.full((n, 4), -7.0, dtype=torch.float32, device="cuda")
+        a = torch.full((n,), 9, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.trace_closest_device(r.data_ptr(), n, h.data_ptr())
+        ctx.trace_any_device(r.data_ptr(), n, a.data_ptr())
+        torch.cuda.synchronize()
+        want_h.append(h), want_a.append(a)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    for rep in range(3):
+        got_h = [torch.full((n, 4), -7.0, dtype=torch.float32, device="cuda") for _ in rays]
+        got_a = [torch.full((n,), 9, dtype=torch.uint8, device="cuda") for _ in rays]
+        torch.cuda.synchronize()
+        for k, r in enumerate(rays):  # no synchronisation between the calls
+            ctx.trace_closest_device(r.data_ptr(), n, got_h[k].data_ptr(), streams[k].cuda_stream)
+            ctx.trace_any_device(r.data_ptr(), n, got_a[k].data_ptr(), streams[(k + 1) % 4].cuda_stream)
+        torch.cuda.synchronize()
+        for k in range(4):
+            assert bool((got_h[k].view(torch.int32) == want_h[k].view(torch.int32)).all()), (rep, k)
+            assert bool((got_a[k] == want_a[k]).all()), (rep, k)
+
+
 def _tri_prims(api, v):
     """(n,3,3) vertices -> TutuPrim triangles with flat normals."""
     v = np.asarray(v, np.float32)

@@ -121,6 +121,25 @@ def test_scene_file_errors(api, tmp_path):
         api.Scene.load(bad)
 
 
+def test_scene_file_with_corrupt_counts_is_an_error_not_a_crash(api, mixed, tmp_path):
+    """Header counts are bounded by the file size before anything is allocated (a flipped count must not become a
+    multi-gigabyte resize or an exception escaping the C ABI)."""
+    p = tmp_path / "m.tscene"
+    mixed.save(p)
+    raw = bytearray(p.read_bytes())
+    for offset in (12, 16, 20, 24):  # n_prims, n_materials, n_bvh_nodes, n_tex[0]
+        bad = bytearray(raw)
+        bad[offset:offset + 4] = (0xFFFFFFF0).to_bytes(4, "little")
+        q = tmp_path / f"bad{offset}.tscene"
+        q.write_bytes(bad)
+        with pytest.raises(api.TutuError) as e:
+            api.Scene.load(q)
+        assert e.value.code == -4
+    (tmp_path / "cut.tscene").write_bytes(bytes(raw[: len(raw) // 2]))
+    with pytest.raises(api.TutuError):
+        api.Scene.load(tmp_path / "cut.tscene")
+
+
 def test_synth_is_deterministic(api, golden):
     a, b = api.synth_heightfield(24, 12345), api.synth_heightfield(24, 12345)
     assert np.array_equal(a, b)

@@ -133,8 +133,14 @@ _lib = None
 CUDA_STREAM_LEGACY = 1
 
 
-def stream_handle(stream: int) -> int:
-    """Maps a torch `cuda_stream` integer to the handle the C ABI expects."""
+CTX_STREAM = "ctx"  # opt-in: the context's own non-blocking stream (NOT ordered with torch's streams)
+
+
+def stream_handle(stream) -> int | None:
+    """Maps a stream argument of the Context methods to the handle the C ABI expects: a torch `cuda_stream`
+    integer (0 = the legacy default stream, where torch's default-stream work is ordered) or CTX_STREAM."""
+    if stream == CTX_STREAM:
+        return None
     return stream if stream else CUDA_STREAM_LEGACY
 
 
@@ -439,10 +445,10 @@ class Context:
         self._ck(lib().tutu_trace_any(self._h, rays_ptr, n, out_ptr))
 
     def trace_closest_device(self, d_rays: int, n: int, d_hits: int, stream: int = 0) -> None:
-        self._ck(lib().tutu_trace_closest_device(self._h, d_rays, n, d_hits, stream or None))  # 0 = ctx stream
+        self._ck(lib().tutu_trace_closest_device(self._h, d_rays, n, d_hits, stream_handle(stream)))
 
     def trace_any_device(self, d_rays: int, n: int, d_out: int, stream: int = 0) -> None:
-        self._ck(lib().tutu_trace_any_device(self._h, d_rays, n, d_out, stream or None))
+        self._ck(lib().tutu_trace_any_device(self._h, d_rays, n, d_out, stream_handle(stream)))
 
     def count_visits(self, d_rays: int, n: int, any_hit: bool) -> tuple[int, int]:
         a, b = C.c_uint64(0), C.c_uint64(0)
@@ -474,10 +480,10 @@ class Context:
     def render_accumulate_device(self, sample_begin: int, sample_count: int, seed: int, d_accum: int,
                                  stream: int = 0) -> None:
         self._ck(lib().tutu_render_path_accumulate_device(self._h, sample_begin, sample_count, seed, d_accum,
-                                                          stream or None))
+                                                          stream_handle(stream)))
 
     def finalize_device(self, d_accum: int, inv_spp: float, d_out: int, stream: int = 0) -> None:
-        self._ck(lib().tutu_finalize_device(self._h, d_accum, inv_spp, d_out, stream or None))
+        self._ck(lib().tutu_finalize_device(self._h, d_accum, inv_spp, d_out, stream_handle(stream)))
 
     # ---- bidirectional path tracing (IIntegrator::integrate of the reference's BDPT)
     def render_bdpt(self, spp: int, seed: int = 1, out: np.ndarray | None = None) -> np.ndarray:
@@ -493,10 +499,10 @@ class Context:
     def render_bdpt_accumulate_device(self, sample_begin: int, sample_count: int, seed: int, d_accum: int,
                                       stream: int = 0) -> None:
         self._ck(lib().tutu_render_bdpt_accumulate_device(self._h, sample_begin, sample_count, seed, d_accum,
-                                                          stream or None))
+                                                          stream_handle(stream)))
 
     def finalize_bdpt_device(self, d_accum: int, inv_spp: float, d_out: int, stream: int = 0) -> None:
-        self._ck(lib().tutu_finalize_bdpt_device(self._h, d_accum, inv_spp, d_out, stream or None))
+        self._ck(lib().tutu_finalize_bdpt_device(self._h, d_accum, inv_spp, d_out, stream_handle(stream)))
 
     # ---- output stage (PPMGenerator::writePixel)
     def quantize(self, rgb: np.ndarray, gamma: float = 0.78) -> np.ndarray:
@@ -506,7 +512,7 @@ class Context:
         return out
 
     def quantize_device(self, d_rgb: int, n_pixels: int, d_out: int, gamma: float = 0.78, stream: int = 0) -> None:
-        self._ck(lib().tutu_quantize_device(self._h, d_rgb, n_pixels, gamma, d_out, stream or None))
+        self._ck(lib().tutu_quantize_device(self._h, d_rgb, n_pixels, gamma, d_out, stream_handle(stream)))
 
     # ---- output stage (Postprocessor: bloom / exposure tone map)
     def postprocess(self, rgb: np.ndarray, mode: str = "hdr_bloom", params: TutuPostParams | None = None) -> np.ndarray:
@@ -520,7 +526,7 @@ class Context:
     def postprocess_device(self, d_rgb: int, width: int, height: int, d_out: int, mode: str = "hdr_bloom",
                            params: TutuPostParams | None = None, stream: int = 0) -> None:
         self._ck(lib().tutu_postprocess_device(self._h, d_rgb, width, height, POST_MODES[mode],
-                                               C.byref(params) if params is not None else None, d_out, stream or None))
+                                               C.byref(params) if params is not None else None, d_out, stream_handle(stream)))
 
     def stats(self) -> dict:
         s = TutuRenderStats()

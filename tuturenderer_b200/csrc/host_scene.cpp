@@ -368,7 +368,10 @@ static void build_fast_tree(FlatScene* fs, const std::vector<uint32_t>& leaf_cod
   fs->inner_fast = fs->inner;
   fs->root_ref_fast = fs->root_ref;
   fs->depth_fast = fs->depth;
-  if (n < 3 || getenv("TUTU_NO_FAST_TREE")) return;
+  if (n < 3) return;
+#ifdef TUTU_EXPERIMENTS
+  if (getenv("TUTU_NO_FAST_TREE")) return;
+#endif
   for (const Box& b : fs->leaf_box)
     for (int a = 0; a < 3; ++a)
       if (!std::isfinite(b.lo[a]) || !std::isfinite(b.hi[a])) return;
@@ -879,11 +882,19 @@ extern "C" int tutu_bvh_build(const TutuPrim* prims, uint32_t n_prims, TutuBvhNo
       set_error("tutu_bvh_build: unknown primitive type");
       return TUTU_E_INVALID;
     }
-  std::vector<TutuBvhNode> nodes;
-  build_bvh(prims, n_prims, &nodes);
-  memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(TutuBvhNode));
-  *n_nodes_out = (uint32_t)nodes.size();
-  return TUTU_OK;
+  try {
+    std::vector<TutuBvhNode> nodes;
+    build_bvh(prims, n_prims, &nodes);
+    memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(TutuBvhNode));
+    *n_nodes_out = (uint32_t)nodes.size();
+    return TUTU_OK;
+  } catch (const std::bad_alloc&) {
+    set_error("tutu_bvh_build: out of host memory");
+    return TUTU_E_NOMEM;
+  } catch (const std::exception& e) {  // std::system_error from std::thread in the parallel build
+    set_error(std::string("tutu_bvh_build: ") + e.what());
+    return TUTU_E_INVALID;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -974,6 +985,23 @@ extern "C" int tutu_scene_file_load(const char* path, TutuSceneFile** out) {
     set_error(std::string("tutu_scene_file_load: not a TUTUSCN1 file: ") + path);
     return TUTU_E_IO;
   }
+  // a corrupt header must not turn into a huge allocation: the counts are bounded by the file size
+  long file_bytes = 0;
+  {
+    const long here = ftell(f.get());
+    if (here < 0 || fseek(f.get(), 0, SEEK_END) != 0 || (file_bytes = ftell(f.get())) < 0 || fseek(f.get(), here, SEEK_SET) != 0) {
+      set_error(std::string("tutu_scene_file_load: cannot size ") + path);
+      return TUTU_E_IO;
+    }
+  }
+  const uint64_t need = (uint64_t)h.n_prims * sizeof(TutuPrim) + (uint64_t)h.n_materials * sizeof(TutuMaterial) +
+                        (uint64_t)h.n_bvh_nodes * sizeof(TutuBvhNode) +
+                        ((uint64_t)h.n_tex[0] + h.n_tex[1] + h.n_tex[2] + h.n_tex[3]) * 8u;
+  if (need + sizeof(FileHeader) > (uint64_t)file_bytes) {
+    set_error(std::string("tutu_scene_file_load: truncated or corrupt file (header counts exceed the file size): ") + path);
+    return TUTU_E_IO;
+  }
+  try {
   std::unique_ptr<TutuSceneFile> sf(new TutuSceneFile());
   bool ok = true;
   sf->prims.resize(h.n_prims);
@@ -991,7 +1019,7 @@ extern "C" int tutu_scene_file_load(const char* path, TutuSceneFile** out) {
     for (uint32_t i = 0; ok && i < h.n_tex[c]; ++i) {
       int32_t wh[2];
       ok &= fread(wh, sizeof(wh), 1, f.get()) == 1;
-      if (!ok || wh[0] < 0 || wh[1] < 0 || (size_t)wh[0] * wh[1] > (1u << 28)) {
+      if (!ok || wh[0] < 0 || wh[1] < 0 || (uint64_t)wh[0] * (uint64_t)wh[1] * 12u > (uint64_t)file_bytes) {
         ok = false;
         break;
       }
@@ -1023,6 +1051,13 @@ extern "C" int tutu_scene_file_load(const char* path, TutuSceneFile** out) {
   d.eta = h.eta;
   *out = sf.release();
   return TUTU_OK;
+  } catch (const std::bad_alloc&) {
+    set_error(std::string("tutu_scene_file_load: out of host memory reading ") + path);
+    return TUTU_E_NOMEM;
+  } catch (const std::exception& e) {
+    set_error(std::string("tutu_scene_file_load: ") + e.what());
+    return TUTU_E_IO;
+  }
 }
 
 extern "C" const TutuSceneDesc* tutu_scene_file_desc(const TutuSceneFile* f) {

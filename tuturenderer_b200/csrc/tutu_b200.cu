@@ -143,6 +143,10 @@ struct TutuCtx {
   // host-buffer ray batches are pipelined in chunks over kHostSlots streams (H2D | walk | D2H overlap)
   cudaStream_t slot_streams[kHostSlotsMax] = {};  // [0] unused (slot 0 runs on `stream`)
   DevBuf d_chunk_rays[kHostSlotsMax], d_chunk_out[kHostSlotsMax];
+  // The work cursor and the binning scratch of a slot are shared by every batch traced through it; batches
+  // may arrive on different caller streams, so each launch waits for the slot's previous user and marks itself
+  // as the last one (the batches of one slot run back to back on the device, whatever their streams).
+  cudaEvent_t slot_last_use[kHostSlotsMax] = {};
   int ray_binning = 1;              // 0 = trace in the caller's order
   uint64_t ray_binning_min = 1u << 16;
 
@@ -202,7 +206,9 @@ int fail_cuda(TutuCtx* ctx, const CudaError& e) {
 #define API_END(ctx)                                                   \
   }                                                                    \
   catch (const CudaError& e) { return fail_cuda((ctx), e); }           \
-  catch (const std::bad_alloc&) { return fail((ctx), TUTU_E_NOMEM, "out of host memory"); }
+  catch (const std::bad_alloc&) { return fail((ctx), TUTU_E_NOMEM, "out of host memory"); } \
+  catch (const std::exception& e) { return fail((ctx), TUTU_E_INVALID, std::string("unexpected exception: ") + e.what()); } \
+  catch (...) { return fail((ctx), TUTU_E_INVALID, "unexpected exception"); }
 
 // ---------------------------------------------------------------------------------------------
 // ray-batch kernels
@@ -590,9 +596,9 @@ int persistent_grid(TutuCtx* ctx, K kernel, int block, size_t dyn_smem = 0) {
   if (dyn_smem) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dyn_smem));
   if (per_sm < 1) per_sm = 1;
-  if (const char* e = getenv("TUTU_GRID_DIV")) {  // experiments only: leave room for a co-running kernel
-    per_sm = std::max(1, per_sm / std::max(1, atoi(e)));
-  }
+#ifdef TUTU_EXPERIMENTS
+  if (const char* e = getenv("TUTU_GRID_DIV")) per_sm = std::max(1, per_sm / std::max(1, atoi(e)));  // room for a co-running kernel
+#endif
   return ctx->sm_count * per_sm;  // a multiple of the SM count: one resident wave
 }
 
@@ -609,6 +615,15 @@ const WideGrids& wide_grids_for(TutuCtx* ctx) {
   if (ctx->wide_grids.smem != sm) CUDA_TRY(wide_grids(ctx->sm_count, sm, &ctx->wide_grids));
   return ctx->wide_grids;
 }
+
+// Orders the stream after the previous batch that used the slot's cursor / binning scratch.
+void slot_acquire(TutuCtx* ctx, int slot, cudaStream_t s) {
+  if (!ctx->slot_last_use[slot])
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_last_use[slot], cudaEventDisableTiming));
+  else
+    CUDA_TRY(cudaStreamWaitEvent(s, ctx->slot_last_use[slot], 0));
+}
+void slot_release(TutuCtx* ctx, int slot, cudaStream_t s) { CUDA_TRY(cudaEventRecord(ctx->slot_last_use[slot], s)); }
 
 // Builds the coherent traversal order of a batch (nullptr = trace in the caller's order).
 const unsigned* bin_rays(TutuCtx* ctx, const float4* rays, uint64_t n, cudaStream_t s, int slot = 0) {
@@ -635,6 +650,7 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
   if (n == 0) return;
   ctx->d_counts.ensure(256);
   unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 4 + 2 * slot;  // cursors: [4] closest, [5] any, [6],[7] slot 1
+  slot_acquire(ctx, slot, s);
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
   if (ctx->traversal_mode >= 10) {
@@ -671,12 +687,14 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
     }
   }
   CUDA_TRY(cudaGetLastError());
+  slot_release(ctx, slot, s);
 }
 
 void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, cudaStream_t s, int slot = 0) {
   if (n == 0) return;
   ctx->d_counts.ensure(256);
   unsigned long long* next = ctx->d_counts.as<unsigned long long>() + 5 + 2 * slot;
+  slot_acquire(ctx, slot, s);
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
   if (ctx->traversal_mode >= 10) {
@@ -712,14 +730,18 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
     }
   }
   CUDA_TRY(cudaGetLastError());
+  slot_release(ctx, slot, s);
 }
+
+// small-scene kernels (flat leaf-box tests) unless traversal mode 4 forces the general tree walk
+bool use_small(const TutuCtx* ctx) { return ctx->small.n > 0 && ctx->traversal_mode != 4; }
 
 int check_scene(TutuCtx* ctx) {
   if (!ctx->has_scene) return fail(ctx, TUTU_E_STATE, "no scene uploaded (call tutu_scene_upload first)");
   return TUTU_OK;
 }
 int check_pipeline(TutuCtx* ctx) {
-  if (ctx->pipeline_cfg == 2 && ctx->small.n <= 0)
+  if (ctx->pipeline_cfg == 2 && !use_small(ctx))
     return fail(ctx, TUTU_E_STATE, "the register-resident pipeline needs a scene of at most 32 primitives");
   return TUTU_OK;
 }
@@ -823,7 +845,9 @@ void resident_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count,
   const uint64_t threads = (uint64_t)ctx->grid_resident * TUTU_RESIDENT_BLOCK;
   // samples per work item: 64, less when the frame is too small to give every lane ~4 items
   uint32_t chunk = 64;
+#ifdef TUTU_EXPERIMENTS
   if (const char* e = getenv("TUTU_RESIDENT_CHUNK")) chunk = (uint32_t)std::max(1, atoi(e));
+#endif
   while (chunk > 1 && npix * ((sample_count + chunk - 1) / chunk) < 4 * threads) chunk /= 2;
   chunk = std::min(chunk, sample_count);
   ResidentArgs a{};
@@ -879,7 +903,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   // per path once its queues fill.  Measured on Cornell (tools/gpu_small_frames.py, device ms wavefront /
   // resident): 0.07 M paths 0.44 / 0.13, 0.26 M 0.57 / 0.27, 1.05 M 0.92 / 0.92, 4.2 M 2.4 / 3.4.
   constexpr uint64_t kResidentBelowPaths = 768u << 10;
-  if (ctx->small.n > 0 && (ctx->pipeline_cfg == 2 || (ctx->pipeline_cfg == 0 &&
+  if (use_small(ctx) && (ctx->pipeline_cfg == 2 || (ctx->pipeline_cfg == 0 &&
                                                        (uint64_t)ctx->flat.raygen.width * ctx->flat.raygen.height * sample_count < kResidentBelowPaths)))
     return resident_render(ctx, sample_begin, sample_count, seed, d_accum, s);
   const FlatScene& f = ctx->flat;
@@ -898,17 +922,20 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   while (n_lanes > 1 && (sample_count < (uint32_t)n_lanes || total / n_lanes < cap_cfg / 2)) --n_lanes;
   if ((int)ctx->wf_lanes.size() < n_lanes) ctx->wf_lanes.resize(n_lanes);
   // the cached grids depend on the scene through the kernel variants and the traversal-stack size
-  const bool wide = ctx->small.n == 0 && ctx->dev.wide != nullptr;
-  const size_t want_stack = ctx->small.n > 0 ? 0 : (wide ? wide_stack_smem(ctx, 256) : stack_smem(ctx, 256, false));
-  if (ctx->grid_lanes != n_lanes || ctx->grid_small != (ctx->small.n > 0) || ctx->grid_shade_block != ctx->shade_block ||
+  const bool small = use_small(ctx);
+  const bool wide = !small && ctx->dev.wide != nullptr;
+  const size_t want_stack = small ? 0 : (wide ? wide_stack_smem(ctx, 256) : stack_smem(ctx, 256, false));
+  if (ctx->grid_lanes != n_lanes || ctx->grid_small != small || ctx->grid_shade_block != ctx->shade_block ||
       ctx->grid_stack_smem != want_stack || ctx->grid_wide != wide) {
     ctx->grid_stack_smem = want_stack;
     ctx->grid_wide = wide;
     ctx->grid_shade_block = ctx->shade_block;
-    ctx->grid_small = ctx->small.n > 0;
-    const int div = getenv("TUTU_GRID_SPLIT") ? n_lanes : 1;  // experiments only: split the resident blocks between the lanes
+    ctx->grid_small = small;
+    int div = 1;
+#ifdef TUTU_EXPERIMENTS
+    if (getenv("TUTU_GRID_SPLIT")) div = n_lanes;  // split the resident blocks between the lanes
+#endif
     auto sized = [&](int full) { return ctx->sm_count * std::max(1, full / ctx->sm_count / div); };
-    const bool small = ctx->small.n > 0;
     ctx->grid_extend = sized(small  ? persistent_grid(ctx, wf_extend_small, kSmallBlock)
                              : wide ? wide_grids_for(ctx).wf_extend
                                     : persistent_grid(ctx, wf_extend<0>, 256, want_stack));
@@ -921,7 +948,6 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   }
   RayGenK rk;
   fill_raygen(f, &rk);
-  const bool small = ctx->small.n > 0;
 
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
@@ -1104,7 +1130,7 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
   int n_lanes = ctx->lanes_cfg > 0 ? std::min(ctx->lanes_cfg, 2) : 2;
   if (n_batches < 2) n_lanes = 1;
   for (int k = 0; k < n_lanes; ++k) bdpt_prepare(ctx, ctx->bdpt_lanes[k], cap);
-  const bool small = ctx->small.n > 0;
+  const bool small = use_small(ctx);
   const BdptCam& cam = f.bdpt_cam;
   const int g_start = persistent_grid(ctx, bdpt_start, 256);
   const int g_vertex = persistent_grid(ctx, bdpt_vertex, 256);
@@ -1229,6 +1255,10 @@ extern "C" int tutu_ctx_create(int device, TutuCtx** out) {
     return fail_cuda(nullptr, e);
   } catch (const std::bad_alloc&) {
     return fail(nullptr, TUTU_E_NOMEM, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(nullptr, TUTU_E_INVALID, std::string("tutu_ctx_create: ") + e.what());
+  } catch (...) {
+    return fail(nullptr, TUTU_E_INVALID, "tutu_ctx_create: unexpected exception");
   }
 }
 
@@ -1239,6 +1269,8 @@ extern "C" void tutu_ctx_destroy(TutuCtx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   for (cudaStream_t st : ctx->slot_streams)
     if (st) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : ctx->slot_last_use)
+    if (ev) cudaEventDestroy(ev);
   delete ctx;
 }
 
@@ -1291,7 +1323,7 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   d.prune_abs = fs.max_edge * (1.0f / 512.0f);
   d.sphere_mask = 0u;
   ctx->small = SmallScene{};
-  if (!fs.empty && fs.n_prims <= (uint32_t)kSmallMax && !getenv("TUTU_NO_SMALL")) {
+  if (!fs.empty && fs.n_prims <= (uint32_t)kSmallMax) {
     ctx->small.n = (int)fs.n_prims;
     SmallScene& sm = ctx->small;
     for (uint32_t k = 0; k < fs.n_prims; ++k) {
@@ -1299,7 +1331,7 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
       for (int a = 0; a < 3; ++a) b[a] = make_float2(fs.leaf_box[k].lo[a], fs.leaf_box[k].hi[a]);
       int j = 0;  // bitwise-identical bounds share one slab test
       while (j < sm.n_boxes && memcmp(sm.box[j], b, sizeof(b)) != 0) ++j;
-      if (j == sm.n_boxes || getenv("TUTU_NO_BOX_DEDUPE")) {
+      if (j == sm.n_boxes) {
         j = sm.n_boxes++;
         memcpy(sm.box[j], b, sizeof(b));
       }
@@ -1313,15 +1345,20 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
     for (const DevMaterial& m : fs.materials) simple = simple && m.type == TUTU_MAT_LAMBERTIAN;
     for (const LeafShade& ls : fs.shade) simple = simple && !(ls.flags & TEX_ACTIVE_BIT);
     ctx->shade_block = simple ? kShadeBlockSimple : TUTU_SHADE_BLOCK;
-    ctx->sort_by_class = !simple && !getenv("TUTU_NO_CLASS_SORT");
-    if (const char* e = getenv("TUTU_SHADE_BLOCK_RT")) ctx->shade_block = atoi(e);  // experiments only
+    ctx->sort_by_class = !simple;
+#ifdef TUTU_EXPERIMENTS
+    if (getenv("TUTU_NO_CLASS_SORT")) ctx->sort_by_class = false;
+    if (const char* e = getenv("TUTU_SHADE_BLOCK_RT")) ctx->shade_block = atoi(e);
+#endif
   }
   d.refill_min = 8;
   d.leaf_batch = kLeafBatch;
-  if (const char* e = getenv("TUTU_LEAF_BATCH")) d.leaf_batch = atoi(e);  // experiments only
-  if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);  // experiments only
-  if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);  // experiments only
+#ifdef TUTU_EXPERIMENTS  // never in the shipped library: the pruning slack is part of the parity argument (trace.cuh)
+  if (const char* e = getenv("TUTU_LEAF_BATCH")) d.leaf_batch = atoi(e);
+  if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);
+  if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);
   if (const char* e = getenv("TUTU_PRUNE_ABS")) d.prune_abs = (float)atof(e);
+#endif
   ctx->scene_bytes = (fs.inner.size() + fs.inner_fast.size()) * sizeof(InnerNode) + fs.geom.size() * sizeof(LeafGeom) +
                      fs.wide.size() * sizeof(WideNode) + fs.wleaf.size() * sizeof(WideLeaf) + fs.wbox.size() * sizeof(WideLeafBox) +
                      fs.shade.size() * sizeof(LeafShade) + fs.leaftex.size() * sizeof(LeafTex) +
@@ -1445,8 +1482,13 @@ constexpr int kHostSlots = 3;
 
 template <class Out, class Launch>
 static void trace_host_pipelined(TutuCtx* ctx, const float* rays, uint64_t n_rays, Out* out, Launch launch) {
+#ifdef TUTU_EXPERIMENTS
   static const int slots_cfg = getenv("TUTU_HOST_SLOTS") ? std::min(kHostSlotsMax, std::max(1, atoi(getenv("TUTU_HOST_SLOTS")))) : kHostSlots;
   static const uint64_t chunk_cfg = getenv("TUTU_HOST_CHUNK_LOG2") ? 1ull << atoi(getenv("TUTU_HOST_CHUNK_LOG2")) : kHostChunk;
+#else
+  const int slots_cfg = kHostSlots;
+  const uint64_t chunk_cfg = kHostChunk;
+#endif
   const uint64_t chunk = std::min<uint64_t>(chunk_cfg, n_rays);
   const int slots = (int)std::min<uint64_t>((uint64_t)slots_cfg, (n_rays + chunk - 1) / chunk);
   cudaStream_t st[kHostSlotsMax];

@@ -36,6 +36,7 @@ __global__ void wf_ctl_after_raygen(WfCtl* ctl, unsigned capacity) {
   for (int c = 0; c < 8; ++c) ctl->class_count[c] = 0;
 }
 __global__ void wf_ctl_after_iter(WfCtl* ctl) {
+  if (ctl->done) return;  // the host polls every few iterations: the launches after the last one are no-ops
   ctl->sum_shadow += ctl->n_shadow;
   ctl->n_cur = ctl->n_next;
   ctl->iterations += 1;
