@@ -35,6 +35,17 @@ def test_pod_sizes_match_header(api):
     assert api.PRIM_DTYPE.itemsize == 124 and api.MATERIAL_DTYPE.itemsize == 56
 
 
+def test_shipped_library_has_no_environment_knobs(api):
+    """The experiment knobs (TUTU_PRUNE_*, TUTU_NO_*, ...) and the losing traversal flavours are compiled only with
+    -DTUTU_EXPERIMENTS; the shipped .so must not read the environment at all (only TUTU_LIB, in api.py, picks a build)."""
+    blob = (ROOT / "tuturenderer_b200" / "libtutu_b200.so").read_bytes()
+    for knob in (b"TUTU_PRUNE_REL", b"TUTU_PRUNE_ABS", b"TUTU_NO_SMALL", b"TUTU_NO_FAST_TREE", b"TUTU_GRID_DIV", b"TUTU_LEAF_BATCH",
+                 b"TUTU_HOST_SLOTS", b"TUTU_SHADE_BLOCK_RT", b"TUTU_NO_CLASS_SORT", b"TUTU_REFILL_MIN"):
+        assert knob not in blob, knob
+    for sym in (b"trace_refill", b"trace_persistent", b"traverse_warp", b"k_trace_variant"):
+        assert sym not in blob, sym
+
+
 def test_no_gpu_is_an_error_not_a_fallback(api):
     import torch
     if torch.cuda.is_available():

@@ -375,6 +375,7 @@ k_trace_closest(const __grid_constant__ DevScene sc, const __grid_constant__ Sma
     const int prim = h.slot >= 0 ? __ldg(sc.slot_to_prim + (h.slot & (int)kSlotMask)) : -1;
     reinterpret_cast<float4*>(out)[i] = make_float4(__int_as_float(prim), h.t, h.u, h.v);
   };
+#ifdef TUTU_EXPERIMENTS
   if (MODE == 2) {
     trace_persistent<false>(
         sc, n, next,
@@ -387,6 +388,7 @@ k_trace_closest(const __grid_constant__ DevScene sc, const __grid_constant__ Sma
         [&](unsigned long long i, const Walk& w) { store(i, w.best); });
     return;
   }
+#endif
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     unsigned long long base = 0;
@@ -427,6 +429,7 @@ __global__ void __launch_bounds__(256)
 k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss,
             const float4* __restrict__ rays, unsigned long long n, uint8_t* __restrict__ out,
             unsigned long long* __restrict__ next, const unsigned* __restrict__ perm = nullptr) {
+#ifdef TUTU_EXPERIMENTS
   if (MODE == 2) {
     trace_persistent<true>(
         sc, n, next,
@@ -439,6 +442,7 @@ k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallSc
         [&](unsigned long long i, const Walk& w) { out[i] = w.best.slot >= 0 ? 1 : 0; });
     return;
   }
+#endif
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
     unsigned long long base = 0;
@@ -463,6 +467,7 @@ k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallSc
   }
 }
 
+#ifdef TUTU_EXPERIMENTS
 // experimental walk flavours behind tutu_set_traversal_mode(ctx, 10 + VARIANT): 32-ray packets
 template <bool ANY, int VARIANT>
 __global__ void __launch_bounds__(256)
@@ -564,6 +569,8 @@ k_trace_variant(const __grid_constant__ DevScene sc, const float4* __restrict__ 
   }
 }
 
+#endif  // TUTU_EXPERIMENTS
+
 template <bool ANY>
 __global__ void __launch_bounds__(256)
 k_trace_count(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned long long n,
@@ -653,6 +660,7 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
   slot_acquire(ctx, slot, s);
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
+#ifdef TUTU_EXPERIMENTS
   if (ctx->traversal_mode >= 10) {
 #define TUTU_VAR_C(V)                                                                       \
   case V: {                                                                                 \
@@ -665,12 +673,14 @@ void launch_closest(TutuCtx* ctx, const float* d_rays, uint64_t n, TutuHit* d_ou
       TUTU_VAR_C(0) TUTU_VAR_C(1) TUTU_VAR_C(2) TUTU_VAR_C(3) TUTU_VAR_C(4) TUTU_VAR_C(5) TUTU_VAR_C(6) TUTU_VAR_C(7)
     }
 #undef TUTU_VAR_C
-  } else if (ctx->traversal_mode == 1) {
-    int grid = persistent_grid(ctx, k_trace_closest<1>, 256);
-    k_trace_closest<1><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
   } else if (ctx->traversal_mode == 2) {
     int grid = persistent_grid(ctx, k_trace_closest<2>, 256);
     k_trace_closest<2><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+  } else
+#endif
+  if (ctx->traversal_mode == 1) {
+    int grid = persistent_grid(ctx, k_trace_closest<1>, 256);
+    k_trace_closest<1><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
   } else {
     if (ctx->small.n > 0 && ctx->traversal_mode == 0) {
       int grid = persistent_grid(ctx, k_trace_closest<3>, 256);
@@ -697,6 +707,7 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
   slot_acquire(ctx, slot, s);
   CUDA_TRY(cudaMemsetAsync(next, 0, sizeof(unsigned long long), s));
   const float4* rays = reinterpret_cast<const float4*>(d_rays);
+#ifdef TUTU_EXPERIMENTS
   if (ctx->traversal_mode >= 10) {
 #define TUTU_VAR_A(V)                                                                      \
   case V: {                                                                                \
@@ -709,12 +720,14 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
       TUTU_VAR_A(0) TUTU_VAR_A(1) TUTU_VAR_A(2) TUTU_VAR_A(3) TUTU_VAR_A(4) TUTU_VAR_A(5) TUTU_VAR_A(6) TUTU_VAR_A(7)
     }
 #undef TUTU_VAR_A
-  } else if (ctx->traversal_mode == 1) {
-    int grid = persistent_grid(ctx, k_trace_any<1>, 256);
-    k_trace_any<1><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
   } else if (ctx->traversal_mode == 2) {
     int grid = persistent_grid(ctx, k_trace_any<2>, 256);
     k_trace_any<2><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
+  } else
+#endif
+  if (ctx->traversal_mode == 1) {
+    int grid = persistent_grid(ctx, k_trace_any<1>, 256);
+    k_trace_any<1><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next);
   } else {
     if (ctx->small.n > 0 && ctx->traversal_mode == 0) {
       int grid = persistent_grid(ctx, k_trace_any<3>, 256);
@@ -1410,8 +1423,13 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
 }
 
 extern "C" int tutu_set_traversal_mode(TutuCtx* ctx, int mode) {
-  if (!ctx || !(mode == 0 || mode == 1 || mode == 2 || mode == 3 || mode == 4 || mode == 6 || (mode >= 10 && mode <= 17)))
-    return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument");
+#ifdef TUTU_EXPERIMENTS
+  const bool experimental = mode == 2 || (mode >= 10 && mode <= 17);  // trace_variants.cuh
+#else
+  const bool experimental = false;
+#endif
+  if (!ctx || !(mode == 0 || mode == 1 || mode == 3 || mode == 4 || mode == 6 || experimental))
+    return fail(ctx, TUTU_E_INVALID, "tutu_set_traversal_mode: bad argument (0, 1, 3, 4 or 6)");
   std::lock_guard<std::mutex> lock(ctx->mu);
   if (mode == 6) {
     // Regular rays walk the compressed 8-wide collapse of the SAH tree (wide.cuh).  Bit-identical hits; measured
