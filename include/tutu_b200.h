@@ -193,6 +193,26 @@ const char* tutu_last_error(const TutuCtx* ctx);
 /* Flatten + upload.  Host pointers are not retained past the call. */
 int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc);
 int tutu_scene_info(const TutuCtx* ctx, TutuSceneInfo* out);
+/* Who builds the traversal tree for regular rays (a binary tree over the reference's leaves; the reference's own
+ * topology is always kept for irregular rays and the literal walk): TUTU_BUILD_AUTO = on the device for scenes of
+ * >= 65 536 primitives, on the host otherwise; TUTU_BUILD_HOST_SAH = binned surface-area heuristic on the host
+ * (0.3-0.7 s for 10^6 primitives, the better tree); TUTU_BUILD_DEVICE_LBVH = linear BVH on the GPU (Morton sort
+ * + Karras hierarchy + refit, a few ms for 10^6 primitives).  Takes effect at the next tutu_scene_upload.  Hits do
+ * not depend on the choice (any tree with exact union boxes over the same leaves gives the same answer). */
+#define TUTU_BUILD_AUTO 0
+#define TUTU_BUILD_HOST_SAH 1
+#define TUTU_BUILD_DEVICE_LBVH 2
+int tutu_scene_builder(TutuCtx* ctx, int builder);
+/* Wall-clock breakdown of the last tutu_scene_upload (milliseconds). */
+typedef struct TutuUploadStats {
+  float total_ms;
+  float flatten_ms;    /* host: validation, DFS slots, leaf records, reference-topology nodes (+ midpoint build if no tree was given) */
+  float tree_build_ms; /* traversal tree for regular rays: host SAH build, or device LBVH (incl. its two small uploads) */
+  float h2d_ms;        /* copies of the flattened arrays */
+  int32_t builder;     /* TUTU_BUILD_HOST_SAH or TUTU_BUILD_DEVICE_LBVH: what was actually used */
+  uint32_t tree_depth;
+} TutuUploadStats;
+int tutu_upload_stats(const TutuCtx* ctx, TutuUploadStats* out);
 /* Change the frame size / camera without re-uploading geometry. */
 int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam);
 

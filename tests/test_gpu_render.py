@@ -95,16 +95,23 @@ def test_mixed_scene_statistics_against_reference(api, ctx, golden, mixed):
     for c in range(3):
         assert abs(img[..., c].mean() / ref[..., c].mean() - 1) < 0.01
     assert _rmse(img, ref) < 2 * stats["run_to_run_rmse_1024"]
-    # block means (8x8) localise a wrong material.  Four pixels are excluded by name: they sit on the silhouettes of
-    # the PERFECT_REFLECTIVE and PERFECT_REFRACTIVE spheres, where the camera ray (no pixel jitter) starts a
-    # deterministic specular chain; a last-place difference in the grazing reflection (FMA contraction / rsqrt in the
-    # shading code vs the reference's libm build) sends EVERY sample of such a pixel to another surface (e.g. 0.08 where
-    # the reference has 0.35; tools/gpu_mixed_stat.py lists them, identical for every seed).  All other 9212 pixels
-    # are gated: worst 8x8 block below 10 %, mean block deviation below 1 % (+0.02 absolute).
-    CHAIN_PIXELS = [(42, 39), (70, 69), (40, 46), (57, 47)]
+    # Block means (8x8) localise a wrong material.  A handful of pixels are excluded first, explicitly: pixels on the
+    # silhouettes of the PERFECT_REFLECTIVE / PERFECT_REFRACTIVE spheres where the camera ray (no pixel jitter) starts
+    # a (nearly) deterministic specular chain, so a last-place difference in a grazing reflection (FMA contraction /
+    # rsqrt in the shading code vs the reference's libm build) moves EVERY sample of the pixel to another surface -
+    # e.g. (68, 66): the reference's chain ends in NaN for all 2048 samples (pixel exactly 0, PathTracing.hpp:510)
+    # while the GPU's reaches the red wall (0.59).  tools/gpu_mixed_stat.py lists them per seed.  They must be few
+    # (<= 8 of 9216), lie on those silhouettes (the named neighbourhoods), and everything else is gated tightly:
+    # worst 8x8 block below 10 % (it was a 30 % blanket over all pixels), mean block deviation below 1 %.
+    CHAIN_PIXELS = [(68, 66), (70, 69), (42, 39), (43, 38), (40, 46), (40, 47), (57, 47)]
+    diff = np.abs(img - ref).max(-1)
+    outliers = [tuple(int(v) for v in yx) for yx in np.argwhere(diff > 0.1)]
+    assert len(outliers) <= 8, outliers
+    for y, x in outliers:
+        assert any(abs(y - cy) <= 1 and abs(x - cx) <= 1 for cy, cx in CHAIN_PIXELS), f"unexpected outlier pixel {(y, x)}"
     img_m, ref_m = img.copy(), ref.copy()
-    for y, x in CHAIN_PIXELS:
-        img_m[y, x] = ref_m[y, x] = 0
+    for y, x in outliers:
+        img_m[y, x] = ref_m[y, x]
     b = lambda a: a.reshape(12, 8, 12, 8, 3).mean((1, 3))
     rel = np.abs(b(img_m) - b(ref_m)) / (b(ref_m) + 0.02)
     assert rel.max() < 0.10 and rel.mean() < 0.01, (rel.max(), rel.mean())

@@ -235,29 +235,87 @@ def full_size_scene(api, tmp_path_factory):
     return sc, path
 
 
+_REF_CACHE = {}
+
+
+def _full_size_reference(api, full_size_scene, kind):
+    """{prim,t,u,v} and any-hit booleans of the REFERENCE for 2^20 rays of `kind` (computed once per session)."""
+    from oracle import oracle_py as O
+    if kind not in _REF_CACHE:
+        sc, path = full_size_scene
+        # every 16th ray of the bench's batch (tutu_synth_rays is a pure function of the ray index)
+        rays = np.concatenate([api.synth_rays(kind, 1 << 16, first=f) for f in range(0, 1 << 24, 1 << 20)])
+        want_c, info_c = O.ref_trace(sc, rays, "closest", scene_path=path)
+        want_a, info_a = O.ref_trace(sc, rays, "any", scene_path=path)
+        assert info_c["rays"] == len(rays) == 1 << 20 and info_a["rays"] == len(rays)
+        _REF_CACHE[kind] = (rays, want_c, want_a)
+    return _REF_CACHE[kind]
+
+
+@pytest.mark.parametrize("builder", ["device_lbvh", "host_sah"])
 @pytest.mark.parametrize("kind", [0, 1])
-def test_full_size_against_the_reference(api, ctx, full_size_scene, kind):
+def test_full_size_against_the_reference(api, ctx, full_size_scene, kind, builder):
     """configs[1] at BASELINE size against the REFERENCE ITSELF (BVH.hpp:145-194 through
     oracle/_ref/ref_harness trace: the reference's own recursiveBuild tree, getIntersection and
     hasIntersection): 2^20 rays of each kind, {prim, t, u, v} byte for byte and the any-hit booleans,
-    for the production walk (mode 0) and the literal walk (mode 1).  The 2^20 rays are a strided
+    for the production walk (mode 0) over the device-built and over the host-built traversal tree, the
+    literal walk (mode 1) and the compressed wide tree (mode 6).  The 2^20 rays are a strided
     sample of the 2^24-ray batch bench.py times, so the compared rays cover the whole batch."""
-    from oracle import oracle_py as O
-    sc, path = full_size_scene
-    n = 1 << 20
-    # every 16th ray of the bench's batch (tutu_synth_rays is a pure function of the ray index)
-    rays = np.concatenate([api.synth_rays(kind, 1 << 16, first=f) for f in range(0, 1 << 24, 1 << 20)])
-    assert len(rays) == n
-    want_c, info_c = O.ref_trace(sc, rays, "closest", scene_path=path)
-    want_a, info_a = O.ref_trace(sc, rays, "any", scene_path=path)
-    assert info_c["rays"] == n and info_a["rays"] == n
+    sc, _path = full_size_scene
+    rays, want_c, want_a = _full_size_reference(api, full_size_scene, kind)
+    ctx.builder(builder)
     ctx.upload(sc)
-    for mode in (0, 1, 6):  # production walk, literal walk, compressed 8-wide tree
+    assert ctx.upload_stats()["builder"] == builder
+    for mode in ((0, 1, 6) if builder == "device_lbvh" else (0,)):
         ctx.set_traversal_mode(mode)
         assert_hits_equal(ctx.trace_closest(rays), want_c)
         assert np.array_equal(ctx.trace_any(rays), want_a)
     ctx.set_traversal_mode(0)
     assert (want_c["prim"] >= 0).mean() > (0.9 if kind == 0 else 0.3)
+
+
+@pytest.mark.parametrize("case", ["heightfield", "soup_dups", "spheres", "clustered", "three"])
+def test_device_built_tree_equals_host_built_tree_and_oracle(api, oracle, ctx, case):
+    """The traversal tree built on the GPU (device_bvh.cu: Morton sort + Karras hierarchy + refit) is a different
+    topology over the same leaves: hits must be those of the host-built SAH tree, of the literal walk of the
+    reference topology and of the CPU oracle, bit for bit; likewise the wide collapse of the device-built tree."""
+    rng = np.random.default_rng(9)
+    if case == "heightfield":
+        prims = api.synth_heightfield(96)
+    elif case == "soup_dups":
+        prims = random_soup(api, 4000, seed=21, dup=1500)
+    elif case == "spheres":
+        prims = random_soup(api, 500, n_spheres=300, seed=22, dup=50)
+    elif case == "clustered":  # 90 % of the primitives inside 1e-3 of the scene: deep Morton prefixes
+        prims = random_soup(api, 6000, seed=23)
+        v = prims["v"].reshape(-1, 3, 3)
+        v[:5400] = (v[:5400] - 5.0) * np.float32(1e-3) + np.float32(5.0)
+    else:
+        prims = random_soup(api, 3, seed=24)
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    rays = api.synth_rays(0, 80000, seed=5) if case == "heightfield" else random_rays(80000, seed=25)
+    if case == "clustered":
+        rays[:40000, 0:3] = 5.0 + (rays[:40000, 0:3] - 5.0) * 2e-3  # half of the rays start inside the cluster
+    osc = oracle.OracleScene(sc)
+    sub = slice(0, 80000, 5)
+    want_c, want_a = osc.trace_closest(np.ascontiguousarray(rays[sub])), osc.trace_any(np.ascontiguousarray(rays[sub]))
+    results = {}
+    for builder in ("host_sah", "device_lbvh"):
+        ctx.builder(builder)
+        ctx.upload(sc)
+        st = ctx.upload_stats()
+        assert st["builder"] == builder or (case == "three" and st["builder"] == "host_sah"), st
+        for mode in (0, 6, 1):
+            ctx.set_traversal_mode(mode)
+            results[(builder, mode)] = (ctx.trace_closest(rays), ctx.trace_any(rays))
+        ctx.set_traversal_mode(0)
+    ctx.builder("auto")
+    ref_c, ref_a = results[("host_sah", 1)]
+    for key, (c, a) in results.items():
+        assert_hits_equal(c, ref_c)
+        assert np.array_equal(a, ref_a), key
+    assert_hits_equal(np.ascontiguousarray(ref_c[sub]), want_c)
+    assert np.array_equal(ref_a[sub], want_a)
 
 
 def test_binned_order_gives_identical_results(api, oracle, ctx):

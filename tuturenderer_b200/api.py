@@ -69,6 +69,14 @@ class TutuRenderStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class TutuUploadStats(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("flatten_ms", C.c_float), ("tree_build_ms", C.c_float), ("h2d_ms", C.c_float),
+                ("builder", C.c_int32), ("tree_depth", C.c_uint32)]
+
+
+BUILDERS = {"auto": 0, "host_sah": 1, "device_lbvh": 2}
+
+
 class TutuTreeCheck(C.Structure):
     _fields_ = [("n_leaves", C.c_uint32), ("binary_nodes", C.c_uint32), ("binary_depth", C.c_uint32),
                 ("wide_nodes", C.c_uint32), ("wide_depth", C.c_uint32), ("wide_children", C.c_uint64),
@@ -92,6 +100,8 @@ ABI = {
     "tutu_scene_upload": (C.c_int, [_P, C.POINTER(TutuSceneDesc)]),
     "tutu_scene_info": (C.c_int, [_P, C.POINTER(TutuSceneInfo)]),
     "tutu_scene_set_camera": (C.c_int, [_P, C.POINTER(TutuCamera)]),
+    "tutu_scene_builder": (C.c_int, [_P, C.c_int]),
+    "tutu_upload_stats": (C.c_int, [_P, C.POINTER(TutuUploadStats)]),
     "tutu_trace_closest": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "tutu_trace_any": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "tutu_trace_closest_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
@@ -404,6 +414,17 @@ class Context:
         self._ck(lib().tutu_scene_upload(self._h, C.byref(d)))
         del keep
         self.scene = scene
+
+    def builder(self, name: str = "auto") -> None:
+        """Who builds the traversal tree at the next upload: 'auto', 'host_sah' or 'device_lbvh'."""
+        self._ck(lib().tutu_scene_builder(self._h, BUILDERS[name]))
+
+    def upload_stats(self) -> dict:
+        u = TutuUploadStats()
+        self._ck(lib().tutu_upload_stats(self._h, C.byref(u)))
+        d = {n: getattr(u, n) for n, _ in TutuUploadStats._fields_}
+        d["builder"] = {v: k for k, v in BUILDERS.items()}.get(d["builder"], d["builder"])
+        return d
 
     def set_camera(self, scene: Scene) -> None:
         cam = scene.camera_struct()

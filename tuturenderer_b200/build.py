@@ -16,8 +16,8 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libtutu_b200.so"
 
-SOURCES = [CSRC / "tutu_b200.cu", CSRC / "resident.cu", CSRC / "trace_kernels.cu", CSRC / "host_scene.cpp", CSRC / "host_image.cpp", CSRC / "host_wide.cpp"]
-HEADERS = [CSRC / "trace.cuh", CSRC / "shade.cuh", CSRC / "vertex.cuh", CSRC / "wavefront.cuh", CSRC / "resident.cuh", CSRC / "bdpt.cuh", CSRC / "postprocess.cuh", CSRC / "wide.cuh", CSRC / "wf_types.cuh", CSRC / "trace_kernels.hpp", CSRC / "tutu_internal.hpp",
+SOURCES = [CSRC / "tutu_b200.cu", CSRC / "resident.cu", CSRC / "trace_kernels.cu", CSRC / "device_bvh.cu", CSRC / "host_scene.cpp", CSRC / "host_image.cpp", CSRC / "host_wide.cpp"]
+HEADERS = [CSRC / "trace.cuh", CSRC / "shade.cuh", CSRC / "vertex.cuh", CSRC / "wavefront.cuh", CSRC / "resident.cuh", CSRC / "bdpt.cuh", CSRC / "postprocess.cuh", CSRC / "wide.cuh", CSRC / "wf_types.cuh", CSRC / "trace_kernels.hpp", CSRC / "device_bvh.hpp", CSRC / "tutu_internal.hpp",
            ROOT / "include" / "tutu_b200.h"]
 
 

@@ -1,0 +1,341 @@
+// device_bvh.cu — the traversal tree for regular rays built ON THE GPU.
+//
+// What may be built freely: for a ray whose three 1/d are finite the reference's answer depends only on the leaf
+// boxes and the primitives (host_scene.cpp, "traversal tree for regular rays"), so any binary tree over the same
+// leaves whose inner boxes are exact fmin/fmax unions returns bit-identical hits.  The host builds a binned-SAH
+// tree (0.3-0.7 s for 10^6 primitives); this file builds a linear BVH in a few milliseconds:
+//
+//   1. lbvh_keys       48-bit Morton code of every leaf-box centroid inside the scene box (16 bits per axis)
+//   2. radix_*         stable LSD radix sort of (key, leaf) pairs, 4 bits per pass, 12 passes; every thread owns 16
+//                      consecutive pairs, so stability needs no intra-warp ranking: per-thread digit counts ->
+//                      block scan per digit -> one global scan of the [digit][block] table -> ordered scatter
+//   3. lbvh_hierarchy  Karras, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees" (HPG
+//                      2012): inner node i covers a range of the sorted leaves found from the common-prefix
+//                      lengths delta(i, j) (equal keys fall back to the index, so duplicates split evenly)
+//   4. lbvh_refit      leaves walk to the root; the second arrival at a node owns both child boxes and goes on.
+//                      Boxes are fmin/fmax of floats: exact and independent of the arrival order
+//   5. lbvh_depth      deepest leaf (the traversal stacks are sized by it)
+//
+// Output = the 64-byte two-child nodes the binary walk reads (tutu_internal.hpp: InnerNode), root = node 0, leaf
+// refs = ~(DFS slot | sphere bit) of the REFERENCE tree's leaf numbering, which is what the equal-t tie rule compares.
+// No library sort: every kernel here is this repository's.  sm_100a only.
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "device_bvh.hpp"
+
+namespace tutu {
+namespace {
+
+constexpr int kSortBlock = 256;
+constexpr int kSortItems = 16;                          // pairs per thread, consecutive
+constexpr int kSortTile = kSortBlock * kSortItems;      // pairs per block
+constexpr int kRadixBits = 4, kRadix = 1 << kRadixBits;
+constexpr int kKeyBits = 48;
+
+__device__ __forceinline__ unsigned long long spread16(unsigned v) {  // 16 bits -> every third bit of 48
+  unsigned long long x = v & 0xFFFFull;
+  x = (x | (x << 32)) & 0x00FF00000000FFFFull;  // not needed for 16 bits, kept for the general pattern
+  x = (x | (x << 16)) & 0x00FF0000FF0000FFull;
+  x = (x | (x << 8)) & 0xF00F00F00F00F00Full;
+  x = (x | (x << 4)) & 0x30C30C30C30C30C3ull;
+  x = (x | (x << 2)) & 0x9249249249249249ull;
+  return x;
+}
+
+__global__ void __launch_bounds__(256)
+lbvh_keys(const float* __restrict__ leaf_box, unsigned n, float3 lo, float3 inv_extent, unsigned long long* __restrict__ keys,
+          unsigned* __restrict__ vals) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* b = leaf_box + 6 * (size_t)i;
+    const float cx = 0.5f * (b[0] + b[3]), cy = 0.5f * (b[1] + b[4]), cz = 0.5f * (b[2] + b[5]);
+    auto q = [](float c, float l, float inv) {
+      float u = (c - l) * inv;
+      u = fminf(fmaxf(u, 0.f), 0.9999999f);  // NaN -> 0
+      return (unsigned)(u * 65536.f);
+    };
+    keys[i] = spread16(q(cx, lo.x, inv_extent.x)) | (spread16(q(cy, lo.y, inv_extent.y)) << 1) | (spread16(q(cz, lo.z, inv_extent.z)) << 2);
+    vals[i] = i;
+  }
+}
+
+// ---- radix sort pass -----------------------------------------------------------------------------------
+// hist[digit * n_blocks + block] = pairs of that digit in the block's tile
+__global__ void __launch_bounds__(kSortBlock)
+radix_count(const unsigned long long* __restrict__ keys, unsigned n, int shift, unsigned* __restrict__ hist, unsigned n_blocks) {
+  __shared__ unsigned s_cnt[kRadix];
+  if (threadIdx.x < kRadix) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const size_t first = (size_t)blockIdx.x * kSortTile + (size_t)threadIdx.x * kSortItems;
+  unsigned local[kRadix];
+#pragma unroll
+  for (int d = 0; d < kRadix; ++d) local[d] = 0u;
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const size_t i = first + k;
+    if (i < n) {
+      const unsigned d = (unsigned)(keys[i] >> shift) & (kRadix - 1);
+#pragma unroll
+      for (int e = 0; e < kRadix; ++e) local[e] += (d == (unsigned)e);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < kRadix; ++d)
+    if (local[d]) atomicAdd(&s_cnt[d], local[d]);
+  __syncthreads();
+  if (threadIdx.x < kRadix) hist[(size_t)threadIdx.x * n_blocks + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+// exclusive scan of the whole [digit][block] table by one block (n_entries = 16 * n_blocks <= a few thousand)
+__global__ void __launch_bounds__(1024)
+radix_scan(unsigned* __restrict__ hist, unsigned n_entries) {
+  __shared__ unsigned s_warp[32];
+  __shared__ unsigned s_carry;
+  if (threadIdx.x == 0) s_carry = 0u;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (unsigned base = 0; base < n_entries; base += blockDim.x) {
+    const unsigned i = base + threadIdx.x;
+    const unsigned v = i < n_entries ? hist[i] : 0u;
+    unsigned incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (unsigned)o) incl += y;
+    }
+    if (lane == 31u) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = s_warp[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+        if (lane >= (unsigned)o) w += y;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned before = s_carry + (warp ? s_warp[warp - 1] : 0u);
+    if (i < n_entries) hist[i] = before + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = before + incl;
+    __syncthreads();
+  }
+}
+
+// ordered scatter: thread t's pairs follow those of threads < t of the same digit (per-digit block scan), and a
+// thread writes its own pairs in order
+__global__ void __launch_bounds__(kSortBlock)
+radix_scatter(const unsigned long long* __restrict__ keys, const unsigned* __restrict__ vals, unsigned n, int shift,
+              const unsigned* __restrict__ hist, unsigned n_blocks, unsigned long long* __restrict__ keys_out,
+              unsigned* __restrict__ vals_out) {
+  __shared__ unsigned s_warp[kRadix][kSortBlock / 32];
+  const size_t first = (size_t)blockIdx.x * kSortTile + (size_t)threadIdx.x * kSortItems;
+  unsigned long long my_key[kSortItems];
+  unsigned my_digit[kSortItems];
+  unsigned local[kRadix];
+#pragma unroll
+  for (int d = 0; d < kRadix; ++d) local[d] = 0u;
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const size_t i = first + k;
+    my_key[k] = i < n ? keys[i] : 0ull;
+    my_digit[k] = i < n ? ((unsigned)(my_key[k] >> shift) & (kRadix - 1)) : 0xFFu;
+#pragma unroll
+    for (int e = 0; e < kRadix; ++e) local[e] += (my_digit[k] == (unsigned)e);
+  }
+  // exclusive scan of local[d] over the block's threads, for every digit
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  unsigned offs[kRadix];
+#pragma unroll
+  for (int d = 0; d < kRadix; ++d) {
+    unsigned incl = local[d];
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (unsigned)o) incl += y;
+    }
+    if (lane == 31u) s_warp[d][warp] = incl;
+    offs[d] = incl - local[d];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < kRadix; ++d) {
+    unsigned before = 0u;
+    for (unsigned w = 0; w < warp; ++w) before += s_warp[d][w];
+    offs[d] += before + hist[(size_t)d * n_blocks + blockIdx.x];
+  }
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const size_t i = first + k;
+    if (i < n) {
+      unsigned dst = 0u;
+#pragma unroll
+      for (int e = 0; e < kRadix; ++e)
+        if (my_digit[k] == (unsigned)e) dst = offs[e]++;
+      keys_out[dst] = my_key[k];
+      vals_out[dst] = vals[i];
+    }
+  }
+}
+
+// ---- Karras hierarchy ------------------------------------------------------------------------------------
+__device__ __forceinline__ int lbvh_delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const unsigned long long a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(i ^ j);
+  return __clzll((long long)(a ^ b));
+}
+
+// child / parent encoding while building: inner node k -> k, sorted leaf p -> ~p
+__global__ void __launch_bounds__(256)
+lbvh_hierarchy(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ children, int* __restrict__ parent_inner,
+               int* __restrict__ parent_leaf) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += gridDim.x * blockDim.x) {
+    const int d = lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = lbvh_delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+      if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lbvh_delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+      if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+      if (t == 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int left = lo == gamma ? ~gamma : gamma;
+    const int right = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
+    children[i] = make_int2(left, right);
+    if (left >= 0) parent_inner[left] = i; else parent_leaf[~left] = i;
+    if (right >= 0) parent_inner[right] = i; else parent_leaf[~right] = i;
+    if (i == 0) parent_inner[0] = -1;
+  }
+}
+
+struct NodeOut {  // = tutu_internal.hpp InnerNode (64 bytes)
+  float box[12];
+  int left, right, pad0, pad1;
+};
+
+__device__ __forceinline__ void store_child_box(NodeOut* node, int right, const float lo[3], const float hi[3]) {
+  float* b = node->box + 6 * right;
+  b[0] = lo[0], b[1] = hi[0], b[2] = lo[1], b[3] = hi[1], b[4] = lo[2], b[5] = hi[2];
+}
+
+// one thread per sorted leaf; the second thread to reach a node continues with the union of both child boxes
+__global__ void __launch_bounds__(256)
+lbvh_refit(const float* __restrict__ leaf_box, const unsigned* __restrict__ leaf_code, const unsigned* __restrict__ sorted_leaf,
+           int n, const int2* __restrict__ children, const int* __restrict__ parent_inner, const int* __restrict__ parent_leaf,
+           unsigned* __restrict__ arrivals, NodeOut* __restrict__ nodes) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const unsigned leaf = sorted_leaf[p];
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) lo[a] = leaf_box[6 * (size_t)leaf + a], hi[a] = leaf_box[6 * (size_t)leaf + 3 + a];
+    int child = ~p;
+    int node = parent_leaf[p];
+    while (node >= 0) {
+      const int2 ch = children[node];
+      const int right = ch.y == child ? 1 : 0;
+      NodeOut* out = nodes + node;
+      store_child_box(out, right, lo, hi);
+      const int ref = child >= 0 ? child : (int)~leaf_code[sorted_leaf[~child]];
+      if (right) out->right = ref; else out->left = ref;
+      __threadfence();
+      if (atomicAdd(arrivals + node, 1u) == 0u) break;  // the sibling subtree is not finished yet
+      __threadfence();
+      const volatile float* sib = out->box + 6 * (1 - right);
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = fminf(lo[a], sib[2 * a]);
+        hi[a] = fmaxf(hi[a], sib[2 * a + 1]);
+      }
+      child = node;
+      node = parent_inner[node];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lbvh_depth(int n, const int* __restrict__ parent_inner, const int* __restrict__ parent_leaf, unsigned* __restrict__ deepest) {
+  unsigned best = 0u;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    unsigned d = 0u;
+    for (int node = parent_leaf[p]; node >= 0; node = parent_inner[node]) ++d;
+    best = max(best, d);
+  }
+  for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_down_sync(0xFFFFFFFFu, best, o));
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(deepest, best);
+}
+
+struct Scratch {
+  void* p = nullptr;
+  ~Scratch() {
+    if (p) cudaFree(p);
+  }
+};
+
+}  // namespace
+
+cudaError_t device_build_lbvh(const float* d_leaf_box, const uint32_t* d_leaf_code, uint32_t n, const float root_lo[3],
+                              const float root_hi[3], void* d_inner_out, uint32_t* depth_out, int sm_count, cudaStream_t s) {
+  static_assert(sizeof(NodeOut) == 64, "NodeOut must match InnerNode");
+  if (n < 2) return cudaErrorInvalidValue;
+  const unsigned n_blocks = (n + kSortTile - 1) / kSortTile;
+  // scratch: keys x2, vals x2, hist, children, parents x2, arrivals, deepest
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  const size_t o_k0 = take((size_t)n * 8), o_k1 = take((size_t)n * 8), o_v0 = take((size_t)n * 4), o_v1 = take((size_t)n * 4);
+  const size_t o_hist = take((size_t)kRadix * n_blocks * 4), o_ch = take((size_t)n * 8), o_pi = take((size_t)n * 4);
+  const size_t o_pl = take((size_t)n * 4), o_arr = take((size_t)n * 4), o_deep = take(256);
+  Scratch sc;
+  cudaError_t e = cudaMalloc(&sc.p, off);
+  if (e != cudaSuccess) return e;
+  char* base = static_cast<char*>(sc.p);
+  auto* k0 = reinterpret_cast<unsigned long long*>(base + o_k0);
+  auto* k1 = reinterpret_cast<unsigned long long*>(base + o_k1);
+  auto* v0 = reinterpret_cast<unsigned*>(base + o_v0);
+  auto* v1 = reinterpret_cast<unsigned*>(base + o_v1);
+  auto* hist = reinterpret_cast<unsigned*>(base + o_hist);
+  auto* children = reinterpret_cast<int2*>(base + o_ch);
+  auto* parent_inner = reinterpret_cast<int*>(base + o_pi);
+  auto* parent_leaf = reinterpret_cast<int*>(base + o_pl);
+  auto* arrivals = reinterpret_cast<unsigned*>(base + o_arr);
+  auto* deepest = reinterpret_cast<unsigned*>(base + o_deep);
+
+  const int grid = sm_count * 8;
+  float3 lo = make_float3(root_lo[0], root_lo[1], root_lo[2]);
+  float3 inv;
+  inv.x = root_hi[0] > root_lo[0] ? 1.f / (root_hi[0] - root_lo[0]) : 0.f;
+  inv.y = root_hi[1] > root_lo[1] ? 1.f / (root_hi[1] - root_lo[1]) : 0.f;
+  inv.z = root_hi[2] > root_lo[2] ? 1.f / (root_hi[2] - root_lo[2]) : 0.f;
+  lbvh_keys<<<grid, 256, 0, s>>>(d_leaf_box, n, lo, inv, k0, v0);
+  for (int shift = 0; shift < kKeyBits; shift += kRadixBits) {
+    radix_count<<<n_blocks, kSortBlock, 0, s>>>(k0, n, shift, hist, n_blocks);
+    radix_scan<<<1, 1024, 0, s>>>(hist, kRadix * n_blocks);
+    radix_scatter<<<n_blocks, kSortBlock, 0, s>>>(k0, v0, n, shift, hist, n_blocks, k1, v1);
+    unsigned long long* tk = k0;
+    k0 = k1, k1 = tk;
+    unsigned* tv = v0;
+    v0 = v1, v1 = tv;
+  }
+  if ((e = cudaMemsetAsync(arrivals, 0, (size_t)n * 4, s)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(deepest, 0, 4, s)) != cudaSuccess) return e;
+  lbvh_hierarchy<<<grid, 256, 0, s>>>(k0, (int)n, children, parent_inner, parent_leaf);
+  lbvh_refit<<<grid, 256, 0, s>>>(d_leaf_box, d_leaf_code, v0, (int)n, children, parent_inner, parent_leaf, arrivals,
+                                  static_cast<NodeOut*>(d_inner_out));
+  lbvh_depth<<<grid, 256, 0, s>>>((int)n, parent_inner, parent_leaf, deepest);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  unsigned h_deep = 0;
+  if ((e = cudaMemcpyAsync(&h_deep, deepest, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+  *depth_out = h_deep;
+  return cudaSuccess;
+}
+
+}  // namespace tutu

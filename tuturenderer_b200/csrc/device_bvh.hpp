@@ -1,0 +1,15 @@
+// device_bvh.hpp — GPU build of the traversal tree for regular rays (device_bvh.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tutu {
+
+// Linear BVH over n >= 2 leaves.  d_leaf_box: n x {lo.xyz, hi.xyz} (exact leaf boxes, by DFS slot of the reference
+// tree); d_leaf_code: n x (slot | sphere bit); root box = union of all leaf boxes.  Writes n - 1 InnerNode records
+// (64 B, tutu_internal.hpp) to d_inner_out, root = node 0, inner boxes = exact fmin/fmax unions, and the number
+// of inner nodes on the longest root-to-leaf path to *depth_out.  Synchronises `s` before returning.
+cudaError_t device_build_lbvh(const float* d_leaf_box, const uint32_t* d_leaf_code, uint32_t n, const float root_lo[3],
+                              const float root_hi[3], void* d_inner_out, uint32_t* depth_out, int sm_count, cudaStream_t s);
+
+}  // namespace tutu

@@ -88,6 +88,22 @@ static inline int max_extent(const Box& b) {  // BoundBox.hpp:43-52
   return 2;
 }
 
+// chunks [begin, end) of [0, n) on up to 16 host threads (serial below 32 Ki items); fn(begin, end, thread index)
+template <class F>
+static void parallel_chunks(size_t n, F fn) {
+  unsigned t = std::thread::hardware_concurrency();
+  t = t < 1 ? 1 : (t > 16 ? 16 : t);
+  if (n < (1u << 15) || t == 1) {
+    fn((size_t)0, n, 0u);
+    return;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(t);
+  for (unsigned k = 0; k < t; ++k) pool.emplace_back([=] { fn(n * k / t, n * (k + 1) / t, k); });
+  for (auto& th : pool) th.join();
+}
+constexpr unsigned kMaxHostThreads = 16;
+
 // ------------------------------------------------------------------------------------------
 // midpoint BVH, reference split rule (BVH.hpp:47-123)
 // ------------------------------------------------------------------------------------------
@@ -238,8 +254,8 @@ static inline void set_node_boxes(InnerNode& in, const Box& l, const Box& r) {
 // what the equal-t tie rule compares.  Irregular rays keep walking the reference topology.
 namespace {
 struct FastBuilder {
-  const std::vector<Box>& lbox;
-  const std::vector<uint32_t>& code;
+  const PodVec<Box>& lbox;
+  const PodVec<uint32_t>& code;
   std::vector<uint32_t> idx;
   std::vector<V3> cen;
   InnerNode* out;
@@ -363,7 +379,7 @@ struct FastBuilder {
 // leaf_code[s] = slot | SPHERE_BIT.  On return fs->inner_fast / root_ref_fast / depth_fast are set;
 // when the leaf boxes are not all finite (or the tree could not respect the depth limit) the
 // reference topology is reused.
-static void build_fast_tree(FlatScene* fs, const std::vector<uint32_t>& leaf_code, int max_depth) {
+static void build_fast_tree(FlatScene* fs, const PodVec<uint32_t>& leaf_code, int max_depth) {
   const uint32_t n = (uint32_t)fs->leaf_box.size();
   fs->inner_fast = fs->inner;
   fs->root_ref_fast = fs->root_ref;
@@ -376,7 +392,7 @@ static void build_fast_tree(FlatScene* fs, const std::vector<uint32_t>& leaf_cod
     for (int a = 0; a < 3; ++a)
       if (!std::isfinite(b.lo[a]) || !std::isfinite(b.hi[a])) return;
   if (FastBuilder::ceil_log2(n) + 2 > max_depth) return;
-  std::vector<InnerNode> out(n - 1);
+  PodVec<InnerNode> out(n - 1);
   FastBuilder fb{fs->leaf_box, leaf_code, {}, {}, out.data(), max_depth};
   fb.idx.resize(n);
   fb.cen.resize(n);
@@ -393,6 +409,8 @@ static void build_fast_tree(FlatScene* fs, const std::vector<uint32_t>& leaf_cod
   fs->root_ref_fast = ref;
   fs->depth_fast = deepest;
 }
+
+void build_host_fast_tree(FlatScene* fs) { build_fast_tree(fs, fs->leaf_code, kFastTreeMaxDepth); }
 
 // ------------------------------------------------------------------------------------------
 // BDPT camera constants — Camera.hpp:12-48, Vector.hpp:228-372, BDPT.hpp:396-418
@@ -520,7 +538,7 @@ static inline bool has_emission(const TutuMaterial& m) {  // Material.hpp:54-56
   return m.emission[0] || m.emission[1] || m.emission[2];
 }
 
-int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
+int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs, bool host_fast_tree) {
   if (!desc || desc->struct_size != sizeof(TutuSceneDesc)) {
     set_error("scene: struct_size mismatch (ABI version skew?)");
     return TUTU_E_INVALID;
@@ -688,14 +706,32 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
   }
 
   // node boxes bottom-up: children always come later than their parent in `order`
-  std::vector<Box> nbox(n_nodes);
-  for (size_t k = order.size(); k-- > 0;) {
-    uint32_t i = order[k];
-    const TutuBvhNode& nd = nodes[i];
-    if (nd.left < 0)
-      nbox[i] = prim_bound(desc->prims[nd.prim]);
-    else
-      nbox[i] = box_union(nbox[nd.left], nbox[nd.right]);  // BVH.hpp:65,119
+  PodVec<Box> nbox(n_nodes);
+  parallel_chunks(n_nodes, [&](size_t b, size_t e, unsigned) {  // leaf boxes are independent of each other
+    for (size_t i = b; i < e; ++i)
+      if (nodes[i].left < 0) nbox[i] = prim_bound(desc->prims[nodes[i].prim]);
+  });
+  {
+    // inner boxes level by level from the deepest one (the nodes of a level are independent of each other)
+    std::vector<uint32_t> level_start(fs->depth + 2, 0);
+    for (uint32_t i = 0; i < n_nodes; ++i)
+      if (nodes[i].left >= 0) level_start[depth_of[i] + 1]++;
+    for (size_t d = 1; d < level_start.size(); ++d) level_start[d] += level_start[d - 1];
+    PodVec<uint32_t> by_level(n - 1);
+    {
+      std::vector<uint32_t> cursor(level_start.begin(), level_start.end() - 1);
+      for (uint32_t i = 0; i < n_nodes; ++i)
+        if (nodes[i].left >= 0) by_level[cursor[depth_of[i]]++] = i;
+    }
+    for (size_t d = level_start.size() - 1; d-- > 0;) {
+      const uint32_t first = level_start[d], count = level_start[d + 1] - first;
+      parallel_chunks(count, [&](size_t b, size_t e, unsigned) {
+        for (size_t k = b; k < e; ++k) {
+          const uint32_t i = by_level[first + k];
+          nbox[i] = box_union(nbox[nodes[i].left], nbox[nodes[i].right]);  // BVH.hpp:65,119
+        }
+      });
+    }
   }
   fs->root_box = nbox[0];
 
@@ -716,7 +752,10 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
   for (uint32_t i = 0; i < n; ++i) any_tex |= desc->prims[i].tex_active != 0;
   if (any_tex) fs->leaftex.resize(n);
 
-  for (uint32_t i = 0; i < n_nodes; ++i) {
+  float max_edge_of[kMaxHostThreads] = {};
+  parallel_chunks(n_nodes, [&](size_t chunk_begin, size_t chunk_end, unsigned tid) {
+  float max_edge = 0.f;  // per thread, combined below
+  for (size_t i = chunk_begin; i < chunk_end; ++i) {
     const TutuBvhNode& nd = nodes[i];
     if (nd.left >= 0) {
       InnerNode& in = fs->inner[inner_of[i]];
@@ -741,7 +780,7 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
       g.f[1] = p.v[1];
       g.f[2] = p.v[2];
       g.f[3] = p.v[3];
-      if (2.f * fabsf(p.v[3]) > fs->max_edge && fabsf(p.v[3]) < 1.0e38f) fs->max_edge = 2.f * fabsf(p.v[3]);
+      if (2.f * fabsf(p.v[3]) > max_edge && fabsf(p.v[3]) < 1.0e38f) max_edge = 2.f * fabsf(p.v[3]);
       sh.flags |= SHADE_SPHERE_BIT;
     } else {
       // Triangle.hpp:25-35: E1, E2 and the unit geometric normal are ray independent, so they
@@ -755,7 +794,7 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
         float l2 = sqrtf(e2.x * e2.x + e2.y * e2.y + e2.z * e2.z);
         float l3 = sqrtf(e3.x * e3.x + e3.y * e3.y + e3.z * e3.z);
         float l = fmaxf(l1, fmaxf(l2, l3));
-        if (l > fs->max_edge && l < 3.0e38f) fs->max_edge = l;
+        if (l > max_edge && l < 3.0e38f) max_edge = l;
       }
       st3(g.f + 0, v0);
       st3(g.f + 3, e1);
@@ -774,11 +813,19 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
       lt.metallic = p.tex_active ? p.tex_metallic : -1;
     }
   }
+  max_edge_of[tid] = max_edge;
+  });
+  for (float m : max_edge_of) fs->max_edge = fmaxf(fs->max_edge, m);
 
   // slot lookup for lights
-  std::vector<int32_t> prim_slot(n, -1);
-  for (uint32_t s = 0; s < n; ++s) prim_slot[fs->slot_to_prim[s]] = (int32_t)s;
-  for (uint32_t i = 0; i < n; ++i) {
+  bool any_light = false;
+  for (uint32_t k = 0; k < desc->n_materials; ++k) any_light = any_light || has_emission(desc->materials[k]);
+  std::vector<int32_t> prim_slot;
+  if (any_light) {
+    prim_slot.assign(n, -1);
+    for (uint32_t s = 0; s < n; ++s) prim_slot[fs->slot_to_prim[s]] = (int32_t)s;
+  }
+  for (uint32_t i = 0; any_light && i < n; ++i) {
     const TutuPrim& p = desc->prims[i];
     const TutuMaterial& m = desc->materials[p.material];
     if (!has_emission(m)) continue;
@@ -806,10 +853,14 @@ int flatten_scene(const TutuSceneDesc* desc, FlatScene* fs) {
   }
 
   // traversal tree for regular rays (the reference topology stays in fs->inner for the others)
-  {
-    std::vector<uint32_t> leaf_code(n);
-    for (uint32_t s = 0; s < n; ++s) leaf_code[s] = s | ((fs->shade[s].flags & SHADE_SPHERE_BIT) ? SPHERE_BIT : 0u);
-    build_fast_tree(fs, leaf_code, 30);
+  fs->leaf_code.resize(n);
+  for (uint32_t s = 0; s < n; ++s) fs->leaf_code[s] = s | ((fs->shade[s].flags & SHADE_SPHERE_BIT) ? SPHERE_BIT : 0u);
+  if (host_fast_tree) {
+    build_fast_tree(fs, fs->leaf_code, kFastTreeMaxDepth);
+  } else {  // the caller replaces this with a device-built tree (or calls build_host_fast_tree on failure)
+    fs->inner_fast.clear();
+    fs->root_ref_fast = fs->root_ref;
+    fs->depth_fast = fs->depth;
   }
   return TUTU_OK;
 }

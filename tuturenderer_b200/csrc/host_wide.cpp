@@ -121,20 +121,36 @@ void build_wide_tree(FlatScene* fs) {
   for (const Box& b : fs->leaf_box)
     for (int a = 0; a < 3; ++a)
       if (!std::isfinite(b.lo[a]) || !std::isfinite(b.hi[a])) return;
-  const std::vector<InnerNode>& bin = fs->inner_fast;
+  const PodVec<InnerNode>& bin = fs->inner_fast;
 
   // ---- which binary nodes become wide nodes: the surface-area dynamic programme of Ylitie et al. (section 3.1) ----
   // C(m, i) = least sum of wide-node surface areas with which the subtree of binary node m can be represented
   // as at most i roots (i = 1: one wide node at m; leaves are single primitives and cost the same in any tree):
   //   C(m, 1) = A(m) + min_k C(left, k) + C(right, 8 - k)          (m's wide node has <= 8 child slots)
   //   C(m, i) = min(C(m, i - 1), min_k C(left, k) + C(right, i - k))
-  // Children of a binary node have larger indices than their parent (pre-order, host_scene.cpp), so one
-  // backwards sweep fills the table.  split[m][i-1] = k chosen for i roots (0 = "use the i - 1 solution").
+  // The table is filled children first: reverse pre-order of the tree (the host SAH tree is stored in pre-order,
+  // a device-built Karras tree is not, so the order is computed).  split[m][i-1] = k chosen for i roots
+  // (0 = "use the i - 1 solution").
   const size_t nb_nodes = bin.size();
   std::vector<float> cost(nb_nodes * 8);
   std::vector<uint8_t> split(nb_nodes * 8);
+  std::vector<uint32_t> preorder;
+  preorder.reserve(nb_nodes);
+  if (fs->root_ref_fast >= 0) {
+    std::vector<uint32_t> todo;
+    todo.push_back((uint32_t)fs->root_ref_fast);
+    while (!todo.empty()) {
+      const uint32_t m = todo.back();
+      todo.pop_back();
+      if (m >= nb_nodes || preorder.size() >= nb_nodes) return;  // not a tree
+      preorder.push_back(m);
+      if (bin[m].right >= 0) todo.push_back((uint32_t)bin[m].right);
+      if (bin[m].left >= 0) todo.push_back((uint32_t)bin[m].left);
+    }
+  }
   auto C = [&](int32_t ref, int i) -> float { return ref < 0 ? 0.f : cost[(size_t)ref * 8 + (size_t)(i - 1)]; };
-  for (size_t m = nb_nodes; m-- > 0;) {
+  for (size_t pi = preorder.size(); pi-- > 0;) {
+    const size_t m = preorder[pi];
     const InnerNode& b = bin[m];
     const float area = box_area(box_join(child_box(b, 0), child_box(b, 1)));
     auto distribute = [&](int slots, uint8_t* k_out) {

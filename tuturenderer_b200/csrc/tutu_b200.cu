@@ -17,6 +17,9 @@
 #include "resident.cuh"
 #include "postprocess.cuh"
 #include "trace_kernels.hpp"
+#include "device_bvh.hpp"
+#include <chrono>
+#include <cmath>
 
 using namespace tutu;
 
@@ -62,8 +65,8 @@ struct DevBuf {
   }
 };
 
-template <class T>
-void upload_vec(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
+template <class T, class A>
+void upload_vec(DevBuf& b, const std::vector<T, A>& v, cudaStream_t s) {
   b.ensure(std::max<size_t>(v.size() * sizeof(T), 16));
   if (!v.empty()) CUDA_TRY(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
 }
@@ -130,6 +133,10 @@ struct TutuCtx {
   DevScene dev{};
   SmallScene small{};  // n = 0 unless the scene has <= kSmallMax primitives
   DevBuf d_inner_fast, d_wide, d_wleaf, d_wbox;
+  DevBuf d_leaf_box, d_leaf_code;  // inputs of the device tree build
+  int builder_cfg = TUTU_BUILD_AUTO;
+  bool device_tree = false;  // d_inner_fast was built on the device (ctx->flat.inner_fast is empty until someone needs it)
+  TutuUploadStats upload_stats{};
   WideGrids wide_grids;  // trace_kernels.cu: persistent grids of the wide-tree kernels for the current stack size
   bool use_wide = false;  // tutu_set_traversal_mode(ctx, 6): regular rays walk the compressed 8-wide tree (built on demand)
   DevBuf d_inner, d_geom, d_shade, d_leaftex, d_slot_to_prim, d_materials, d_lights, d_texels;
@@ -1289,15 +1296,57 @@ extern "C" void tutu_ctx_destroy(TutuCtx* ctx) {
 
 extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   API_BEGIN(ctx)
+  using Clock = std::chrono::steady_clock;
+  auto ms_since = [](Clock::time_point t) { return std::chrono::duration<float, std::milli>(Clock::now() - t).count(); };
+  const Clock::time_point t_start = Clock::now();
+  constexpr uint32_t kDeviceBuildMin = 1u << 16;
+  const bool want_device = desc && (ctx->builder_cfg == TUTU_BUILD_DEVICE_LBVH ||
+                                    (ctx->builder_cfg == TUTU_BUILD_AUTO && desc->n_prims >= kDeviceBuildMin));
   FlatScene fs;
-  int rc = flatten_scene(desc, &fs);
+  int rc = flatten_scene(desc, &fs, false);  // the traversal tree is built (and timed) below
   if (rc != TUTU_OK) return fail(ctx, rc, get_error());
-  if (ctx->use_wide) build_wide_tree(&fs);
+  TutuUploadStats us{};
+  us.builder = TUTU_BUILD_HOST_SAH;
+  us.flatten_ms = ms_since(t_start);
+  cudaStream_t s = ctx->stream;
+  bool device_tree = false;
+  const Clock::time_point t_build = Clock::now();
+  if (!want_device) {
+    build_host_fast_tree(&fs);
+  } else {
+    bool finite = fs.n_prims >= 3;
+    for (size_t k = 0; finite && k < fs.leaf_box.size(); ++k)
+      for (int a = 0; a < 3; ++a) finite = finite && std::isfinite(fs.leaf_box[k].lo[a]) && std::isfinite(fs.leaf_box[k].hi[a]);
+    if (finite) {
+      upload_vec(ctx->d_leaf_box, fs.leaf_box, s);
+      upload_vec(ctx->d_leaf_code, fs.leaf_code, s);
+      ctx->d_inner_fast.ensure((size_t)(fs.n_prims - 1) * sizeof(InnerNode));
+      uint32_t depth = 0;
+      CUDA_TRY(device_build_lbvh(ctx->d_leaf_box.as<float>(), ctx->d_leaf_code.as<uint32_t>(), fs.n_prims, fs.root_box.lo,
+                                 fs.root_box.hi, ctx->d_inner_fast.p, &depth, ctx->sm_count, s));
+      if (depth >= 1 && depth <= (uint32_t)kFastTreeMaxDepth) {
+        device_tree = true;
+        fs.root_ref_fast = 0;
+        fs.depth_fast = depth;
+        us.builder = TUTU_BUILD_DEVICE_LBVH;
+      }
+    }
+    if (!device_tree) build_host_fast_tree(&fs);  // non-finite boxes, tiny scenes, or a tree deeper than the stacks
+  }
+  us.tree_build_ms = ms_since(t_build);
+  if (ctx->use_wide) {
+    if (device_tree) {  // the wide collapse runs on the host: fetch the binary tree it collapses
+      fs.inner_fast.resize(fs.n_prims - 1);
+      CUDA_TRY(cudaMemcpyAsync(fs.inner_fast.data(), ctx->d_inner_fast.p, fs.inner_fast.size() * sizeof(InnerNode), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    build_wide_tree(&fs);
+  }
   if (std::max(fs.depth, fs.depth_fast) > (uint32_t)kStackSize)
     return fail(ctx, TUTU_E_INVALID, "scene: BVH deeper than the traversal stack (" + std::to_string(fs.depth) + ")");
-  cudaStream_t s = ctx->stream;
+  const Clock::time_point t_h2d = Clock::now();
   upload_vec(ctx->d_inner, fs.inner, s);
-  upload_vec(ctx->d_inner_fast, fs.inner_fast, s);
+  if (!device_tree) upload_vec(ctx->d_inner_fast, fs.inner_fast, s);
   upload_vec(ctx->d_wide, fs.wide, s);
   upload_vec(ctx->d_wleaf, fs.wleaf, s);
   upload_vec(ctx->d_wbox, fs.wbox, s);
@@ -1310,6 +1359,8 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   upload_vec(ctx->d_texels, fs.texels, s);
   for (int c = 0; c < 4; ++c) upload_vec(ctx->d_texh[c], fs.tex_headers[c], s);
   CUDA_TRY(cudaStreamSynchronize(s));
+  us.h2d_ms = ms_since(t_h2d);
+  us.tree_depth = fs.depth_fast;
   DevScene& d = ctx->dev;
   d.inner = ctx->d_inner.as<float4>();
   d.inner_fast = ctx->d_inner_fast.as<float4>();
@@ -1378,7 +1429,10 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
                      fs.slot_to_prim.size() * 4 + fs.materials.size() * sizeof(DevMaterial) +
                      fs.lights.size() * sizeof(DevLight) + fs.texels.size() * 4;
   ctx->flat = std::move(fs);
+  ctx->device_tree = device_tree;
   ctx->has_scene = true;
+  us.total_ms = ms_since(t_start);
+  ctx->upload_stats = us;
   return TUTU_OK;
   API_END(ctx)
 }
@@ -1397,12 +1451,27 @@ extern "C" int tutu_scene_info(const TutuCtx* ctx, TutuSceneInfo* out) {
   out->height = (uint32_t)f.raygen.height;
   out->device_bytes = ctx->scene_bytes;
   const bool wide = ctx->dev.wide != nullptr;
-  out->trav_nodes = wide ? (uint32_t)f.wide.size() : (uint32_t)f.inner_fast.size();
+  out->trav_nodes = wide ? (uint32_t)f.wide.size() : (ctx->device_tree ? f.n_prims - 1 : (uint32_t)f.inner_fast.size());
   out->trav_depth = wide ? f.wide_depth : f.depth_fast;
   out->trav_width = wide ? 8 : 2;
   out->trav_node_bytes = wide ? (uint32_t)sizeof(WideNode) : (uint32_t)sizeof(InnerNode);
   out->trav_leaf_bytes = wide ? (uint32_t)sizeof(WideLeaf) : (uint32_t)sizeof(LeafGeom);
   out->reserved = 0;
+  return TUTU_OK;
+}
+
+extern "C" int tutu_scene_builder(TutuCtx* ctx, int builder) {
+  if (!ctx || builder < TUTU_BUILD_AUTO || builder > TUTU_BUILD_DEVICE_LBVH)
+    return fail(ctx, TUTU_E_INVALID, "tutu_scene_builder: builder must be TUTU_BUILD_AUTO, _HOST_SAH or _DEVICE_LBVH");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->builder_cfg = builder;
+  return TUTU_OK;
+}
+
+extern "C" int tutu_upload_stats(const TutuCtx* ctx, TutuUploadStats* out) {
+  if (!ctx || !out) return fail(nullptr, TUTU_E_INVALID, "tutu_upload_stats: null argument");
+  if (!ctx->has_scene) return fail(const_cast<TutuCtx*>(ctx), TUTU_E_STATE, "no scene uploaded");
+  *out = ctx->upload_stats;
   return TUTU_OK;
 }
 
@@ -1440,6 +1509,11 @@ extern "C" int tutu_set_traversal_mode(TutuCtx* ctx, int mode) {
       ctx->use_wide = true;
       if (ctx->has_scene && ctx->flat.wide.empty()) {
         CUDA_TRY(cudaDeviceSynchronize());  // nothing may still read the buffers that are replaced below
+        if (ctx->device_tree && ctx->flat.inner_fast.empty()) {  // the collapse runs on the host
+          ctx->flat.inner_fast.resize(ctx->flat.n_prims - 1);
+          CUDA_TRY(cudaMemcpy(ctx->flat.inner_fast.data(), ctx->d_inner_fast.p, ctx->flat.inner_fast.size() * sizeof(InnerNode),
+                              cudaMemcpyDeviceToHost));
+        }
         build_wide_tree(&ctx->flat);
         upload_vec(ctx->d_wide, ctx->flat.wide, ctx->stream);
         upload_vec(ctx->d_wleaf, ctx->flat.wleaf, ctx->stream);

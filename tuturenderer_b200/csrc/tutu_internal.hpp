@@ -3,6 +3,9 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <memory>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/tutu_b200.h"
@@ -153,6 +156,27 @@ struct BdptCamConsts {
   int32_t width, height;
 };
 
+// std::vector without value-initialisation of trivially constructible elements: resize(n) of the 10^6-entry leaf
+// tables would otherwise zero-fill ~200 MB single-threaded before the (parallel) loops that fill them.
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = DefaultInitAllocator<U>;
+  };
+  using std::allocator<T>::allocator;
+  template <class U>
+  void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+    ::new (static_cast<void*>(p)) U;
+  }
+  template <class U, class... A>
+  void construct(U* p, A&&... a) {
+    ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+  }
+};
+template <class T>
+using PodVec = std::vector<T, DefaultInitAllocator<T>>;
+
 struct FlatScene {
   uint32_t n_prims = 0;
   uint32_t n_ref_nodes = 0;
@@ -161,19 +185,20 @@ struct FlatScene {
   bool empty = true;
   Box root_box{};
   float max_edge = 0.f;  // longest triangle edge / sphere diameter (pruning slack)
-  std::vector<InnerNode> inner;       // the reference's topology (irregular rays, literal walk)
-  std::vector<InnerNode> inner_fast;  // SAH topology over the same leaves (regular rays), host_scene.cpp
+  PodVec<InnerNode> inner;       // the reference's topology (irregular rays, literal walk)
+  PodVec<InnerNode> inner_fast;  // SAH topology over the same leaves (regular rays), host_scene.cpp
   int32_t root_ref_fast = 0;
   uint32_t depth_fast = 0;
   std::vector<WideNode> wide;      // compressed 8-wide collapse of inner_fast (empty: the device walks inner_fast)
   std::vector<WideLeaf> wleaf;
   std::vector<WideLeafBox> wbox;
   uint32_t wide_depth = 0;         // levels of wide nodes, root = 1
-  std::vector<LeafGeom> geom;
-  std::vector<LeafShade> shade;
+  PodVec<LeafGeom> geom;
+  PodVec<LeafShade> shade;
   std::vector<LeafTex> leaftex;
-  std::vector<int32_t> slot_to_prim;
-  std::vector<Box> leaf_box;  // per leaf slot (small-scene fast path)
+  PodVec<int32_t> slot_to_prim;
+  PodVec<Box> leaf_box;  // per leaf slot (small-scene fast path, traversal-tree builders)
+  PodVec<uint32_t> leaf_code;  // per leaf slot: slot | SPHERE_BIT
   std::vector<DevMaterial> materials;
   std::vector<DevLight> lights;
   std::vector<TexHeader> tex_headers[4];
@@ -195,7 +220,10 @@ const std::string& get_error();
 extern const char* (*g_ctx_error_hook)(const TutuCtx*);
 
 // Validates the desc, builds the BVH if none is given, flattens to device layout.
-int flatten_scene(const TutuSceneDesc* desc, FlatScene* out);
+// host_fast_tree = false leaves inner_fast empty (the caller builds the traversal tree on the device)
+int flatten_scene(const TutuSceneDesc* desc, FlatScene* out, bool host_fast_tree = true);
+constexpr int kFastTreeMaxDepth = 30;  // traversal trees deeper than this are rejected (stack size, trace.cuh kStackSize)
+void build_host_fast_tree(FlatScene* fs);  // binned SAH over the leaves (host_scene.cpp)
 // host_wide.cpp
 void build_wide_tree(FlatScene* fs);
 uint64_t verify_wide_tree(const FlatScene& fs);
