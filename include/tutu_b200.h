@@ -194,11 +194,13 @@ const char* tutu_last_error(const TutuCtx* ctx);
 int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc);
 int tutu_scene_info(const TutuCtx* ctx, TutuSceneInfo* out);
 /* Who builds the traversal tree for regular rays (a binary tree over the reference's leaves; the reference's own
- * topology is always kept for irregular rays and the literal walk): TUTU_BUILD_AUTO = on the device for scenes of
- * >= 65 536 primitives, on the host otherwise; TUTU_BUILD_HOST_SAH = binned surface-area heuristic on the host
- * (0.3-0.7 s for 10^6 primitives, the better tree); TUTU_BUILD_DEVICE_LBVH = linear BVH on the GPU (Morton sort
- * + Karras hierarchy + refit, a few ms for 10^6 primitives).  Takes effect at the next tutu_scene_upload.  Hits do
- * not depend on the choice (any tree with exact union boxes over the same leaves gives the same answer). */
+ * topology is always kept for irregular rays and the literal walk): TUTU_BUILD_HOST_SAH = binned surface-area
+ * heuristic on the host (0.24 s for 10^6 primitives on 16 threads; the better tree: 34 node visits per ray on
+ * configs[1]); TUTU_BUILD_DEVICE_LBVH = linear BVH on the GPU (Morton keys, radix sort, Karras hierarchy, refit:
+ * 29 ms for 10^6 primitives incl. its uploads, but 91 node visits per ray): for previews and scenes that change
+ * every frame; TUTU_BUILD_AUTO = the host SAH tree (DESIGN.md 5.8 has the measurements).  Takes effect at the next
+ * tutu_scene_upload.  Hits do not depend on the choice (any tree with exact union boxes over the same leaves gives
+ * the same answer); trees deeper than 30 levels fall back to the host builder. */
 #define TUTU_BUILD_AUTO 0
 #define TUTU_BUILD_HOST_SAH 1
 #define TUTU_BUILD_DEVICE_LBVH 2

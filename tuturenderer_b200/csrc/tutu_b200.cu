@@ -979,6 +979,19 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
     bool done = false;
   };
   std::vector<Run> runs(n_lanes);
+  struct BlockGraph {  // one captured block of iterations per lane, valid for this render only (seed, sample range)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;
+    BlockGraph() = default;
+    BlockGraph(const BlockGraph&) = delete;
+    BlockGraph& operator=(const BlockGraph&) = delete;
+    ~BlockGraph() {
+      if (exec) cudaGraphExecDestroy(exec);
+      if (graph) cudaGraphDestroy(graph);
+    }
+  };
+  std::vector<BlockGraph> graphs(n_lanes);
   uint64_t launches = 0;
   try {
     for (int k = 0; k < n_lanes; ++k) {  // queue pools first: a (re)allocation is not device time of the render
@@ -1001,62 +1014,93 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
       timers.emplace_back(ctx->profile_stages != 0);
       runs[k].done = lane_total == 0;
     }
-    const int poll_every = 8;
-    for (uint64_t it = 0;; ++it) {
+    // One wavefront iteration of lane k on its stream: raygen -> extend -> (classify) -> shade -> shadow + the two
+    // one-thread control kernels.  Returns the number of launches.
+    auto enqueue_iteration = [&](int k, bool first_iteration) -> uint64_t {
+      WfLane& L = ctx->wf_lanes[k];
+      cudaStream_t ls = L.stream;
+      StageTimer& timer = timers[k];
+      const int cur = runs[k].cur;
+      uint64_t n_launch = 6;
+      timer.mark(0, ls);
+      wf_raygen<<<ctx->grid_raygen, 256, 0, ls>>>(L.b, cur, rk, runs[k].s_begin);
+      wf_ctl_after_raygen<<<1, 1, 0, ls>>>(L.b.ctl, L.b.capacity);
+      timer.mark(1, ls);
+      if (small)
+        wf_extend_small<<<ctx->grid_extend, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
+      else if (wide)
+        CUDA_TRY(wide_launch_wf_extend(ctx->grid_extend, want_stack, ls, ctx->dev, L.b, cur));
+      else
+        wf_extend<0><<<ctx->grid_extend, 256, want_stack, ls>>>(ctx->dev, ctx->small, L.b, cur);
+      if (first_iteration && k + 1 < n_lanes) {
+        // stagger the lanes by one stage so that unlike kernels (traverse / shade) overlap
+        CUDA_TRY(cudaEventRecord(L.ev_done, ls));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->wf_lanes[k + 1].stream, L.ev_done, 0));
+      }
+      timer.mark(2, ls);
+      if (L.b.class_perm) {
+        wf_classify<<<ctx->sm_count * 8, 256, 0, ls>>>(ctx->dev, L.b);
+        n_launch += 1;
+      }
+      wf_shade<<<ctx->grid_shade, ctx->shade_block, 0, ls>>>(ctx->dev, L.b, cur, seed);
+      timer.mark(3, ls);
+      if (small)
+        wf_shadow_small<<<ctx->grid_shadow, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
+      else if (wide)
+        CUDA_TRY(wide_launch_wf_shadow(ctx->grid_shadow, want_stack, ls, ctx->dev, L.b, cur ^ 1));
+      else
+        wf_shadow<0><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
+      timer.mark(0, ls);
+      wf_ctl_after_iter<<<1, 1, 0, ls>>>(L.b.ctl);
+      runs[k].cur ^= 1;
+      return n_launch;
+    };
+    // The host looks at a lane's control block every kBlockIters iterations.  The first block is enqueued launch
+    // by launch (it carries the stagger between the lanes); every further block of a lane is ONE graph launch: the
+    // block's launches + the control-block read-back, captured once per render from the lane's stream (an even
+    // number of iterations, so the ping-pong index `cur` is the same at every block start).
+    constexpr int kBlockIters = 8;
+    static_assert(kBlockIters % 2 == 0, "a block must leave the ping-pong index where it found it");
+    const bool use_graphs = ctx->profile_stages == 0;
+    for (uint64_t block = 0;; ++block) {
       bool any = false;
       for (int k = 0; k < n_lanes; ++k) {
         if (runs[k].done) continue;
         any = true;
         WfLane& L = ctx->wf_lanes[k];
-        cudaStream_t ls = L.stream;
-        StageTimer& timer = timers[k];
-        const int cur = runs[k].cur;
-        timer.mark(0, ls);
-        wf_raygen<<<ctx->grid_raygen, 256, 0, ls>>>(L.b, cur, rk, runs[k].s_begin);
-        wf_ctl_after_raygen<<<1, 1, 0, ls>>>(L.b.ctl, L.b.capacity);
-        timer.mark(1, ls);
-        if (small)
-          wf_extend_small<<<ctx->grid_extend, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
-        else if (wide)
-          CUDA_TRY(wide_launch_wf_extend(ctx->grid_extend, want_stack, ls, ctx->dev, L.b, cur));
-        else
-          wf_extend<0><<<ctx->grid_extend, 256, want_stack, ls>>>(ctx->dev, ctx->small, L.b, cur);
-        if (it == 0 && k + 1 < n_lanes) {
-          // stagger the lanes by one stage so that unlike kernels (traverse / shade) overlap
-          CUDA_TRY(cudaEventRecord(L.ev_done, ls));
-          CUDA_TRY(cudaStreamWaitEvent(ctx->wf_lanes[k + 1].stream, L.ev_done, 0));
+        if (block == 0 || !use_graphs) {
+          for (int it = 0; it < kBlockIters; ++it) launches += enqueue_iteration(k, block == 0 && it == 0);
+          CUDA_TRY(cudaMemcpyAsync(L.ctl_host, L.b.ctl, sizeof(WfCtl), cudaMemcpyDeviceToHost, L.stream));
+          continue;
         }
-        timer.mark(2, ls);
-        if (L.b.class_perm) {
-          wf_classify<<<ctx->sm_count * 8, 256, 0, ls>>>(ctx->dev, L.b);
-          launches += 1;
+        if (!graphs[k].exec) {
+          CUDA_TRY(cudaStreamBeginCapture(L.stream, cudaStreamCaptureModeThreadLocal));
+          uint64_t n_launch = 0;
+          try {
+            for (int it = 0; it < kBlockIters; ++it) n_launch += enqueue_iteration(k, false);
+            CUDA_TRY(cudaMemcpyAsync(L.ctl_host, L.b.ctl, sizeof(WfCtl), cudaMemcpyDeviceToHost, L.stream));
+          } catch (...) {
+            cudaGraph_t broken = nullptr;
+            cudaStreamEndCapture(L.stream, &broken);
+            if (broken) cudaGraphDestroy(broken);
+            throw;
+          }
+          CUDA_TRY(cudaStreamEndCapture(L.stream, &graphs[k].graph));
+          CUDA_TRY(cudaGraphInstantiate(&graphs[k].exec, graphs[k].graph, 0));
+          graphs[k].launches = n_launch;
         }
-        wf_shade<<<ctx->grid_shade, ctx->shade_block, 0, ls>>>(ctx->dev, L.b, cur, seed);
-        timer.mark(3, ls);
-        if (small)
-          wf_shadow_small<<<ctx->grid_shadow, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
-        else if (wide)
-          CUDA_TRY(wide_launch_wf_shadow(ctx->grid_shadow, want_stack, ls, ctx->dev, L.b, cur ^ 1));
-        else
-          wf_shadow<0><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
-        timer.mark(0, ls);
-        wf_ctl_after_iter<<<1, 1, 0, ls>>>(L.b.ctl);
-        launches += 6;
-        runs[k].cur ^= 1;
-        if ((it + 1) % poll_every == 0)
-          CUDA_TRY(cudaMemcpyAsync(L.ctl_host, L.b.ctl, sizeof(WfCtl), cudaMemcpyDeviceToHost, ls));
+        CUDA_TRY(cudaGraphLaunch(graphs[k].exec, L.stream));
+        launches += graphs[k].launches;
       }
       if (!any) break;
-      if ((it + 1) % poll_every == 0) {
-        CUDA_TRY(cudaGetLastError());
-        for (int k = 0; k < n_lanes; ++k) {
-          if (runs[k].done) continue;
-          WfLane& L = ctx->wf_lanes[k];
-          CUDA_TRY(cudaStreamSynchronize(L.stream));
-          if (L.ctl_host->done) {
-            runs[k].done = true;
-            timers[k].mark(0, L.stream);
-          }
+      CUDA_TRY(cudaGetLastError());
+      for (int k = 0; k < n_lanes; ++k) {
+        if (runs[k].done) continue;
+        WfLane& L = ctx->wf_lanes[k];
+        CUDA_TRY(cudaStreamSynchronize(L.stream));
+        if (L.ctl_host->done) {
+          runs[k].done = true;
+          timers[k].mark(0, L.stream);
         }
       }
     }
@@ -1299,9 +1343,11 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   using Clock = std::chrono::steady_clock;
   auto ms_since = [](Clock::time_point t) { return std::chrono::duration<float, std::milli>(Clock::now() - t).count(); };
   const Clock::time_point t_start = Clock::now();
-  constexpr uint32_t kDeviceBuildMin = 1u << 16;
-  const bool want_device = desc && (ctx->builder_cfg == TUTU_BUILD_DEVICE_LBVH ||
-                                    (ctx->builder_cfg == TUTU_BUILD_AUTO && desc->n_prims >= kDeviceBuildMin));
+  // TUTU_BUILD_AUTO takes the host's binned-SAH tree at every size.  Measured on a B200 (tools/gpu_build_ab.py, 999 698
+  // triangles): the device LBVH cuts the upload from 338 to 120 ms (tree 238 -> 29 ms) but its spatial-median
+  // splits cost 91 instead of 34 node visits per ray (closest hit 842 vs 2089 Mrays/s; glass scene 766 vs 922
+  // Mpaths/s, Veach BDPT 56.8 vs 62.2 Msamples/s): it pays only for jobs that trace fewer than ~3 x 10^8 rays per upload.
+  const bool want_device = desc && ctx->builder_cfg == TUTU_BUILD_DEVICE_LBVH;
   FlatScene fs;
   int rc = flatten_scene(desc, &fs, false);  // the traversal tree is built (and timed) below
   if (rc != TUTU_OK) return fail(ctx, rc, get_error());
