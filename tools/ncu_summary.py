@@ -81,7 +81,13 @@ def full(rep: str, prefix: str) -> None:
     idx = {h: i for i, h in enumerate(hdr)}
     lines = [f"# ncu --set full --clock-control none, report {rep.split('/')[-1]} (read with ncu -i --page raw --csv)",
              "# one block per profiled launch; values are per launch"]
-    traffic: dict[str, dict] = defaultdict(lambda: {"launches": 0, "dram_bytes": 0.0, "us": 0.0})
+    traffic: dict[str, dict] = defaultdict(lambda: {"launches": 0, "dram_bytes": 0.0, "us": 0.0, "l1tex_pct": 0.0, "dram_pct": 0.0,
+                                                    "lanes": 0.0, "l1_hit_pct": 0.0, "l2_hit_pct": 0.0, "registers": 0})
+    def num(r, key):
+        try:
+            return float(r[idx[key]].replace(",", ""))
+        except (KeyError, ValueError):
+            return 0.0
     for r in body:
         name = short(r[idx["Kernel Name"]])
         lines.append("")
@@ -100,11 +106,22 @@ def full(rep: str, prefix: str) -> None:
             t["launches"] += 1
             t["dram_bytes"] += rd + wr
             t["us"] += us
+            t["l1tex_pct"] += num(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed")
+            t["dram_pct"] += num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") or num(r, "dram__throughput.avg.pct_of_peak_sustained_elapsed")
+            t["lanes"] += num(r, "smsp__thread_inst_executed_per_inst_executed.ratio")
+            t["l1_hit_pct"] += num(r, "l1tex__t_sector_hit_rate.pct")
+            t["l2_hit_pct"] += num(r, "lts__t_sector_hit_rate.pct")
+            t["registers"] = int(num(r, "launch__registers_per_thread"))
         except (KeyError, ValueError):
             pass
     open(prefix + ".txt", "w").write("\n".join(lines) + "\n")
     js = {k: {"launches_profiled": v["launches"], "dram_bytes_per_launch": v["dram_bytes"] / v["launches"],
-              "us_per_launch_under_ncu": v["us"] / v["launches"]} for k, v in traffic.items()}
+              "us_per_launch_under_ncu": v["us"] / v["launches"],
+              "dram_gbs_under_ncu": v["dram_bytes"] / v["us"] * 1e-3,
+              "dram_pct_of_peak": v["dram_pct"] / v["launches"], "l1tex_pct_of_peak": v["l1tex_pct"] / v["launches"],
+              "l1_hit_pct": v["l1_hit_pct"] / v["launches"], "l2_hit_pct": v["l2_hit_pct"] / v["launches"],
+              "active_threads_per_warp_instruction": v["lanes"] / v["launches"], "registers": v["registers"]}
+          for k, v in traffic.items()}
     json.dump(js, open(prefix + "_traffic.json", "w"), indent=1)
     print(f"wrote {prefix}.txt and {prefix}_traffic.json ({len(body)} launches)")
 

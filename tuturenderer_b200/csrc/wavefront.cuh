@@ -359,10 +359,19 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
       s1 = __ldcs(b.st1[cur] + i);
       const float4 s2 = __ldcs(b.st2[cur] + i);
       const float4 hit = __ldcs(b.hit + i);
+#ifndef TUTU_SHADE_S3_LAZY
+      // st3 only matters to a vertex reached through x_inter, but `mode` sits in s2: waiting for s2 before asking
+      // for s3 puts a second memory round trip on the critical path of a latency-bound kernel.  Read it with the
+      // others (16 B more for the ~1 in 4 queue entries that are fresh paths; their value is never looked at).
+      const float4 s3 = __ldcs(b.st3[cur] + i);
+      const uint32_t dm = __float_as_uint(s2.w);
+      const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
+#else
       const uint32_t dm = __float_as_uint(s2.w);
       const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
       float4 s3 = make_float4(0, 0, 0, 0);
       if (mode == kModeXInter) s3 = __ldcs(b.st3[cur] + i);
+#endif
       pixel = __float_as_uint(s0.w);
       L = mk(s2.x, s2.y, s2.z);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
