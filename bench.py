@@ -153,7 +153,9 @@ def image_parity(ref_n: np.ndarray, gpu_n: np.ndarray, gpu_hi: np.ndarray, n: in
             "channel_mean_ratio_ref_over_gpu": [float(ref_n[:, c].mean() / gpu_hi[:, c].mean()) for c in range(3)],
             "rmse_reference": r_ref, "rmse_gpu": r_gpu, "rmse_ratio_gpu_over_reference": r_gpu / r_ref,
             "relmse_reference": relmse(ref_n, gpu_hi), "relmse_gpu": relmse(gpu_n, gpu_hi),
-            "background_mask_equal": bool(np.array_equal((ref_n == 0).all(1), (gpu_hi == 0).all(1)))}
+            # deterministic set: pixels whose primary ray misses everything are exactly bkgcolor (0) in every render
+            "background_pixels_gpu": int((gpu_hi == 0).all(1).sum()),
+            "background_pixels_also_exactly_zero_in_reference": int(((gpu_hi == 0).all(1) & (ref_n == 0).all(1)).sum())}
 
 
 def cpu_rays_baseline(scene, rays: np.ndarray, scene_path):
@@ -229,18 +231,24 @@ def workload_config(args) -> dict:
                          "(5 GB per lane) through the 126 MB L2; no flush needed"}
 
 
-def profile_record(kernel: str) -> dict | None:
+def profile_record(kernel: str, tag: str | None = None) -> dict | None:
     """ncu --set full figures of `kernel` from this round's capture (profiles/r02_traffic.json, written by
-    tools/ncu_summary.py from the committed .txt summaries): DRAM bytes per launch, L1/TEX and DRAM
-    throughput %.  Static evidence of the same code, not a live measurement."""
-    for name in ("r02_traffic.json", "r01_traffic.json"):
-        f = ROOT / "profiles" / name
-        if not f.exists():
-            continue
-        for k, rec in json.loads(f.read_text()).items():
-            if k.split("<")[0] == kernel.split("<")[0] and (("<" not in kernel) or k == kernel):
-                return dict(rec, source=f"profiles/{name}")
-    return None
+    tools/ncu_summary.py from the committed summaries): DRAM bytes per launch, DRAM / L1-TEX throughput in % of peak,
+    hit rates, active threads per warp instruction.  `tag` picks the capture of a kernel profiled on several
+    workloads ("glass").  Static evidence of the same code on a short fixed workload, not a live measurement."""
+    f = ROOT / "profiles" / "r02_traffic.json"
+    if not f.exists():
+        return None
+    table = json.loads(f.read_text())
+    base = kernel.split("<")[0]
+    names = [k for k in table if k.split("<")[0].split("@")[0] == base]
+    if tag:
+        names = [k for k in names if k.endswith("@" + tag)] or names
+    else:
+        names = [k for k in names if "@" not in k] or names
+    if not names:
+        return None
+    return dict(table[names[0]], kernel_profiled=names[0], source="profiles/r02_traffic.json")
 
 
 # --------------------------------------------------------------------------------------------
@@ -362,7 +370,7 @@ def stage_roofline(st: dict, alg: dict, peaks: dict, kernels: dict) -> dict:
     stage_ms = {k: st[f"{k}_ms"] for k in ("extend", "shade", "shadow")}
     dom = max(stage_ms, key=stage_ms.get)
     ach = alg[dom] / (stage_ms[dom] * 1e-3) * 1e-9 if stage_ms[dom] > 0 else 0.0
-    prof = profile_record(kernels[dom])
+    prof = profile_record(kernels[dom], "glass")
     total = sum(stage_ms.values()) + st["other_ms"]
     return {"bound": "hbm", "limiter": "l1tex" if dom != "shade" else "latency", "kernel": kernels[dom], "achieved": ach,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],

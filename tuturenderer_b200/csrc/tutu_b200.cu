@@ -233,10 +233,17 @@ int fail_cuda(TutuCtx* ctx, const CudaError& e) {
 // ray enters the scene box and of an octahedral direction bin, and the tracer walks a permutation.
 // Each ray's result is computed exactly as before and written to its own slot, so the output is
 // independent of the order (tests compare sorted vs unsorted bit for bit).
-constexpr int kBinOriginBits = 5;  // per axis
+constexpr int kBinOriginBits = 5;  // per axis, for the largest batches; small batches use fewer (bin_origin_bits)
 constexpr int kBinDirBits = 3;     // per octahedral axis
 constexpr int kBinKeyBits = 3 * kBinOriginBits + 2 * kBinDirBits;
-constexpr unsigned kBinCount = 1u << kBinKeyBits;
+constexpr unsigned kBinCount = 1u << kBinKeyBits;  // capacity of the histogram buffer
+// Origin bits per axis for a batch of n rays: about 8 rays per bin (2^24 rays -> 5 bits = 2^21 bins; 2^16 rays -> 2
+// bits = 2^12 bins), so that clearing and scanning the histogram stays small next to the walk for small batches.
+inline int bin_origin_bits(uint64_t n) {
+  int lg = 0;
+  while ((1ull << (lg + 1)) <= n) ++lg;
+  return std::min(kBinOriginBits, std::max(2, (lg - 9) / 3));
+}
 
 __device__ __forceinline__ unsigned spread3(unsigned v) {  // 10 bits -> every third bit
   v &= 0x3FFu;
@@ -247,7 +254,7 @@ __device__ __forceinline__ unsigned spread3(unsigned v) {  // 10 bits -> every t
   return v;
 }
 
-__device__ __forceinline__ unsigned ray_bin_key(const DevScene& sc, const float4 o, const float4 d) {
+__device__ __forceinline__ unsigned ray_bin_key(const DevScene& sc, const float4 o, const float4 d, int origin_bits) {
   // entry point into the root box (plain fp32: ordering only, never a hit decision)
   const float ix = 1.f / d.x, iy = 1.f / d.y, iz = 1.f / d.z;
   const float ax = (sc.root_lo[0] - o.x) * ix, bx = (sc.root_hi[0] - o.x) * ix;
@@ -256,7 +263,7 @@ __device__ __forceinline__ unsigned ray_bin_key(const DevScene& sc, const float4
   float te = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
   if (!(te < 3.0e38f)) te = 0.f;
   const float px = o.x + te * d.x, py = o.y + te * d.y, pz = o.z + te * d.z;
-  const float cells = (float)(1 << kBinOriginBits);
+  const float cells = (float)(1 << origin_bits);
   auto q = [&](float p, float lo, float hi) {
     const float w = hi - lo;
     float u = w > 0.f ? (p - lo) / w : 0.f;
@@ -276,14 +283,14 @@ __device__ __forceinline__ unsigned ray_bin_key(const DevScene& sc, const float4
   const unsigned du = (unsigned)(fminf(fmaxf(u * 0.5f + 0.5f, 0.f), 0.999999f) * dcells);
   const unsigned dv = (unsigned)(fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 0.999999f) * dcells);
   const unsigned dirbin = (du << kBinDirBits) | dv;
-  return (dirbin << (3 * kBinOriginBits)) | (cell & ((1u << (3 * kBinOriginBits)) - 1u));
+  return (dirbin << (3 * origin_bits)) | (cell & ((1u << (3 * origin_bits)) - 1u));
 }
 
 __global__ void __launch_bounds__(256)
-k_bin_count(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned n, unsigned* __restrict__ keys,
-            unsigned* __restrict__ hist) {
+k_bin_count(const __grid_constant__ DevScene sc, const float4* __restrict__ rays, unsigned n, int origin_bits,
+            unsigned* __restrict__ keys, unsigned* __restrict__ hist) {
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned k = ray_bin_key(sc, __ldg(rays + 2 * (size_t)i), __ldg(rays + 2 * (size_t)i + 1));
+    const unsigned k = ray_bin_key(sc, __ldg(rays + 2 * (size_t)i), __ldg(rays + 2 * (size_t)i + 1), origin_bits);
     keys[i] = k;
     atomicAdd(hist + k, 1u);
   }
@@ -325,10 +332,10 @@ k_bin_scan_totals(const unsigned* __restrict__ hist, unsigned* __restrict__ tota
 }
 
 __global__ void __launch_bounds__(1024)
-k_bin_scan_chunks(unsigned* __restrict__ totals) {
+k_bin_scan_chunks(unsigned* __restrict__ totals, unsigned n_chunks) {
   __shared__ unsigned ws[32];
   const unsigned t = threadIdx.x, lane = t & 31u;
-  const unsigned v = t < kScanChunks ? totals[t] : 0u;
+  const unsigned v = t < n_chunks ? totals[t] : 0u;
   unsigned incl = v;
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -345,7 +352,7 @@ k_bin_scan_chunks(unsigned* __restrict__ totals) {
     ws[t] = w;
   }
   __syncthreads();
-  if (t < kScanChunks) totals[t] = incl - v + ((t >> 5) ? ws[(t >> 5) - 1] : 0u);
+  if (t < n_chunks) totals[t] = incl - v + ((t >> 5) ? ws[(t >> 5) - 1] : 0u);
 }
 
 __global__ void __launch_bounds__(256)
@@ -649,12 +656,14 @@ const unsigned* bin_rays(TutuCtx* ctx, const float4* rays, uint64_t n, cudaStrea
   unsigned* keys = ctx->d_bin_keys[slot].as<unsigned>();
   unsigned* perm = ctx->d_bin_perm[slot].as<unsigned>();
   unsigned* hist = ctx->d_bin_hist[slot].as<unsigned>();
-  CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)kBinCount * sizeof(unsigned), s));
+  const int origin_bits = bin_origin_bits(n);
+  const unsigned bins = 1u << (3 * origin_bits + 2 * kBinDirBits), chunks = bins / kScanChunk;  // only the bins in use
+  CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)bins * sizeof(unsigned), s));
   const int grid = ctx->sm_count * 8;
-  k_bin_count<<<grid, 256, 0, s>>>(ctx->dev, rays, (unsigned)n, keys, hist);
-  k_bin_scan_totals<<<kScanChunks, 256, 0, s>>>(hist, hist + kBinCount);
-  k_bin_scan_chunks<<<1, 1024, 0, s>>>(hist + kBinCount);
-  k_bin_scan_apply<<<kScanChunks, 256, 0, s>>>(hist, hist + kBinCount);
+  k_bin_count<<<grid, 256, 0, s>>>(ctx->dev, rays, (unsigned)n, origin_bits, keys, hist);
+  k_bin_scan_totals<<<chunks, 256, 0, s>>>(hist, hist + kBinCount);
+  k_bin_scan_chunks<<<1, 1024, 0, s>>>(hist + kBinCount, chunks);
+  k_bin_scan_apply<<<chunks, 256, 0, s>>>(hist, hist + kBinCount);
   k_bin_scatter<<<grid, 256, 0, s>>>(keys, (unsigned)n, hist, perm);
   CUDA_TRY(cudaGetLastError());
   return perm;
