@@ -85,6 +85,34 @@ def test_cornell_statistics_against_reference(api, ctx, golden, cornell):
     assert _rmse(big, ref) < 2 * stats["run_to_run_rmse_2048"]
 
 
+def test_cornell_256_gates_of_the_survey(api, ctx, golden, cornell):
+    """SURVEY.md §8(d) correctness gates at the size and sample counts it states: Cornell 256x256, R* = mean of four
+    independent 1024-spp REFERENCE runs (tests/tools/make_golden.py --c256).
+    Gate 1 (noise level): RMSE and relMSE of GPU renders at N = 16 and at N = 1024 spp against R* within +-10 % of the
+    reference's own figures at the same N (N = 1024: the reference's leave-one-out figure, each run against the mean of
+    the other three; the GPU render is compared with the stored three-run mean, which has the same expectation).
+    Gate 2 (bias): 16 384 GPU spp against R*: channel means within 0.5 %, per-pixel RMSE below 2x the reference's
+    run-to-run RMSE at 1024 spp.  Gate 3: background and emission pixel sets identical."""
+    st = json.loads((golden / "stats.json").read_text())["cornell_256"]
+    ref4 = np.fromfile(golden / "cornell_256_ref_mean_4096.f32", np.float32).reshape(256, 256, 3)
+    ref3 = np.fromfile(golden / "cornell_256_ref_mean_3072.f32", np.float32).reshape(256, 256, 3)
+    ctx.upload(cornell.with_size(256, 256))
+    imgs16 = [ctx.render_path(16, seed=s) for s in (1, 2, 3, 4)]
+    assert abs(np.mean([_rmse(i, ref4) for i in imgs16]) / st["rmse_16"] - 1) < 0.10
+    assert abs(np.mean([_relmse(i, ref4) for i in imgs16]) / st["relmse_16"] - 1) < 0.10
+    imgs1024 = [ctx.render_path(1024, seed=s) for s in (5, 6, 7)]
+    assert abs(np.mean([_rmse(i, ref3) for i in imgs1024]) / st["rmse_1024_leave_one_out"] - 1) < 0.10
+    assert abs(np.mean([_relmse(i, ref3) for i in imgs1024]) / st["relmse_1024_leave_one_out"] - 1) < 0.10
+    big = ctx.render_path(16384, seed=8)
+    for c in range(3):
+        assert abs(big[..., c].mean() / st["channel_means"][c] - 1) < 0.005
+    assert _rmse(big, ref4) < 2 * st["run_to_run_rmse_1024"]
+    assert np.array_equal((big == 0).all(-1), (ref4 == 0).all(-1)) and int((big == 0).all(-1).sum()) == st["background_pixels"]
+    on_light = lambda a: np.isclose(a, LIGHT, rtol=1e-5, atol=0).all(-1)  # every sample is the emission (fp32 sums: 1e-5, not bitwise)
+    assert np.array_equal(on_light(imgs16[0]), on_light(ref4)) and np.array_equal(on_light(big), on_light(ref4))
+    assert int(on_light(big).sum()) == st["emission_pixels"] == 380
+
+
 def test_mixed_scene_statistics_against_reference(api, ctx, golden, mixed):
     """Every material / texture / sphere path (configs[3] stand-in)."""
     stats = json.loads((golden / "stats.json").read_text())["mixed_96"]

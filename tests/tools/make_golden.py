@@ -179,6 +179,36 @@ def ppm_golden():
     print("ppm golden written")
 
 
+def c256_goldens():
+    """SURVEY.md §8(d) gates at their stated size: Cornell 256x256.  R* = mean of four independent 1024-spp reference
+    runs; the reference's own noise level at N = 16 and N = 1024 spp against it (N = 1024 leave-one-out: each run
+    against the mean of the other three), its run-to-run RMSE at 1024 spp, and the deterministic pixel masks."""
+    O.build(ref=True)
+    stats = json.loads((G / "stats.json").read_text())
+    def rmse(a, b): return float(np.sqrt(((a - b) ** 2).mean()))
+    def relmse(a, b): return float((((a - b) ** 2) / (b ** 2 + 1e-2)).mean())
+    file = G / "cornell_256.tscene"
+    runs = [O.ref_render_file(file, 1024, width=256, height=256)[0].astype(np.float64) for _ in range(4)]
+    mean4 = sum(runs) / 4
+    mean4.astype(np.float32).tofile(G / "cornell_256_ref_mean_4096.f32")
+    loo = [(sum(runs) - r) / 3 for r in runs]  # mean of the other three
+    # the first three runs' mean is stored too: a GPU 1024-spp render against it has the same expected RMSE as the
+    # reference's leave-one-out figure (sigma^2 / 1024 + sigma^2 / 3072)
+    (sum(runs[:3]) / 3).astype(np.float32).tofile(G / "cornell_256_ref_mean_3072.f32")
+    imgs16 = [O.ref_render_file(file, 16, width=256, height=256)[0] for _ in range(4)]
+    stats["cornell_256"] = {
+        "ref_spp_total": 4096, "image_mean": float(mean4.mean()), "channel_means": [float(x) for x in mean4.mean((0, 1))],
+        "rmse_16": float(np.mean([rmse(i, mean4) for i in imgs16])), "relmse_16": float(np.mean([relmse(i, mean4) for i in imgs16])),
+        "rmse_1024_leave_one_out": float(np.mean([rmse(r, m) for r, m in zip(runs, loo)])),
+        "relmse_1024_leave_one_out": float(np.mean([relmse(r, m) for r, m in zip(runs, loo)])),
+        "run_to_run_rmse_1024": float(np.mean([rmse(runs[0], runs[1]), rmse(runs[2], runs[3])])),
+        "background_pixels": int((mean4 == 0).all(-1).sum()),
+        # pixels whose primary ray hits the light: every sample is the emission (summed in fp32: equal to 1e-5, not bitwise)
+        "emission_pixels": int(np.isclose(mean4, np.float32([47.8348007, 38.5663986, 31.0807991]), rtol=1e-5, atol=0).all(-1).sum())}
+    print(stats["cornell_256"])
+    (G / "stats.json").write_text(json.dumps(stats, indent=1))
+
+
 def post_inputs():
     """Postprocessor fixtures' inputs: (a) 40 rows x 48 columns with emissive patches (|rgb| > 3) in the interior, in
     the corners (the u == 0 / v == 0 wrap-around of Texture::getRGBat) and values around the tone map's
@@ -214,7 +244,9 @@ def post_golden():
 
 
 if __name__ == "__main__":
-    if "--post" in sys.argv:
+    if "--c256" in sys.argv:
+        c256_goldens()
+    elif "--post" in sys.argv:
         post_golden()
     elif "--ppm" in sys.argv:
         ppm_golden()
