@@ -108,7 +108,7 @@ def test_cornell_256_gates_of_the_survey(api, ctx, golden, cornell):
         assert abs(big[..., c].mean() / st["channel_means"][c] - 1) < 0.005
     assert _rmse(big, ref4) < 2 * st["run_to_run_rmse_1024"]
     assert np.array_equal((big == 0).all(-1), (ref4 == 0).all(-1)) and int((big == 0).all(-1).sum()) == st["background_pixels"]
-    on_light = lambda a: np.isclose(a, LIGHT, rtol=1e-5, atol=0).all(-1)  # every sample is the emission (fp32 sums: 1e-5, not bitwise)
+    on_light = lambda a: np.isclose(a, LIGHT, rtol=1e-4, atol=0).all(-1)  # every sample is the emission (fp32 sums of 1024 terms: 1e-4, not bitwise)
     assert np.array_equal(on_light(imgs16[0]), on_light(ref4)) and np.array_equal(on_light(big), on_light(ref4))
     assert int(on_light(big).sum()) == st["emission_pixels"] == 380
 

@@ -203,8 +203,8 @@ def c256_goldens():
         "relmse_1024_leave_one_out": float(np.mean([relmse(r, m) for r, m in zip(runs, loo)])),
         "run_to_run_rmse_1024": float(np.mean([rmse(runs[0], runs[1]), rmse(runs[2], runs[3])])),
         "background_pixels": int((mean4 == 0).all(-1).sum()),
-        # pixels whose primary ray hits the light: every sample is the emission (summed in fp32: equal to 1e-5, not bitwise)
-        "emission_pixels": int(np.isclose(mean4, np.float32([47.8348007, 38.5663986, 31.0807991]), rtol=1e-5, atol=0).all(-1).sum())}
+        # pixels whose primary ray hits the light: every sample is the emission (summed in fp32: equal to 1e-4, not bitwise)
+        "emission_pixels": int(np.isclose(mean4, np.float32([47.8348007, 38.5663986, 31.0807991]), rtol=1e-4, atol=0).all(-1).sum())}
     print(stats["cornell_256"])
     (G / "stats.json").write_text(json.dumps(stats, indent=1))
 
