@@ -254,10 +254,15 @@ static inline void set_node_boxes(InnerNode& in, const Box& l, const Box& r) {
 // what the equal-t tie rule compares.  Irregular rays keep walking the reference topology.
 namespace {
 struct FastBuilder {
-  const PodVec<Box>& lbox;
+  // The builder partitions 28-byte records {leaf box, leaf id} in place instead of an index array: every pass
+  // over a node's primitives is then a sequential scan (with indices the 10^6-leaf build spent its time on cache
+  // misses of box[idx[k]]).  The centroid is recomputed from the box.
+  struct Rec {
+    Box box;
+    uint32_t id;
+  };
   const PodVec<uint32_t>& code;
-  std::vector<uint32_t> idx;
-  std::vector<V3> cen;
+  PodVec<Rec> rec;
   InnerNode* out;
   int max_depth;
   uint32_t depth_seen = 0;
@@ -277,6 +282,7 @@ struct FastBuilder {
       b.hi[a] = fmaxf(b.hi[a], o.hi[a]);
     }
   }
+  static V3 centroid(const Box& b) { return {0.5f * (b.lo[0] + b.hi[0]), 0.5f * (b.lo[1] + b.hi[1]), 0.5f * (b.lo[2] + b.hi[2])}; }
   static int ceil_log2(uint32_t n) {
     int l = 0;
     while ((1ull << l) < n) ++l;
@@ -287,37 +293,89 @@ struct FastBuilder {
   // in pre-order.  Returns the child ref and the exact union box.
   int32_t build(uint32_t first, uint32_t count, uint32_t base, int depth, Box* box_out, int par_levels, uint32_t* deepest) {
     if (count == 1) {
-      *box_out = lbox[idx[first]];
-      return (int32_t)~code[idx[first]];
+      *box_out = rec[first].box;
+      return (int32_t)~code[rec[first].id];
     }
     if ((uint32_t)depth + 1 > *deepest) *deepest = (uint32_t)depth + 1;
     uint32_t nl = count / 2;
     bool median = (max_depth - depth) <= ceil_log2(count) + 1;
     if (!median) {
-      Box cb = empty_box();
-      for (uint32_t k = first; k < first + count; ++k) {
-        const V3& c = cen[idx[k]];
-        cb.lo[0] = fminf(cb.lo[0], c.x), cb.hi[0] = fmaxf(cb.hi[0], c.x);
-        cb.lo[1] = fminf(cb.lo[1], c.y), cb.hi[1] = fmaxf(cb.hi[1], c.y);
-        cb.lo[2] = fminf(cb.lo[2], c.z), cb.hi[2] = fmaxf(cb.hi[2], c.z);
-      }
+      // Centroid bounds and the 3 x 16 bins in one pass each; nodes of more than 128 Ki primitives split both
+      // passes over the host threads (min / max and counts merge exactly, so the tree does not depend on it).
+      const unsigned workers = (par_levels > 0 && count > (1u << 17)) ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+      auto chunk = [&](unsigned w) { return std::pair<uint32_t, uint32_t>(first + (uint32_t)((uint64_t)count * w / workers), first + (uint32_t)((uint64_t)count * (w + 1) / workers)); };
+      auto for_workers = [&](auto fn) {
+        if (workers == 1) {
+          fn(0u);
+          return;
+        }
+        std::vector<std::thread> pool;
+        for (unsigned w = 0; w < workers; ++w) pool.emplace_back([&fn, w] { fn(w); });
+        for (auto& t : pool) t.join();
+      };
+      Box cb_one = empty_box();  // no heap allocation on the (million-fold) single-worker path
+      std::vector<Box> cb_many;
+      if (workers > 1) cb_many.assign(workers, empty_box());
+      Box* cbs = workers > 1 ? cb_many.data() : &cb_one;
+      for_workers([&](unsigned w) {
+        Box c0 = empty_box();
+        const auto r = chunk(w);
+        for (uint32_t k = r.first; k < r.second; ++k) {
+          const V3 c = centroid(rec[k].box);
+          c0.lo[0] = fminf(c0.lo[0], c.x), c0.hi[0] = fmaxf(c0.hi[0], c.x);
+          c0.lo[1] = fminf(c0.lo[1], c.y), c0.hi[1] = fmaxf(c0.hi[1], c.y);
+          c0.lo[2] = fminf(c0.lo[2], c.z), c0.hi[2] = fmaxf(c0.hi[2], c.z);
+        }
+        cbs[w] = c0;
+      });
+      Box cb = cbs[0];
+      for (unsigned w = 1; w < workers; ++w) grow(cb, cbs[w]);
       constexpr int NB = 16;
+      struct Bins {
+        uint32_t cnt[3][NB];
+        Box bb[3][NB];
+      };
+      float scale3[3];
+      bool use_axis[3];
+      for (int a = 0; a < 3; ++a) {
+        const float ext = cb.hi[a] - cb.lo[a];
+        use_axis[a] = ext > 0.f;
+        scale3[a] = use_axis[a] ? NB / ext : 0.f;
+      }
+      Bins bins_one;
+      std::vector<Bins> bins_many;
+      if (workers > 1) bins_many.resize(workers);
+      Bins* bins = workers > 1 ? bins_many.data() : &bins_one;
+      for_workers([&](unsigned w) {
+        Bins& B = bins[w];
+        for (int a = 0; a < 3; ++a)
+          for (int k = 0; k < NB; ++k) B.cnt[a][k] = 0, B.bb[a][k] = empty_box();
+        const auto r = chunk(w);
+        for (uint32_t k = r.first; k < r.second; ++k) {
+          const Box& lb = rec[k].box;
+          const V3 cc = centroid(lb);
+          const float c3[3] = {cc.x, cc.y, cc.z};
+          for (int a = 0; a < 3; ++a) {
+            if (!use_axis[a]) continue;
+            int bk = (int)((c3[a] - cb.lo[a]) * scale3[a]);
+            bk = bk < 0 ? 0 : (bk >= NB ? NB - 1 : bk);
+            B.cnt[a][bk]++;
+            grow(B.bb[a][bk], lb);
+          }
+        }
+      });
+      for (unsigned w = 1; w < workers; ++w)
+        for (int a = 0; a < 3; ++a)
+          for (int k = 0; k < NB; ++k) {
+            bins[0].cnt[a][k] += bins[w].cnt[a][k];
+            if (bins[w].cnt[a][k]) grow(bins[0].bb[a][k], bins[w].bb[a][k]);
+          }
       float best = FLT_MAX;
       int best_axis = -1, best_split = 0;
       for (int a = 0; a < 3; ++a) {
-        const float ext = cb.hi[a] - cb.lo[a];
-        if (!(ext > 0.f)) continue;
-        const float scale = NB / ext;
-        uint32_t cnt[NB] = {0};
-        Box bb[NB];
-        for (int b = 0; b < NB; ++b) bb[b] = empty_box();
-        for (uint32_t k = first; k < first + count; ++k) {
-          const float c = a == 0 ? cen[idx[k]].x : a == 1 ? cen[idx[k]].y : cen[idx[k]].z;
-          int b = (int)((c - cb.lo[a]) * scale);
-          b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-          cnt[b]++;
-          grow(bb[b], lbox[idx[k]]);
-        }
+        if (!use_axis[a]) continue;
+        const uint32_t* cnt = bins[0].cnt[a];
+        const Box* bb = bins[0].bb[a];
         float right_area[NB];
         uint32_t right_cnt[NB];
         Box acc = empty_box();
@@ -341,13 +399,14 @@ struct FastBuilder {
       if (best_axis >= 0) {
         const int a = best_axis;
         const float scale = NB / (cb.hi[a] - cb.lo[a]);
-        auto mid = std::partition(idx.begin() + first, idx.begin() + first + count, [&](uint32_t i) {
-          const float c = a == 0 ? cen[i].x : a == 1 ? cen[i].y : cen[i].z;
+        auto mid = std::partition(rec.begin() + first, rec.begin() + first + count, [&](const Rec& r) {
+          const V3 cc = centroid(r.box);
+          const float c = a == 0 ? cc.x : a == 1 ? cc.y : cc.z;
           int b = (int)((c - cb.lo[a]) * scale);
           b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
           return b < best_split;
         });
-        nl = (uint32_t)(mid - (idx.begin() + first));
+        nl = (uint32_t)(mid - (rec.begin() + first));
         if (nl == 0 || nl == count) nl = count / 2;  // cannot happen; keeps the recursion well founded
       }
     }
@@ -393,14 +452,9 @@ static void build_fast_tree(FlatScene* fs, const PodVec<uint32_t>& leaf_code, in
       if (!std::isfinite(b.lo[a]) || !std::isfinite(b.hi[a])) return;
   if (FastBuilder::ceil_log2(n) + 2 > max_depth) return;
   PodVec<InnerNode> out(n - 1);
-  FastBuilder fb{fs->leaf_box, leaf_code, {}, {}, out.data(), max_depth};
-  fb.idx.resize(n);
-  fb.cen.resize(n);
-  for (uint32_t i = 0; i < n; ++i) {
-    fb.idx[i] = i;
-    const Box& b = fs->leaf_box[i];
-    fb.cen[i] = {0.5f * (b.lo[0] + b.hi[0]), 0.5f * (b.lo[1] + b.hi[1]), 0.5f * (b.lo[2] + b.hi[2])};
-  }
+  FastBuilder fb{leaf_code, {}, out.data(), max_depth};
+  fb.rec.resize(n);
+  for (uint32_t i = 0; i < n; ++i) fb.rec[i] = {fs->leaf_box[i], i};
   Box root;
   uint32_t deepest = 0;
   const int32_t ref = fb.build(0, n, 0, 0, &root, 4, &deepest);
