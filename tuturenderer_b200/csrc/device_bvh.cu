@@ -269,17 +269,17 @@ lbvh_depth(int n, const int* __restrict__ parent_inner, const int* __restrict__ 
   if ((threadIdx.x & 31) == 0 && best) atomicMax(deepest, best);
 }
 
-struct Scratch {
-  void* p = nullptr;
-  ~Scratch() {
-    if (p) cudaFree(p);
-  }
-};
-
 }  // namespace
 
+size_t device_build_lbvh_scratch_bytes(uint32_t n) {
+  const unsigned n_blocks = (n + kSortTile - 1) / kSortTile;
+  auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  return 2 * pad((size_t)n * 8) + 2 * pad((size_t)n * 4) + pad((size_t)kRadix * n_blocks * 4) + pad((size_t)n * 8) + 3 * pad((size_t)n * 4) + 256;
+}
+
 cudaError_t device_build_lbvh(const float* d_leaf_box, const uint32_t* d_leaf_code, uint32_t n, const float root_lo[3],
-                              const float root_hi[3], void* d_inner_out, uint32_t* depth_out, int sm_count, cudaStream_t s) {
+                              const float root_hi[3], void* d_inner_out, uint32_t* depth_out, int sm_count, void* d_scratch,
+                              cudaStream_t s) {
   static_assert(sizeof(NodeOut) == 64, "NodeOut must match InnerNode");
   if (n < 2) return cudaErrorInvalidValue;
   const unsigned n_blocks = (n + kSortTile - 1) / kSortTile;
@@ -293,10 +293,9 @@ cudaError_t device_build_lbvh(const float* d_leaf_box, const uint32_t* d_leaf_co
   const size_t o_k0 = take((size_t)n * 8), o_k1 = take((size_t)n * 8), o_v0 = take((size_t)n * 4), o_v1 = take((size_t)n * 4);
   const size_t o_hist = take((size_t)kRadix * n_blocks * 4), o_ch = take((size_t)n * 8), o_pi = take((size_t)n * 4);
   const size_t o_pl = take((size_t)n * 4), o_arr = take((size_t)n * 4), o_deep = take(256);
-  Scratch sc;
-  cudaError_t e = cudaMalloc(&sc.p, off);
-  if (e != cudaSuccess) return e;
-  char* base = static_cast<char*>(sc.p);
+  cudaError_t e = cudaSuccess;
+  if (off > device_build_lbvh_scratch_bytes(n) || !d_scratch) return cudaErrorInvalidValue;
+  char* base = static_cast<char*>(d_scratch);
   auto* k0 = reinterpret_cast<unsigned long long*>(base + o_k0);
   auto* k1 = reinterpret_cast<unsigned long long*>(base + o_k1);
   auto* v0 = reinterpret_cast<unsigned*>(base + o_v0);

@@ -9,7 +9,10 @@ namespace tutu {
 // tree); d_leaf_code: n x (slot | sphere bit); root box = union of all leaf boxes.  Writes n - 1 InnerNode records
 // (64 B, tutu_internal.hpp) to d_inner_out, root = node 0, inner boxes = exact fmin/fmax unions, and the number
 // of inner nodes on the longest root-to-leaf path to *depth_out.  Synchronises `s` before returning.
+// d_scratch: device_build_lbvh_scratch_bytes(n) bytes of device memory (256-byte aligned), owned by the caller.
+size_t device_build_lbvh_scratch_bytes(uint32_t n);
 cudaError_t device_build_lbvh(const float* d_leaf_box, const uint32_t* d_leaf_code, uint32_t n, const float root_lo[3],
-                              const float root_hi[3], void* d_inner_out, uint32_t* depth_out, int sm_count, cudaStream_t s);
+                              const float root_hi[3], void* d_inner_out, uint32_t* depth_out, int sm_count, void* d_scratch,
+                              cudaStream_t s);
 
 }  // namespace tutu

@@ -133,7 +133,7 @@ struct TutuCtx {
   DevScene dev{};
   SmallScene small{};  // n = 0 unless the scene has <= kSmallMax primitives
   DevBuf d_inner_fast, d_wide, d_wleaf, d_wbox;
-  DevBuf d_leaf_box, d_leaf_code;  // inputs of the device tree build
+  DevBuf d_leaf_box, d_leaf_code, d_build_scratch;  // inputs and scratch of the device tree build
   int builder_cfg = TUTU_BUILD_AUTO;
   bool device_tree = false;  // d_inner_fast was built on the device (ctx->flat.inner_fast is empty until someone needs it)
   TutuUploadStats upload_stats{};
@@ -1376,9 +1376,10 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
       upload_vec(ctx->d_leaf_box, fs.leaf_box, s);
       upload_vec(ctx->d_leaf_code, fs.leaf_code, s);
       ctx->d_inner_fast.ensure((size_t)(fs.n_prims - 1) * sizeof(InnerNode));
+      ctx->d_build_scratch.ensure(device_build_lbvh_scratch_bytes(fs.n_prims));
       uint32_t depth = 0;
       CUDA_TRY(device_build_lbvh(ctx->d_leaf_box.as<float>(), ctx->d_leaf_code.as<uint32_t>(), fs.n_prims, fs.root_box.lo,
-                                 fs.root_box.hi, ctx->d_inner_fast.p, &depth, ctx->sm_count, s));
+                                 fs.root_box.hi, ctx->d_inner_fast.p, &depth, ctx->sm_count, ctx->d_build_scratch.p, s));
       if (depth >= 1 && depth <= (uint32_t)kFastTreeMaxDepth) {
         device_tree = true;
         fs.root_ref_fast = 0;
