@@ -109,8 +109,10 @@ def test_cornell_256_gates_of_the_survey(api, ctx, golden, cornell):
     assert _rmse(big, ref4) < 2 * st["run_to_run_rmse_1024"]
     assert np.array_equal((big == 0).all(-1), (ref4 == 0).all(-1)) and int((big == 0).all(-1).sum()) == st["background_pixels"]
     on_light = lambda a: np.isclose(a, LIGHT, rtol=1e-4, atol=0).all(-1)  # every sample is the emission (fp32 sums of 1024 terms: 1e-4, not bitwise)
-    assert np.array_equal(on_light(imgs16[0]), on_light(ref4)) and np.array_equal(on_light(big), on_light(ref4))
-    assert int(on_light(big).sum()) == st["emission_pixels"] == 380
+    assert np.array_equal(on_light(imgs16[0]), on_light(ref4)) and np.array_equal(on_light(imgs1024[0]), on_light(ref4))
+    assert int(on_light(imgs1024[0]).sum()) == st["emission_pixels"] == 380
+    # (the 16 384-sample sum of 47.83 loses more than 1e-4 to fp32 rounding; its light pixels are held to 2e-3)
+    assert np.array_equal(np.isclose(big, LIGHT, rtol=2e-3, atol=0).all(-1), on_light(ref4))
 
 
 def test_mixed_scene_statistics_against_reference(api, ctx, golden, mixed):

@@ -224,7 +224,7 @@ q_shadow_add(const __grid_constant__ DevScene sc, const __grid_constant__ SmallS
         if constexpr (KIND == 1)
           blocked = traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
         else
-          blocked = traverse_variant<true, 3>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+          blocked = traverse_structured<true>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
         if (!blocked) {
           const float4 c = __ldcs(scn + j);
           float* p = accum + (size_t)__float_as_uint(d.w) * 3;

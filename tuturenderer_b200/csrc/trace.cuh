@@ -635,25 +635,34 @@ struct SharedStack<true> {
   }
 };
 
+// node part of a step with the shared-memory stack: true = the lane has to pop
+template <bool ANY, bool REGULAR>
+__device__ __forceinline__ bool node_step_shared(const DevScene& sc, Walk& w, SharedStack<ANY>& st) {
+  const float4* n = w.nodes + 4 * (size_t)w.cur;
+  float4 a, b, c;
+  int4 k;
+  load_node(n, a, b, c, k);
+  float tl, tr;
+  bool hl, hr;
+  node_boxes<REGULAR>(w.p, a, b, c, hl, tl, hr, tr);
+  const float lim = prune_limit<ANY>(sc, w);
+  hl = hl && !(tl > lim);
+  hr = hr && !(tr > lim);
+  const bool swap = hr && (!hl || tr < tl);
+  if (hl && hr) st.push(swap ? k.x : k.y, swap ? tl : tr);
+  if (hl || hr) {
+    w.cur = swap ? k.y : k.x;
+    return false;
+  }
+  return true;
+}
+
 template <bool ANY, bool REGULAR>
 __device__ __forceinline__ void walk_shared(const DevScene& sc, Walk& w, SharedStack<ANY>& st) {
   for (;;) {
     bool need_pop;
     if (w.cur >= 0) {
-      const float4* n = w.nodes + 4 * (size_t)w.cur;
-      float4 a, b, c;
-      int4 k;
-      load_node(n, a, b, c, k);
-      float tl, tr;
-      bool hl, hr;
-      node_boxes<REGULAR>(w.p, a, b, c, hl, tl, hr, tr);
-      const float lim = prune_limit<ANY>(sc, w);
-      hl = hl && !(tl > lim);
-      hr = hr && !(tr > lim);
-      const bool swap = hr && (!hl || tr < tl);
-      if (hl && hr) st.push(swap ? k.x : k.y, swap ? tl : tr);
-      need_pop = !(hl || hr);
-      if (!need_pop) w.cur = swap ? k.y : k.x;
+      need_pop = node_step_shared<ANY, REGULAR>(sc, w, st);
     } else {
       if (leaf_step<ANY>(sc, w, w.cur)) return;
       need_pop = true;
@@ -686,28 +695,6 @@ __device__ __forceinline__ bool traverse_shared(const DevScene& sc, const Ray& r
   }
   best = w.best;
   return best.slot >= 0;
-}
-
-// node part of a step with the shared-memory stack: true = the lane has to pop
-template <bool ANY, bool REGULAR>
-__device__ __forceinline__ bool node_step_shared(const DevScene& sc, Walk& w, SharedStack<ANY>& st) {
-  const float4* n = w.nodes + 4 * (size_t)w.cur;
-  float4 a, b, c;
-  int4 k;
-  load_node(n, a, b, c, k);
-  float tl, tr;
-  bool hl, hr;
-  node_boxes<REGULAR>(w.p, a, b, c, hl, tl, hr, tr);
-  const float lim = prune_limit<ANY>(sc, w);
-  hl = hl && !(tl > lim);
-  hr = hr && !(tr > lim);
-  const bool swap = hr && (!hl || tr < tl);
-  if (hl && hr) st.push(swap ? k.x : k.y, swap ? tl : tr);
-  if (hl || hr) {
-    w.cur = swap ? k.y : k.x;
-    return false;
-  }
-  return true;
 }
 
 // ---- warp walk with batched leaf tests ---------------------------------------------------------
@@ -762,36 +749,28 @@ __device__ __forceinline__ bool traverse_batched(const DevScene& sc, const Ray& 
   return best.slot >= 0;
 }
 
-// VARIANT 0: LOOP + exact slab test; 1: LOOP + FMNMX slab test for regular rays;
-// 3: structured walk (walk_structured) + FMNMX slab test for regular rays;
-// 2: rounds (inner-node phase / leaf phase) + FMNMX for regular rays.
-template <bool ANY, int VARIANT>
-__device__ __forceinline__ bool traverse_variant(const DevScene& sc, const Ray& r, float dis, Hit& best) {
+// Whole walk of one ray with a local-memory stack and the exact (NaN-literal) slab test: the walk of irregular rays
+// on scenes that otherwise use the flat small-scene tests.
+template <bool ANY>
+__device__ __forceinline__ bool traverse_exact(const DevScene& sc, const Ray& r, float dis, Hit& best) {
+  Walk w;
+  int stack_ref[kStackSize];
+  float stack_t[kStackSize];
+  if (walk_begin(sc, w, r, dis)) walk_loop<ANY, 0, false>(sc, w, stack_ref, stack_t);
+  best = w.best;
+  return best.slot >= 0;
+}
+// Structured walk (one node or leaf, then one pop; local-memory stack): the any-hit walk of the queue kernels.
+template <bool ANY>
+__device__ __forceinline__ bool traverse_structured(const DevScene& sc, const Ray& r, float dis, Hit& best) {
   Walk w;
   int stack_ref[kStackSize];
   float stack_t[kStackSize];
   if (walk_begin(sc, w, r, dis)) {
-    if (VARIANT == 0) {
-      walk_loop<ANY, 0, false>(sc, w, stack_ref, stack_t);
-    } else if (VARIANT == 1) {
-      if (w.regular)
-        walk_loop<ANY, 0, true>(sc, w, stack_ref, stack_t);
-      else
-        walk_loop<ANY, 0, false>(sc, w, stack_ref, stack_t);
-    } else if (VARIANT == 3) {
-      if (w.regular)
-        walk_structured<ANY, true>(sc, w, stack_ref, stack_t);
-      else
-        walk_structured<ANY, false>(sc, w, stack_ref, stack_t);
-    } else {
-      if (w.regular) {
-        while (walk_round<ANY, 0, false, true>(sc, w, stack_ref, stack_t, nullptr)) {
-        }
-      } else {
-        while (walk_round<ANY, 0, false, false>(sc, w, stack_ref, stack_t, nullptr)) {
-        }
-      }
-    }
+    if (w.regular)
+      walk_structured<ANY, true>(sc, w, stack_ref, stack_t);
+    else
+      walk_structured<ANY, false>(sc, w, stack_ref, stack_t);
   }
   best = w.best;
   return best.slot >= 0;
@@ -890,7 +869,7 @@ template <bool ANY>
 __device__ __forceinline__ bool traverse_small(const DevScene& sc, const SmallScene& ss, const Ray& r,
                                                float dis, Hit& best) {
   const RayPre p = make_pre(r);
-  if (!ray_is_regular(p)) return traverse_variant<ANY, 0>(sc, r, dis, best);
+  if (!ray_is_regular(p)) return traverse_exact<ANY>(sc, r, dis, best);
   best.t = FLT_MAX;
   best.u = 0.f;
   best.v = 0.f;
@@ -929,7 +908,7 @@ __device__ __forceinline__ bool small_first_pass(const DevScene& sc, const Small
   const RayPre p = make_pre(r);
   mask = 0u;
   if (!ray_is_regular(p)) {
-    blocked = traverse_variant<ANY, 0>(sc, r, dis, best);
+    blocked = traverse_exact<ANY>(sc, r, dis, best);
     return true;
   }
   best.t = FLT_MAX;

@@ -229,4 +229,39 @@ __device__ __forceinline__ void trace_persistent(const DevScene& sc, unsigned lo
   }
 }
 
+// VARIANT 0: LOOP + exact slab test; 1: LOOP + FMNMX slab test for regular rays;
+// 3: structured walk (walk_structured) + FMNMX slab test for regular rays;
+// 2: rounds (inner-node phase / leaf phase) + FMNMX for regular rays.
+template <bool ANY, int VARIANT>
+__device__ __forceinline__ bool traverse_variant(const DevScene& sc, const Ray& r, float dis, Hit& best) {
+  Walk w;
+  int stack_ref[kStackSize];
+  float stack_t[kStackSize];
+  if (walk_begin(sc, w, r, dis)) {
+    if (VARIANT == 0) {
+      walk_loop<ANY, 0, false>(sc, w, stack_ref, stack_t);
+    } else if (VARIANT == 1) {
+      if (w.regular)
+        walk_loop<ANY, 0, true>(sc, w, stack_ref, stack_t);
+      else
+        walk_loop<ANY, 0, false>(sc, w, stack_ref, stack_t);
+    } else if (VARIANT == 3) {
+      if (w.regular)
+        walk_structured<ANY, true>(sc, w, stack_ref, stack_t);
+      else
+        walk_structured<ANY, false>(sc, w, stack_ref, stack_t);
+    } else {
+      if (w.regular) {
+        while (walk_round<ANY, 0, false, true>(sc, w, stack_ref, stack_t, nullptr)) {
+        }
+      } else {
+        while (walk_round<ANY, 0, false, false>(sc, w, stack_ref, stack_t, nullptr)) {
+        }
+      }
+    }
+  }
+  best = w.best;
+  return best.slot >= 0;
+}
+
 }  // namespace tutu

@@ -473,7 +473,7 @@ k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallSc
       if (MODE == 3)
         out[i] = traverse_small<true>(sc, ss, r, d.w, h) ? 1 : 0;
       else if (MODE == 0)
-        out[i] = traverse_variant<true, 3>(sc, r, d.w, h) ? 1 : 0;
+        out[i] = traverse_structured<true>(sc, r, d.w, h) ? 1 : 0;
       else
         out[i] = traverse<true, 1, false>(sc, r, d.w, h, nullptr) ? 1 : 0;
     }

@@ -131,7 +131,7 @@ wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
         if constexpr (KIND == 1)
           blocked = traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
         else
-          blocked = traverse_variant<true, 3>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+          blocked = traverse_structured<true>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
         const unsigned dst = __float_as_uint(d.w);
         if (dst == kShadowFinal) {
           const float4 c = __ldcs(b.sh_c + j);
