@@ -16,7 +16,8 @@ TUTU_PROF_SPP=128 TUTU_LANES=1 run $NCU -k regex:'wf_shade|wf_extend_small|wf_sh
 run python tools/prof_glass.py
 run $NCU -k regex:'wf_extend|wf_shade|wf_shadow|wf_classify' --launch-skip 16 -c 4 -o $O/r02_glass python tools/prof_glass.py
 run python tools/prof_run.py bdpt
-run $NCU -k regex:'q_extend|bdpt_connect|bdpt_vertex|q_shadow_add' --launch-skip 8 -c 4 -o $O/r02_bdpt python tools/prof_run.py bdpt
+run $NCU -k regex:'q_extend|bdpt_vertex' --launch-skip 4 -c 4 -o $O/r02_bdpt python tools/prof_run.py bdpt
+run $NCU -k regex:'bdpt_connect|q_shadow_add' --launch-skip 4 -c 4 -o $O/r02_bdpt_connect python tools/prof_run.py bdpt
 run python bench.py --steps 2 --warmup 3 --spp 64 --no-cpu --no-extras --no-rays
 run ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --spp 64 --no-cpu --no-extras --no-rays
 } > $O/r02_capture.log 2>&1

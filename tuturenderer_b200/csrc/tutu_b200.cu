@@ -1369,7 +1369,7 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   if (!want_device) {
     build_host_fast_tree(&fs);
   } else {
-    bool finite = fs.n_prims >= 3;
+    bool finite = fs.n_prims >= 3 && fs.n_prims <= (1u << 28);  // device_bvh.cu indexes leaf ranges with int arithmetic
     for (size_t k = 0; finite && k < fs.leaf_box.size(); ++k)
       for (int a = 0; a < 3; ++a) finite = finite && std::isfinite(fs.leaf_box[k].lo[a]) && std::isfinite(fs.leaf_box[k].hi[a]);
     if (finite) {
