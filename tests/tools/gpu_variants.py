@@ -1,4 +1,5 @@
-"""Development aid: times the traversal flavours (tutu_set_traversal_mode 0 = persistent, 10/11/12 =
+"""Development aid (needs an experiment build: build.build_variant("exp", ["TUTU_EXPERIMENTS"]) and TUTU_LIB=<that .so>;
+the shipped library rejects these modes): times the traversal flavours (tutu_set_traversal_mode 0 = persistent, 10/11/12 =
 packet LOOP exact / LOOP FMNMX / rounds) on (a) Cornell bounce rays and (b) the height-field batches."""
 import sys, time
 from pathlib import Path

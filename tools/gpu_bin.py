@@ -32,7 +32,7 @@ for kind in (0, 1):
     rays = api.synth_rays(kind, N)
     d_rays = torch.from_numpy(rays).cuda()
     res = {}
-    MODES = [(3, "caller order"), (0, "binned"), (16, "refill+bin"), (17, "leafbatch+bin")]
+    MODES = [(3, "caller order"), (0, "binned")]  # an experiment build (TUTU_LIB, -DTUTU_EXPERIMENTS) also knows (16, "refill+bin"), (17, "leafbatch+bin")
     for mode, label in MODES:
         ctx.set_traversal_mode(mode)
         d_hits = torch.empty((N, 4), dtype=torch.float32, device="cuda")

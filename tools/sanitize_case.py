@@ -18,7 +18,7 @@ hf = api.Scene.load(G / "hf24.tscene")
 ctx.upload(hf)
 r = api.synth_rays(0, 70000, seed=5)
 r[::97, 4:7] = (0, -1, 0)
-for mode in (0, 1, 3, 13, 15, 16, 17):
+for mode in (0, 1, 3, 4, 6):  # production, literal, caller order, tree walk, compressed wide tree (experiment builds add 2, 10-17)
     ctx.set_traversal_mode(mode)
     ctx.trace_closest(r); ctx.trace_any(r)
 ctx.set_traversal_mode(0)
