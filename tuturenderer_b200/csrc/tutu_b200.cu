@@ -762,6 +762,10 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
   slot_release(ctx, slot, s);
 }
 
+// staging buffers of wf_shade (wavefront.cuh); scenes shaded through class lists gather their records and need none
+size_t shade_stage_smem(const TutuCtx* ctx) {
+  return ctx->sort_by_class ? 0 : (size_t)ctx->shade_block * kShadeStages * 7 * sizeof(float4);
+}
 // small-scene kernels (flat leaf-box tests) unless traversal mode 4 forces the general tree walk
 bool use_small(const TutuCtx* ctx) { return ctx->small.n > 0 && ctx->traversal_mode != 4; }
 
@@ -968,7 +972,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
     ctx->grid_extend = sized(small  ? persistent_grid(ctx, wf_extend_small, kSmallBlock)
                              : wide ? wide_grids_for(ctx).wf_extend
                                     : persistent_grid(ctx, wf_extend<0>, 256, want_stack));
-    ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, ctx->shade_block));
+    ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, ctx->shade_block, shade_stage_smem(ctx)));
     ctx->grid_shadow = sized(small  ? persistent_grid(ctx, wf_shadow_small, kSmallBlock)
                              : wide ? wide_grids_for(ctx).wf_shadow
                                     : persistent_grid(ctx, wf_shadow<0>, 256));
@@ -1051,7 +1055,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         wf_classify<<<ctx->sm_count * 8, 256, 0, ls>>>(ctx->dev, L.b);
         n_launch += 1;
       }
-      wf_shade<<<ctx->grid_shade, ctx->shade_block, 0, ls>>>(ctx->dev, L.b, cur, seed);
+      wf_shade<<<ctx->grid_shade, ctx->shade_block, shade_stage_smem(ctx), ls>>>(ctx->dev, L.b, cur, seed);
       timer.mark(3, ls);
       if (small)
         wf_shadow_small<<<ctx->grid_shadow, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);

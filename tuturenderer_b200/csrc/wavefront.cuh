@@ -298,18 +298,65 @@ wf_classify(const __grid_constant__ DevScene sc, WfBuffers b) {
   }
 }
 
-// Compiled for up to 256 threads / 2 blocks per SM (128 registers); the launch picks the block size:
-// a block waits at two barriers for one global atomic per iteration, so small blocks keep more
-// independent groups in flight per SM, but many small blocks on different material code paths thrash
-// the instruction cache.  Measured (Mpaths/s, 1024^2): Cornell 256x2 1606 / 128x4 1652 / 64x8 1670;
-// glass + textures scene 426 / 353 / 317.  -> 64 threads for all-Lambertian untextured scenes, else 256.
+// Compiled for up to 256 threads / 2 blocks per SM (128 registers); the launch picks the block size.  With direct
+// loads small blocks were better on Cornell (a block waits at two barriers for one global atomic per iteration:
+// 256x2 1606 / 128x4 1652 / 64x8 1670 Mpaths/s in round 1); with the staged records (above) one 256-thread block
+// amortises the seven bulk copies and the mbarrier wait best, and mixed-material scenes always wanted 256 (many
+// small blocks on different material code paths thrash the instruction cache: 426 / 353 / 317).
 #ifndef TUTU_SHADE_MIN_BLOCKS
 #define TUTU_SHADE_MIN_BLOCKS 2
 #endif
 #ifndef TUTU_SHADE_BLOCK
 #define TUTU_SHADE_BLOCK 256
 #endif
-constexpr int kShadeBlockSimple = 64;
+#ifndef TUTU_SHADE_BLOCK_SIMPLE
+#define TUTU_SHADE_BLOCK_SIMPLE 256
+#endif
+constexpr int kShadeBlockSimple = TUTU_SHADE_BLOCK_SIMPLE;
+
+// ---- TMA staging of the queue records ------------------------------------------------------------------------
+// A block's records of one iteration are seven contiguous 16 B x blockDim slices of the queue arrays.  One thread asks
+// the bulk-copy engine for the NEXT iteration's slices (cp.async.bulk = UBLKCP, completion counted on an mbarrier)
+// before the block shades the current ones, so the HBM latency that every block iteration used to start with (ncu,
+// profiles/r02_steady_shade_stalls.txt: 19 % of wf_shade's stall samples on the first use of the queue loads) is
+// overlapped with shading.  Measured on Cornell 1024^2 (tools/gpu_cornell_perf.py, Mpaths/s): direct loads 64 / 128 /
+// 256 threads per block 2066 / 2047 / 1975; staged, 2 stages 1920 / 2092 / 2109; staged, 3 stages, 256 threads 2051
+// (the third stage costs L1).  -> 256-thread blocks with two stages; scenes shaded through class lists gather their
+// records and keep the direct loads.
+#ifndef TUTU_SHADE_STAGES
+#define TUTU_SHADE_STAGES 2
+#endif
+constexpr unsigned kShadeStages = TUTU_SHADE_STAGES;  // block iterations in flight: the current one + (stages - 1) being fetched
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+               : "=r"(ok)
+               : "r"(smem_addr(bar)), "r"(parity)
+               : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// the seven slices of the iteration that starts at queue index `base` into stage buffer `stage`
+__device__ __forceinline__ void shade_stage_fetch(const WfBuffers& b, int cur, unsigned base, unsigned n, float4* stage,
+                                                  unsigned long long* bar) {
+  const unsigned count = min(blockDim.x, n - base), bytes = count * 16u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy reads of this buffer are done (barriers)
+  mbar_expect_tx(bar, 7u * bytes);
+  const float4* src[7] = {b.ray_o[cur], b.ray_d[cur], b.st0[cur], b.st1[cur], b.st2[cur], b.st3[cur], b.hit};
+#pragma unroll
+  for (int a = 0; a < 7; ++a) bulk_g2s(stage + a * blockDim.x, src[a] + base, bytes, bar);
+}
 
 template <int SPEC>
 __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffers& b, int cur, uint64_t seed,
@@ -332,10 +379,39 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
     }
     __syncthreads();
   }
+  extern __shared__ __align__(128) float4 s_stage[];  // [stages][7 arrays][blockDim]; none for class-list scenes
+  __shared__ unsigned long long s_full[kShadeStages];
+  const bool piped = b.class_perm == nullptr;          // class lists gather their records: direct loads
+  const unsigned stride = gridDim.x * blockDim.x;
+  if (piped) {
+    if (threadIdx.x == 0) {
+      for (unsigned k = 0; k < kShadeStages; ++k) mbar_init(&s_full[k], 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (unsigned k = 0; k + 1 < kShadeStages; ++k) {  // prologue: the first stages - 1 iterations
+        const unsigned at = blockIdx.x * blockDim.x + k * stride;
+        if (at < n) shade_stage_fetch(b, cur, at, n, s_stage + k * 7u * blockDim.x, &s_full[k]);
+      }
+  }
+  unsigned iter = 0u;
   for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const unsigned j = base + threadIdx.x;
     const bool valid = j < n;
     unsigned i = j;
+    const unsigned slot = iter % kShadeStages;
+    const float4* stage = s_stage + slot * 7u * blockDim.x;
+    if (piped) {
+      // fetch iteration iter + stages - 1 into the buffer that iteration iter - 1 read (every thread has passed that
+      // iteration's barriers), then wait for this iteration's records
+      const unsigned ahead = (iter + kShadeStages - 1u) % kShadeStages;
+      const unsigned long long next = (unsigned long long)base + (unsigned long long)(kShadeStages - 1u) * stride;
+      if (threadIdx.x == 0 && next < n) shade_stage_fetch(b, cur, (unsigned)next, n, s_stage + ahead * 7u * blockDim.x, &s_full[ahead]);
+      while (!mbar_try_wait(&s_full[slot], (iter / kShadeStages) & 1u)) {
+      }
+    }
+    ++iter;
     if (b.class_perm && valid) {
       unsigned c = 0u, start = 0u;
 #pragma unroll
@@ -351,27 +427,21 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
     uint32_t pixel = 0;
     float4 s1 = make_float4(0, 0, 0, 0);
     if (valid) {
-      // queue records are touched once per iteration: stream them past L1/L2 residency (.cs) so
-      // the scene tables stay cached
-      const float4 o = __ldcs(b.ray_o[cur] + i);
-      const float4 d = __ldcs(b.ray_d[cur] + i);
-      const float4 s0 = __ldcs(b.st0[cur] + i);
-      s1 = __ldcs(b.st1[cur] + i);
-      const float4 s2 = __ldcs(b.st2[cur] + i);
-      const float4 hit = __ldcs(b.hit + i);
-#ifndef TUTU_SHADE_S3_LAZY
-      // st3 only matters to a vertex reached through x_inter, but `mode` sits in s2: waiting for s2 before asking
-      // for s3 puts a second memory round trip on the critical path of a latency-bound kernel.  Read it with the
-      // others (16 B more for the ~1 in 4 queue entries that are fresh paths; their value is never looked at).
-      const float4 s3 = __ldcs(b.st3[cur] + i);
+      // queue records: from the staging buffer, or (class lists) straight from HBM — touched once per iteration, so
+      // streamed past L1/L2 residency (.cs) to keep the scene tables cached.  st3 only matters to a vertex reached
+      // through x_inter, but it is fetched with the others: asking for it after s2 has told the mode would put a
+      // second memory round trip on the critical path.
+      float4 o, d, s0, s2, hit, s3;
+      if (piped) {
+        const unsigned t = threadIdx.x, bd = blockDim.x;
+        o = stage[t], d = stage[bd + t], s0 = stage[2 * bd + t], s1 = stage[3 * bd + t], s2 = stage[4 * bd + t];
+        s3 = stage[5 * bd + t], hit = stage[6 * bd + t];
+      } else {
+        o = __ldcs(b.ray_o[cur] + i), d = __ldcs(b.ray_d[cur] + i), s0 = __ldcs(b.st0[cur] + i), s1 = __ldcs(b.st1[cur] + i);
+        s2 = __ldcs(b.st2[cur] + i), hit = __ldcs(b.hit + i), s3 = __ldcs(b.st3[cur] + i);
+      }
       const uint32_t dm = __float_as_uint(s2.w);
       const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
-#else
-      const uint32_t dm = __float_as_uint(s2.w);
-      const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
-      float4 s3 = make_float4(0, 0, 0, 0);
-      if (mode == kModeXInter) s3 = __ldcs(b.st3[cur] + i);
-#endif
       pixel = __float_as_uint(s0.w);
       L = mk(s2.x, s2.y, s2.z);
       Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
