@@ -226,9 +226,9 @@ def workload_config(args) -> dict:
                         "scene = reference src/main_cornellBox.cpp via tests/golden/cornell_256.tscene)",
             "width": WIDTH, "height": HEIGHT, "spp": args.spp, "max_depth": 6,
             "parallelism": f"spp split over {args.gpus} GPU(s), one fp32 reduce of the {WIDTH * HEIGHT * 3 * 4 / 1e6:.1f} MB accumulation buffer",
-            "wavefront": "2 interleaved lanes x 16 Mi paths in flight",
-            "l2_policy": "inputs larger than L2: each wavefront iteration streams 16 Mi paths x ~330 B of queue records "
-                         "(5 GB per lane) through the 126 MB L2; no flush needed"}
+            "wavefront": "one lane x 32 Mi paths in flight (the default for scenes shaded in queue order)",
+            "l2_policy": "inputs larger than L2: each wavefront iteration streams 32 Mi paths x ~330 B of queue records "
+                         "(10 GB) through the 126 MB L2; no flush needed"}
 
 
 def profile_record(kernel: str, tag: str | None = None) -> dict | None:
@@ -630,11 +630,10 @@ def main():
         "wf_shadow": shd * (B_SHADOW + 32),
     }
     iters = max(cnt["iterations"], 1)
-    # The timed region runs two wavefront lanes on separate streams without per-kernel events (their kernels
-    # interleave and co-run at the hand-over points, so event-to-event times between them are not kernel
-    # durations).  The stage shares come from the profiled one-lane pass above, where the kernels of an
-    # iteration run back to back on one stream with CUDA events between them; each kernel is charged its
-    # share of the timed region's wall time — the quantity the ncu launch list (profiles/) checks.
+    # The timed region runs without per-kernel events (they would add a gap after every launch).  The stage shares
+    # come from the profiled pass above — the same lane, the kernels of an iteration back to back on one stream with
+    # CUDA events between them; each kernel is charged its share of the timed region's wall time — the quantity the
+    # ncu launch list (profiles/) checks.
     wall_ms = agg["gpu_ms"]
     stage_sum = sum(stage_ms.values()) + prof_stats["other_ms"]
     charged_ms = {k: v / stage_sum * wall_ms for k, v in stage_ms.items()}
@@ -644,8 +643,8 @@ def main():
                 "frac": ach / peaks["hbm_gbs"], "traffic": prof.get("dram_bytes_per_launch") if prof else None, "ncu": prof,
                 "peak_source": "fallback 6650 GB/s" if peaks.get("fallback") else "MEASURED_PEAKS.json hbm_gbs (measured)",
                 "avg_launch_ms": charged_ms[dominant] / iters, "algorithmic_bytes_per_launch": alg[dominant] / iters,
-                "duration_note": f"stage shares from a profiled one-lane pass of {prof_spp} spp (CUDA events between the kernels on "
-                                 "one stream); each kernel is charged share x wall ms of the timed two-lane region "
+                "duration_note": f"stage shares from a profiled pass of {prof_spp} spp (CUDA events between the kernels on "
+                                 "the lane's stream); each kernel is charged share x wall ms of the timed region "
                                  "(attribution, checked against the ncu launch list under profiles/)",
                 "stage_share": {k: v / stage_sum for k, v in stage_ms.items()},
                 "stage_ms_per_step": {k: v / args.steps for k, v in charged_ms.items()},

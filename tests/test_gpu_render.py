@@ -35,7 +35,9 @@ def _relmse(a, b):
     return float((((a - b) ** 2) / (b ** 2 + 1e-2)).mean())
 
 
-@pytest.mark.parametrize("name,size,spp", [("cornell_256", 64, 8), ("mixed", 48, 16)])
+# the two larger cases give wf_shade's blocks enough iterations to append through their reserves (wavefront.cuh:
+# "queue appends"; a lost or doubled queue entry would show in the ray counts and in the image)
+@pytest.mark.parametrize("name,size,spp", [("cornell_256", 64, 8), ("mixed", 48, 16), ("cornell_256", 320, 10), ("mixed", 224, 6)])
 def test_same_stream_as_oracle(api, oracle, ctx, golden, name, size, spp):
     sc = api.Scene.load(golden / f"{name}.tscene").with_size(size, size)
     ctx.upload(sc)
@@ -269,7 +271,9 @@ def test_pipelines_give_the_same_paths(api, ctx, cornell, mixed):
     tests as the wavefront on the same random numbers.  The two are compiled in different translation
     units, so FMA contraction may differ in the last place: images agree to float noise except for a
     handful of paths that flip a branch (ray counts within 1e-4)."""
-    for sc, spp in ((cornell.with_size(80, 80), 12), (_cornell_with_spheres(api, cornell).with_size(64, 64), 8)):
+    # (the 640^2 render is large enough for wf_shade to append through its reserves and leave dead queue entries)
+    for sc, spp in ((cornell.with_size(80, 80), 12), (_cornell_with_spheres(api, cornell).with_size(64, 64), 8),
+                    (cornell.with_size(640, 640), 10)):
         ctx.upload(sc)
         ctx.pipeline("wavefront")
         a = ctx.render_path(spp, seed=8)

@@ -10,8 +10,8 @@ ctx = api.Context(0)
 ctx.upload(sc)
 for SPP in (128,):
   for lanes in (1, 2):
-    for pif in (16 << 20,):
-        for prof in (True,):
+    for pif in (16 << 20, 32 << 20):
+        for prof in (False, True):
             ctx.configure(pif, prof, lanes)
             ctx.render_path(16, seed=1)
             ctx.render_path(SPP, seed=2)

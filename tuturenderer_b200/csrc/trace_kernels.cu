@@ -94,7 +94,10 @@ wf_extend_wide(const __grid_constant__ DevScene sc, WfBuffers b, int cur) {
         const float4 o = __ldcs(ro + i);
         const float4 d = __ldcs(rd + i);
         Hit h;
-        trace_ray<false, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack + threadIdx.x, blockDim.x);
+        if (__float_as_uint(o.w) == kDeadQueueEntry)  // unused end of a reserved chunk (wf_types.cuh)
+          h.t = 0.f, h.u = 0.f, h.v = 0.f, h.slot = kDeadSlot;
+        else
+          trace_ray<false, 1>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack + threadIdx.x, blockDim.x);
         __stcs(b.hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
       }
       __syncwarp();
@@ -113,9 +116,9 @@ wf_shadow_wide(const __grid_constant__ DevScene sc, WfBuffers b, int nxt) {
 #pragma unroll 1
     for (unsigned k = 0; k < kPacketRays; k += 32u) {
       const unsigned j = (unsigned)base + k + lane;
-      if (j < n) {
-        const float4 o = __ldcs(b.sh_o + j);
-        const float4 d = __ldcs(b.sh_d + j);
+      float4 o = make_float4(0.f, 0.f, 0.f, __uint_as_float(kDeadQueueEntry)), d = o;
+      if (j < n) o = __ldcs(b.sh_o + j), d = __ldcs(b.sh_d + j);
+      if (__float_as_uint(o.w) != kDeadQueueEntry) {
         Hit h;
         const bool blocked = trace_ray<true, 2>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h, s_stack + threadIdx.x, blockDim.x);
         const unsigned dst = __float_as_uint(d.w);

@@ -798,27 +798,30 @@ void fill_raygen(const FlatScene& f, RayGenK* k) {
 // default is two lanes of 16 Mi paths.
 void lane_prepare(TutuCtx* ctx, WfLane& L, uint64_t cap) {
   cap = (cap + 255) & ~(uint64_t)255;
-  if (cap > L.capacity) {
-    const size_t n_arrays = 2 * 6 + 1 + 4;  // 2*(6 queues) + hit + 4 shadow arrays, float4 each
-    L.pool.ensure(n_arrays * cap * sizeof(float4));
-    L.capacity = cap;
-  }
+  if (cap > L.capacity) L.capacity = cap;
   cap = L.capacity;
+  // wf_shade's blocks hold up to kAppendIters x blockDim reserved entries each (wavefront.cuh: queue appends), so a queue of
+  // `cap` live entries can extend this far past `cap`; WfBuffers::capacity stays the number of paths in flight
+  const uint64_t shading_blocks = std::min<uint64_t>((uint64_t)std::max(ctx->grid_shade, 1), cap / ctx->shade_block + 1);
+  const uint64_t slack = (shading_blocks * kAppendIters * ctx->shade_block + 255) & ~(uint64_t)255;
+  const uint64_t phys = cap + slack;
+  const size_t n_arrays = 2 * 6 + 1 + 4;  // 2*(6 queues) + hit + 4 shadow arrays, float4 each
+  L.pool.ensure(n_arrays * phys * sizeof(float4));
   float4* p = L.pool.as<float4>();
   WfBuffers& b = L.b;
   for (int k = 0; k < 2; ++k) {
-    b.ray_o[k] = p, p += cap;
-    b.ray_d[k] = p, p += cap;
-    b.st0[k] = p, p += cap;
-    b.st1[k] = p, p += cap;
-    b.st2[k] = p, p += cap;
-    b.st3[k] = p, p += cap;
+    b.ray_o[k] = p, p += phys;
+    b.ray_d[k] = p, p += phys;
+    b.st0[k] = p, p += phys;
+    b.st1[k] = p, p += phys;
+    b.st2[k] = p, p += phys;
+    b.st3[k] = p, p += phys;
   }
-  b.hit = p, p += cap;
-  b.sh_o = p, p += cap;
-  b.sh_d = p, p += cap;
-  b.sh_c = p, p += cap;
-  b.sh_L = p, p += cap;
+  b.hit = p, p += phys;
+  b.sh_o = p, p += phys;
+  b.sh_d = p, p += phys;
+  b.sh_c = p, p += phys;
+  b.sh_L = p, p += phys;
   L.ctl.ensure(sizeof(WfCtl));
   b.ctl = L.ctl.as<WfCtl>();
   b.capacity = (unsigned)cap;
@@ -950,8 +953,13 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   // flight = 1556 / 1634 / 1667 / 1680.  Two lanes with every kernel launched at its FULL persistent grid
   // (the lanes then mostly alternate; one lane's next kernel fills the SMs that the other's draining kernel
   // frees): 2 x 16 Mi = 1725 vs 1659 for 1 x 16 Mi.  (Grids halved per lane: 1441.)
-  int n_lanes = ctx->lanes_cfg > 0 ? ctx->lanes_cfg : 2;
-  const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)16 << 20;
+  // Defaults (Cornell 1024^2, tools/gpu_cornell_lanes.py): scenes shaded in queue order run one lane of 32 Mi paths —
+  // wf_shade's 64-thread blocks leave no tails for a second lane to fill, and longer launches amortise the per-iteration
+  // overhead (1 x 16 / 1 x 32 / 1 x 64 / 2 x 16 Mi: 2155 / 2185 / 2200 / 2120 Mpaths/s); scenes shaded through class
+  // lists (256-thread blocks) keep two lanes of 16 Mi (glass scene: 934 against 932 Mpaths/s for 1 x 32 Mi).
+  const bool one_lane = !ctx->sort_by_class;
+  int n_lanes = ctx->lanes_cfg > 0 ? ctx->lanes_cfg : (one_lane ? 1 : 2);
+  const uint64_t cap_cfg = ctx->paths_in_flight_cfg ? ctx->paths_in_flight_cfg : (uint64_t)(one_lane ? 32 : 16) << 20;
   while (n_lanes > 1 && (sample_count < (uint32_t)n_lanes || total / n_lanes < cap_cfg / 2)) --n_lanes;
   if ((int)ctx->wf_lanes.size() < n_lanes) ctx->wf_lanes.resize(n_lanes);
   // the cached grids depend on the scene through the kernel variants and the traversal-stack size

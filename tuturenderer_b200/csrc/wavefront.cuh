@@ -23,7 +23,7 @@ namespace tutu {
 
 // ---- control ---------------------------------------------------------------------------------
 __global__ void wf_ctl_after_raygen(WfCtl* ctl, unsigned capacity) {
-  const unsigned free_slots = capacity - ctl->n_cur;
+  const unsigned free_slots = capacity > ctl->n_cur ? capacity - ctl->n_cur : 0u;  // n_cur may include dead entries
   const unsigned long long left = ctl->total_paths - ctl->next_path;
   const unsigned add = (unsigned)(left < (unsigned long long)free_slots ? left : free_slots);
   ctl->n_cur += add;
@@ -32,15 +32,18 @@ __global__ void wf_ctl_after_raygen(WfCtl* ctl, unsigned capacity) {
   ctl->n_shadow = 0;
   ctl->cursor_extend = 0;
   ctl->cursor_shadow = 0;
-  ctl->sum_extend += ctl->n_cur;
+  ctl->dead_next = 0;
+  ctl->dead_shadow = 0;
+  ctl->sum_extend += ctl->n_cur - ctl->dead_cur;
   for (int c = 0; c < 8; ++c) ctl->class_count[c] = 0;
 }
 __global__ void wf_ctl_after_iter(WfCtl* ctl) {
   if (ctl->done) return;  // the host polls every few iterations: the launches after the last one are no-ops
-  ctl->sum_shadow += ctl->n_shadow;
+  ctl->sum_shadow += ctl->n_shadow - ctl->dead_shadow;
   ctl->n_cur = ctl->n_next;
+  ctl->dead_cur = ctl->dead_next;
   ctl->iterations += 1;
-  ctl->done = (ctl->n_cur == 0 && ctl->next_path >= ctl->total_paths) ? 1u : 0u;
+  ctl->done = (ctl->n_cur == ctl->dead_cur && ctl->next_path >= ctl->total_paths) ? 1u : 0u;
 }
 
 // ---- raygen: PathTracing.hpp:499-509 ---------------------------------------------------------
@@ -50,7 +53,7 @@ __global__ void wf_ctl_after_iter(WfCtl* ctl) {
 __global__ void __launch_bounds__(256)
 wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
   const WfCtl c = *b.ctl;
-  const unsigned free_slots = b.capacity - c.n_cur;
+  const unsigned free_slots = b.capacity > c.n_cur ? b.capacity - c.n_cur : 0u;
   const unsigned long long left = c.total_paths - c.next_path;
   const unsigned add = (unsigned)(left < (unsigned long long)free_slots ? left : free_slots);
   const unsigned npix = (unsigned)k.width * (unsigned)k.height;
@@ -98,7 +101,9 @@ wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
         const float4 o = __ldcs(ro + i);
         const float4 d = __ldcs(rd + i);
         Hit h;
-        if constexpr (KIND == 1)
+        if (__float_as_uint(o.w) == kDeadQueueEntry)
+          h.t = 0.f, h.u = 0.f, h.v = 0.f, h.slot = kDeadSlot;
+        else if constexpr (KIND == 1)
           traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
         else  // incoherent queue: per-lane walk (batched primitive tests only pay on sorted batches)
           traverse_shared<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack);
@@ -123,9 +128,9 @@ wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
 #pragma unroll 1
     for (unsigned k = 0; k < kPacketRays; k += 32u) {
       const unsigned j = (unsigned)base + k + lane;
-      if (j < n) {
-        const float4 o = __ldcs(b.sh_o + j);
-        const float4 d = __ldcs(b.sh_d + j);
+      float4 o = make_float4(0.f, 0.f, 0.f, __uint_as_float(kDeadQueueEntry)), d = o;
+      if (j < n) o = __ldcs(b.sh_o + j), d = __ldcs(b.sh_d + j);
+      if (__float_as_uint(o.w) != kDeadQueueEntry) {
         Hit h;
         bool blocked;
         if constexpr (KIND == 1)
@@ -183,10 +188,15 @@ wf_extend_small(const __grid_constant__ DevScene sc, const __grid_constant__ Sma
       if (i < n) {
         const float4 o = __ldcs(ro + i);
         const float4 d = __ldcs(rd + i);
-        r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
-        bool blocked;
-        more = !small_first_pass<false>(sc, ss, r, 0.f, h, mask, blocked);
-        if (!more) sink(i, r, 0.f, h, false);
+        if (__float_as_uint(o.w) == kDeadQueueEntry) {
+          h.t = 0.f, h.u = 0.f, h.v = 0.f, h.slot = kDeadSlot;
+          sink(i, r, 0.f, h, false);
+        } else {
+          r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+          bool blocked;
+          more = !small_first_pass<false>(sc, ss, r, 0.f, h, mask, blocked);
+          if (!more) sink(i, r, 0.f, h, false);
+        }
       }
       parked = small_park_push(pk, parked, more, r, 0.f, i, h, mask);
       while (parked >= 32u) parked = small_park_drain<false>(sc, pk, parked, false, sink);
@@ -230,9 +240,9 @@ wf_shadow_small(const __grid_constant__ DevScene sc, const __grid_constant__ Sma
       Hit h{};
       unsigned mask = 0u;
       float dis = 0.f;
-      if (j < n) {
-        const float4 o = __ldcs(b.sh_o + j);
-        const float4 d = __ldcs(b.sh_d + j);
+      float4 o = make_float4(0.f, 0.f, 0.f, __uint_as_float(kDeadQueueEntry)), d = o;
+      if (j < n) o = __ldcs(b.sh_o + j), d = __ldcs(b.sh_d + j);
+      if (__float_as_uint(o.w) != kDeadQueueEntry) {
         r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
         dis = o.w;
         bool blocked;
@@ -258,6 +268,7 @@ wf_shadow_small(const __grid_constant__ DevScene sc, const __grid_constant__ Sma
 constexpr int kShadeClasses = 8;  // 0 miss | 1 + MaterialType (Lambertian .. UNLIT) | 7 textured Lambertian
 __device__ __forceinline__ int shade_class(const DevScene& sc, const float4 hit) {
   const int code = __float_as_int(hit.w);
+  if (code == kDeadSlot) return -1;
   if (code < 0) return 0;
   const uint32_t flags = __float_as_uint(__ldg(sc.shade + 4 * (size_t)((uint32_t)code & kSlotMask) + 3).w);
   const int type = __float_as_int(__ldg(sc.materials + 4 * (size_t)(flags & 0x3FFFFFFFu)).w);
@@ -310,7 +321,7 @@ wf_classify(const __grid_constant__ DevScene sc, WfBuffers b) {
 #define TUTU_SHADE_BLOCK 256
 #endif
 #ifndef TUTU_SHADE_BLOCK_SIMPLE
-#define TUTU_SHADE_BLOCK_SIMPLE 256
+#define TUTU_SHADE_BLOCK_SIMPLE 64
 #endif
 constexpr int kShadeBlockSimple = TUTU_SHADE_BLOCK_SIMPLE;
 
@@ -358,17 +369,31 @@ __device__ __forceinline__ void shade_stage_fetch(const WfBuffers& b, int cur, u
   for (int a = 0; a < 7; ++a) bulk_g2s(stage + a * blockDim.x, src[a] + base, bytes, bar);
 }
 
+// ---- queue appends -----------------------------------------------------------------------------------------------
+// Survivors and shadow rays are appended to two queues whose counters live in one 64-bit word.  Round 1 took one
+// atomicAdd per block iteration (after per-warp atomics had put half of the kernel's stall samples on the shuffle that
+// waits for them); the block then sat at a barrier for the L2 round trip of that atomic once per iteration (ncu,
+// profiles/r02_steady_shade_stalls.txt: 21 % of the stall samples on the barriers of a 256-thread block).  Now a block
+// keeps a reserve of kAppendIters x blockDim entries per queue and takes its entries from the reserve: the global atomic — and
+// the second barrier that publishes its result — happen only in the iterations whose appends do not fit (about one in
+// eight to twelve).  The appends of such an iteration fill the old reserve to its last entry and continue in the new
+// one, so a queue has no holes except the unused end of each block's LAST reserve; a block's requests shrink as it
+// runs out of iterations (its last ones ask for exactly what they need), it writes dead markers (wf_types.cuh) over
+// what is left when it exits and adds the count to WfCtl::dead_*.
+struct AppendState {
+  unsigned lo[2], rem[2];  // [path queue, shadow queue]: next free entry of the reserve, entries left in it
+};
+
 template <int SPEC>
 __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffers& b, int cur, uint64_t seed,
-                                              unsigned (*s_cnt)[TUTU_SHADE_BLOCK / 32], unsigned* s_base, unsigned* s_pref) {
+                                              unsigned (*s_cnt)[TUTU_SHADE_BLOCK / 32], AppendState* s_app, unsigned* s_new,
+                                              unsigned* s_pref) {
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
-  // ncu (profiles/r01_shade_stalls.txt): with one atomicAdd per WARP on the two queue counters,
-  // half of this kernel's stall samples sat on the shuffles waiting for those results — ~2 x 10^5
-  // same-address atomics per launch serialise in one L2 slice.  The counts are therefore first
-  // combined per BLOCK in shared memory (one global atomic per counter per block-iteration).
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned n_warps = blockDim.x >> 5;
   // class lists (wf_classify): entry j of the concatenated lists -> queue index
+  unsigned n_listed = n;
   if (b.class_perm) {
     if (threadIdx.x == 0) {
       unsigned acc = 0u;
@@ -376,13 +401,16 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
         s_pref[c] = acc;
         acc += b.ctl->class_count[c];
       }
+      s_pref[kShadeClasses] = acc;
     }
     __syncthreads();
+    n_listed = s_pref[kShadeClasses];  // dead queue entries are in no list
   }
   extern __shared__ __align__(128) float4 s_stage[];  // [stages][7 arrays][blockDim]; none for class-list scenes
   __shared__ unsigned long long s_full[kShadeStages];
   const bool piped = b.class_perm == nullptr;          // class lists gather their records: direct loads
   const unsigned stride = gridDim.x * blockDim.x;
+  if (threadIdx.x == 0) s_app[0] = AppendState{{0u, 0u}, {0u, 0u}};
   if (piped) {
     if (threadIdx.x == 0) {
       for (unsigned k = 0; k < kShadeStages; ++k) mbar_init(&s_full[k], 1u);
@@ -395,23 +423,24 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
         if (at < n) shade_stage_fetch(b, cur, at, n, s_stage + k * 7u * blockDim.x, &s_full[k]);
       }
   }
+  const unsigned first = blockIdx.x * blockDim.x;
+  const unsigned n_iters = first < n_listed ? (n_listed - 1u - first) / stride + 1u : 0u;  // block iterations of this block
   unsigned iter = 0u;
-  for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+  for (unsigned base = first; iter < n_iters; base += stride, ++iter) {
     const unsigned j = base + threadIdx.x;
-    const bool valid = j < n;
+    const bool valid = j < n_listed;
     unsigned i = j;
     const unsigned slot = iter % kShadeStages;
     const float4* stage = s_stage + slot * 7u * blockDim.x;
     if (piped) {
       // fetch iteration iter + stages - 1 into the buffer that iteration iter - 1 read (every thread has passed that
-      // iteration's barriers), then wait for this iteration's records
+      // iteration's barrier), then wait for this iteration's records
       const unsigned ahead = (iter + kShadeStages - 1u) % kShadeStages;
       const unsigned long long next = (unsigned long long)base + (unsigned long long)(kShadeStages - 1u) * stride;
       if (threadIdx.x == 0 && next < n) shade_stage_fetch(b, cur, (unsigned)next, n, s_stage + ahead * 7u * blockDim.x, &s_full[ahead]);
       while (!mbar_try_wait(&s_full[slot], (iter / kShadeStages) & 1u)) {
       }
     }
-    ++iter;
     if (b.class_perm && valid) {
       unsigned c = 0u, start = 0u;
 #pragma unroll
@@ -440,41 +469,63 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
         o = __ldcs(b.ray_o[cur] + i), d = __ldcs(b.ray_d[cur] + i), s0 = __ldcs(b.st0[cur] + i), s1 = __ldcs(b.st1[cur] + i);
         s2 = __ldcs(b.st2[cur] + i), hit = __ldcs(b.hit + i), s3 = __ldcs(b.st3[cur] + i);
       }
-      const uint32_t dm = __float_as_uint(s2.w);
-      const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
-      pixel = __float_as_uint(s0.w);
-      L = mk(s2.x, s2.y, s2.z);
-      Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
-      shade_vertex<SPEC>(sc, seed, r, hit, pixel, __float_as_uint(s1.w), depth, mode, dm, mk(s0.x, s0.y, s0.z),
-                   mk(s1.x, s1.y, s1.z), L, s3, d.w, o.w, out);
+      if (__float_as_int(hit.w) != kDeadSlot) {
+        const uint32_t dm = __float_as_uint(s2.w);
+        const uint32_t depth = dm & 0xFFu, mode = (dm >> 8) & 1u;
+        pixel = __float_as_uint(s0.w);
+        L = mk(s2.x, s2.y, s2.z);
+        Ray r{o.x, o.y, o.z, d.x, d.y, d.z};
+        shade_vertex<SPEC>(sc, seed, r, hit, pixel, __float_as_uint(s1.w), depth, mode, dm, mk(s0.x, s0.y, s0.z),
+                     mk(s1.x, s1.y, s1.z), L, s3, d.w, o.w, out);
+      }
     }
-    // queue appends: warp ballots -> block prefix in shared memory -> one atomicAdd per counter
+    // queue appends (above): warp ballots -> counts in shared memory -> every warp sums the counts of the warps before it
+    const unsigned par = iter & 1u;
     const unsigned cmask = __ballot_sync(0xFFFFFFFFu, out.cont);
     const unsigned smask = __ballot_sync(0xFFFFFFFFu, out.shadow);
-    if (lane == 0) {
-      s_cnt[0][warp] = (unsigned)__popc(cmask);
-      s_cnt[1][warp] = (unsigned)__popc(smask);
+    const unsigned mine = (unsigned)__popc(cmask) | ((unsigned)__popc(smask) << 16);  // both counts in one word (<= 1024 each)
+    if (lane == 0) s_cnt[par][warp] = mine;
+    __syncthreads();  // the one barrier of an iteration whose appends fit the reserve; it also ends the reads of `stage`
+    constexpr unsigned kMaxWarps = TUTU_SHADE_BLOCK / 32;
+    unsigned scan = lane < n_warps ? s_cnt[par][lane] : 0u;  // inclusive prefix over the warps, by shuffles
+#pragma unroll
+    for (unsigned o = 1; o < kMaxWarps; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xFFFFFFFFu, scan, o);
+      if (lane >= o) scan += t;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned tc = 0, ts = 0;
-      const int n_warps = (int)(blockDim.x >> 5);
-      for (int w = 0; w < n_warps; ++w) {
-        const unsigned c = s_cnt[0][w], d = s_cnt[1][w];
-        s_cnt[0][w] = tc, s_cnt[1][w] = ts;  // exclusive prefixes
-        tc += c, ts += d;
+    const unsigned total = __shfl_sync(0xFFFFFFFFu, scan, kMaxWarps - 1), before = __shfl_sync(0xFFFFFFFFu, scan, warp) - mine;
+    const unsigned tc = total & 0xFFFFu, ts = total >> 16;
+    unsigned pc = before & 0xFFFFu, ps = before >> 16;
+    const AppendState st = s_app[par];
+    const bool need_c = tc > st.rem[0], need_s = ts > st.rem[1];
+    unsigned new_c = 0u, new_s = 0u;
+    // the reserve a block asks for shrinks with the iterations it has left (half of what they could append at most), so
+    // what is left over when it exits stays small whatever the size of the queue
+    const unsigned left = n_iters - 1u - iter;
+    const unsigned keep = min(kAppendIters, left / 2u) * blockDim.x;
+    if (need_c | need_s) {  // block-uniform
+      if (threadIdx.x == 0) {  // both counters in one atomic: {n_shadow : n_next}
+        const unsigned long long want = ((unsigned long long)(need_s ? ts - st.rem[1] + keep : 0u) << 32) |
+                                        (unsigned long long)(need_c ? tc - st.rem[0] + keep : 0u);
+        const unsigned long long got = atomicAdd(reinterpret_cast<unsigned long long*>(&b.ctl->n_next), want);
+        s_new[0] = (unsigned)got;
+        s_new[1] = (unsigned)(got >> 32);
       }
-      unsigned long long base2 = 0ull;
-      if (tc | ts)  // both queue counters in one atomic: {n_shadow : n_next}
-        base2 = atomicAdd(reinterpret_cast<unsigned long long*>(&b.ctl->n_next), ((unsigned long long)ts << 32) | tc);
-      s_base[0] = (unsigned)base2;
-      s_base[1] = (unsigned)(base2 >> 32);
+      __syncthreads();
+      new_c = s_new[0], new_s = s_new[1];
     }
-    __syncthreads();
+    if (threadIdx.x == 0) {
+      AppendState nx;
+      nx.lo[0] = need_c ? new_c + (tc - st.rem[0]) : st.lo[0] + tc;
+      nx.rem[0] = need_c ? keep : st.rem[0] - tc;
+      nx.lo[1] = need_s ? new_s + (ts - st.rem[1]) : st.lo[1] + ts;
+      nx.rem[1] = need_s ? keep : st.rem[1] - ts;
+      s_app[par ^ 1u] = nx;  // read after the next iteration's barrier
+    }
     const unsigned lt = (1u << lane) - 1u;
-    const unsigned ci = s_base[0] + s_cnt[0][warp] + (unsigned)__popc(cmask & lt);
-    const unsigned si = s_base[1] + s_cnt[1][warp] + (unsigned)__popc(smask & lt);
-    __syncthreads();  // s_cnt / s_base are rewritten by the next iteration
+    pc += (unsigned)__popc(cmask & lt), ps += (unsigned)__popc(smask & lt);
+    const unsigned ci = pc < st.rem[0] ? st.lo[0] + pc : new_c + (pc - st.rem[0]);
+    const unsigned si = ps < st.rem[1] ? st.lo[1] + ps : new_s + (ps - st.rem[1]);
     if (out.cont) {
       __stcs(b.ray_o[nxt] + ci, make_float4(out.o.x, out.o.y, out.o.z, out.rr_u));
       __stcs(b.ray_d[nxt] + ci, make_float4(out.d.x, out.d.y, out.d.z, out.q));
@@ -491,18 +542,30 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
       b.sh_d[si] = make_float4(out.sd.x, out.sd.y, out.sd.z, __uint_as_float(out.cont ? ci : kShadowFinal));
       b.sh_c[si] = make_float4(out.sc.x, out.sc.y, out.sc.z, __uint_as_float(pixel));
       if (!out.cont) b.sh_L[si] = make_float4(L.x, L.y, L.z, 0.f);
-    } else if (valid && out.finished) {
+    } else if (out.finished) {
       accum_add(b.accum, b.ctl, pixel, L);
     }
+  }
+  // what is left of the reserves: dead entries
+  __syncthreads();
+  const AppendState st = s_app[iter & 1u];
+  for (unsigned t = threadIdx.x; t < st.rem[0]; t += blockDim.x)
+    b.ray_o[nxt][st.lo[0] + t] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kDeadQueueEntry));
+  for (unsigned t = threadIdx.x; t < st.rem[1]; t += blockDim.x)
+    b.sh_o[st.lo[1] + t] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kDeadQueueEntry));
+  if (threadIdx.x == 0) {
+    if (st.rem[0]) atomicAdd(&b.ctl->dead_next, st.rem[0]);
+    if (st.rem[1]) atomicAdd(&b.ctl->dead_shadow, st.rem[1]);
   }
 }
 
 __global__ void __launch_bounds__(TUTU_SHADE_BLOCK, TUTU_SHADE_MIN_BLOCKS)
 wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
   __shared__ unsigned s_cnt[2][TUTU_SHADE_BLOCK / 32];
-  __shared__ unsigned s_base[2];
-  __shared__ unsigned s_pref[kShadeClasses];
-  wf_shade_body<0>(sc, b, cur, seed, s_cnt, s_base, s_pref);
+  __shared__ AppendState s_app[2];
+  __shared__ unsigned s_new[2];
+  __shared__ unsigned s_pref[kShadeClasses + 1];
+  wf_shade_body<0>(sc, b, cur, seed, s_cnt, s_app, s_new, s_pref);
 }
 // ---- finalize: color = estimate * SPP_inv (PathTracing.hpp:513) -------------------------------
 __global__ void wf_finalize(const float* __restrict__ accum, float inv_spp, float* __restrict__ out, size_t n) {

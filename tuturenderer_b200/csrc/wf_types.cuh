@@ -9,6 +9,16 @@ namespace tutu {
 constexpr uint32_t kShadowFinalDst = 0xFFFFFFFFu;  // sh_d.w of a shadow ray whose path has already ended (= vertex.cuh kShadowFinal)
 constexpr uint32_t kDeadQueueEntry = 0xFFFFFFFFu;  // BDPT walk queue: q_d.w of an entry to skip (= bdpt.cuh kDeadEntry)
 
+// wf_shade reserves queue space in chunks (wavefront.cuh: "queue appends"), so a queue may hold a few entries that no
+// path was written to: the unused end of a block's last chunk.  The block marks them before it exits — ray_o.w (the
+// roulette number) / sh_o.w (the distance) = kDeadQueueEntry — the tracers skip them, wf_extend* writes kDeadSlot into
+// their hit record so that wf_classify / wf_shade skip them too, and WfCtl::dead_* keeps the ray statistics exact.
+#ifndef TUTU_APPEND_ITERS
+#define TUTU_APPEND_ITERS 8
+#endif
+constexpr unsigned kAppendIters = TUTU_APPEND_ITERS;  // a block's reserve per queue = this x blockDim entries; 0 = one atomic per block iteration
+constexpr int kDeadSlot = -2;                          // Hit::slot of a dead queue entry (-1 = miss)
+
 struct WfCtl {
   unsigned n_cur;
   unsigned done;
@@ -24,6 +34,8 @@ struct WfCtl {
   unsigned long long cursor_extend;  // ray-queue cursors of the persistent tracers
   unsigned long long cursor_shadow;
   unsigned class_count[8];  // wf_classify: queue entries per shading class (kShadeClasses)
+  // dead entries (see kAppendIters) of the current path queue, of the one being written and of the shadow queue
+  unsigned dead_cur, dead_next, dead_shadow, reserved;
 };
 static_assert(offsetof(WfCtl, n_next) % 8 == 0 && offsetof(WfCtl, n_shadow) == offsetof(WfCtl, n_next) + 4,
               "n_next/n_shadow must form one aligned 64-bit word");
