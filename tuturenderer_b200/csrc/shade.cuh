@@ -43,9 +43,19 @@ __device__ __forceinline__ float norm2(f3 a) { return dot(a, a); }
 __device__ __forceinline__ f3 cross(f3 a, f3 b) {
   return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
+// MUFU.RSQ alone.  rsqrtf() is the same instruction wrapped in six more that rescale subnormal arguments (ncu: 9 % of
+// wf_shade's instructions over ~40 inlined normalisations, profiles/r02k_shade_lines.txt); for normal arguments the two
+// return the same bits.
+__device__ __forceinline__ float rsqrt_normal(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ f3 normalized(f3 v) {  // Vector.hpp:213-220
   const float l2 = v.x * v.x + v.y * v.y + v.z * v.z;
-  const float inv = l2 > 0.f ? rsqrtf(l2) : 1.f;  // a select, not a branch: v * 1 is v (mag == 0 and NaN included)
+  // a select, not a branch: v * 1 is v (mag == 0 and NaN included; so is a vector shorter than 1.1e-19, whose squared
+  // length is subnormal — the reference would still normalise it, no direction or normal of a scene gets there)
+  const float inv = l2 >= 1.17549435e-38f ? rsqrt_normal(l2) : 1.f;
   return mk(v.x * inv, v.y * inv, v.z * inv);
 }
 __device__ __forceinline__ bool FLOAT_EQUAL(float x, float y) { return fabsf(x - y) < 0.0001f; }
