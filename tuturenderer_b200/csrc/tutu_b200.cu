@@ -76,6 +76,10 @@ void upload_vec(DevBuf& b, const std::vector<T, A>& v, cudaStream_t s) {
 struct WfLane {
   DevBuf pool, ctl, class_perm;
   WfBuffers b{};
+  CUtensorMap pool_map{};  // 3-D view {4 floats, entries, arrays} of `pool` for wf_shade's TMA tile fetch
+  const void* map_base = nullptr;  // what pool_map was encoded for
+  uint64_t map_phys = 0;
+  int map_block = 0;
   uint64_t capacity = 0;
   cudaStream_t stream = nullptr;
   WfCtl* ctl_host = nullptr;  // pinned
@@ -90,6 +94,10 @@ struct WfLane {
     std::swap(class_perm.p, o.class_perm.p);
     std::swap(class_perm.bytes, o.class_perm.bytes);
     b = o.b;
+    std::swap(pool_map, o.pool_map);
+    std::swap(map_base, o.map_base);
+    std::swap(map_phys, o.map_phys);
+    std::swap(map_block, o.map_block);
     std::swap(capacity, o.capacity);
     std::swap(stream, o.stream);
     std::swap(ctl_host, o.ctl_host);
@@ -793,6 +801,30 @@ void fill_raygen(const FlatScene& f, RayGenK* k) {
 // ---------------------------------------------------------------------------------------------
 // wavefront host loop
 // ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+void encode_pool_map(CUtensorMap* map, void* pool, uint64_t entries, uint64_t arrays, int block) {
+  using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) throw CudaError{cudaErrorNotSupported, "cuTensorMapEncodeTiled (driver entry point)", __FILE__, __LINE__};
+    encode = reinterpret_cast<Encode>(fn);
+  }
+  // {floats of a run of `run` entries (<= 256, the box limit), runs, arrays}: the box rows are 1 KB of contiguous memory
+  const cuuint64_t run = std::min(block, 64);
+  const cuuint64_t dims[3] = {4 * run, entries / run, arrays};
+  const cuuint64_t strides[2] = {run * sizeof(float4), entries * sizeof(float4)};  // bytes between runs, between arrays
+  const cuuint32_t box[3] = {(cuuint32_t)(4 * run), (cuuint32_t)(block / run), 7};
+  const cuuint32_t elem[3] = {1, 1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, pool, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaError{cudaErrorInvalidValue, "cuTensorMapEncodeTiled (queue pool view)", __FILE__, __LINE__};
+}
+
 // One wavefront "lane": its own queues, control block and stream.  Lanes run interleaved on separate
 // streams, staggered by one stage, every kernel at its full persistent grid; the
 // default is two lanes of 16 Mi paths.
@@ -809,15 +841,19 @@ void lane_prepare(TutuCtx* ctx, WfLane& L, uint64_t cap) {
   L.pool.ensure(n_arrays * phys * sizeof(float4));
   float4* p = L.pool.as<float4>();
   WfBuffers& b = L.b;
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 2; ++k) {  // set 0 | hit | set 1: the seven arrays wf_shade reads are adjacent for either k
     b.ray_o[k] = p, p += phys;
     b.ray_d[k] = p, p += phys;
     b.st0[k] = p, p += phys;
     b.st1[k] = p, p += phys;
     b.st2[k] = p, p += phys;
     b.st3[k] = p, p += phys;
+    if (k == 0) b.hit = p, p += phys;
   }
-  b.hit = p, p += phys;
+  if (L.map_base != L.pool.p || L.map_phys != phys || L.map_block != ctx->shade_block) {
+    encode_pool_map(&L.pool_map, L.pool.p, phys, n_arrays, ctx->shade_block);
+    L.map_base = L.pool.p, L.map_phys = phys, L.map_block = ctx->shade_block;
+  }
   b.sh_o = p, p += phys;
   b.sh_d = p, p += phys;
   b.sh_c = p, p += phys;
@@ -1063,7 +1099,7 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         wf_classify<<<ctx->sm_count * 8, 256, 0, ls>>>(ctx->dev, L.b);
         n_launch += 1;
       }
-      wf_shade<<<ctx->grid_shade, ctx->shade_block, shade_stage_smem(ctx), ls>>>(ctx->dev, L.b, cur, seed);
+      wf_shade<<<ctx->grid_shade, ctx->shade_block, shade_stage_smem(ctx), ls>>>(ctx->dev, L.pool_map, L.b, cur, seed);
       timer.mark(3, ls);
       if (small)
         wf_shadow_small<<<ctx->grid_shadow, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);

@@ -16,6 +16,7 @@
 // raygen every iteration, so the wavefront stays full until the last samples.
 #pragma once
 #include <cstddef>
+#include <cuda.h>  // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include "vertex.cuh"
 #include "wf_types.cuh"
 
@@ -353,20 +354,19 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
                : "memory");
   return ok != 0u;
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+// One tile of the queue pool: blockDim entries of 7 arrays, a box of the 3-D view {floats of a run of <= 64 entries, runs,
+// arrays} that the host encodes over the lane's pool (tutu_b200.cu: encode_pool_map).  The pool is laid out
+// as  set 0 (ray_o ray_d st0 st1 st2 st3) | hit | set 1 | shadow arrays,  so the seven arrays wf_shade reads are adjacent
+// for either ping-pong index: rows 0..6 for cur = 0 (hit last), rows 6..12 for cur = 1 (hit first).  Entries past the end
+// of the pool arrive as zeros, entries past the end of the queue are never looked at.  One instruction per block iteration;
+// the seven 1-D bulk copies it replaces cost 140 warp instructions (ncu: 4.5 % of the kernel, all in warp 0).
+__device__ __forceinline__ void shade_stage_fetch(const CUtensorMap* map, int cur, unsigned base, float4* stage, unsigned long long* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy reads of this buffer are done (barrier)
+  mbar_expect_tx(bar, 7u * 16u * blockDim.x);
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_addr(stage)),
+               "l"(map), "r"(0), "r"((int)(base / min(blockDim.x, 64u))), "r"(cur ? 6 : 0), "r"(smem_addr(bar))
                : "memory");
-}
-// the seven slices of the iteration that starts at queue index `base` into stage buffer `stage`
-__device__ __forceinline__ void shade_stage_fetch(const WfBuffers& b, int cur, unsigned base, unsigned n, float4* stage,
-                                                  unsigned long long* bar) {
-  const unsigned count = min(blockDim.x, n - base), bytes = count * 16u;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy reads of this buffer are done (barriers)
-  mbar_expect_tx(bar, 7u * bytes);
-  const float4* src[7] = {b.ray_o[cur], b.ray_d[cur], b.st0[cur], b.st1[cur], b.st2[cur], b.st3[cur], b.hit};
-#pragma unroll
-  for (int a = 0; a < 7; ++a) bulk_g2s(stage + a * blockDim.x, src[a] + base, bytes, bar);
 }
 
 // ---- queue appends -----------------------------------------------------------------------------------------------
@@ -385,9 +385,9 @@ struct AppendState {
 };
 
 template <int SPEC>
-__device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffers& b, int cur, uint64_t seed,
-                                              unsigned (*s_cnt)[TUTU_SHADE_BLOCK / 32], AppendState* s_app, unsigned* s_new,
-                                              unsigned* s_pref) {
+__device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffers& b, const CUtensorMap* pool_map, int cur,
+                                              uint64_t seed, unsigned (*s_cnt)[TUTU_SHADE_BLOCK / 32], AppendState* s_app,
+                                              unsigned* s_new, unsigned* s_pref) {
   const int nxt = cur ^ 1;
   const unsigned n = b.ctl->n_cur;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -420,7 +420,7 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
     if (threadIdx.x == 0)
       for (unsigned k = 0; k + 1 < kShadeStages; ++k) {  // prologue: the first stages - 1 iterations
         const unsigned at = blockIdx.x * blockDim.x + k * stride;
-        if (at < n) shade_stage_fetch(b, cur, at, n, s_stage + k * 7u * blockDim.x, &s_full[k]);
+        if (at < n) shade_stage_fetch(pool_map, cur, at, s_stage + k * 7u * blockDim.x, &s_full[k]);
       }
   }
   const unsigned first = blockIdx.x * blockDim.x;
@@ -437,7 +437,7 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
       // iteration's barrier), then wait for this iteration's records
       const unsigned ahead = (iter + kShadeStages - 1u) % kShadeStages;
       const unsigned long long next = (unsigned long long)base + (unsigned long long)(kShadeStages - 1u) * stride;
-      if (threadIdx.x == 0 && next < n) shade_stage_fetch(b, cur, (unsigned)next, n, s_stage + ahead * 7u * blockDim.x, &s_full[ahead]);
+      if (threadIdx.x == 0 && next < n) shade_stage_fetch(pool_map, cur, (unsigned)next, s_stage + ahead * 7u * blockDim.x, &s_full[ahead]);
       while (!mbar_try_wait(&s_full[slot], (iter / kShadeStages) & 1u)) {
       }
     }
@@ -462,9 +462,10 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
       // second memory round trip on the critical path.
       float4 o, d, s0, s2, hit, s3;
       if (piped) {
-        const unsigned t = threadIdx.x, bd = blockDim.x;
-        o = stage[t], d = stage[bd + t], s0 = stage[2 * bd + t], s1 = stage[3 * bd + t], s2 = stage[4 * bd + t];
-        s3 = stage[5 * bd + t], hit = stage[6 * bd + t];
+        const unsigned bd = blockDim.x;
+        const float4* rec = stage + (cur ? bd : 0u) + threadIdx.x;  // tile rows: cur = 0: set 0 then hit; cur = 1: hit then set 1
+        o = rec[0], d = rec[bd], s0 = rec[2 * bd], s1 = rec[3 * bd], s2 = rec[4 * bd], s3 = rec[5 * bd];
+        hit = stage[(cur ? 0u : 6u * bd) + threadIdx.x];
       } else {
         o = __ldcs(b.ray_o[cur] + i), d = __ldcs(b.ray_d[cur] + i), s0 = __ldcs(b.st0[cur] + i), s1 = __ldcs(b.st1[cur] + i);
         s2 = __ldcs(b.st2[cur] + i), hit = __ldcs(b.hit + i), s3 = __ldcs(b.st3[cur] + i);
@@ -560,12 +561,12 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
 }
 
 __global__ void __launch_bounds__(TUTU_SHADE_BLOCK, TUTU_SHADE_MIN_BLOCKS)
-wf_shade(const __grid_constant__ DevScene sc, WfBuffers b, int cur, uint64_t seed) {
+wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ CUtensorMap pool_map, WfBuffers b, int cur, uint64_t seed) {
   __shared__ unsigned s_cnt[2][TUTU_SHADE_BLOCK / 32];
   __shared__ AppendState s_app[2];
   __shared__ unsigned s_new[2];
   __shared__ unsigned s_pref[kShadeClasses + 1];
-  wf_shade_body<0>(sc, b, cur, seed, s_cnt, s_app, s_new, s_pref);
+  wf_shade_body<0>(sc, b, &pool_map, cur, seed, s_cnt, s_app, s_new, s_pref);
 }
 // ---- finalize: color = estimate * SPP_inv (PathTracing.hpp:513) -------------------------------
 __global__ void wf_finalize(const float* __restrict__ accum, float inv_spp, float* __restrict__ out, size_t n) {
