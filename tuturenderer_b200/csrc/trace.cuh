@@ -73,13 +73,15 @@ __device__ __forceinline__ float cross_c(float a, float b, float c, float d) {  
 __device__ __forceinline__ void normalize_rn(float& x, float& y, float& z) {
   float mag = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
   if (mag > 0.f) {
-    float inv = __fdiv_rn(1.f, mag);
+    float inv = __frcp_rn(mag);
     x = __fmul_rn(x, inv);
     y = __fmul_rn(y, inv);
     z = __fmul_rn(z, inv);
   }
 }
 
+// __frcp_rn(x) is the correctly rounded 1/x, i.e. the same float as the reference's `1 / x` (IEEE division), in about half
+// the instructions of __fdiv_rn(1.f, x).
 struct RayPre {  // per-ray constants of the slab test
   float ox, oy, oz;
   float ix, iy, iz;     // 1/d, IEEE (inf for 0)
@@ -89,9 +91,9 @@ struct RayPre {  // per-ray constants of the slab test
 __device__ __forceinline__ RayPre make_pre(const Ray& r) {
   RayPre p;
   p.ox = r.ox, p.oy = r.oy, p.oz = r.oz;
-  p.ix = __fdiv_rn(1.f, r.dx);
-  p.iy = __fdiv_rn(1.f, r.dy);
-  p.iz = __fdiv_rn(1.f, r.dz);
+  p.ix = __frcp_rn(r.dx);
+  p.iy = __frcp_rn(r.dy);
+  p.iz = __frcp_rn(r.dz);
   p.nx = r.dx < 0.f;
   p.ny = r.dy < 0.f;
   p.nz = r.dz < 0.f;
@@ -137,7 +139,7 @@ __device__ __forceinline__ bool tri_test(const float4* __restrict__ g, const Ray
   const float s2x = cross_c(sy, e1z, sz, e1y);
   const float s2y = cross_c(sz, e1x, sx, e1z);
   const float s2z = cross_c(sx, e1y, sy, e1x);
-  const float left = __fdiv_rn(1.0f, det);
+  const float left = __frcp_rn(det);
   t = __fmul_rn(left, dot_rn(s2x, s2y, s2z, e2x, e2y, e2z));
   u = __fmul_rn(left, dot_rn(s1x, s1y, s1z, sx, sy, sz));
   v = __fmul_rn(left, dot_rn(s2x, s2y, s2z, r.dx, r.dy, r.dz));
