@@ -33,7 +33,13 @@ __device__ __forceinline__ f3 operator-(f3 a) { return mk(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ f3 operator*(f3 a, f3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ f3 operator*(f3 a, float c) { return mk(a.x * c, a.y * c, a.z * c); }
 __device__ __forceinline__ f3 operator*(float c, f3 a) { return mk(a.x * c, a.y * c, a.z * c); }
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+// a / b as a * MUFU.RCP(b): what __fdividef(a, b) computes for a normal b (same bits), without the three instructions
+// that rescale a subnormal divisor (which this one flushes to zero: a / 0); 15 call sites in the Lambertian path.
+__device__ __forceinline__ float fdiv(float a, float b) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return a * r;
+}
 __device__ __forceinline__ f3 operator/(f3 a, float c) {
   const float r = fdiv(1.f, c);
   return mk(a.x * r, a.y * r, a.z * r);

@@ -360,12 +360,13 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
 // for either ping-pong index: rows 0..6 for cur = 0 (hit last), rows 6..12 for cur = 1 (hit first).  Entries past the end
 // of the pool arrive as zeros, entries past the end of the queue are never looked at.  One instruction per block iteration;
 // the seven 1-D bulk copies it replaces cost 140 warp instructions (ncu: 4.5 % of the kernel, all in warp 0).
-__device__ __forceinline__ void shade_stage_fetch(const CUtensorMap* map, int cur, unsigned base, float4* stage, unsigned long long* bar) {
+// `run_index` = base / (entries per run) = (block iterations before this one in the whole grid) x (runs per block).
+__device__ __forceinline__ void shade_stage_fetch(const CUtensorMap* map, int cur, unsigned run_index, float4* stage, unsigned long long* bar) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy reads of this buffer are done (barrier)
   mbar_expect_tx(bar, 7u * 16u * blockDim.x);
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                    smem_addr(stage)),
-               "l"(map), "r"(0), "r"((int)(base / min(blockDim.x, 64u))), "r"(cur ? 6 : 0), "r"(smem_addr(bar))
+               "l"(map), "r"(0), "r"((int)run_index), "r"(cur ? 6 : 0), "r"(smem_addr(bar))
                : "memory");
 }
 
@@ -410,6 +411,7 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
   __shared__ unsigned long long s_full[kShadeStages];
   const bool piped = b.class_perm == nullptr;          // class lists gather their records: direct loads
   const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned runs_per_block = blockDim.x / min(blockDim.x, 64u);  // encode_pool_map: a run is min(block, 64) entries
   if (threadIdx.x == 0) s_app[0] = AppendState{{0u, 0u}, {0u, 0u}};
   if (piped) {
     if (threadIdx.x == 0) {
@@ -420,7 +422,7 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
     if (threadIdx.x == 0)
       for (unsigned k = 0; k + 1 < kShadeStages; ++k) {  // prologue: the first stages - 1 iterations
         const unsigned at = blockIdx.x * blockDim.x + k * stride;
-        if (at < n) shade_stage_fetch(pool_map, cur, at, s_stage + k * 7u * blockDim.x, &s_full[k]);
+        if (at < n) shade_stage_fetch(pool_map, cur, (blockIdx.x + k * gridDim.x) * runs_per_block, s_stage + k * 7u * blockDim.x, &s_full[k]);
       }
   }
   const unsigned first = blockIdx.x * blockDim.x;
@@ -437,7 +439,9 @@ __device__ __forceinline__ void wf_shade_body(const DevScene& sc, const WfBuffer
       // iteration's barrier), then wait for this iteration's records
       const unsigned ahead = (iter + kShadeStages - 1u) % kShadeStages;
       const unsigned long long next = (unsigned long long)base + (unsigned long long)(kShadeStages - 1u) * stride;
-      if (threadIdx.x == 0 && next < n) shade_stage_fetch(pool_map, cur, (unsigned)next, s_stage + ahead * 7u * blockDim.x, &s_full[ahead]);
+      if (threadIdx.x == 0 && next < n)
+        shade_stage_fetch(pool_map, cur, (blockIdx.x + (iter + kShadeStages - 1u) * gridDim.x) * runs_per_block, s_stage + ahead * 7u * blockDim.x,
+                          &s_full[ahead]);
       while (!mbar_try_wait(&s_full[slot], (iter / kShadeStages) & 1u)) {
       }
     }
