@@ -16,8 +16,8 @@ part=${1:-a}
 if [ "$part" = a ]; then
 run python tools/prof_run.py rays
 run $NCU -k regex:'k_trace_closest|k_trace_any' -o $O/r02_rays python tools/prof_run.py rays
-TUTU_PROF_SPP=128 TUTU_LANES=1 run python tools/prof_run.py render
-TUTU_PROF_SPP=128 TUTU_LANES=1 run $NCU -k regex:'wf_shade|wf_extend_small|wf_shadow_small' --launch-skip 30 -c 3 -o $O/r02_steady python tools/prof_run.py render
+TUTU_PROF_SPP=256 TUTU_LANES=1 run python tools/prof_run.py render
+TUTU_PROF_SPP=256 TUTU_LANES=1 run $NCU -k regex:'wf_shade|wf_extend_small|wf_shadow_small' --launch-skip 30 -c 3 -o $O/r02_steady python tools/prof_run.py render
 run python bench.py --steps 2 --warmup 3 --spp 64 --no-cpu --no-extras --no-rays
 run ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_launches_bench.csv python bench.py --steps 2 --warmup 3 --spp 64 --no-cpu --no-extras --no-rays
 else
