@@ -205,7 +205,7 @@ def run_reference(args) -> None:
     value = WIDTH * HEIGHT * spp * len(times) / total * 1e-6
     sample = (f"each step: Cornell {WIDTH}x{HEIGHT} @ {spp} spp ({WIDTH * HEIGHT * spp / 1e6:.1f} Mpaths) through "
               f"the reference's PathTracing (sub_render_pt row worker on {threads} host threads)")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": value / PUBLISHED_MPATHS, "dtype": "f32",
@@ -218,7 +218,7 @@ def run_reference(args) -> None:
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": min(threads, cores), "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def workload_config(args) -> dict:
@@ -516,8 +516,26 @@ def c1_bench(torch, api) -> dict:
 # --------------------------------------------------------------------------------------------
 # main arm
 # --------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def quiet_stdout() -> None:
+    """Rank 0 prints ONE JSON line: everything else that libraries write to fd 1 (NCCL's version banner, subprocess
+    chatter) is sent to stderr, and emit() writes the line to the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -694,7 +712,7 @@ def main():
                                       "shadow": shd * world / (charged_ms["wf_shadow"] * 1e-3) * 1e-6 if charged_ms["wf_shadow"] else None},
             "nan_samples": cnt["nan_samples"],
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
