@@ -12,8 +12,8 @@
 // (PathTracing.hpp:510) keeps its meaning.
 //
 // Queues live in HBM as float4 SoA, ping-pong per iteration; survivors and shadow rays are
-// appended through warp-aggregated atomics (one atomicAdd per warp).  Free slots are refilled by
-// raygen every iteration, so the wavefront stays full until the last samples.
+// appended into space that each block of wf_shade reserves in chunks ("queue appends" below).  Free
+// slots are refilled by raygen every iteration, so the wavefront stays full until the last samples.
 #pragma once
 #include <cstddef>
 #include <cuda.h>  // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
@@ -310,11 +310,10 @@ wf_classify(const __grid_constant__ DevScene sc, WfBuffers b) {
   }
 }
 
-// Compiled for up to 256 threads / 2 blocks per SM (128 registers); the launch picks the block size.  With direct
-// loads small blocks were better on Cornell (a block waits at two barriers for one global atomic per iteration:
-// 256x2 1606 / 128x4 1652 / 64x8 1670 Mpaths/s in round 1); with the staged records (above) one 256-thread block
-// amortises the seven bulk copies and the mbarrier wait best, and mixed-material scenes always wanted 256 (many
-// small blocks on different material code paths thrash the instruction cache: 426 / 353 / 317).
+// Compiled for up to 256 threads / 2 blocks per SM (128 registers); the launch picks the block size: 64 threads for scenes
+// shaded in queue order (Cornell 1024^2, Mpaths/s with 32 / 64 / 96 / 128 / 256 threads: 2049 / 2184 / 2130 / 2172 / 2073 —
+// small blocks keep the one barrier of an iteration between two warps), 256 for mixed-material scenes (many small
+// blocks on different material code paths thrash the instruction cache: 426 / 353 / 317 Mpaths/s with 256 / 128 / 64).
 #ifndef TUTU_SHADE_MIN_BLOCKS
 #define TUTU_SHADE_MIN_BLOCKS 2
 #endif
@@ -327,14 +326,12 @@ wf_classify(const __grid_constant__ DevScene sc, WfBuffers b) {
 constexpr int kShadeBlockSimple = TUTU_SHADE_BLOCK_SIMPLE;
 
 // ---- TMA staging of the queue records ------------------------------------------------------------------------
-// A block's records of one iteration are seven contiguous 16 B x blockDim slices of the queue arrays.  One thread asks
-// the bulk-copy engine for the NEXT iteration's slices (cp.async.bulk = UBLKCP, completion counted on an mbarrier)
-// before the block shades the current ones, so the HBM latency that every block iteration used to start with (ncu,
-// profiles/r02_steady_shade_stalls.txt: 19 % of wf_shade's stall samples on the first use of the queue loads) is
-// overlapped with shading.  Measured on Cornell 1024^2 (tools/gpu_cornell_perf.py, Mpaths/s): direct loads 64 / 128 /
-// 256 threads per block 2066 / 2047 / 1975; staged, 2 stages 1920 / 2092 / 2109; staged, 3 stages, 256 threads 2051
-// (the third stage costs L1).  -> 256-thread blocks with two stages; scenes shaded through class lists gather their
-// records and keep the direct loads.
+// A block's records of one iteration are seven 16 B x blockDim slices of the queue arrays.  One thread asks the copy
+// engine for the NEXT iteration's slices (one cp.async.bulk.tensor tile, completion counted on an mbarrier) before
+// the block shades the current ones, so the HBM latency that every block iteration used to start with (ncu before the
+// change: 19 % of wf_shade's stall samples on the first use of the queue loads) is overlapped with shading, and no
+// registers are spent on bytes in flight.  Two stages; a third costs L1 and measured slower (2184 -> 2164 Mpaths/s).
+// Scenes shaded through class lists gather their records and keep the direct loads.
 #ifndef TUTU_SHADE_STAGES
 #define TUTU_SHADE_STAGES 2
 #endif
