@@ -271,8 +271,10 @@ int tutu_render_bdpt_accumulate_device(TutuCtx* ctx, uint32_t sample_begin, uint
 int tutu_finalize_bdpt_device(TutuCtx* ctx, const float* d_accum, float inv_spp, float* d_rgb_out,
                               void* stream);
 int tutu_render_stats(const TutuCtx* ctx, TutuRenderStats* out);
-/* Knobs: paths in flight per wavefront lane (0 = default 16 Mi; BDPT: samples per batch, default
- * 4 Mi), number of interleaved wavefront lanes (0 = default 2), per-stage event timing on/off. */
+/* Knobs: paths in flight per wavefront lane (0 = default: 32 Mi for scenes shaded in queue order — a single
+ * untextured Lambertian material class, e.g. the Cornell box — else 16 Mi; BDPT: samples per batch, default
+ * 4 Mi), number of interleaved wavefront lanes (0 = default: 1 resp. 2 for the same two cases), per-stage
+ * event timing on/off. */
 int tutu_render_configure(TutuCtx* ctx, uint64_t paths_in_flight, int lanes, int profile_stages);
 /* Path-tracing pipeline: 0 = automatic (default), 1 = wavefront (queues in HBM, any scene), 2 =
  * register-resident persistent kernel (scenes of <= 32 primitives, whose geometry fits the kernel's
