@@ -252,14 +252,14 @@ def _full_size_reference(api, full_size_scene, kind):
     return _REF_CACHE[kind]
 
 
-@pytest.mark.parametrize("builder", ["device_lbvh", "host_sah"])
+@pytest.mark.parametrize("builder", ["device_lbvh", "device_ploc", "host_sah"])
 @pytest.mark.parametrize("kind", [0, 1])
 def test_full_size_against_the_reference(api, ctx, full_size_scene, kind, builder):
     """configs[1] at BASELINE size against the REFERENCE ITSELF (BVH.hpp:145-194 through
     oracle/_ref/ref_harness trace: the reference's own recursiveBuild tree, getIntersection and
     hasIntersection): 2^20 rays of each kind, {prim, t, u, v} byte for byte and the any-hit booleans,
-    for the production walk (mode 0) over the device-built and over the host-built traversal tree, the
-    literal walk (mode 1) and the compressed wide tree (mode 6).  The 2^20 rays are a strided
+    for the production walk (mode 0) over the two device-built trees (linear BVH, PLOC) and over the host-built
+    traversal tree, the literal walk (mode 1) and the compressed wide tree (mode 6).  The 2^20 rays are a strided
     sample of the 2^24-ray batch bench.py times, so the compared rays cover the whole batch."""
     sc, _path = full_size_scene
     rays, want_c, want_a = _full_size_reference(api, full_size_scene, kind)
@@ -276,8 +276,8 @@ def test_full_size_against_the_reference(api, ctx, full_size_scene, kind, builde
 
 @pytest.mark.parametrize("case", ["heightfield", "soup_dups", "spheres", "clustered", "three"])
 def test_device_built_tree_equals_host_built_tree_and_oracle(api, oracle, ctx, case):
-    """The traversal tree built on the GPU (device_bvh.cu: Morton sort + Karras hierarchy + refit) is a different
-    topology over the same leaves: hits must be those of the host-built SAH tree, of the literal walk of the
+    """The traversal trees built on the GPU (device_bvh.cu: Morton sort + Karras hierarchy + refit, or Morton sort +
+    locally-ordered clustering) are different topologies over the same leaves: hits must be those of the host-built SAH tree, of the literal walk of the
     reference topology and of the CPU oracle, bit for bit; likewise the wide collapse of the device-built tree."""
     rng = np.random.default_rng(9)
     if case == "heightfield":
@@ -300,7 +300,7 @@ def test_device_built_tree_equals_host_built_tree_and_oracle(api, oracle, ctx, c
     sub = slice(0, 80000, 5)
     want_c, want_a = osc.trace_closest(np.ascontiguousarray(rays[sub])), osc.trace_any(np.ascontiguousarray(rays[sub]))
     results = {}
-    for builder in ("host_sah", "device_lbvh"):
+    for builder in ("host_sah", "device_lbvh", "device_ploc"):
         ctx.builder(builder)
         ctx.upload(sc)
         st = ctx.upload_stats()

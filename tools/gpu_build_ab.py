@@ -17,7 +17,7 @@ N = 1 << 24
 stream = api.stream_handle(torch.cuda.current_stream().cuda_stream)
 rays = {k: torch.from_numpy(api.synth_rays(k, N)).cuda() for k in (0, 1)}
 hits = {}
-for builder in ('host_sah', 'device_lbvh'):
+for builder in ('host_sah', 'device_lbvh', 'device_ploc'):
     ctx.builder(builder)
     ctx.upload(sc)
     for rep in range(2):
@@ -45,16 +45,17 @@ for builder in ('host_sah', 'device_lbvh'):
         print(' ', builder, 'kind', kind, rec, flush=True)
         hits[(builder, kind)] = (h, a)
 for kind in (0, 1):
-    same = bool((hits[('host_sah', kind)][0].view(torch.int32) == hits[('device_lbvh', kind)][0].view(torch.int32)).all()) and \
-        bool((hits[('host_sah', kind)][1] == hits[('device_lbvh', kind)][1]).all())
-    print('kind', kind, 'device-built == host-built:', same)
+    for dev in ('device_lbvh', 'device_ploc'):
+        same = bool((hits[('host_sah', kind)][0].view(torch.int32) == hits[(dev, kind)][0].view(torch.int32)).all()) and \
+            bool((hits[('host_sah', kind)][1] == hits[(dev, kind)][1]).all())
+        print('kind', kind, dev, '== host-built:', same)
 ctx.close()
 del rays, hits
 
 for name, file, w, h, kind in (('glass', 'glass_c4.tscene', 1024, 1024, 'pt'), ('veach', 'veach_80x60.tscene', 800, 600, 'bdpt')):
     sc = api.Scene.load(G + file).with_size(w, h)
     ctx = api.Context(0)
-    for builder in ('host_sah', 'device_lbvh'):
+    for builder in ('host_sah', 'device_lbvh', 'device_ploc'):
         ctx.builder(builder)
         ctx.upload(sc)
         render = ctx.render_path if kind == 'pt' else ctx.render_bdpt

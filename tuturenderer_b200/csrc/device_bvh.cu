@@ -19,6 +19,7 @@
 // Output = the 64-byte two-child nodes the binary walk reads (tutu_internal.hpp: InnerNode), root = node 0, leaf
 // refs = ~(DFS slot | sphere bit) of the REFERENCE tree's leaf numbering, which is what the equal-t tie rule compares.
 // No library sort: every kernel here is this repository's.  sm_100a only.
+#include <algorithm>
 #include <cfloat>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -269,6 +270,187 @@ lbvh_depth(int n, const int* __restrict__ parent_inner, const int* __restrict__ 
   if ((threadIdx.x & 31) == 0 && best) atomicMax(deepest, best);
 }
 
+
+// ---- PLOC: parallel locally-ordered clustering ---------------------------------------------------------------
+// Meister & Bittner, "Parallel Locally-Ordered Clustering for Bounding Volume Hierarchy Construction" (TVCG 2018).
+// Clusters start as the Morton-sorted leaves.  One iteration: every cluster finds, among the kPlocRadius clusters on
+// either side of it in the array, the one whose union with it has the smallest surface area (ties: the lower index);
+// pairs that chose each other become one inner node, which takes the place of the pair's first cluster; the array
+// is compacted in order (so it stays Morton-ordered) and the next iteration runs on the shorter array.  The distance
+// is symmetric and the tie rule total, so every iteration merges at least the globally best pair.  Bottom-up merging
+// by surface area gives a tree of SAH quality (measured below) in about thirty passes over a shrinking array.
+// Nodes are numbered from n - 2 downwards in creation order, so the last merge is node 0 = the root.
+#ifndef TUTU_PLOC_RADIUS
+#define TUTU_PLOC_RADIUS 8
+#endif
+constexpr int kPlocRadius = TUTU_PLOC_RADIUS;
+constexpr int kScanBlock = 256, kScanItems = 8, kScanTile = kScanBlock * kScanItems;
+
+struct PlocCtl {
+  unsigned n_cur;      // clusters in the current array
+  unsigned next_node;  // nodes [next_node, n - 1) are taken
+  unsigned merged, kept;  // totals of the current iteration (written by ploc_scan_partials)
+};
+
+__device__ __forceinline__ float ploc_area(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi) {
+  const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y),
+              dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+  return dx * dy + dy * dz + dz * dx;
+}
+
+// cluster p = sorted leaf p: lo.w = bits(~p) (the id: inner node >= 0, sorted leaf ~p)
+__global__ void __launch_bounds__(256)
+ploc_init(const float* __restrict__ leaf_box, const unsigned* __restrict__ sorted_leaf, unsigned n, float4* __restrict__ lo,
+          float4* __restrict__ hi, PlocCtl* ctl) {
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const float* b = leaf_box + 6 * (size_t)sorted_leaf[p];
+    lo[p] = make_float4(b[0], b[1], b[2], __int_as_float(~(int)p));
+    hi[p] = make_float4(b[3], b[4], b[5], 0.f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->n_cur = n, ctl->next_node = n - 1, ctl->merged = 0, ctl->kept = 0;
+}
+
+__global__ void __launch_bounds__(256)
+ploc_nearest(const float4* __restrict__ lo, const float4* __restrict__ hi, const PlocCtl* __restrict__ ctl, unsigned* __restrict__ nn) {
+  const unsigned n = ctl->n_cur;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 alo = lo[i], ahi = hi[i];
+    const unsigned first = i > (unsigned)kPlocRadius ? i - kPlocRadius : 0u, last = min(n - 1u, i + kPlocRadius);
+    float best = FLT_MAX;
+    unsigned arg = i;
+    for (unsigned j = first; j <= last; ++j) {
+      if (j == i) continue;
+      const float a = ploc_area(alo, ahi, lo[j], hi[j]);
+      if (a < best) best = a, arg = j;  // strict: the lower index wins a tie
+    }
+    nn[i] = arg;
+  }
+}
+
+// flags of cluster i: merged = it is the first of a mutual pair (becomes a node), kept = it survives the iteration
+__device__ __forceinline__ unsigned ploc_flags(const unsigned* __restrict__ nn, unsigned i) {
+  const unsigned j = nn[i];
+  const bool mutual = j != i && nn[j] == i;
+  const unsigned merged = mutual && i < j, kept = !(mutual && i > j);
+  return merged | (kept << 16);
+}
+
+// per-tile sums of (merged, kept), packed 2 x 16 bits per thread, 2 x 32 per tile
+__global__ void __launch_bounds__(kScanBlock)
+ploc_count(const unsigned* __restrict__ nn, const PlocCtl* __restrict__ ctl, uint2* __restrict__ tile_sum) {
+  const unsigned n = ctl->n_cur;
+  __shared__ unsigned s_m[kScanBlock / 32], s_k[kScanBlock / 32];
+  for (unsigned tile = blockIdx.x; (size_t)tile * kScanTile < n; tile += gridDim.x) {
+    const unsigned first = tile * kScanTile + threadIdx.x * kScanItems;
+    unsigned acc = 0u;
+    for (int k = 0; k < kScanItems; ++k)
+      if (first + k < n) acc += ploc_flags(nn, first + k);
+    unsigned m = acc & 0xFFFFu, kp = acc >> 16;
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_down_sync(0xFFFFFFFFu, m, o), kp += __shfl_down_sync(0xFFFFFFFFu, kp, o);
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m, s_k[threadIdx.x >> 5] = kp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned tm = 0, tk = 0;
+      for (int w = 0; w < kScanBlock / 32; ++w) tm += s_m[w], tk += s_k[w];
+      tile_sum[tile] = make_uint2(tm, tk);
+    }
+    __syncthreads();
+  }
+}
+
+// exclusive scan of the tile sums by one block; totals into ctl
+__global__ void __launch_bounds__(1024)
+ploc_scan_tiles(uint2* __restrict__ tile_sum, PlocCtl* ctl) {
+  const unsigned n_tiles = (ctl->n_cur + kScanTile - 1) / kScanTile;
+  __shared__ unsigned s_m[1024], s_k[1024];
+  __shared__ unsigned carry_m, carry_k;
+  if (threadIdx.x == 0) carry_m = 0, carry_k = 0;
+  __syncthreads();
+  for (unsigned base = 0; base < n_tiles; base += 1024) {
+    const unsigned t = base + threadIdx.x;
+    const uint2 v = t < n_tiles ? tile_sum[t] : make_uint2(0, 0);
+    s_m[threadIdx.x] = v.x, s_k[threadIdx.x] = v.y;
+    __syncthreads();
+    for (unsigned o = 1; o < 1024; o <<= 1) {
+      const unsigned am = threadIdx.x >= o ? s_m[threadIdx.x - o] : 0u, ak = threadIdx.x >= o ? s_k[threadIdx.x - o] : 0u;
+      __syncthreads();
+      s_m[threadIdx.x] += am, s_k[threadIdx.x] += ak;
+      __syncthreads();
+    }
+    if (t < n_tiles) tile_sum[t] = make_uint2(carry_m + s_m[threadIdx.x] - v.x, carry_k + s_k[threadIdx.x] - v.y);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_m += s_m[1023], carry_k += s_k[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ctl->merged = carry_m, ctl->kept = carry_k;
+}
+
+__device__ __forceinline__ int ploc_final_ref(int id, const unsigned* __restrict__ leaf_code, const unsigned* __restrict__ sorted_leaf) {
+  return id >= 0 ? id : (int)~leaf_code[sorted_leaf[~id]];
+}
+
+// writes the nodes of the mutual pairs and the next cluster array (order preserved)
+__global__ void __launch_bounds__(kScanBlock)
+ploc_merge(const float4* __restrict__ lo, const float4* __restrict__ hi, const unsigned* __restrict__ nn, const uint2* __restrict__ tile_sum,
+           const PlocCtl* __restrict__ ctl, const unsigned* __restrict__ leaf_code, const unsigned* __restrict__ sorted_leaf,
+           float4* __restrict__ lo_out, float4* __restrict__ hi_out, NodeOut* __restrict__ nodes, int* __restrict__ parent_inner,
+           int* __restrict__ parent_leaf) {
+  const unsigned n = ctl->n_cur, next_node = ctl->next_node;
+  __shared__ unsigned s_m[kScanBlock], s_k[kScanBlock];
+  for (unsigned tile = blockIdx.x; (size_t)tile * kScanTile < n; tile += gridDim.x) {
+    const unsigned first = tile * kScanTile + threadIdx.x * kScanItems;
+    unsigned fl[kScanItems];
+    unsigned acc = 0u;
+    for (int k = 0; k < kScanItems; ++k) {
+      fl[k] = first + k < n ? ploc_flags(nn, first + k) : 0u;
+      acc += fl[k];
+    }
+    s_m[threadIdx.x] = acc & 0xFFFFu, s_k[threadIdx.x] = acc >> 16;
+    __syncthreads();
+    for (unsigned o = 1; o < kScanBlock; o <<= 1) {
+      const unsigned am = threadIdx.x >= o ? s_m[threadIdx.x - o] : 0u, ak = threadIdx.x >= o ? s_k[threadIdx.x - o] : 0u;
+      __syncthreads();
+      s_m[threadIdx.x] += am, s_k[threadIdx.x] += ak;
+      __syncthreads();
+    }
+    const uint2 base = tile_sum[tile];
+    unsigned rank_m = base.x + s_m[threadIdx.x] - (acc & 0xFFFFu), rank_k = base.y + s_k[threadIdx.x] - (acc >> 16);
+    __syncthreads();
+    for (int k = 0; k < kScanItems; ++k) {
+      const unsigned i = first + k;
+      if (i >= n) break;
+      const bool merged = fl[k] & 1u, kept = (fl[k] >> 16) & 1u;
+      if (merged) {
+        const unsigned j = nn[i];
+        const int node = (int)(next_node - 1u - rank_m);
+        const float4 alo = lo[i], ahi = hi[i], blo = lo[j], bhi = hi[j];
+        const int ida = __float_as_int(alo.w), idb = __float_as_int(blo.w);
+        NodeOut* out = nodes + node;
+        const float l0[3] = {alo.x, alo.y, alo.z}, h0[3] = {ahi.x, ahi.y, ahi.z}, l1[3] = {blo.x, blo.y, blo.z}, h1[3] = {bhi.x, bhi.y, bhi.z};
+        store_child_box(out, 0, l0, h0);
+        store_child_box(out, 1, l1, h1);
+        out->left = ploc_final_ref(ida, leaf_code, sorted_leaf);
+        out->right = ploc_final_ref(idb, leaf_code, sorted_leaf);
+        out->pad0 = out->pad1 = 0;
+        if (ida >= 0) parent_inner[ida] = node; else parent_leaf[~ida] = node;
+        if (idb >= 0) parent_inner[idb] = node; else parent_leaf[~idb] = node;
+        lo_out[rank_k] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), __int_as_float(node));
+        hi_out[rank_k] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+      } else if (kept) {
+        lo_out[rank_k] = lo[i];
+        hi_out[rank_k] = hi[i];
+      }
+      rank_m += merged, rank_k += kept;
+    }
+  }
+}
+
+__global__ void ploc_advance(PlocCtl* ctl, int* __restrict__ parent_inner) {
+  ctl->next_node -= ctl->merged;
+  ctl->n_cur = ctl->kept;
+  if (ctl->kept == 1u) parent_inner[0] = -1;  // the last merge was the root
+}
+
 }  // namespace
 
 size_t device_build_lbvh_scratch_bytes(uint32_t n) {
@@ -334,6 +516,98 @@ cudaError_t device_build_lbvh(const float* d_leaf_box, const uint32_t* d_leaf_co
   if ((e = cudaMemcpyAsync(&h_deep, deepest, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
   if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
   *depth_out = h_deep;
+  return cudaSuccess;
+}
+
+size_t device_build_ploc_scratch_bytes(uint32_t n) {
+  auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t n_tiles = ((size_t)n + kScanTile - 1) / kScanTile;
+  // the Morton sort's buffers (keys x2, vals x2, hist) + cluster arrays x2 (lo, hi) + nn + tile sums + parents x2 + ctl + deepest
+  const unsigned n_blocks = (n + kSortTile - 1) / kSortTile;
+  return 2 * pad((size_t)n * 8) + 2 * pad((size_t)n * 4) + pad((size_t)kRadix * n_blocks * 4) + 4 * pad((size_t)n * 16) + pad((size_t)n * 4) +
+         pad(n_tiles * 8) + 2 * pad((size_t)n * 4) + 2 * 256;
+}
+
+cudaError_t device_build_ploc(const float* d_leaf_box, const uint32_t* d_leaf_code, uint32_t n, const float root_lo[3],
+                              const float root_hi[3], void* d_inner_out, uint32_t* depth_out, uint32_t* iterations_out, int sm_count,
+                              void* d_scratch, cudaStream_t s) {
+  if (n < 2 || !d_scratch) return cudaErrorInvalidValue;
+  const unsigned n_blocks = (n + kSortTile - 1) / kSortTile;
+  const size_t n_tiles = ((size_t)n + kScanTile - 1) / kScanTile;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  const size_t o_k0 = take((size_t)n * 8), o_k1 = take((size_t)n * 8), o_v0 = take((size_t)n * 4), o_v1 = take((size_t)n * 4);
+  const size_t o_hist = take((size_t)kRadix * n_blocks * 4);
+  const size_t o_lo0 = take((size_t)n * 16), o_hi0 = take((size_t)n * 16), o_lo1 = take((size_t)n * 16), o_hi1 = take((size_t)n * 16);
+  const size_t o_nn = take((size_t)n * 4), o_tiles = take(n_tiles * 8), o_pi = take((size_t)n * 4), o_pl = take((size_t)n * 4);
+  const size_t o_ctl = take(256), o_deep = take(256);
+  if (off > device_build_ploc_scratch_bytes(n)) return cudaErrorInvalidValue;
+  char* base = static_cast<char*>(d_scratch);
+  auto* k0 = reinterpret_cast<unsigned long long*>(base + o_k0);
+  auto* k1 = reinterpret_cast<unsigned long long*>(base + o_k1);
+  auto* v0 = reinterpret_cast<unsigned*>(base + o_v0);
+  auto* v1 = reinterpret_cast<unsigned*>(base + o_v1);
+  auto* hist = reinterpret_cast<unsigned*>(base + o_hist);
+  float4* lo[2] = {reinterpret_cast<float4*>(base + o_lo0), reinterpret_cast<float4*>(base + o_lo1)};
+  float4* hi[2] = {reinterpret_cast<float4*>(base + o_hi0), reinterpret_cast<float4*>(base + o_hi1)};
+  auto* nn = reinterpret_cast<unsigned*>(base + o_nn);
+  auto* tiles = reinterpret_cast<uint2*>(base + o_tiles);
+  auto* parent_inner = reinterpret_cast<int*>(base + o_pi);
+  auto* parent_leaf = reinterpret_cast<int*>(base + o_pl);
+  auto* ctl = reinterpret_cast<PlocCtl*>(base + o_ctl);
+  auto* deepest = reinterpret_cast<unsigned*>(base + o_deep);
+  cudaError_t e = cudaSuccess;
+
+  const int grid = sm_count * 8;
+  float3 lo3 = make_float3(root_lo[0], root_lo[1], root_lo[2]);
+  float3 inv;
+  inv.x = root_hi[0] > root_lo[0] ? 1.f / (root_hi[0] - root_lo[0]) : 0.f;
+  inv.y = root_hi[1] > root_lo[1] ? 1.f / (root_hi[1] - root_lo[1]) : 0.f;
+  inv.z = root_hi[2] > root_lo[2] ? 1.f / (root_hi[2] - root_lo[2]) : 0.f;
+  lbvh_keys<<<grid, 256, 0, s>>>(d_leaf_box, n, lo3, inv, k0, v0);
+  for (int shift = 0; shift < kKeyBits; shift += kRadixBits) {
+    radix_count<<<n_blocks, kSortBlock, 0, s>>>(k0, n, shift, hist, n_blocks);
+    radix_scan<<<1, 1024, 0, s>>>(hist, kRadix * n_blocks);
+    radix_scatter<<<n_blocks, kSortBlock, 0, s>>>(k0, v0, n, shift, hist, n_blocks, k1, v1);
+    unsigned long long* tk = k0;
+    k0 = k1, k1 = tk;
+    unsigned* tv = v0;
+    v0 = v1, v1 = tv;
+  }
+  if ((e = cudaMemsetAsync(deepest, 0, 4, s)) != cudaSuccess) return e;
+  ploc_init<<<grid, 256, 0, s>>>(d_leaf_box, v0, n, lo[0], hi[0], ctl);
+  // the host looks at the cluster count every few iterations; every iteration merges at least one pair
+  const int tile_grid = (int)std::min<size_t>(n_tiles, (size_t)sm_count * 8);
+  unsigned iterations = 0;
+  int cur = 0;
+  PlocCtl h{};
+  h.n_cur = n;
+  while (h.n_cur > 1u) {
+    for (int k = 0; k < 8; ++k, ++iterations) {
+      ploc_nearest<<<grid, 256, 0, s>>>(lo[cur], hi[cur], ctl, nn);
+      ploc_count<<<tile_grid, kScanBlock, 0, s>>>(nn, ctl, tiles);
+      ploc_scan_tiles<<<1, 1024, 0, s>>>(tiles, ctl);
+      ploc_merge<<<tile_grid, kScanBlock, 0, s>>>(lo[cur], hi[cur], nn, tiles, ctl, d_leaf_code, v0, lo[cur ^ 1], hi[cur ^ 1],
+                                                  static_cast<NodeOut*>(d_inner_out), parent_inner, parent_leaf);
+      ploc_advance<<<1, 1, 0, s>>>(ctl, parent_inner);
+      cur ^= 1;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    if (iterations > 100000u) return cudaErrorUnknown;
+  }
+  lbvh_depth<<<grid, 256, 0, s>>>((int)n, parent_inner, parent_leaf, deepest);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  unsigned h_deep = 0;
+  if ((e = cudaMemcpyAsync(&h_deep, deepest, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+  *depth_out = h_deep;
+  if (iterations_out) *iterations_out = iterations;
   return cudaSuccess;
 }
 

@@ -15,4 +15,11 @@ cudaError_t device_build_lbvh(const float* d_leaf_box, const uint32_t* d_leaf_co
                               const float root_hi[3], void* d_inner_out, uint32_t* depth_out, int sm_count, void* d_scratch,
                               cudaStream_t s);
 
+// The same interface for a tree built by parallel locally-ordered clustering (PLOC): Morton-sorted leaves are merged
+// bottom-up, nearest neighbour by surface area within a window, until one cluster is left.  iterations_out: merge passes.
+size_t device_build_ploc_scratch_bytes(uint32_t n);
+cudaError_t device_build_ploc(const float* d_leaf_box, const uint32_t* d_leaf_code, uint32_t n, const float root_lo[3],
+                              const float root_hi[3], void* d_inner_out, uint32_t* depth_out, uint32_t* iterations_out, int sm_count,
+                              void* d_scratch, cudaStream_t s);
+
 }  // namespace tutu

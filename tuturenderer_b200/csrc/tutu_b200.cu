@@ -1404,7 +1404,8 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   // triangles): the device LBVH cuts the upload from 338 to 120 ms (tree 238 -> 29 ms) but its spatial-median
   // splits cost 91 instead of 34 node visits per ray (closest hit 842 vs 2089 Mrays/s; glass scene 766 vs 922
   // Mpaths/s, Veach BDPT 56.8 vs 62.2 Msamples/s): it pays only for jobs that trace fewer than ~3 x 10^8 rays per upload.
-  const bool want_device = desc && ctx->builder_cfg == TUTU_BUILD_DEVICE_LBVH;
+  const bool want_ploc = desc && ctx->builder_cfg == TUTU_BUILD_DEVICE_PLOC;
+  const bool want_device = desc && (ctx->builder_cfg == TUTU_BUILD_DEVICE_LBVH || want_ploc);
   FlatScene fs;
   int rc = flatten_scene(desc, &fs, false);  // the traversal tree is built (and timed) below
   if (rc != TUTU_OK) return fail(ctx, rc, get_error());
@@ -1424,15 +1425,19 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
       upload_vec(ctx->d_leaf_box, fs.leaf_box, s);
       upload_vec(ctx->d_leaf_code, fs.leaf_code, s);
       ctx->d_inner_fast.ensure((size_t)(fs.n_prims - 1) * sizeof(InnerNode));
-      ctx->d_build_scratch.ensure(device_build_lbvh_scratch_bytes(fs.n_prims));
+      ctx->d_build_scratch.ensure(want_ploc ? device_build_ploc_scratch_bytes(fs.n_prims) : device_build_lbvh_scratch_bytes(fs.n_prims));
       uint32_t depth = 0;
-      CUDA_TRY(device_build_lbvh(ctx->d_leaf_box.as<float>(), ctx->d_leaf_code.as<uint32_t>(), fs.n_prims, fs.root_box.lo,
-                                 fs.root_box.hi, ctx->d_inner_fast.p, &depth, ctx->sm_count, ctx->d_build_scratch.p, s));
+      if (want_ploc)
+        CUDA_TRY(device_build_ploc(ctx->d_leaf_box.as<float>(), ctx->d_leaf_code.as<uint32_t>(), fs.n_prims, fs.root_box.lo,
+                                   fs.root_box.hi, ctx->d_inner_fast.p, &depth, nullptr, ctx->sm_count, ctx->d_build_scratch.p, s));
+      else
+        CUDA_TRY(device_build_lbvh(ctx->d_leaf_box.as<float>(), ctx->d_leaf_code.as<uint32_t>(), fs.n_prims, fs.root_box.lo,
+                                   fs.root_box.hi, ctx->d_inner_fast.p, &depth, ctx->sm_count, ctx->d_build_scratch.p, s));
       if (depth >= 1 && depth <= (uint32_t)kFastTreeMaxDepth) {
         device_tree = true;
         fs.root_ref_fast = 0;
         fs.depth_fast = depth;
-        us.builder = TUTU_BUILD_DEVICE_LBVH;
+        us.builder = want_ploc ? TUTU_BUILD_DEVICE_PLOC : TUTU_BUILD_DEVICE_LBVH;
       }
     }
     if (!device_tree) build_host_fast_tree(&fs);  // non-finite boxes, tiny scenes, or a tree deeper than the stacks
@@ -1565,7 +1570,7 @@ extern "C" int tutu_scene_info(const TutuCtx* ctx, TutuSceneInfo* out) {
 }
 
 extern "C" int tutu_scene_builder(TutuCtx* ctx, int builder) {
-  if (!ctx || builder < TUTU_BUILD_AUTO || builder > TUTU_BUILD_DEVICE_LBVH)
+  if (!ctx || builder < TUTU_BUILD_AUTO || builder > TUTU_BUILD_DEVICE_PLOC)
     return fail(ctx, TUTU_E_INVALID, "tutu_scene_builder: builder must be TUTU_BUILD_AUTO, _HOST_SAH or _DEVICE_LBVH");
   std::lock_guard<std::mutex> lock(ctx->mu);
   ctx->builder_cfg = builder;
