@@ -263,7 +263,7 @@ def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict)
     sc = api.Scene(prims=prims, materials=api.default_material(), bvh_nodes=nodes)
     ctx = ctx_cls(torch.cuda.current_device())
     uploads = {}
-    for builder in ("device_lbvh", "host_sah"):  # the last one stays: it is what "auto" picks
+    for builder in ("device_lbvh", "device_ploc", "host_sah", "device_sah"):  # the last one stays: it is what "auto" picks
         ctx.builder(builder)
         ctx.upload(sc)  # first upload allocates the device buffers
         t0 = time.perf_counter()
@@ -272,14 +272,15 @@ def rays_bench(torch, ctx_cls, rank: int, world: int, do_cpu: bool, peaks: dict)
     ctx.builder("auto")
     n_local = RAYS_N // world
     first = rank * n_local
-    out = {"upload_ms": uploads["host_sah"]["wall_ms"], "upload": uploads, "reference_tree_build_ms": ref_tree_ms,
+    out = {"upload_ms": uploads["device_sah"]["wall_ms"], "upload": uploads, "reference_tree_build_ms": ref_tree_ms,
            "upload_note": "tutu_scene_upload of the 999 698-triangle scene with the reference's tree given (wall clock, pageable "
                           "host arrays): flatten_ms = host validation + DFS slots + leaf records + reference-topology nodes, "
-                          "tree_build_ms = the traversal tree for regular rays (device: Morton sort + Karras hierarchy + refit; "
-                          "host: binned SAH), h2d_ms = copies.  reference_tree_build_ms = tutu_bvh_build (host, the reference's "
-                          "std::sort split rule) for hosts that do not hand over the reference's own tree.  The timed batches "
-                          "below walk the host-built SAH tree (TUTU_BUILD_AUTO): the device LBVH uploads 3x faster but "
-                          "costs 2.7x the node visits per ray"}
+                          "tree_build_ms = the traversal tree for regular rays (device_sah: the host's binned-SAH split rule, "
+                          "level-synchronous on the GPU; device_lbvh / device_ploc: Morton sort + Karras hierarchy or locally-ordered "
+                          "clustering; host_sah: binned SAH on the host threads), h2d_ms = copies.  reference_tree_build_ms = "
+                          "tutu_bvh_build (host, the reference's std::sort split rule) for hosts that do not hand over the "
+                          "reference's own tree.  The timed batches below walk the device-built SAH tree (TUTU_BUILD_AUTO), which "
+                          "is the host builder's tree; LBVH and PLOC trees cost 2-2.7x the node visits per ray"}
     stream = api.stream_handle(torch.cuda.current_stream().cuda_stream)
     scene_path = None
     for kind, label in ((0, "coherent_topdown"), (1, "incoherent_inside")):

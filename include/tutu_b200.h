@@ -194,19 +194,20 @@ const char* tutu_last_error(const TutuCtx* ctx);
 int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc);
 int tutu_scene_info(const TutuCtx* ctx, TutuSceneInfo* out);
 /* Who builds the traversal tree for regular rays (a binary tree over the reference's leaves; the reference's own
- * topology is always kept for irregular rays and the literal walk): TUTU_BUILD_HOST_SAH = binned surface-area
- * heuristic on the host (0.24 s for 10^6 primitives on 16 threads; the better tree: 34 node visits per ray on
- * configs[1]); TUTU_BUILD_DEVICE_LBVH = linear BVH on the GPU (Morton keys, radix sort, Karras hierarchy, refit:
- * 29 ms for 10^6 primitives incl. its uploads, but 91 node visits per ray): for previews and scenes that change
- * every frame; TUTU_BUILD_DEVICE_PLOC = the same Morton order merged bottom-up by surface area (parallel
- * locally-ordered clustering: 8 ms tree build, 69 node visits per ray); TUTU_BUILD_AUTO = the host SAH tree
- * (DESIGN.md 5.8 has the measurements).  Takes effect at the next
+ * topology is always kept for irregular rays and the literal walk).  TUTU_BUILD_HOST_SAH = binned surface-area
+ * heuristic on the host (0.16 s for 10^6 primitives on 16 threads; 34 node visits per ray on configs[1]);
+ * TUTU_BUILD_DEVICE_SAH = the same split rule on the GPU, level-synchronous (the same tree in 9.6 ms);
+ * TUTU_BUILD_DEVICE_LBVH = linear BVH on the GPU (Morton keys, radix sort, Karras hierarchy, refit: 6.7 ms, but 91
+ * node visits per ray); TUTU_BUILD_DEVICE_PLOC = the same Morton order merged bottom-up by surface area (parallel
+ * locally-ordered clustering: 8.4 ms, 69 node visits per ray); TUTU_BUILD_AUTO = the device SAH builder for scenes
+ * of more than 64 primitives, the host's below (DESIGN.md 5.8 has the measurements).  Takes effect at the next
  * tutu_scene_upload.  Hits do not depend on the choice (any tree with exact union boxes over the same leaves gives
- * the same answer); trees deeper than 30 levels fall back to the host builder. */
+ * the same answer); device-built trees deeper than 30 levels fall back to the host builder. */
 #define TUTU_BUILD_AUTO 0
 #define TUTU_BUILD_HOST_SAH 1
 #define TUTU_BUILD_DEVICE_LBVH 2
 #define TUTU_BUILD_DEVICE_PLOC 3 /* GPU: Morton sort + parallel locally-ordered clustering (bottom-up merges by surface area) */
+#define TUTU_BUILD_DEVICE_SAH 4  /* GPU: the host builder's binned-SAH split rule, level-synchronous (the same tree) */
 int tutu_scene_builder(TutuCtx* ctx, int builder);
 /* Wall-clock breakdown of the last tutu_scene_upload (milliseconds). */
 typedef struct TutuUploadStats {
@@ -214,7 +215,7 @@ typedef struct TutuUploadStats {
   float flatten_ms;    /* host: validation, DFS slots, leaf records, reference-topology nodes (+ midpoint build if no tree was given) */
   float tree_build_ms; /* traversal tree for regular rays: host SAH build, or device LBVH (incl. its two small uploads) */
   float h2d_ms;        /* copies of the flattened arrays */
-  int32_t builder;     /* TUTU_BUILD_HOST_SAH, TUTU_BUILD_DEVICE_LBVH or TUTU_BUILD_DEVICE_PLOC: what was actually used */
+  int32_t builder;     /* TUTU_BUILD_HOST_SAH or one of TUTU_BUILD_DEVICE_*: what was actually used */
   uint32_t tree_depth;
 } TutuUploadStats;
 int tutu_upload_stats(const TutuCtx* ctx, TutuUploadStats* out);

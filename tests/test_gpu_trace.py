@@ -252,14 +252,14 @@ def _full_size_reference(api, full_size_scene, kind):
     return _REF_CACHE[kind]
 
 
-@pytest.mark.parametrize("builder", ["device_lbvh", "device_ploc", "host_sah"])
+@pytest.mark.parametrize("builder", ["device_lbvh", "device_ploc", "device_sah", "host_sah"])
 @pytest.mark.parametrize("kind", [0, 1])
 def test_full_size_against_the_reference(api, ctx, full_size_scene, kind, builder):
     """configs[1] at BASELINE size against the REFERENCE ITSELF (BVH.hpp:145-194 through
     oracle/_ref/ref_harness trace: the reference's own recursiveBuild tree, getIntersection and
     hasIntersection): 2^20 rays of each kind, {prim, t, u, v} byte for byte and the any-hit booleans,
-    for the production walk (mode 0) over the two device-built trees (linear BVH, PLOC) and over the host-built
-    traversal tree, the literal walk (mode 1) and the compressed wide tree (mode 6).  The 2^20 rays are a strided
+    for the production walk (mode 0) over the three device-built trees (linear BVH, PLOC, binned SAH) and over the
+    host-built traversal tree, the literal walk (mode 1) and the compressed wide tree (mode 6).  The 2^20 rays are a strided
     sample of the 2^24-ray batch bench.py times, so the compared rays cover the whole batch."""
     sc, _path = full_size_scene
     rays, want_c, want_a = _full_size_reference(api, full_size_scene, kind)
@@ -300,7 +300,7 @@ def test_device_built_tree_equals_host_built_tree_and_oracle(api, oracle, ctx, c
     sub = slice(0, 80000, 5)
     want_c, want_a = osc.trace_closest(np.ascontiguousarray(rays[sub])), osc.trace_any(np.ascontiguousarray(rays[sub]))
     results = {}
-    for builder in ("host_sah", "device_lbvh", "device_ploc"):
+    for builder in ("host_sah", "device_lbvh", "device_ploc", "device_sah"):
         ctx.builder(builder)
         ctx.upload(sc)
         st = ctx.upload_stats()
@@ -316,6 +316,48 @@ def test_device_built_tree_equals_host_built_tree_and_oracle(api, oracle, ctx, c
         assert np.array_equal(a, ref_a), key
     assert_hits_equal(np.ascontiguousarray(ref_c[sub]), want_c)
     assert np.array_equal(ref_a[sub], want_a)
+
+
+@pytest.mark.parametrize("case", ["heightfield", "soup", "spheres", "tiny"])
+def test_device_sah_builder_grows_the_host_builders_tree(api, ctx, case):
+    """device_bvh.cu's top-down builder repeats the host builder's split rule operation for operation
+    (host_scene.cpp: FastBuilder), so wherever no node falls back to halving by record order the two trees are the
+    same tree: equal depth, and every ray visits exactly the same number of nodes and primitives (summed over 2^18
+    rays of both kinds), besides returning the same hits."""
+    import torch
+    if case == "heightfield":
+        prims = api.synth_heightfield(160)
+    elif case == "soup":
+        prims = random_soup(api, 30000, seed=31)
+    elif case == "spheres":
+        prims = random_soup(api, 3000, n_spheres=1200, seed=32)
+    else:
+        prims = random_soup(api, 40, seed=33)
+    sc = api.Scene(prims=prims, materials=api.default_material())
+    n = 1 << 18
+    batches = [api.synth_rays(0, n, seed=6) if case == "heightfield" else random_rays(n, seed=35), random_rays(n, seed=36)]
+    seen = {}
+    for builder in ("host_sah", "device_sah"):
+        ctx.builder(builder)
+        ctx.upload(sc)
+        st = ctx.upload_stats()
+        assert st["builder"] == builder, st
+        rec = [st["tree_depth"]]
+        for rays in batches:
+            d = torch.from_numpy(rays).cuda()
+            for any_hit in (False, True):
+                rec.append(ctx.count_visits(d.data_ptr(), len(rays), any_hit))
+            rec.append((ctx.trace_closest(rays), ctx.trace_any(rays)))
+        seen[builder] = rec
+    ctx.builder("auto")
+    a, b = seen["host_sah"], seen["device_sah"]
+    assert a[0] == b[0]
+    for x, y in zip(a[1:], b[1:]):
+        if isinstance(x[0], np.ndarray):
+            assert_hits_equal(x[0], y[0])
+            assert np.array_equal(x[1], y[1])
+        else:
+            assert x == y, (x, y)
 
 
 def test_binned_order_gives_identical_results(api, oracle, ctx):

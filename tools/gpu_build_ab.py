@@ -17,7 +17,7 @@ N = 1 << 24
 stream = api.stream_handle(torch.cuda.current_stream().cuda_stream)
 rays = {k: torch.from_numpy(api.synth_rays(k, N)).cuda() for k in (0, 1)}
 hits = {}
-for builder in ('host_sah', 'device_lbvh', 'device_ploc'):
+for builder in ('host_sah', 'device_lbvh', 'device_ploc', 'device_sah'):
     ctx.builder(builder)
     ctx.upload(sc)
     for rep in range(2):
@@ -45,7 +45,7 @@ for builder in ('host_sah', 'device_lbvh', 'device_ploc'):
         print(' ', builder, 'kind', kind, rec, flush=True)
         hits[(builder, kind)] = (h, a)
 for kind in (0, 1):
-    for dev in ('device_lbvh', 'device_ploc'):
+    for dev in ('device_lbvh', 'device_ploc', 'device_sah'):
         same = bool((hits[('host_sah', kind)][0].view(torch.int32) == hits[(dev, kind)][0].view(torch.int32)).all()) and \
             bool((hits[('host_sah', kind)][1] == hits[(dev, kind)][1]).all())
         print('kind', kind, dev, '== host-built:', same)
@@ -55,7 +55,7 @@ del rays, hits
 for name, file, w, h, kind in (('glass', 'glass_c4.tscene', 1024, 1024, 'pt'), ('veach', 'veach_80x60.tscene', 800, 600, 'bdpt')):
     sc = api.Scene.load(G + file).with_size(w, h)
     ctx = api.Context(0)
-    for builder in ('host_sah', 'device_lbvh', 'device_ploc'):
+    for builder in ('host_sah', 'device_lbvh', 'device_ploc', 'device_sah'):
         ctx.builder(builder)
         ctx.upload(sc)
         render = ctx.render_path if kind == 'pt' else ctx.render_bdpt

@@ -74,7 +74,7 @@ class TutuUploadStats(C.Structure):
                 ("builder", C.c_int32), ("tree_depth", C.c_uint32)]
 
 
-BUILDERS = {"auto": 0, "host_sah": 1, "device_lbvh": 2, "device_ploc": 3}
+BUILDERS = {"auto": 0, "host_sah": 1, "device_lbvh": 2, "device_ploc": 3, "device_sah": 4}
 
 
 class TutuTreeCheck(C.Structure):

@@ -22,4 +22,11 @@ cudaError_t device_build_ploc(const float* d_leaf_box, const uint32_t* d_leaf_co
                               const float root_hi[3], void* d_inner_out, uint32_t* depth_out, uint32_t* iterations_out, int sm_count,
                               void* d_scratch, cudaStream_t s);
 
+// Top-down binned SAH with the host builder's split rule (host_scene.cpp: FastBuilder): the same tree, node for node,
+// wherever the host does not fall back to halving a node by its current record order.  max_depth: the host's depth
+// budget (kFastTreeMaxDepth).  levels_out: level-synchronous passes over the nodes of more than 64 primitives.
+size_t device_build_sah_scratch_bytes(uint32_t n);
+cudaError_t device_build_sah(const float* d_leaf_box, const uint32_t* d_leaf_code, uint32_t n, int max_depth, void* d_inner_out,
+                             uint32_t* depth_out, uint32_t* levels_out, int sm_count, void* d_scratch, cudaStream_t s);
+
 }  // namespace tutu
