@@ -1,6 +1,6 @@
 """Short, fixed workload for ncu (never a bench number): `render` = Cornell 1024x1024 @ 24 spp,
 `rays` = 4 Mi rays of each synthetic kind against the 999 698-triangle height-field, `bdpt` = the
-Veach room 800x600 @ 4 spp through tutu_render_bdpt."""
+Veach room 800x600 @ 4 spp through tutu_render_bdpt, `build` = one upload of that height-field per device tree builder."""
 import sys
 from pathlib import Path
 import numpy as np
@@ -18,6 +18,13 @@ if what == "render":
     ctx.configure(0, False, int(os.environ.get("TUTU_LANES", "0")))
     img = ctx.render_path(int(os.environ.get("TUTU_PROF_SPP", "24")), seed=5)
     print("render mean", float(img.mean()), ctx.stats())
+elif what == "build":  # the traversal-tree builders on the 999 698-triangle scene (launch list only)
+    prims = api.synth_heightfield(707)
+    sc = api.Scene(prims=prims, materials=api.default_material(), bvh_nodes=api.bvh_build(prims))
+    for builder in ("device_sah", "device_ploc", "device_lbvh"):
+        ctx.builder(builder)
+        ctx.upload(sc)
+        print(builder, ctx.upload_stats())
 elif what == "bdpt":
     sc = api.Scene.load(ROOT / "tests/golden/veach_80x60.tscene").with_size(800, 600)
     ctx.upload(sc)
