@@ -25,6 +25,7 @@ merged = {}
 for name, workload in captures.items():
     run(T / "ncu_summary.py", "full", G / f"r02_{name}.ncu-rep", P / f"r02_{name}_full")
     for k, v in json.loads((P / f"r02_{name}_full_traffic.json").read_text()).items():
+        k = k.split("::")[-1]  # kernels of an anonymous namespace come as "<unnamed>::name"
         key = f"{k}@glass" if name == "glass" and k in merged else k
         merged[key] = dict(v, capture=f"profiles/r02_{name}_full.txt", workload=workload)
         if key != k:
