@@ -368,6 +368,13 @@ int tutu_scene_file_save(const TutuSceneDesc* desc, const char* path);
  * kind: 0 = top-down rays (coherent, ~all hit), 1 = incoherent rays from inside the bounds. */
 int tutu_synth_heightfield(uint32_t G, uint64_t seed, TutuPrim* prims_out);
 int tutu_synth_rays(int kind, uint64_t seed, uint64_t first, uint64_t n_rays, float* rays_out);
+/* Debug aid (compute-sanitizer stand-in, tests/test_gpu_guards.py): in a library compiled with -DTUTU_GUARDS every
+ * device allocation sits between two 64 KB bands of a byte pattern; this synchronises the device and counts the live
+ * allocations and the band bytes that were overwritten (bands of allocations freed since start-up included).  The
+ * shipped library has no bands and returns TUTU_E_STATE. */
+int tutu_debug_guard_check(uint64_t* n_buffers, uint64_t* n_bad_bytes);
+/* Self-test of that detector: zeroes n_bytes of the upper band of the oldest live allocation (guard builds only). */
+int tutu_debug_guard_poke(uint32_t n_bytes);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libtutu_b200.so"
 
 TUTU_OK = 0
+TUTU_E_INVALID, TUTU_E_CUDA, TUTU_E_STATE, TUTU_E_IO, TUTU_E_NOMEM = -1, -2, -3, -4, -5
 PRIM_TRIANGLE, PRIM_SPHERE = 0, 1
 MAT_LAMBERTIAN, MAT_PERFECT_REFLECTIVE, MAT_PERFECT_REFRACTIVE, MAT_MICROFACET_R, MAT_MICROFACET_T, MAT_UNLIT = range(6)
 TEX_DIFFUSE, TEX_NORMAL, TEX_ROUGHNESS, TEX_METALLIC = range(4)
@@ -134,6 +135,8 @@ ABI = {
     "tutu_scene_file_save": (C.c_int, [C.POINTER(TutuSceneDesc), C.c_char_p]),
     "tutu_synth_heightfield": (C.c_int, [C.c_uint32, C.c_uint64, _P]),
     "tutu_synth_rays": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
+    "tutu_debug_guard_check": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tutu_debug_guard_poke": (C.c_int, [C.c_uint32]),
 }
 
 _lib = None
@@ -324,6 +327,13 @@ def synth_rays(kind: int, n: int, seed: int = 12345, first: int = 0, out: np.nda
         out = np.empty((n, RAY_FLOATS), np.float32)
     _check(lib().tutu_synth_rays(kind, seed, first, n, _ptr(out)))
     return out
+
+
+def guard_check() -> tuple[int, int]:
+    """(live device allocations, overwritten guard-band bytes) of a -DTUTU_GUARDS build; TutuError otherwise."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().tutu_debug_guard_check(C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def write_ppm(path, rgb8: np.ndarray, binary: bool = False) -> None:

@@ -58,6 +58,17 @@ def build_variant(name: str, defines: list[str]) -> Path:
     return out
 
 
+def build_guard_library(force: bool = False) -> Path:
+    """libtutu_b200_guard.so (-DTUTU_GUARDS): the same sources with 64 KB pattern bands around every device allocation
+    and a registry behind tutu_debug_guard_check; loaded only by tests/test_gpu_guards.py through TUTU_LIB."""
+    out = PKG / "libtutu_b200_guard.so"
+    if not force and out.exists():
+        t = out.stat().st_mtime
+        if not any(p.stat().st_mtime > t for p in SOURCES + HEADERS + [Path(__file__)]):
+            return out
+    return build_variant("guard", ["TUTU_GUARDS"])
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB

@@ -41,6 +41,31 @@ struct CudaError {
     if (_e != cudaSuccess) throw CudaError{_e, #expr, __FILE__, __LINE__}; \
   } while (0)
 
+// Every device allocation of the library goes through DevBuf.  A -DTUTU_GUARDS build (libtutu_b200_guard.so,
+// tests/test_gpu_guards.py) surrounds each allocation with kGuardBytes of a byte pattern on either side and keeps a
+// registry of the live buffers; tutu_debug_guard_check() counts the guard bytes that no longer hold the pattern.
+// compute-sanitizer is closed on the GPU pool, so this is the library's own check for writes outside an allocation.
+#ifdef TUTU_GUARDS
+constexpr size_t kGuardBytes = 64 << 10;
+constexpr int kGuardPattern = 0xA5;
+std::mutex g_guard_mu;
+std::vector<std::pair<void*, size_t>> g_guard_live;  // {first byte after the lower band, bytes}: DevBuf objects may move
+uint64_t g_guard_bad_freed = 0;                      // overwritten band bytes of allocations that were freed since
+// overwritten bytes in the two bands of one allocation (synchronises the device)
+uint64_t guard_bad_bytes(const void* p, size_t bytes) {
+  static std::vector<unsigned char> host(kGuardBytes);
+  uint64_t bad = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  for (const char* g : {static_cast<const char*>(p) - kGuardBytes, static_cast<const char*>(p) + bytes}) {
+    if (cudaMemcpy(host.data(), g, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    for (unsigned char c : host) bad += c != (unsigned char)kGuardPattern;
+  }
+  return bad;
+}
+#else
+constexpr size_t kGuardBytes = 0;
+#endif
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -49,15 +74,32 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+#ifdef TUTU_GUARDS
+      std::lock_guard<std::mutex> lock(g_guard_mu);
+      g_guard_bad_freed += guard_bad_bytes(p, bytes);  // a buffer that is replaced by a larger one is checked on its way out
+      g_guard_live.erase(std::remove_if(g_guard_live.begin(), g_guard_live.end(), [&](const auto& e) { return e.first == p; }),
+                         g_guard_live.end());
+#endif
+      cudaFree(static_cast<char*>(p) - kGuardBytes);
+    }
     p = nullptr;
     bytes = 0;
   }
   void ensure(size_t n) {
     if (n <= bytes) return;
     release();
-    CUDA_TRY(cudaMalloc(&p, n));
+    void* base = nullptr;
+    CUDA_TRY(cudaMalloc(&base, n + 2 * kGuardBytes));
+    p = static_cast<char*>(base) + kGuardBytes;
     bytes = n;
+#ifdef TUTU_GUARDS
+    // blocking memsets: the guards are in place before any stream can touch the buffer
+    CUDA_TRY(cudaMemset(base, kGuardPattern, kGuardBytes));
+    CUDA_TRY(cudaMemset(static_cast<char*>(p) + n, kGuardPattern, kGuardBytes));
+    std::lock_guard<std::mutex> lock(g_guard_mu);
+    g_guard_live.emplace_back(p, n);
+#endif
   }
   template <class T>
   T* as() const {
@@ -1345,6 +1387,45 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
 // =============================================================================================
 // C ABI
 // =============================================================================================
+// Guard bands of every live device allocation (only in a -DTUTU_GUARDS build, see DevBuf).
+extern "C" int tutu_debug_guard_check(uint64_t* n_buffers, uint64_t* n_bad_bytes) {
+  if (!n_buffers || !n_bad_bytes) return fail(nullptr, TUTU_E_INVALID, "tutu_debug_guard_check: null argument");
+  *n_buffers = 0;
+  *n_bad_bytes = 0;
+#ifdef TUTU_GUARDS
+  try {
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(g_guard_mu);
+    *n_bad_bytes = g_guard_bad_freed;
+    for (const auto& b : g_guard_live) {
+      *n_bad_bytes += guard_bad_bytes(b.first, b.second);
+      ++*n_buffers;
+    }
+    return TUTU_OK;
+  } catch (const CudaError& e) {
+    return fail_cuda(nullptr, e);
+  } catch (...) {
+    return fail(nullptr, TUTU_E_INVALID, "tutu_debug_guard_check: unexpected exception");
+  }
+#else
+  return fail(nullptr, TUTU_E_STATE, "tutu_debug_guard_check: this library was built without -DTUTU_GUARDS");
+#endif
+}
+
+// Self-test of the detector: overwrites `n_bytes` of the upper band of the oldest live allocation.
+extern "C" int tutu_debug_guard_poke(uint32_t n_bytes) {
+#ifdef TUTU_GUARDS
+  std::lock_guard<std::mutex> lock(g_guard_mu);
+  if (g_guard_live.empty() || n_bytes > kGuardBytes) return fail(nullptr, TUTU_E_STATE, "tutu_debug_guard_poke: nothing to poke");
+  const auto& b = g_guard_live.front();
+  if (cudaMemset(static_cast<char*>(b.first) + b.second, 0, n_bytes) != cudaSuccess) return fail(nullptr, TUTU_E_CUDA, "tutu_debug_guard_poke: cudaMemset failed");
+  return TUTU_OK;
+#else
+  (void)n_bytes;
+  return fail(nullptr, TUTU_E_STATE, "tutu_debug_guard_poke: this library was built without -DTUTU_GUARDS");
+#endif
+}
+
 extern "C" int tutu_ctx_create(int device, TutuCtx** out) {
   if (!out) return fail(nullptr, TUTU_E_INVALID, "tutu_ctx_create: null out pointer");
   *out = nullptr;
