@@ -243,6 +243,11 @@ int tutu_trace_any_device(TutuCtx* ctx, const float* d_rays, uint64_t n_rays,
  * child boxes quantised outwards, decoded exactly; built on the first use).  Same hits bit for bit; on a B200 it
  * is slower than the binary walk, so it is an option. */
 int tutu_set_traversal_mode(TutuCtx* ctx, int mode);
+/* Where the tree kernels keep their per-ray traversal stack: 0 = decided per scene (the default: local memory while the
+ * traversal arrays — both node arrays and the leaf geometry — are at most 32 MB and live in L1/L2 next to it, shared
+ * memory above that, where the stack's local-memory lines would compete with the node fetches),
+ * 1 = shared memory, 2 = local memory.  Same results either way; the tests run both. */
+int tutu_traversal_stack(TutuCtx* ctx, int where);
 /* Visit counters for the algorithmic-bytes figure: traces the batch with counting kernels and
  * returns total inner-node fetches and primitive tests. */
 int tutu_trace_count_visits(TutuCtx* ctx, const float* d_rays, uint64_t n_rays, int any_hit,

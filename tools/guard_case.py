@@ -49,6 +49,9 @@ for builder in ("auto", "host_sah", "device_lbvh", "device_ploc", "device_sah"):
         ctx.set_traversal_mode(mode)
         ctx.trace_closest(r); ctx.trace_any(r)
     ctx.set_traversal_mode(0)
+    for stack in ("shared", "local", "auto"):
+        ctx.traversal_stack(stack)
+        ctx.trace_closest(r); ctx.trace_any(r)
 ctx.builder("auto")
 check("height-field, all builders and modes")
 # a bigger tree through the device builder, device-resident batch
@@ -73,6 +76,10 @@ for name, size in (("mixed", (97, 61)), ("glass_c4", (160, 120)), ("veach_80x60"
     ctx.render_path(3, seed=7)
     ctx.configure(0, False, 0)
     ctx.render_bdpt(3, seed=8)
+    for stack in ("shared", "local", "auto"):   # both stack flavours of the tree kernels (tutu_traversal_stack)
+        ctx.traversal_stack(stack)
+        ctx.render_path(2, seed=10)
+        ctx.render_bdpt(1, seed=11)
     for mode in (6, 0):
         ctx.set_traversal_mode(mode)
         ctx.render_path(2, seed=9)

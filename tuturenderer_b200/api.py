@@ -108,6 +108,7 @@ ABI = {
     "tutu_trace_closest_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "tutu_trace_any_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "tutu_set_traversal_mode": (C.c_int, [_P, C.c_int]),
+    "tutu_traversal_stack": (C.c_int, [_P, C.c_int]),
     "tutu_trace_count_visits": (C.c_int, [_P, _P, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tutu_render_path": (C.c_int, [_P, C.c_uint32, C.c_uint64, _P]),
     "tutu_render_path_accumulate_device": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P]),
@@ -452,6 +453,12 @@ class Context:
 
     def set_traversal_mode(self, mode: int) -> None:
         self._ck(lib().tutu_set_traversal_mode(self._h, mode))
+
+    STACKS = {"auto": 0, "shared": 1, "local": 2}
+
+    def traversal_stack(self, where: str = "auto") -> None:
+        """Traversal stack of the tree kernels: 'auto' (by the size of the traversal arrays), 'shared', 'local'."""
+        self._ck(lib().tutu_traversal_stack(self._h, self.STACKS[where]))
 
     # ---- ray batches (host buffers)
     def trace_closest(self, rays: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:

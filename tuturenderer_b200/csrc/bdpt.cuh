@@ -166,13 +166,14 @@ __global__ void bdpt_ctl_after_shadow(BdptCtl* ctl) {
 }
 
 // ---- generic queue tracers (same packet scheme as wf_extend / wf_shadow) --------------------------
-// KIND: 0 = binary trees (trace.cuh), 1 = small scene (flat tests); the wide-tree tracers are in trace_kernels.cu
+// KIND: 0 = binary trees, traversal stack in shared memory, 1 = small scene (flat tests), 2 = binary trees, stack in local
+// memory (as in wavefront.cuh); the wide-tree tracers are in trace_kernels.cu
 template <int KIND>
 __global__ void __launch_bounds__(256)
 q_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, const float4* __restrict__ ro,
          const float4* __restrict__ rd, float4* __restrict__ hit, const unsigned* __restrict__ n_ptr,
          unsigned long long* cursor) {
-  extern __shared__ unsigned long long s_stack[];  // !SMALL: traversal stack (trace.cuh: SharedStack)
+  extern __shared__ unsigned long long s_stack[];  // KIND 0: traversal stack (trace.cuh: SharedStack)
   const unsigned n = *n_ptr;
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
@@ -191,6 +192,8 @@ q_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene
         if (__float_as_uint(d.w) != kDeadEntry) {
           if constexpr (KIND == 1)
             traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
+          else if constexpr (KIND == 2)
+            traverse_structured<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
           else
             traverse_shared<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack);
         }
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(256)
 q_shadow_add(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, const float4* __restrict__ so,
              const float4* __restrict__ sd, const float4* __restrict__ scn, float* __restrict__ accum,
              const unsigned* __restrict__ n_ptr, unsigned long long* cursor) {
+  extern __shared__ unsigned long long s_stack[];  // KIND 0: traversal stack, 32-bit entries (trace.cuh: SharedStack<true>)
   const unsigned n = *n_ptr;
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
@@ -223,8 +227,10 @@ q_shadow_add(const __grid_constant__ DevScene sc, const __grid_constant__ SmallS
         bool blocked;
         if constexpr (KIND == 1)
           blocked = traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
-        else
+        else if constexpr (KIND == 2)
           blocked = traverse_structured<true>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+        else
+          blocked = traverse_shared<true>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h, s_stack);
         if (!blocked) {
           const float4 c = __ldcs(scn + j);
           float* p = accum + (size_t)__float_as_uint(d.w) * 3;

@@ -169,6 +169,7 @@ struct BdptLane {
   }
 };
 
+constexpr size_t kLocalStackMaxTreeBytes = 32u << 20;  // traversal arrays up to this size: stack in local memory
 constexpr int kHostSlotsMax = 4;  // host-buffer ray batches: chunks in flight (trace_host_pipelined)
 struct TutuCtx {
   int device = 0;
@@ -225,6 +226,12 @@ struct TutuCtx {
   size_t grid_stack_smem = 0;
   bool grid_small = false;
   bool grid_wide = false;
+  bool grid_stack_shared = false;
+  // Traversal stack of the tree kernels: shared memory for trees that do not fit near the SM, local memory for small
+  // ones (decided at upload from the bytes of the traversal arrays)
+  bool stack_shared = true;
+  int stack_cfg = 0;  // tutu_traversal_stack: 0 = by tree size, 1 = shared memory, 2 = local memory
+  size_t tree_bytes = 0;  // traversal arrays of the uploaded scene (both topologies' nodes + leaf geometry)
   int profile_stages = 0;
   // 0 = automatic (register-resident kernel for small renders of scenes that fit the constant bank, else
   // wavefront), 1 = wavefront, 2 = register-resident (fails on scenes that do not fit)
@@ -493,6 +500,7 @@ __global__ void __launch_bounds__(256)
 k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss,
             const float4* __restrict__ rays, unsigned long long n, uint8_t* __restrict__ out,
             unsigned long long* __restrict__ next, const unsigned* __restrict__ perm = nullptr) {
+  extern __shared__ unsigned long long s_stack[];  // MODE 0: traversal stack, 32-bit entries (trace.cuh: SharedStack<true>)
 #ifdef TUTU_EXPERIMENTS
   if (MODE == 2) {
     trace_persistent<true>(
@@ -523,6 +531,8 @@ k_trace_any(const __grid_constant__ DevScene sc, const __grid_constant__ SmallSc
       if (MODE == 3)
         out[i] = traverse_small<true>(sc, ss, r, d.w, h) ? 1 : 0;
       else if (MODE == 0)
+        out[i] = traverse_shared<true>(sc, r, d.w, h, s_stack) ? 1 : 0;
+      else if (MODE == 4)
         out[i] = traverse_structured<true>(sc, r, d.w, h) ? 1 : 0;
       else
         out[i] = traverse<true, 1, false>(sc, r, d.w, h, nullptr) ? 1 : 0;
@@ -804,8 +814,14 @@ void launch_any(TutuCtx* ctx, const float* d_rays, uint64_t n, uint8_t* d_out, c
       CUDA_TRY(wide_launch_batch(true, g.batch_any, g.smem, s, ctx->dev, rays, n, nullptr, d_out, next, perm));
     } else {
       const unsigned* perm = bin_rays(ctx, rays, n, s, slot);
-      int grid = persistent_grid(ctx, k_trace_any<0>, 256);
-      k_trace_any<0><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next, perm);
+      if (ctx->stack_shared) {
+        const size_t sm = stack_smem(ctx, 256, true);
+        int grid = persistent_grid(ctx, k_trace_any<0>, 256, sm);
+        k_trace_any<0><<<grid, 256, sm, s>>>(ctx->dev, ctx->small, rays, n, d_out, next, perm);
+      } else {
+        int grid = persistent_grid(ctx, k_trace_any<4>, 256);
+        k_trace_any<4><<<grid, 256, 0, s>>>(ctx->dev, ctx->small, rays, n, d_out, next, perm);
+      }
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -1043,10 +1059,13 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
   // the cached grids depend on the scene through the kernel variants and the traversal-stack size
   const bool small = use_small(ctx);
   const bool wide = !small && ctx->dev.wide != nullptr;
-  const size_t want_stack = small ? 0 : (wide ? wide_stack_smem(ctx, 256) : stack_smem(ctx, 256, false));
+  const bool stack_shared = ctx->stack_shared;
+  const size_t want_stack = small ? 0 : (wide ? wide_stack_smem(ctx, 256) : (stack_shared ? stack_smem(ctx, 256, false) : 0));
+  const size_t want_stack_any = (small || wide || !stack_shared) ? 0 : stack_smem(ctx, 256, true);
   if (ctx->grid_lanes != n_lanes || ctx->grid_small != small || ctx->grid_shade_block != ctx->shade_block ||
-      ctx->grid_stack_smem != want_stack || ctx->grid_wide != wide) {
+      ctx->grid_stack_smem != want_stack || ctx->grid_wide != wide || ctx->grid_stack_shared != stack_shared) {
     ctx->grid_stack_smem = want_stack;
+    ctx->grid_stack_shared = stack_shared;
     ctx->grid_wide = wide;
     ctx->grid_shade_block = ctx->shade_block;
     ctx->grid_small = small;
@@ -1057,11 +1076,13 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
     auto sized = [&](int full) { return ctx->sm_count * std::max(1, full / ctx->sm_count / div); };
     ctx->grid_extend = sized(small  ? persistent_grid(ctx, wf_extend_small, kSmallBlock)
                              : wide ? wide_grids_for(ctx).wf_extend
-                                    : persistent_grid(ctx, wf_extend<0>, 256, want_stack));
+                             : stack_shared ? persistent_grid(ctx, wf_extend<0>, 256, want_stack)
+                                            : persistent_grid(ctx, wf_extend<2>, 256));
     ctx->grid_shade = sized(persistent_grid(ctx, wf_shade, ctx->shade_block, shade_stage_smem(ctx)));
     ctx->grid_shadow = sized(small  ? persistent_grid(ctx, wf_shadow_small, kSmallBlock)
                              : wide ? wide_grids_for(ctx).wf_shadow
-                                    : persistent_grid(ctx, wf_shadow<0>, 256));
+                             : stack_shared ? persistent_grid(ctx, wf_shadow<0>, 256, want_stack_any)
+                                            : persistent_grid(ctx, wf_shadow<2>, 256));
     ctx->grid_raygen = sized(persistent_grid(ctx, wf_raygen, 256));
     ctx->grid_lanes = n_lanes;
   }
@@ -1129,8 +1150,10 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         wf_extend_small<<<ctx->grid_extend, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
       else if (wide)
         CUDA_TRY(wide_launch_wf_extend(ctx->grid_extend, want_stack, ls, ctx->dev, L.b, cur));
-      else
+      else if (stack_shared)
         wf_extend<0><<<ctx->grid_extend, 256, want_stack, ls>>>(ctx->dev, ctx->small, L.b, cur);
+      else
+        wf_extend<2><<<ctx->grid_extend, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur);
       if (first_iteration && k + 1 < n_lanes) {
         // stagger the lanes by one stage so that unlike kernels (traverse / shade) overlap
         CUDA_TRY(cudaEventRecord(L.ev_done, ls));
@@ -1147,8 +1170,10 @@ void wf_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uint6
         wf_shadow_small<<<ctx->grid_shadow, kSmallBlock, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
       else if (wide)
         CUDA_TRY(wide_launch_wf_shadow(ctx->grid_shadow, want_stack, ls, ctx->dev, L.b, cur ^ 1));
+      else if (stack_shared)
+        wf_shadow<0><<<ctx->grid_shadow, 256, want_stack_any, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
       else
-        wf_shadow<0><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
+        wf_shadow<2><<<ctx->grid_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, L.b, cur ^ 1);
       timer.mark(0, ls);
       wf_ctl_after_iter<<<1, 1, 0, ls>>>(L.b.ctl);
       runs[k].cur ^= 1;
@@ -1299,13 +1324,17 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
   const int g_vertex = persistent_grid(ctx, bdpt_vertex, 256);
   const int g_connect = persistent_grid(ctx, bdpt_connect, 256);
   const bool wide = !small && ctx->dev.wide != nullptr;
-  const size_t sm_stack = wide ? wide_stack_smem(ctx, 256) : stack_smem(ctx, 256, false);
+  const bool stack_shared = ctx->stack_shared;
+  const size_t sm_stack = wide ? wide_stack_smem(ctx, 256) : (stack_shared ? stack_smem(ctx, 256, false) : 0);
+  const size_t sm_stack_any = (wide || !stack_shared) ? 0 : stack_smem(ctx, 256, true);
   const int g_extend = small  ? persistent_grid(ctx, q_extend<1>, 256)
                        : wide ? wide_grids_for(ctx).q_extend
-                              : persistent_grid(ctx, q_extend<0>, 256, sm_stack);
+                      : stack_shared ? persistent_grid(ctx, q_extend<0>, 256, sm_stack)
+                                     : persistent_grid(ctx, q_extend<2>, 256);
   const int g_shadow = small  ? persistent_grid(ctx, q_shadow_add<1>, 256)
                        : wide ? wide_grids_for(ctx).q_shadow
-                              : persistent_grid(ctx, q_shadow_add<0>, 256);
+                      : stack_shared ? persistent_grid(ctx, q_shadow_add<0>, 256, sm_stack_any)
+                                     : persistent_grid(ctx, q_shadow_add<2>, 256);
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
@@ -1333,8 +1362,10 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
           q_extend<1><<<g_extend, 256, 0, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
         else if (wide)
           CUDA_TRY(wide_launch_q_extend(g_extend, sm_stack, ls, ctx->dev, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend));
-        else
+        else if (stack_shared)
           q_extend<0><<<g_extend, 256, sm_stack, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+        else
+          q_extend<2><<<g_extend, 256, 0, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
         bdpt_vertex<<<g_vertex, 256, 0, ls>>>(ctx->dev, cam, b, cur, first, sample_begin, seed);
         bdpt_ctl_after_walk<<<1, 1, 0, ls>>>(b.ctl);
         launches += 3;
@@ -1346,8 +1377,10 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
           q_shadow_add<1><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
         else if (wide)
           CUDA_TRY(wide_launch_q_shadow_add(g_shadow, sm_stack, ls, ctx->dev, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow));
+        else if (stack_shared)
+          q_shadow_add<0><<<g_shadow, 256, sm_stack_any, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
         else
-          q_shadow_add<0><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+          q_shadow_add<2><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
         bdpt_ctl_after_shadow<<<1, 1, 0, ls>>>(b.ctl);
         launches += 3;
       }
@@ -1615,6 +1648,9 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
   }
   d.refill_min = 8;
   d.leaf_batch = kLeafBatch;
+  // stack flavour of the tree kernels: see TutuCtx::stack_shared (a device-built tree has n - 1 nodes and no host copy)
+  ctx->tree_bytes = (2 * fs.inner.size()) * sizeof(InnerNode) + fs.geom.size() * sizeof(LeafGeom);
+  ctx->stack_shared = ctx->stack_cfg ? ctx->stack_cfg == 1 : ctx->tree_bytes > kLocalStackMaxTreeBytes;
 #ifdef TUTU_EXPERIMENTS  // never in the shipped library: the pruning slack is part of the parity argument (trace.cuh)
   if (const char* e = getenv("TUTU_LEAF_BATCH")) d.leaf_batch = atoi(e);
   if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);
@@ -1686,6 +1722,14 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
   ctx->flat.raygen = rg;
   ctx->flat.bdpt_cam = bc;
   ctx->flat.camera = *cam;
+  return TUTU_OK;
+}
+
+extern "C" int tutu_traversal_stack(TutuCtx* ctx, int where) {
+  if (!ctx || where < 0 || where > 2) return fail(ctx, TUTU_E_INVALID, "tutu_traversal_stack: bad argument (0, 1 or 2)");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->stack_cfg = where;
+  if (ctx->has_scene) ctx->stack_shared = where ? where == 1 : ctx->tree_bytes > kLocalStackMaxTreeBytes;
   return TUTU_OK;
 }
 

@@ -81,11 +81,12 @@ wf_raygen(WfBuffers b, int cur, RayGenK k, unsigned sample_begin) {
 // Ray packets pulled from the queue with one atomicAdd per warp (lane 0) and a shuffle
 // broadcast: a warp that drew short rays moves on to the next packet instead of idling behind the
 // slowest warp of a statically partitioned grid.
-// KIND: 0 = binary trees (trace.cuh), 1 = small scene (flat tests); the wide-tree tracers are in trace_kernels.cu
+// KIND: 0 = binary trees, traversal stack in shared memory (trees too big for L1: DESIGN.md 5.10), 1 = small scene (flat
+// tests), 2 = binary trees, stack in local memory; the wide-tree tracers are in trace_kernels.cu
 template <int KIND>
 __global__ void __launch_bounds__(256)
 wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int cur) {
-  extern __shared__ unsigned long long s_stack[];  // !SMALL: traversal stack (trace.cuh: SharedStack)
+  extern __shared__ unsigned long long s_stack[];  // KIND 0: traversal stack (trace.cuh: SharedStack)
   const unsigned n = b.ctl->n_cur;
   const float4* __restrict__ ro = b.ray_o[cur];
   const float4* __restrict__ rd = b.ray_d[cur];
@@ -106,7 +107,9 @@ wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
           h.t = 0.f, h.u = 0.f, h.v = 0.f, h.slot = kDeadSlot;
         else if constexpr (KIND == 1)
           traverse_small<false>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
-        else  // incoherent queue: per-lane walk (batched primitive tests only pay on sorted batches)
+        else if constexpr (KIND == 2)  // incoherent queue: per-lane walk (batched primitive tests only pay on sorted batches)
+          traverse_structured<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h);
+        else
           traverse_shared<false>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, 0.f, h, s_stack);
         __stcs(b.hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot)));
       }
@@ -119,6 +122,7 @@ wf_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
 template <int KIND>
 __global__ void __launch_bounds__(256)
 wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene ss, WfBuffers b, int nxt) {
+  extern __shared__ unsigned long long s_stack[];  // KIND 0: traversal stack, 32-bit entries (trace.cuh: SharedStack<true>)
   const unsigned n = b.ctl->n_shadow;
   const unsigned lane = threadIdx.x & 31u;
   for (;;) {
@@ -136,8 +140,10 @@ wf_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScen
         bool blocked;
         if constexpr (KIND == 1)
           blocked = traverse_small<true>(sc, ss, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
-        else
+        else if constexpr (KIND == 2)
           blocked = traverse_structured<true>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h);
+        else
+          blocked = traverse_shared<true>(sc, Ray{o.x, o.y, o.z, d.x, d.y, d.z}, o.w, h, s_stack);
         const unsigned dst = __float_as_uint(d.w);
         if (dst == kShadowFinal) {
           const float4 c = __ldcs(b.sh_c + j);
