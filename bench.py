@@ -395,8 +395,11 @@ def bdpt_bench(torch, api, rank: int, world: int, do_cpu: bool, spp: int, peaks:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(3):
-        r.render_bdpt(16 * world, SEED + k, rank, world)  # 7.7 M samples per rank: the 4 Mi-sample batch pools reach their size
+    # warm-up: the 4 Mi-sample batch pools reach their size, and one render of 9 batches per rank lets the library measure its
+    # two queue tracers on this scene (tutu_bdpt_queue_tracer), as the first render of a long job would
+    r.render_bdpt(72 * world, SEED, rank, world)
+    for k in range(1, 3):
+        r.render_bdpt(16 * world, SEED + k, rank, world)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -412,7 +415,7 @@ def bdpt_bench(torch, api, rank: int, world: int, do_cpu: bool, spp: int, peaks:
                        f"bidirectional path tracing (BASELINE.json configs[4]), samples split over {world} GPU(s)",
            "msamples_per_s": npix * spp / gpu_ms * 1e-3, "gpu_ms": gpu_ms, "n_gpus": world,
            "closest_rays_per_sample": st["extend_rays"] / max(st["paths"], 1), "any_rays_per_sample": st["shadow_rays"] / max(st["paths"], 1),
-           "kernel_launches": st["kernel_launches"]}
+           "kernel_launches": st["kernel_launches"], "queue_tracer": r.ctx.bdpt_queue_tracer_measured()}
     if rank == 0:
         out["image_mean"] = float(img.mean())
     if world == 1:

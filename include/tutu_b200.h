@@ -248,6 +248,14 @@ int tutu_set_traversal_mode(TutuCtx* ctx, int mode);
  * memory above that, where the stack's local-memory lines would compete with the node fetches),
  * 1 = shared memory, 2 = local memory.  Same results either way; the tests run both. */
 int tutu_traversal_stack(TutuCtx* ctx, int where);
+/* Queue tracers of tutu_render_bdpt on scenes with a tree (closest hit for the sub-path walks, any hit for the connections):
+ * 1 = every warp walks one packet of 32 queue entries at a time; 2 = persistent lanes: a warp refills its idle lanes from the
+ * queue and runs its lanes' node steps and primitive tests as separate phases; 0 (the default) = measured
+ * per scene: the first render of at least 8 batches runs one batch with each, alone, and the faster one is kept until the
+ * next tutu_scene_upload.  Same results either way.  tutu_bdpt_queue_tracer_measured reports that measurement: *tracer =
+ * -1 (none yet), 0 (packets) or 1 (lanes), and the two batch times in ms. */
+int tutu_bdpt_queue_tracer(TutuCtx* ctx, int tracer);
+int tutu_bdpt_queue_tracer_measured(const TutuCtx* ctx, int* tracer, float* ms_packets, float* ms_lanes);
 /* Visit counters for the algorithmic-bytes figure: traces the batch with counting kernels and
  * returns total inner-node fetches and primitive tests. */
 int tutu_trace_count_visits(TutuCtx* ctx, const float* d_rays, uint64_t n_rays, int any_hit,

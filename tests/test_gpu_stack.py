@@ -72,3 +72,44 @@ def test_full_size_any_hit_identical_with_either_stack(api, ctx):
         assert_hits_equal(res["auto"][1], res["local"][1])
         blocked = res["auto"][0].mean()
         assert 0.01 < blocked < 0.99  # both answers occur (97 % of the top-down rays are blocked)
+
+
+@pytest.mark.parametrize("stack", ["shared", "local"])
+@pytest.mark.parametrize("tracer", ["packets", "lanes"])
+@pytest.mark.parametrize("name,w,h,spp", [("veach_80x60", 40, 30, 8), ("mixed", 48, 48, 4)])
+def test_bdpt_queue_tracers_same_stream_as_oracle(api, oracle, ctx, golden, name, w, h, spp, tracer, stack):
+    """q_extend / q_shadow_add as packet tracers and as persistent-lane tracers (tutu_bdpt_queue_tracer), with either stack,
+    against the oracle's BDPT on the same stream; gates of test_gpu_bdpt.py::test_bdpt_same_stream_as_oracle."""
+    sc = api.Scene.load(golden / f"{name}.tscene").with_size(w, h)
+    ctx.traversal_stack(stack)
+    ctx.bdpt_queue_tracer(tracer)
+    ctx.upload(sc)
+    g = ctx.render_bdpt(spp, seed=21)
+    st = ctx.stats()
+    o, cnt = oracle.OracleScene(sc).render_bdpt(spp, seed=21, counters=True)
+    d = np.abs(g - o)
+    assert (d > 1e-3 * (1 + np.abs(o))).any(-1).mean() < 0.02
+    assert np.median(d) < 1e-5
+    assert cnt[0] * 0.85 <= st["extend_rays"] <= cnt[0] * 1.15 and st["shadow_rays"] <= cnt[1]
+
+
+def test_bdpt_queue_tracer_is_measured_per_scene(api, ctx, golden):
+    """The automatic choice: a render of >= 8 batches runs one batch with each tracer and keeps the faster one until the
+    next upload; the image is the same whichever wins (same sample set; sums of atomics in another order)."""
+    sc = api.Scene.load(golden / "veach_80x60.tscene").with_size(400, 300)
+    ctx.upload(sc)
+    ctx.configure(1 << 20, False, 0)  # batches of 2^20 samples (default 2^22)
+    assert ctx.bdpt_queue_tracer_measured()["tracer"] is None
+    ctx.render_bdpt(2, seed=1)  # 240 000 samples = one batch: too short to measure
+    assert ctx.bdpt_queue_tracer_measured()["tracer"] is None
+    img = ctx.render_bdpt(80, seed=2)  # 9.6 M samples = 10 batches of 2^20
+    m = ctx.bdpt_queue_tracer_measured()
+    assert m["tracer"] in ("packets", "lanes") and m["ms_packets"] > 0 and m["ms_lanes"] > 0
+    assert (m["tracer"] == "lanes") == (m["ms_lanes"] < m["ms_packets"])
+    for forced in ("packets", "lanes"):
+        ctx.bdpt_queue_tracer(forced)
+        other = ctx.render_bdpt(80, seed=2)
+        assert np.allclose(img, other, rtol=2e-3, atol=1e-5)
+    ctx.bdpt_queue_tracer("auto")
+    ctx.upload(sc)
+    assert ctx.bdpt_queue_tracer_measured()["tracer"] is None

@@ -79,7 +79,9 @@ for name, size in (("mixed", (97, 61)), ("glass_c4", (160, 120)), ("veach_80x60"
     for stack in ("shared", "local", "auto"):   # both stack flavours of the tree kernels (tutu_traversal_stack)
         ctx.traversal_stack(stack)
         ctx.render_path(2, seed=10)
-        ctx.render_bdpt(1, seed=11)
+        for tracer in ("packets", "lanes", "auto"):   # both BDPT queue tracers (tutu_bdpt_queue_tracer)
+            ctx.bdpt_queue_tracer(tracer)
+            ctx.render_bdpt(1, seed=11)
     for mode in (6, 0):
         ctx.set_traversal_mode(mode)
         ctx.render_path(2, seed=9)

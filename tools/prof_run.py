@@ -1,6 +1,7 @@
 """Short, fixed workload for ncu (never a bench number): `render` = Cornell 1024x1024 @ 24 spp,
 `rays` = 4 Mi rays of each synthetic kind against the 999 698-triangle height-field, `bdpt` = the
 Veach room 800x600 @ 4 spp through tutu_render_bdpt, `build` = one upload of that height-field per device tree builder."""
+import os
 import sys
 from pathlib import Path
 import numpy as np
@@ -28,6 +29,7 @@ elif what == "build":  # the traversal-tree builders on the 999 698-triangle sce
 elif what == "bdpt":
     sc = api.Scene.load(ROOT / "tests/golden/veach_80x60.tscene").with_size(800, 600)
     ctx.upload(sc)
+    ctx.bdpt_queue_tracer(os.environ.get("TUTU_PROF_TRACER", "lanes"))  # what the library measures to be faster on this scene
     img = ctx.render_bdpt(4, seed=5)
     print("bdpt mean", float(img.mean()), ctx.stats())
 else:

@@ -109,6 +109,8 @@ ABI = {
     "tutu_trace_any_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P]),
     "tutu_set_traversal_mode": (C.c_int, [_P, C.c_int]),
     "tutu_traversal_stack": (C.c_int, [_P, C.c_int]),
+    "tutu_bdpt_queue_tracer": (C.c_int, [_P, C.c_int]),
+    "tutu_bdpt_queue_tracer_measured": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tutu_trace_count_visits": (C.c_int, [_P, _P, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tutu_render_path": (C.c_int, [_P, C.c_uint32, C.c_uint64, _P]),
     "tutu_render_path_accumulate_device": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P]),
@@ -459,6 +461,17 @@ class Context:
     def traversal_stack(self, where: str = "auto") -> None:
         """Traversal stack of the tree kernels: 'auto' (by the size of the traversal arrays), 'shared', 'local'."""
         self._ck(lib().tutu_traversal_stack(self._h, self.STACKS[where]))
+
+    TRACERS = {"auto": 0, "packets": 1, "lanes": 2}
+
+    def bdpt_queue_tracer(self, name: str = "auto") -> None:
+        """Queue tracers of render_bdpt on scenes with a tree: 'auto' (measured per scene), 'packets', 'lanes'."""
+        self._ck(lib().tutu_bdpt_queue_tracer(self._h, self.TRACERS[name]))
+
+    def bdpt_queue_tracer_measured(self) -> dict:
+        t, a, b = C.c_int(0), C.c_float(0), C.c_float(0)
+        self._ck(lib().tutu_bdpt_queue_tracer_measured(self._h, C.byref(t), C.byref(a), C.byref(b)))
+        return {"tracer": {-1: None, 0: "packets", 1: "lanes"}[t.value], "ms_packets": a.value, "ms_lanes": b.value}
 
     # ---- ray batches (host buffers)
     def trace_closest(self, rays: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:

@@ -176,6 +176,31 @@ q_extend(const __grid_constant__ DevScene sc, const __grid_constant__ SmallScene
   extern __shared__ unsigned long long s_stack[];  // KIND 0: traversal stack (trace.cuh: SharedStack)
   const unsigned n = *n_ptr;
   const unsigned lane = threadIdx.x & 31u;
+  if constexpr (KIND == 0 || KIND == 2) {
+    if (sc.queue_lanes) {  // persistent lanes, phase-separated steps (trace.cuh: trace_queue_lanes)
+      auto store = [&](unsigned i, const Hit& h, bool) { __stcs(hit + i, make_float4(h.t, h.u, h.v, __int_as_float(h.slot))); };
+      auto load = [&](unsigned i, Ray& r, float& dis) {
+        const float4 o = __ldcs(ro + i), d = __ldcs(rd + i);
+        if (__float_as_uint(d.w) == kDeadEntry) {
+          __stcs(hit + i, make_float4(FLT_MAX, 0.f, 0.f, __int_as_float(-1)));
+          return false;
+        }
+        r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+        dis = 0.f;
+        return true;
+      };
+      if constexpr (KIND == 0) {
+        SharedStack<false> st;
+        st.base = s_stack + threadIdx.x;
+        st.stride = blockDim.x;
+        trace_queue_lanes<false>(sc, n, cursor, st, load, store);
+      } else {
+        LocalStack<false> st;
+        trace_queue_lanes<false>(sc, n, cursor, st, load, store);
+      }
+      return;
+    }
+  }
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kPacketRays);
@@ -212,6 +237,35 @@ q_shadow_add(const __grid_constant__ DevScene sc, const __grid_constant__ SmallS
   extern __shared__ unsigned long long s_stack[];  // KIND 0: traversal stack, 32-bit entries (trace.cuh: SharedStack<true>)
   const unsigned n = *n_ptr;
   const unsigned lane = threadIdx.x & 31u;
+  if constexpr (KIND == 0 || KIND == 2) {
+    if (sc.queue_lanes) {  // persistent lanes, phase-separated steps (trace.cuh: trace_queue_lanes)
+      auto load = [&](unsigned j, Ray& r, float& dis) {
+        const float4 o = __ldcs(so + j), d = __ldcs(sd + j);
+        r = Ray{o.x, o.y, o.z, d.x, d.y, d.z};
+        dis = o.w;
+        return true;
+      };
+      auto store = [&](unsigned j, const Hit&, bool blocked) {
+        if (!blocked) {
+          const float4 c = __ldcs(scn + j);
+          float* p = accum + (size_t)__float_as_uint(__ldcs(sd + j).w) * 3;
+          atomicAdd(p + 0, c.x);
+          atomicAdd(p + 1, c.y);
+          atomicAdd(p + 2, c.z);
+        }
+      };
+      if constexpr (KIND == 0) {
+        SharedStack<true> st;
+        st.base = reinterpret_cast<unsigned*>(s_stack) + threadIdx.x;
+        st.stride = blockDim.x;
+        trace_queue_lanes<true>(sc, n, cursor, st, load, store);
+      } else {
+        LocalStack<true> st;
+        trace_queue_lanes<true>(sc, n, cursor, st, load, store);
+      }
+      return;
+    }
+  }
   for (;;) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kPacketRays);

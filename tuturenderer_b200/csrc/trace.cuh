@@ -49,6 +49,8 @@ struct DevScene {
   float prune_abs;
   int refill_min;  // persistent tracer: refill once this many lanes of a warp are idle
   int leaf_batch;  // traverse_batched: waiting lanes that trigger the primitive tests
+  int queue_lanes; // BDPT queue tracers: 1 = persistent lanes with phase-separated steps (trace_queue_lanes), 0 = one packet at a time
+  int lanes_leaf_batch;  // trace_queue_lanes: waiting lanes that trigger the primitive tests
   unsigned sphere_mask;  // small scenes: bit s set = leaf slot s is a sphere
 };
 
@@ -638,8 +640,8 @@ struct SharedStack<true> {
 };
 
 // node part of a step with the shared-memory stack: true = the lane has to pop
-template <bool ANY, bool REGULAR>
-__device__ __forceinline__ bool node_step_shared(const DevScene& sc, Walk& w, SharedStack<ANY>& st) {
+template <bool ANY, bool REGULAR, class Stack>
+__device__ __forceinline__ bool node_step_shared(const DevScene& sc, Walk& w, Stack& st) {
   const float4* n = w.nodes + 4 * (size_t)w.cur;
   float4 a, b, c;
   int4 k;
@@ -749,6 +751,131 @@ __device__ __forceinline__ bool traverse_batched(const DevScene& sc, const Ray& 
   }
   best = w.best;
   return best.slot >= 0;
+}
+
+// ---- traversal stack in local memory (same interface as SharedStack) -------------------------------
+template <bool ANY>
+struct LocalStack;
+template <>
+struct LocalStack<false> {
+  unsigned long long e[kStackSize];
+  int sp = 0;
+  __device__ __forceinline__ void push(int ref, float t) {
+    e[sp] = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)ref;
+    ++sp;
+  }
+  __device__ __forceinline__ void pop(int& ref, float& t) {
+    --sp;
+    const unsigned long long v = e[sp];
+    ref = (int)(unsigned)v;
+    t = __uint_as_float((unsigned)(v >> 32));
+  }
+};
+template <>
+struct LocalStack<true> {
+  unsigned e[kStackSize];
+  int sp = 0;
+  __device__ __forceinline__ void push(int ref, float) {
+    e[sp] = (unsigned)ref;
+    ++sp;
+  }
+  __device__ __forceinline__ void pop(int& ref, float& t) {
+    --sp;
+    ref = (int)e[sp];
+    t = 0.f;
+  }
+};
+
+// ---- queue tracer: persistent lanes, phase-separated steps ------------------------------------------
+// ncu on the incoherent queues (profiles/r02_q_extend_lanes.txt: 5.8 of 32 lanes; r02_glass_extend_lanes.txt: 9): a
+// warp that walks 32 rays to completion idles behind its longest walk, and within a step its lanes are spread over
+// node code, primitive test and pop.  Each remedy alone lost its measurement: handing idle lanes
+// new rays desynchronises the warp, so that EVERY step runs all three code paths for a few lanes each
+// (trace_variants.cuh: trace_refill); making lanes wait on their leaf until enough wait leaves them idle next to the
+// finished ones (traverse_batched on queues).  Together they fit: a warp owns a chunk of the queue and refills its idle
+// lanes from it whenever `refill_min` are idle, and every iteration of the warp is ONE phase — a node step for the
+// lanes that stand on an inner node, or, once `leaf_batch` lanes wait on a leaf (or nobody stands on a node), the
+// primitive tests of the waiting lanes — followed by the pops of the lanes that need one.
+//   load(i, ray, dis) -> false for a dead queue entry (the callee has then written its result itself)
+//   store(i, hit, any)   any = best.slot >= 0
+constexpr unsigned kQueueChunk = 256;
+constexpr int kLanesLeafBatch = 16;  // Veach room, Msamples/s at 8 / 16 / 20: 73.2 / 74.1 / 71.9
+constexpr int kLanesRefillMin = 8;
+template <bool ANY, class Stack, class Load, class Store>
+__device__ __forceinline__ void trace_queue_lanes(const DevScene& sc, unsigned n, unsigned long long* cursor, Stack& st,
+                                                  Load load, Store store) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  Walk w;
+  w.cur = 0;
+  w.regular = true;
+  bool active = false;
+  unsigned my = 0u;
+  unsigned chunk_next = 0u, chunk_end = 0u;  // warp-uniform
+  bool exhausted = false;                    // warp-uniform
+  bool all_regular = true;                   // warp-uniform; re-evaluated at every refill (stale "false" is only slower)
+  for (;;) {
+    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (!exhausted && (idle == 0xFFFFFFFFu || __popc(idle) >= sc.refill_min)) {
+      if (chunk_next == chunk_end) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kQueueChunk);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        chunk_next = base < n ? (unsigned)base : n;
+        chunk_end = base + kQueueChunk < n ? (unsigned)base + kQueueChunk : n;
+        if (chunk_next >= n) exhausted = true;
+      }
+      const unsigned avail = chunk_end - chunk_next < 32u ? chunk_end - chunk_next : 32u;
+      const unsigned rank = (unsigned)__popc(idle & lt);
+      if (!active && rank < avail) {
+        my = chunk_next + rank;
+        Ray r;
+        float dis = 0.f;
+        if (load(my, r, dis)) {
+          st.sp = 0;
+          if (walk_begin(sc, w, r, dis))
+            active = true;
+          else
+            store(my, w.best, false);  // missed the scene box: w.best is the miss record
+        }
+      }
+      const unsigned want = (unsigned)__popc(idle);
+      chunk_next += want < avail ? want : avail;
+      all_regular = __all_sync(0xFFFFFFFFu, !active || w.regular);
+    }
+    const unsigned at_node = __ballot_sync(0xFFFFFFFFu, active && w.cur >= 0);
+    const unsigned at_leaf = __ballot_sync(0xFFFFFFFFu, active && w.cur < 0);
+    if ((at_node | at_leaf) == 0u) {
+      if (exhausted) return;
+      continue;
+    }
+    bool need_pop = false;
+    if (__popc(at_leaf) >= sc.lanes_leaf_batch || at_node == 0u) {
+      if (active && w.cur < 0) {
+        if (leaf_step<ANY>(sc, w, w.cur)) {  // any-hit: blocked
+          active = false;
+          store(my, w.best, true);
+        } else {
+          need_pop = true;
+        }
+      }
+    } else if (active && w.cur >= 0) {
+      need_pop = all_regular ? node_step_shared<ANY, true>(sc, w, st) : node_step_shared<ANY, false>(sc, w, st);
+    }
+    if (need_pop) {
+      for (;;) {
+        if (st.sp == 0) {
+          active = false;
+          store(my, w.best, w.best.slot >= 0);
+          break;
+        }
+        float t;
+        st.pop(w.cur, t);
+        if (!ANY && t > prune_limit<ANY>(sc, w)) continue;
+        break;
+      }
+    }
+  }
 }
 
 // Whole walk of one ray with a local-memory stack and the exact (NaN-literal) slab test: the walk of irregular rays

@@ -169,6 +169,7 @@ struct BdptLane {
   }
 };
 
+constexpr uint64_t kBdptTuneMinBatches = 8;  // shorter renders keep the packet tracer (two batches run alone for the measurement)
 constexpr size_t kLocalStackMaxTreeBytes = 32u << 20;  // traversal arrays up to this size: stack in local memory
 constexpr int kHostSlotsMax = 4;  // host-buffer ray batches: chunks in flight (trace_host_pipelined)
 struct TutuCtx {
@@ -230,6 +231,12 @@ struct TutuCtx {
   // Traversal stack of the tree kernels: shared memory for trees that do not fit near the SM, local memory for small
   // ones (decided at upload from the bytes of the traversal arrays)
   bool stack_shared = true;
+  // BDPT queue tracers (q_extend / q_shadow_add on scenes with a tree): one packet of rays at a time, or persistent lanes with
+  // phase-separated steps (trace.cuh: trace_queue_lanes).  Which one is faster depends on the scene, so the first
+  // render of at least kBdptTuneMinBatches batches times one batch with each and keeps the winner for the scene.
+  int bdpt_tracer_cfg = 0;     // tutu_bdpt_queue_tracer: 0 = measured per scene, 1 = packets, 2 = persistent lanes
+  int bdpt_tracer_tuned = -1;  // -1 = not measured yet for the uploaded scene, else 0 = packets / 1 = lanes
+  float bdpt_tune_ms[2] = {0.f, 0.f};
   int stack_cfg = 0;  // tutu_traversal_stack: 0 = by tree size, 1 = shared memory, 2 = local memory
   size_t tree_bytes = 0;  // traversal arrays of the uploaded scene (both topologies' nodes + leaf geometry)
   int profile_stages = 0;
@@ -1347,11 +1354,24 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
       CUDA_TRY(cudaStreamWaitEvent(L.stream, e0, 0));
       CUDA_TRY(cudaMemsetAsync(L.b.ctl, 0, sizeof(BdptCtl), L.stream));
     }
+    // queue tracer of this render (see TutuCtx::bdpt_tracer_cfg): forced, already measured for this scene, or measured now
+    const bool tree_kernels = !small && !wide;
+    int tracer = ctx->bdpt_tracer_cfg ? ctx->bdpt_tracer_cfg - 1 : (ctx->bdpt_tracer_tuned >= 0 ? ctx->bdpt_tracer_tuned : 0);
+    const bool tune = tree_kernels && !ctx->bdpt_tracer_cfg && ctx->bdpt_tracer_tuned < 0 && n_batches >= kBdptTuneMinBatches;
+    cudaEvent_t et[3] = {nullptr, nullptr, nullptr};
+    if (tune)
+      for (cudaEvent_t& e : et) CUDA_TRY(cudaEventCreate(&e));
+    DevScene dv = ctx->dev;
     uint64_t batch = 0;
     for (uint64_t first = 0; first < total; first += cap, ++batch) {
-      BdptLane& L = ctx->bdpt_lanes[batch % n_lanes];
+      // while measuring, batches 0 (lanes) and 1 (packets) run alone, back to back on the first lane's stream; the
+      // lanes go first, so whatever a cold start costs counts against them
+      const bool measuring = tune && batch < 2;
+      BdptLane& L = ctx->bdpt_lanes[measuring ? 0 : batch % n_lanes];
       BdptBuffers& b = L.b;
       cudaStream_t ls = L.stream;
+      dv.queue_lanes = tree_kernels ? (measuring ? 1 - (int)batch : tracer) : 0;
+      if (measuring) CUDA_TRY(cudaEventRecord(et[batch], ls));
       const unsigned n = (unsigned)std::min<uint64_t>(cap, total - first);
       bdpt_start<<<g_start, 256, 0, ls>>>(ctx->dev, cam, b, first, n, sample_begin, seed);
       bdpt_ctl_begin<<<1, 1, 0, ls>>>(b.ctl, 2 * n);
@@ -1363,9 +1383,9 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
         else if (wide)
           CUDA_TRY(wide_launch_q_extend(g_extend, sm_stack, ls, ctx->dev, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend));
         else if (stack_shared)
-          q_extend<0><<<g_extend, 256, sm_stack, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+          q_extend<0><<<g_extend, 256, sm_stack, ls>>>(dv, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
         else
-          q_extend<2><<<g_extend, 256, 0, ls>>>(ctx->dev, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
+          q_extend<2><<<g_extend, 256, 0, ls>>>(dv, ctx->small, b.q_o[cur], b.q_d[cur], b.hit, &b.ctl->n_cur, &b.ctl->cursor_extend);
         bdpt_vertex<<<g_vertex, 256, 0, ls>>>(ctx->dev, cam, b, cur, first, sample_begin, seed);
         bdpt_ctl_after_walk<<<1, 1, 0, ls>>>(b.ctl);
         launches += 3;
@@ -1378,14 +1398,26 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
         else if (wide)
           CUDA_TRY(wide_launch_q_shadow_add(g_shadow, sm_stack, ls, ctx->dev, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow));
         else if (stack_shared)
-          q_shadow_add<0><<<g_shadow, 256, sm_stack_any, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+          q_shadow_add<0><<<g_shadow, 256, sm_stack_any, ls>>>(dv, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
         else
-          q_shadow_add<2><<<g_shadow, 256, 0, ls>>>(ctx->dev, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
+          q_shadow_add<2><<<g_shadow, 256, 0, ls>>>(dv, ctx->small, b.sh_o, b.sh_d, b.sh_c, b.accum, &b.ctl->n_shadow, &b.ctl->cursor_shadow);
         bdpt_ctl_after_shadow<<<1, 1, 0, ls>>>(b.ctl);
         launches += 3;
       }
       CUDA_TRY(cudaGetLastError());
+      if (measuring) {
+        CUDA_TRY(cudaEventRecord(et[batch + 1], ls));
+        if (batch == 1) {  // both measured: the rest of the render (and later renders of this scene) take the faster one
+          CUDA_TRY(cudaEventSynchronize(et[2]));
+          CUDA_TRY(cudaEventElapsedTime(&ctx->bdpt_tune_ms[1], et[0], et[1]));
+          CUDA_TRY(cudaEventElapsedTime(&ctx->bdpt_tune_ms[0], et[1], et[2]));
+          tracer = ctx->bdpt_tune_ms[1] < ctx->bdpt_tune_ms[0] ? 1 : 0;
+          ctx->bdpt_tracer_tuned = tracer;
+        }
+      }
     }
+    if (tune)
+      for (cudaEvent_t e : et) cudaEventDestroy(e);
     for (int k = 0; k < n_lanes; ++k) {
       BdptLane& L = ctx->bdpt_lanes[k];
       CUDA_TRY(cudaMemcpyAsync(L.ctl_host, L.b.ctl, sizeof(BdptCtl), cudaMemcpyDeviceToHost, L.stream));
@@ -1646,13 +1678,17 @@ extern "C" int tutu_scene_upload(TutuCtx* ctx, const TutuSceneDesc* desc) {
     if (const char* e = getenv("TUTU_SHADE_BLOCK_RT")) ctx->shade_block = atoi(e);
 #endif
   }
-  d.refill_min = 8;
+  d.refill_min = kLanesRefillMin;
   d.leaf_batch = kLeafBatch;
+  d.queue_lanes = 0;  // set per batch by bdpt_render
+  d.lanes_leaf_batch = kLanesLeafBatch;
+  ctx->bdpt_tracer_tuned = -1;  // a new scene: bdpt_render measures both queue tracers again
   // stack flavour of the tree kernels: see TutuCtx::stack_shared (a device-built tree has n - 1 nodes and no host copy)
   ctx->tree_bytes = (2 * fs.inner.size()) * sizeof(InnerNode) + fs.geom.size() * sizeof(LeafGeom);
   ctx->stack_shared = ctx->stack_cfg ? ctx->stack_cfg == 1 : ctx->tree_bytes > kLocalStackMaxTreeBytes;
 #ifdef TUTU_EXPERIMENTS  // never in the shipped library: the pruning slack is part of the parity argument (trace.cuh)
   if (const char* e = getenv("TUTU_LEAF_BATCH")) d.leaf_batch = atoi(e);
+  if (const char* e = getenv("TUTU_LANES_LEAF_BATCH")) d.lanes_leaf_batch = atoi(e);
   if (const char* e = getenv("TUTU_REFILL_MIN")) d.refill_min = atoi(e);
   if (const char* e = getenv("TUTU_PRUNE_REL")) d.prune_rel = (float)atof(e);
   if (const char* e = getenv("TUTU_PRUNE_ABS")) d.prune_abs = (float)atof(e);
@@ -1722,6 +1758,21 @@ extern "C" int tutu_scene_set_camera(TutuCtx* ctx, const TutuCamera* cam) {
   ctx->flat.raygen = rg;
   ctx->flat.bdpt_cam = bc;
   ctx->flat.camera = *cam;
+  return TUTU_OK;
+}
+
+extern "C" int tutu_bdpt_queue_tracer(TutuCtx* ctx, int tracer) {
+  if (!ctx || tracer < 0 || tracer > 2) return fail(ctx, TUTU_E_INVALID, "tutu_bdpt_queue_tracer: bad argument (0, 1 or 2)");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->bdpt_tracer_cfg = tracer;
+  return TUTU_OK;
+}
+
+extern "C" int tutu_bdpt_queue_tracer_measured(const TutuCtx* ctx, int* tracer, float* ms_packets, float* ms_lanes) {
+  if (!ctx || !tracer || !ms_packets || !ms_lanes) return fail(const_cast<TutuCtx*>(ctx), TUTU_E_INVALID, "tutu_bdpt_queue_tracer_measured: null argument");
+  *tracer = ctx->bdpt_tracer_tuned;
+  *ms_packets = ctx->bdpt_tune_ms[0];
+  *ms_lanes = ctx->bdpt_tune_ms[1];
   return TUTU_OK;
 }
 
