@@ -1,4 +1,4 @@
-"""Traversal stack in shared memory vs in local memory (experiment build, TUTU_STACK_SHARED=0/1 read at upload) as a
+"""Traversal stack in shared memory vs in local memory (tutu_traversal_stack) as a
 function of the tree size: any-hit batches (both ray kinds) over height-fields of G x G quads, the glass scene, the Veach room."""
 import os, sys, json
 sys.path.insert(0, '/root/repo')
@@ -13,8 +13,7 @@ for G in (24, 64, 128, 200, 280, 400, 707):
     sc = api.Scene(prims=prims, materials=api.default_material(), bvh_nodes=api.bvh_build(prims))
     rec = {'G': G, 'tris': len(prims), 'tree_MB': round(len(prims) * (2 * 64 + 48) / 2**20, 2)}
     for shared in (0, 1):
-        os.environ['TUTU_STACK_SHARED'] = str(shared)
-        ctx = api.Context(0); ctx.upload(sc)
+        ctx = api.Context(0); ctx.traversal_stack('shared' if shared else 'local'); ctx.upload(sc)
         for kind in (0, 1):
             rays = torch.from_numpy(api.synth_rays(kind, N)).cuda()
             a = torch.empty(N, dtype=torch.uint8, device='cuda')
@@ -31,17 +30,16 @@ for G in (24, 64, 128, 200, 280, 400, 707):
         ctx.close()
     print(json.dumps(rec), flush=True)
 for shared in (0, 1):
-    os.environ['TUTU_STACK_SHARED'] = str(shared)
     rec = {'shared': shared}
     sc = api.Scene.load(G_ + 'glass_c4.tscene').with_size(1024, 1024)
-    ctx = api.Context(0); ctx.upload(sc)
+    ctx = api.Context(0); ctx.traversal_stack('shared' if shared else 'local'); ctx.upload(sc)
     for k in range(2):
         ctx.render_path(32, seed=k)
     img = ctx.render_path(128, seed=9)
     rec['glass'] = round(1024 * 1024 * 128 / ctx.stats()['gpu_ms'] * 1e-3, 1); rec['glass_mean'] = round(float(img.mean()), 6)
     ctx.close()
     sc = api.Scene.load(G_ + 'veach_80x60.tscene').with_size(800, 600)
-    ctx = api.Context(0); ctx.upload(sc)
+    ctx = api.Context(0); ctx.traversal_stack('shared' if shared else 'local'); ctx.bdpt_queue_tracer('packets'); ctx.upload(sc)
     for k in range(2):
         ctx.render_bdpt(16, seed=k)
     im = ctx.render_bdpt(128, seed=9)
