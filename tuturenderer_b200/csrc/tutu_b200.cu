@@ -1358,9 +1358,16 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
     const bool tree_kernels = !small && !wide;
     int tracer = ctx->bdpt_tracer_cfg ? ctx->bdpt_tracer_cfg - 1 : (ctx->bdpt_tracer_tuned >= 0 ? ctx->bdpt_tracer_tuned : 0);
     const bool tune = tree_kernels && !ctx->bdpt_tracer_cfg && ctx->bdpt_tracer_tuned < 0 && n_batches >= kBdptTuneMinBatches;
-    cudaEvent_t et[3] = {nullptr, nullptr, nullptr};
+    struct TuneEvents {  // destroyed on every way out of the render
+      cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+      ~TuneEvents() {
+        for (cudaEvent_t x : e)
+          if (x) cudaEventDestroy(x);
+      }
+    } tune_events;
+    cudaEvent_t* et = tune_events.e;
     if (tune)
-      for (cudaEvent_t& e : et) CUDA_TRY(cudaEventCreate(&e));
+      for (int k = 0; k < 3; ++k) CUDA_TRY(cudaEventCreate(&et[k]));
     DevScene dv = ctx->dev;
     uint64_t batch = 0;
     for (uint64_t first = 0; first < total; first += cap, ++batch) {
@@ -1416,8 +1423,6 @@ void bdpt_render(TutuCtx* ctx, uint32_t sample_begin, uint32_t sample_count, uin
         }
       }
     }
-    if (tune)
-      for (cudaEvent_t e : et) cudaEventDestroy(e);
     for (int k = 0; k < n_lanes; ++k) {
       BdptLane& L = ctx->bdpt_lanes[k];
       CUDA_TRY(cudaMemcpyAsync(L.ctl_host, L.b.ctl, sizeof(BdptCtl), cudaMemcpyDeviceToHost, L.stream));
